@@ -1,0 +1,128 @@
+/*
+ * noisediff_b200 — C ABI of the B200-native NoiseDiff sampling hot path.
+ *
+ * The reference (IVRL/NoiseDiff) is pure Python/PyTorch and has no FFI; this header is the boundary a maintainer
+ * binds from Python (ctypes — see INTEGRATION.md).  Each entry point names the reference interface it replaces
+ * (paths relative to the reference tree).  Conventions:
+ *   - every function returns 0 on success, non-zero on failure; ndiff_last_error() then describes the failure.
+ *     Nothing throws across the boundary.
+ *   - "dev" pointers are CUDA device pointers owned by the caller (e.g. torch tensors); "host" pointers are CPU
+ *     memory.  The library owns only its packed weights, workspace and CUDA graphs.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Calls are asynchronous on that
+ *     stream unless stated otherwise.
+ *   - an engine belongs to one device and one caller thread at a time (the reference is single-threaded too).
+ *   - tensors use the reference's layouts: images fp32 NCHW (B,4,H,W); position fp32 (B,2,H,W); indices int64.
+ */
+#ifndef NOISEDIFF_B200_H_
+#define NOISEDIFF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NDIFF_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define NDIFF_API __attribute__((visibility("default")))
+#else
+#define NDIFF_API
+#endif
+
+typedef struct ndiff_engine ndiff_engine;
+
+/* Geometry of one engine: the network of NoiseDiffNet(args) (models/archs/Diffusion_arch.py:447-573) for a fixed
+ * micro-batch and crop.  dim = args.dim (64), height/width = crop (multiples of 8, ref :578). */
+typedef struct ndiff_config {
+    int32_t dim;
+    int32_t batch;
+    int32_t height;
+    int32_t width;
+    int32_t device;      /* CUDA ordinal */
+    int32_t flags;       /* NDIFF_FLAG_* */
+} ndiff_config;
+
+#define NDIFF_FLAG_CONV_DIRECT 1   /* debug: 3x3 convs load every tap from L2 instead of the halo layout */
+#define NDIFF_FLAG_NO_GRAPH    2   /* debug: launch kernels eagerly instead of replaying a CUDA graph */
+
+/* One reverse step's scalars; the caller derives them from GaussianDiffusion's fp32 buffers
+ * (models/denoising_diffusion_pytorch.py:240-266) so the arithmetic constants are the reference's own:
+ *   x0  = clamp(p*x + q*net_out, -1, 1) if clip          predict_start_from_v/_noise :298-320, clamp :361
+ *   eps = (r1*x - x0) / r2                                predict_noise_from_start :304-308
+ *   x'  = ((a*x0 + b*x) + c*eps) + sigma*z                q_posterior :322-329 + p_sample :366-373 (c = 0)
+ *                                                         ddim_sample :427-437 (b = 0)                       */
+typedef struct ndiff_step {
+    int32_t t;
+    float p, q, a, b, c, r1, r2, sigma;
+    int32_t clip;
+    int32_t reserved[2];
+} ndiff_step;
+
+NDIFF_API int32_t     ndiff_abi_version(void);
+NDIFF_API const char* ndiff_last_error(void);
+
+/* Lifetime.  Replaces NoiseDiffNet.__init__ + .to(device) (Diffusion_arch.py:447-573, models/modules.py:73-83). */
+NDIFF_API int32_t ndiff_engine_create(const ndiff_config* cfg, ndiff_engine** out);
+NDIFF_API void    ndiff_engine_destroy(ndiff_engine* e);
+
+/* Weights.  Replaces load_state_dict (models/trainer_diffusion.py:333-349): call once per state_dict entry with the
+ * reference's key (e.g. "downs.0.0.block1.proj.weight") and fp32 data (host or device pointer), then finalize —
+ * which fails if any of the live keys is missing or mis-shaped.  Dead keys (attn.to_q/to_k, norm1) are accepted
+ * and ignored. */
+NDIFF_API int32_t ndiff_load_param(ndiff_engine* e, const char* name, const float* data, int32_t ndim, const int64_t* shape);
+NDIFF_API int32_t ndiff_finalize_params(ndiff_engine* e, void* stream);
+
+/* Condition.  Replaces the step-invariant head of NoiseDiffNet.forward (Diffusion_arch.py:580-591): position
+ * encoding + pos MLP + ResnetBlock2 scale/shift maps, ISO embedding -> collapsed cross-attention vectors. */
+NDIFF_API int32_t ndiff_set_condition(ndiff_engine* e, const float* clean_dev, const float* position_dev,
+                            const int64_t* iso_idx_dev, void* stream);
+
+/* One network evaluation.  Replaces NoiseDiffNet.forward(x, time, condition) (Diffusion_arch.py:577-646). */
+NDIFF_API int32_t ndiff_forward(ndiff_engine* e, const float* x_dev, const int64_t* time_dev, float* out_dev, void* stream);
+
+/* Reverse chain.  Replaces GaussianDiffusion.p_sample_loop / ddim_sample
+ * (models/denoising_diffusion_pytorch.py:375-444).
+ *   begin : uploads the step table (host), sets x_T from x_init_dev (fp32 NCHW) or, if NULL, from Philox(seed).
+ *   run   : executes the next n steps (one CUDA-graph replay each).  noise_dev: injected N(0,1) draws
+ *           [n][B,4,H,W] fp32 NCHW for those steps, or NULL for in-kernel Philox.  teacher_dev (optional):
+ *           network inputs [n][B,4,H,W] replacing the running state (teacher-forced parity checks).
+ *           snapshots_dev (optional): receives x after each of the n steps, [n][B,4,H,W].
+ *   read  : copies the current state to out_dev (fp32 NCHW). */
+NDIFF_API int32_t ndiff_chain_begin(ndiff_engine* e, const ndiff_step* steps_host, int32_t n_steps, const float* x_init_dev,
+                          uint64_t seed, void* stream);
+NDIFF_API int32_t ndiff_chain_run(ndiff_engine* e, int32_t n, const float* noise_dev, const float* teacher_dev,
+                        float* snapshots_dev, void* stream);
+NDIFF_API int32_t ndiff_chain_read(ndiff_engine* e, float* out_dev, void* stream);
+
+/* End-to-end convenience with HOST buffers (what Trainer.test() does per batch, models/trainer_diffusion.py:256-317:
+ * host->device copies, full chain, device->host copy).  Synchronous. */
+NDIFF_API int32_t ndiff_sample_host(ndiff_engine* e, const float* clean_host, const float* position_host,
+                          const int64_t* iso_idx_host, const ndiff_step* steps_host, int32_t n_steps, uint64_t seed,
+                          float* out_host);
+
+/* Introspection used by tests / bench. */
+NDIFF_API int32_t ndiff_debug_tensor(ndiff_engine* e, const char* name, float* out_dev_nchw, int64_t* shape4, void* stream);
+NDIFF_API int64_t ndiff_launches_per_step(const ndiff_engine* e);
+NDIFF_API double  ndiff_conv_flops_per_step(const ndiff_engine* e);    /* executed tensor-core FLOPs per network evaluation */
+NDIFF_API int32_t ndiff_time_layers(ndiff_engine* e, int32_t iters, float* ms_out, char* names_out, int32_t names_cap,
+                          int32_t* n_out, void* stream);
+
+/* Single-operator entry points (parity tests of the individual kernels; pointers are device pointers, activations
+ * bf16 NHWC). */
+NDIFF_API int32_t ndiff_op_conv(int32_t mode, int32_t B, int32_t H, int32_t W, const void* src0, int32_t C0, const void* src1,
+                      int32_t C1, int32_t taps_y, int32_t taps_x, int32_t pad_y, int32_t pad_x, const void* weight_packed,
+                      int32_t Cout, const float* bias, const float* vec, int32_t vec_ld, const void* res, int32_t act,
+                      float* stats, int32_t groups, void* out, int32_t force_nt, int32_t tile_w, void* stream);
+NDIFF_API int32_t ndiff_op_gn_apply(const void* x, void* out, const float* stats, const float* gamma, const float* beta,
+                          const float* ss, int32_t ss_ld, int32_t ss_off, const void* maps, const void* res1,
+                          const void* res2, int32_t B, int32_t HW, int32_t C, int32_t G, void* stream);
+NDIFF_API int32_t ndiff_op_layernorm(const void* x, const float* vec, int32_t vec_ld, const float* g, const float* beta, void* out,
+                           int32_t B, int32_t HW, int32_t C, void* stream);
+NDIFF_API int32_t ndiff_op_philox_normal(float* out, int64_t n4, uint64_t seed, uint64_t stream_id, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NOISEDIFF_B200_H_ */

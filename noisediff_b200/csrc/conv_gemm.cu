@@ -1,0 +1,429 @@
+// noisediff_b200 — tcgen05 implicit-GEMM convolution over NHWC bf16 activations (sm_100a).
+//
+// GEMM view (SURVEY.md §8a "3x3 conv shape census"): M = pixels, N = C_out, K = taps * C_in.
+//   A (M x K)  : activations, K-major.  One smem row = one pixel's 64-channel block = 128 B -> SWIZZLE_128B rows.
+//                TMA boxes {64 ch, TW, rows, 1 image} land a TH x TW pixel tile directly in that layout; a conv tap is
+//                a shifted window, so out-of-image pixels are the TMA's zero fill (pad = 1 for free).
+//   B (N x K)  : weights, repacked once to bf16 [C_out][cblk][tap][64], K-major, 2-D TMA boxes {64, NT}.
+//   D (M x N)  : fp32 accumulator in TMEM, 128 lanes (pixels) x NT columns, double-buffered across tiles.
+// Persistent CTA, 8 warps: w0 = TMA producer, w1 = MMA issuer (one elected lane issues tcgen05.mma),
+// w2 = TMEM allocator, w4..7 = epilogue (tcgen05.ld -> bias / per-sample vector / residual / GELU / GroupNorm
+// partial sums -> bf16 NHWC stores).  Replaces the reference's aten::conv2d / aten::linear calls inside
+// Block.proj, res_conv, Downsample, AttnBlock.{ff,proj_out} and Mlp.fc* (models/archs/Diffusion_arch.py:128-443).
+#include "conv_gemm.cuh"
+
+#include <cstring>
+#include <mutex>
+
+namespace ndiff {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kEpiWarp0 = 4;
+
+struct SmemTail {  // lives after the operand rings
+    uint64_t fullA[8], emptyA[8], fullB[16], emptyB[16];
+    uint64_t tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base;
+    float stats[32];
+};
+
+template <int NT>
+__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // dynamic smem is only guaranteed 16-B aligned by the ABI; SWIZZLE_128B wants 1024
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int kBStage = NT * 128;
+    uint8_t* ringA = smem;
+    uint8_t* ringB = ringA + a.a_stages * a.a_stage_bytes;
+    SmemTail* tail = reinterpret_cast<SmemTail*>(ringB + a.b_stages * kBStage);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int CB = a.cb0 + a.cb1;
+    const int TAPS = a.taps_y * a.taps_x;
+    const bool halo = a.mode == kHalo3;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&a.tmA0);
+        if (a.cb1 > 0) tma_prefetch_desc(&a.tmA1);
+        tma_prefetch_desc(&a.tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < a.a_stages; ++i) { mbar_init(&tail->fullA[i], 1); mbar_init(&tail->emptyA[i], 1); }
+        for (int i = 0; i < a.b_stages; ++i) { mbar_init(&tail->fullB[i], 1); mbar_init(&tail->emptyB[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tail->tmem_full[i], 1); mbar_init(&tail->tmem_empty[i], 4); }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc<2 * NT>(&tail->tmem_base);
+    if (threadIdx.x < 32) tail->stats[threadIdx.x] = 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tail->tmem_base;
+
+    if (warp == 0) {
+        // ================================ TMA producer =========================================================
+        if (lane == 0) {
+            int sa = 0, pa = 0, sb = 0, pb = 0;
+            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+                const int nt = tile % a.n_tiles;
+                int m = tile / a.n_tiles;
+                const int tx = m % a.tiles_x; m /= a.tiles_x;
+                const int ty = m % a.tiles_y;
+                const int b = m / a.tiles_y;
+                const int x0 = tx * a.TW, y0 = ty * a.TH;
+                for (int cb = 0; cb < CB; ++cb) {
+                    const CUtensorMap* tm = cb < a.cb0 ? &a.tmA0 : &a.tmA1;
+                    const int c0 = (cb < a.cb0 ? cb : cb - a.cb0) * 64;
+                    if (halo) {
+                        mbar_wait(&tail->emptyA[sa], pa ^ 1);
+                        mbar_expect_tx(&tail->fullA[sa], 3 * a.a_copy_bytes);
+                        uint8_t* dst = ringA + sa * a.a_stage_bytes;
+                        for (int kx = 0; kx < 3; ++kx)
+                            tma_load_4d(dst + kx * a.a_copy_bytes, tm, &tail->fullA[sa], c0, x0 + kx - 1, y0 - 1, b);
+                        if (++sa == a.a_stages) { sa = 0; pa ^= 1; }
+                    }
+                    for (int tap = 0; tap < TAPS; ++tap) {
+                        if (!halo) {
+                            mbar_wait(&tail->emptyA[sa], pa ^ 1);
+                            mbar_expect_tx(&tail->fullA[sa], 128 * 128);
+                            uint8_t* dst = ringA + sa * a.a_stage_bytes;
+                            const int ky = tap / a.taps_x, kx = tap - ky * a.taps_x;
+                            if (a.mode == kS2D)
+                                tma_load_5d(dst, tm, &tail->fullA[sa], c0, kx, x0, ky, b * a.H + y0);
+                            else
+                                tma_load_4d(dst, tm, &tail->fullA[sa], c0, x0 + kx - a.pad_x, y0 + ky - a.pad_y, b);
+                            if (++sa == a.a_stages) { sa = 0; pa ^= 1; }
+                        }
+                        mbar_wait(&tail->emptyB[sb], pb ^ 1);
+                        mbar_expect_tx(&tail->fullB[sb], kBStage);
+                        tma_load_2d(ringB + sb * kBStage, &a.tmB, &tail->fullB[sb], (cb * TAPS + tap) * 64, nt * NT);
+                        if (++sb == a.b_stages) { sb = 0; pb ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ===========================================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, NT);
+            int sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
+            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+                mbar_wait(&tail->tmem_empty[acc], pacc ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * NT;
+                uint32_t first = 1;
+                for (int cb = 0; cb < CB; ++cb) {
+                    if (halo) { mbar_wait(&tail->fullA[sa], pa); }
+                    for (int tap = 0; tap < TAPS; ++tap) {
+                        if (!halo) { mbar_wait(&tail->fullA[sa], pa); }
+                        mbar_wait(&tail->fullB[sb], pb);
+                        tc_fence_after();
+                        uint32_t a_addr = smem_u32(ringA + sa * a.a_stage_bytes);
+                        if (halo) {
+                            const int ky = tap / 3, kx = tap - ky * 3;
+                            a_addr += kx * a.a_copy_bytes + ky * a.TW * 128;
+                        }
+                        const uint32_t b_addr = smem_u32(ringB + sb * kBStage);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
+                                      first ? 0u : 1u);
+                            first = 0;
+                        }
+                        umma_commit(&tail->emptyB[sb]);
+                        if (++sb == a.b_stages) { sb = 0; pb ^= 1; }
+                        if (!halo) {
+                            umma_commit(&tail->emptyA[sa]);
+                            if (++sa == a.a_stages) { sa = 0; pa ^= 1; }
+                        }
+                    }
+                    if (halo) {
+                        umma_commit(&tail->emptyA[sa]);
+                        if (++sa == a.a_stages) { sa = 0; pa ^= 1; }
+                    }
+                }
+                umma_commit(&tail->tmem_full[acc]);
+                if (++acc == 2) { acc = 0; pacc ^= 1; }
+            }
+        }
+    } else if (warp >= kEpiWarp0) {
+        // ================================ epilogue =============================================================
+        const int q = warp & 3;              // TMEM lane quarter this warp may read
+        const int ethread = threadIdx.x - kEpiWarp0 * 32;
+        int acc = 0, pacc = 0;
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+            const int nt = tile % a.n_tiles;
+            int m = tile / a.n_tiles;
+            const int tx = m % a.tiles_x; m /= a.tiles_x;
+            const int ty = m % a.tiles_y;
+            const int b = m / a.tiles_y;
+            const int r = q * 32 + lane;
+            const int y = ty * a.TH + (r >> a.lgTW), x = tx * a.TW + (r & (a.TW - 1));
+            const bool valid = (y < a.H) && (x < a.W);
+            const size_t pix = (static_cast<size_t>(b) * a.H + y) * a.W + x;
+            const int n0 = nt * NT;
+
+            mbar_wait(&tail->tmem_full[acc], pacc);
+            tc_fence_after();
+#pragma unroll 1
+            for (int ch = 0; ch < NT / 32; ++ch) {
+                uint32_t raw[32];
+                tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * NT + ch * 32, raw);
+                tmem_ld_wait();
+                const int nbase = n0 + ch * 32;
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+                if (a.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + nbase + j));
+                        v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+                    }
+                }
+                if (a.act == kActGelu) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                }
+                if (a.vec) {
+                    const float* vp = a.vec + static_cast<size_t>(b) * a.vec_ld + nbase;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(vp + j));
+                        v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+                    }
+                }
+                if (a.res && valid) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(a.res + pix * a.res_ld + nbase);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 u = __ldg(rp + j);
+                        float2 f;
+                        f = unpack_bf16(u.x); v[j * 8 + 0] += f.x; v[j * 8 + 1] += f.y;
+                        f = unpack_bf16(u.y); v[j * 8 + 2] += f.x; v[j * 8 + 3] += f.y;
+                        f = unpack_bf16(u.z); v[j * 8 + 4] += f.x; v[j * 8 + 5] += f.y;
+                        f = unpack_bf16(u.w); v[j * 8 + 6] += f.x; v[j * 8 + 7] += f.y;
+                    }
+                }
+                if (a.stats) {
+                    float s[4], sq[4];
+                    const float msk = valid ? 1.f : 0.f;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { const float w = v[g * 8 + j]; t0 += w; t1 += w * w; }
+                        s[g] = t0 * msk; sq[g] = t1 * msk;
+                    }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) { s[g] = warp_sum(s[g]); sq[g] = warp_sum(sq[g]); }
+                    if (lane == 0) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const int gl = (ch * 32 + g * 8) >> a.lgs;
+                            atomicAdd(&tail->stats[gl * 2], s[g]);
+                            atomicAdd(&tail->stats[gl * 2 + 1], sq[g]);
+                        }
+                    }
+                }
+                if (valid) {
+                    uint4* op = reinterpret_cast<uint4*>(a.out + pix * a.out_ld + nbase);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 u;
+                        u.x = pack_bf16(v[j * 8 + 0], v[j * 8 + 1]);
+                        u.y = pack_bf16(v[j * 8 + 2], v[j * 8 + 3]);
+                        u.z = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]);
+                        u.w = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
+                        op[j] = u;
+                    }
+                }
+            }
+            // accumulator drained: hand the TMEM stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tail->tmem_empty[acc]);
+            if (++acc == 2) { acc = 0; pacc ^= 1; }
+
+            if (a.stats) {
+                named_bar_sync(1, 128);
+                const int ng = NT >> a.lgs;
+                if (ethread < ng * 2) {
+                    const int g = (n0 >> a.lgs) + (ethread >> 1);
+                    atomicAdd(&a.stats[(static_cast<size_t>(b) * a.G + g) * 2 + (ethread & 1)], tail->stats[ethread]);
+                    tail->stats[ethread] = 0.f;
+                }
+                named_bar_sync(1, 128);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<2 * NT>(tmem_base);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+int ilog2(int v) {
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return l;
+}
+
+}  // namespace
+
+int encode_tensor_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, bool swizzle128) {
+    EncodeTiledFn fn = get_encode_fn();
+    NDIFF_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the CUDA driver");
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        std::string s = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)) + " (rank " +
+                        std::to_string(rank) + ", dims";
+        for (int i = 0; i < rank; ++i) s += " " + std::to_string(dims[i]);
+        s += ", strides";
+        for (int i = 0; i + 1 < rank; ++i) s += " " + std::to_string(strides_bytes[i]);
+        s += ", box";
+        for (int i = 0; i < rank; ++i) s += " " + std::to_string(box[i]);
+        s += ")";
+        set_error(s);
+        return 1;
+    }
+    return 0;
+}
+
+int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
+    ConvGemmArgs& a = plan->args;
+    memset(&a, 0, sizeof(a));
+    NDIFF_REQUIRE(d.C0 > 0 && d.C0 % 64 == 0 && d.C1 % 64 == 0, "channel counts must be multiples of 64");
+    NDIFF_REQUIRE(d.Cout % 64 == 0, "C_out must be a multiple of 64");
+    int NT = d.force_nt ? d.force_nt : (d.Cout % 128 == 0 ? 128 : 64);
+    NDIFF_REQUIRE((NT == 64 || NT == 128) && d.Cout % NT == 0, "unsupported N tile");
+    plan->NT = NT;
+    a.mode = d.mode;
+    a.B = d.B; a.H = d.H; a.W = d.W;
+    int TW = d.TW;
+    if (TW == 0) {
+        if (d.mode == kHalo3) TW = d.H >= 16 ? 8 : 16;
+        else TW = d.W >= 64 ? 64 : (d.W >= 32 ? 32 : (d.W >= 16 ? 16 : 8));
+    }
+    NDIFF_REQUIRE(TW >= 8 && TW <= 128 && (TW & (TW - 1)) == 0, "tile width must be a power of two in [8,128]");
+    a.TW = TW; a.TH = 128 / TW; a.lgTW = ilog2(TW);
+    a.tiles_x = (d.W + a.TW - 1) / a.TW;
+    a.tiles_y = (d.H + a.TH - 1) / a.TH;
+    a.cb0 = d.C0 / 64; a.cb1 = d.C1 / 64;
+    if (d.mode == kHalo3) { a.taps_y = 3; a.taps_x = 3; a.pad_y = 1; a.pad_x = 1; }
+    else if (d.mode == kS2D) { a.taps_y = 2; a.taps_x = 2; a.pad_y = 0; a.pad_x = 0; }
+    else { a.taps_y = d.taps_y; a.taps_x = d.taps_x; a.pad_y = d.pad_y; a.pad_x = d.pad_x; }
+    a.n_tiles = d.Cout / NT;
+    a.total_tiles = d.B * a.tiles_y * a.tiles_x * a.n_tiles;
+    const int b_stage = NT * 128;
+    if (d.mode == kHalo3) {
+        a.a_copy_bytes = (a.TH + 2) * a.TW * 128;
+        a.a_stage_bytes = 3 * a.a_copy_bytes;
+        a.a_stages = 2;
+        a.b_stages = NT == 128 ? 5 : 8;
+    } else {
+        a.a_copy_bytes = 128 * 128;
+        a.a_stage_bytes = 128 * 128;
+        a.a_stages = NT == 128 ? 6 : 8;
+        a.b_stages = a.a_stages;
+    }
+    NDIFF_REQUIRE(a.a_stage_bytes % 1024 == 0 && a.a_copy_bytes % 1024 == 0, "operand stages must stay 1024-B aligned");
+    plan->smem_bytes = 1024 + a.a_stages * a.a_stage_bytes + a.b_stages * b_stage + static_cast<int>(sizeof(SmemTail));
+    NDIFF_REQUIRE(plan->smem_bytes <= 227 * 1024, "shared-memory budget exceeded");
+    plan->grid = a.total_tiles < num_sms ? a.total_tiles : num_sms;
+
+    // ---- tensor maps -------------------------------------------------------------------------------------
+    const int Hin = d.mode == kS2D ? 2 * d.H : d.H, Win = d.mode == kS2D ? 2 * d.W : d.W;
+    for (int s = 0; s < 2; ++s) {
+        const __nv_bfloat16* src = s == 0 ? d.src0 : d.src1;
+        const int C = s == 0 ? d.C0 : d.C1;
+        if (C == 0) continue;
+        NDIFF_REQUIRE(src != nullptr, "null activation source");
+        CUtensorMap* tm = s == 0 ? &a.tmA0 : &a.tmA1;
+        if (s == 0 && d.custom_src0) {
+            uint32_t box[4] = {64, static_cast<uint32_t>(a.TW), static_cast<uint32_t>(a.TH), 1};
+            if (encode_tensor_map(tm, src, 4, d.cdim, d.cstride, box, true)) return 1;
+        } else if (d.mode == kS2D) {
+            // input [B, 2H, 2W, C] viewed as (C, p2, W, p1, B*H)
+            uint64_t dims[5] = {static_cast<uint64_t>(C), 2, static_cast<uint64_t>(d.W), 2,
+                                static_cast<uint64_t>(d.B) * d.H};
+            uint64_t str[4] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(C) * 4,
+                               static_cast<uint64_t>(Win) * C * 2, static_cast<uint64_t>(Win) * C * 4};
+            uint32_t box[5] = {64, 1, static_cast<uint32_t>(a.TW), 1, static_cast<uint32_t>(a.TH)};
+            if (encode_tensor_map(tm, src, 5, dims, str, box, true)) return 1;
+        } else {
+            uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin),
+                                static_cast<uint64_t>(d.B)};
+            uint64_t str[3] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(Win) * C * 2,
+                               static_cast<uint64_t>(Hin) * Win * C * 2};
+            uint32_t box[4] = {64, static_cast<uint32_t>(a.TW),
+                               static_cast<uint32_t>(d.mode == kHalo3 ? a.TH + 2 : a.TH), 1};
+            if (encode_tensor_map(tm, src, 4, dims, str, box, true)) return 1;
+        }
+    }
+    {
+        const uint64_t Ktot = static_cast<uint64_t>(a.cb0 + a.cb1) * a.taps_y * a.taps_x * 64;
+        uint64_t dims[2] = {Ktot, static_cast<uint64_t>(d.Cout)};
+        uint64_t str[1] = {Ktot * 2};
+        uint32_t box[2] = {64, static_cast<uint32_t>(NT)};
+        NDIFF_REQUIRE(d.weight != nullptr, "null weight");
+        if (encode_tensor_map(&a.tmB, d.weight, 2, dims, str, box, true)) return 1;
+    }
+    a.bias = d.bias; a.vec = d.vec; a.vec_ld = d.vec_ld; a.res = d.res; a.res_ld = d.res_ld;
+    a.out = d.out; a.out_ld = d.out_ld; a.act = d.act;
+    a.stats = d.stats; a.G = d.groups;
+    if (d.stats) {
+        const int gs = d.Cout / d.groups;
+        NDIFF_REQUIRE(gs >= 8 && (gs & (gs - 1)) == 0 && gs <= NT, "GroupNorm group size must be a power of two in [8, NT]");
+        a.lgs = ilog2(gs);
+    }
+    NDIFF_REQUIRE(d.out != nullptr && d.out_ld % 8 == 0, "output must be 16-byte aligned per pixel");
+    return 0;
+}
+
+int conv_gemm_init() {
+    NDIFF_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    NDIFF_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    return 0;
+}
+
+int conv_gemm_launch(const ConvGemmPlan& plan, cudaStream_t stream) {
+    if (plan.NT == 64)
+        conv_gemm_kernel<64><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.args);
+    else
+        conv_gemm_kernel<128><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.args);
+    NDIFF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace ndiff

@@ -1,0 +1,80 @@
+// noisediff_b200 — tcgen05 implicit-GEMM convolution over NHWC bf16 activations (declarations).
+#pragma once
+#include "common.cuh"
+
+namespace ndiff {
+
+enum ConvMode : int {
+    kDirect = 0,  // every (channel-block, tap) k-block loads its own shifted 128-pixel box (1x1, 7x7-row trick, debug 3x3)
+    kHalo3 = 1,   // 3x3 pad 1: per channel block three kx-shifted (TH+2)xTW halo boxes; 9 taps are row offsets into them
+    kS2D = 2,     // 2x2 stride-2 (space-to-depth + 1x1) through a 5-D view of the input
+};
+enum ConvAct : int { kActNone = 0, kActGelu = 1 };
+
+// Kernel arguments (one struct, passed as a __grid_constant__ so the three tensor maps stay in param space).
+struct ConvGemmArgs {
+    CUtensorMap tmA0, tmA1, tmB;
+    int mode;
+    int B, H, W;           // OUTPUT spatial size (input is the same except kS2D: 2H x 2W)
+    int TH, TW, lgTW;      // pixel tile (TH*TW == 128, TW power of two >= 8)
+    int tiles_x, tiles_y;  // tiles per image
+    int cb0, cb1;          // 64-channel blocks taken from source 0 / source 1 (concat order: 0 then 1)
+    int taps_y, taps_x, pad_y, pad_x;  // tap grid of kDirect (kHalo3: 3,3,1,1; kS2D: 2,2,0,0)
+    int n_tiles;           // Cout / NT
+    int total_tiles;
+    int a_stages, b_stages;
+    int a_stage_bytes, a_copy_bytes;
+    // epilogue
+    const float* bias;           // [Cout] or null
+    const float* vec;            // per-sample vector [B][vec_ld] added to every pixel, or null
+    int vec_ld;
+    const __nv_bfloat16* res;    // residual [B,H,W,res_ld] (same channel offset as the output), or null
+    int res_ld;
+    __nv_bfloat16* out;          // [B,H,W,out_ld]
+    int out_ld;
+    int act;
+    float* stats;                // GroupNorm partial sums [B][G][2] (sum, sum of squares) or null
+    int lgs;                     // log2(channels per group)
+    int G;
+};
+
+// Host-side description of one convolution / GEMM launch, built once per layer at plan time.
+struct ConvGemmPlan {
+    ConvGemmArgs args;
+    int NT;          // 64 or 128
+    int grid;
+    int smem_bytes;
+};
+
+struct ConvGemmDesc {
+    int mode = kDirect;
+    int B = 0, H = 0, W = 0;            // output spatial size
+    const __nv_bfloat16* src0 = nullptr; int C0 = 0;   // NHWC bf16, C0 % 64 == 0
+    const __nv_bfloat16* src1 = nullptr; int C1 = 0;   // optional second concat source
+    int taps_y = 1, taps_x = 1, pad_y = 0, pad_x = 0;
+    // kDirect special: source 0 described by an explicit (possibly overlapping-window) 4-D map
+    bool custom_src0 = false;
+    uint64_t cdim[4] = {0, 0, 0, 0};     // dims innermost first
+    uint64_t cstride[3] = {0, 0, 0};     // byte strides of dims 1..3
+    const __nv_bfloat16* weight = nullptr;  // [Cout][Ktot] bf16, K order [cblk][tap][64]
+    int Cout = 0;
+    const float* bias = nullptr;
+    const float* vec = nullptr; int vec_ld = 0;
+    const __nv_bfloat16* res = nullptr; int res_ld = 0;
+    __nv_bfloat16* out = nullptr; int out_ld = 0;
+    int act = kActNone;
+    float* stats = nullptr; int groups = 0;
+    int force_nt = 0;                    // 0 = auto
+    int TW = 0;                          // 0 = auto
+};
+
+// Fills `plan` (tensor maps, tiling, smem).  Returns 0 on success, 1 with set_error() otherwise.
+int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan);
+int conv_gemm_launch(const ConvGemmPlan& plan, cudaStream_t stream);
+int conv_gemm_init();   // one-time kernel attribute setup for the current device (call outside stream capture)
+
+// Driver entry point for tensor-map encoding, resolved at run time (no link-time libcuda dependency).
+int encode_tensor_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, bool swizzle128);
+
+}  // namespace ndiff

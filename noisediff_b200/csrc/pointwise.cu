@@ -1,0 +1,639 @@
+// noisediff_b200 — HBM-bound kernels around the tensor-core convolutions (sm_100a).
+// All activations are NHWC bf16 (16-byte vectors of 8 channels); the chain state x_t is NHWC fp32 (one float4 / pixel).
+#include "pointwise.cuh"
+
+namespace ndiff {
+
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    float2 t;
+    t = unpack_bf16(u.x); f[0] = t.x; f[1] = t.y;
+    t = unpack_bf16(u.y); f[2] = t.x; f[3] = t.y;
+    t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
+    t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 u;
+    u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]);
+    u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+    return u;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// GroupNorm apply
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kGnThreads = 256;
+constexpr int kGnVecPerThread = 8;
+
+__global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnApplyArgs a) {
+    __shared__ float sA[512], sB[512];
+    const int b = blockIdx.y;
+    const int C = a.C, gs = C / a.G;
+    const float inv_n = 1.0f / (static_cast<float>(a.HW) * gs);
+    for (int c = threadIdx.x; c < C; c += kGnThreads) {
+        const int g = c / gs;
+        const float s = a.stats[(b * a.G + g) * 2], ss = a.stats[(b * a.G + g) * 2 + 1];
+        const float mean = s * inv_n;
+        const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + a.eps);
+        float A = rstd * a.gamma[c];
+        float Bc = a.beta[c] - mean * A;
+        if (a.ss) {
+            const float sc = a.ss[static_cast<size_t>(b) * a.ss_ld + a.ss_off + c] + 1.0f;
+            const float sh = a.ss[static_cast<size_t>(b) * a.ss_ld + a.ss_off + C + c];
+            A *= sc;
+            Bc = Bc * sc + sh;
+        }
+        sA[c] = A; sB[c] = Bc;
+    }
+    __syncthreads();
+    const int cv = C >> 3;                                   // 16-B vectors per pixel
+    const size_t nvec = static_cast<size_t>(a.HW) * cv;      // per sample
+    const size_t base = static_cast<size_t>(b) * nvec;
+    const uint4* xin = reinterpret_cast<const uint4*>(a.x) + base;
+    uint4* xout = reinterpret_cast<uint4*>(a.out) + base;
+    const uint4* r1 = a.res1 ? reinterpret_cast<const uint4*>(a.res1) + base : nullptr;
+    const uint4* r2 = a.res2 ? reinterpret_cast<const uint4*>(a.res2) + base : nullptr;
+    const uint4* mp = a.maps ? reinterpret_cast<const uint4*>(a.maps) + base * 2 : nullptr;
+    const size_t v0 = static_cast<size_t>(blockIdx.x) * (kGnThreads * kGnVecPerThread) + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < kGnVecPerThread; ++i) {
+        const size_t v = v0 + static_cast<size_t>(i) * kGnThreads;
+        if (v >= nvec) break;
+        const int c0 = static_cast<int>(v % cv) * 8;
+        float f[8];
+        unpack8(__ldg(xin + v), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = f[j] * sA[c0 + j] + sB[c0 + j];
+        if (mp) {
+            const size_t pix = v / cv;
+            float sc[8], sh[8];
+            unpack8(__ldg(mp + pix * (2 * cv) + (c0 >> 3)), sc);
+            unpack8(__ldg(mp + pix * (2 * cv) + cv + (c0 >> 3)), sh);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = f[j] * (sc[j] + 1.0f) + sh[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = silu(f[j]);
+        if (r1) {
+            float r[8];
+            unpack8(__ldg(r1 + v), r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += r[j];
+        }
+        if (r2) {
+            float r[8];
+            unpack8(__ldg(r2 + v), r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += r[j];
+        }
+        xout[v] = pack8(f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LayerNorm over channels of (x + vec[b]); one warp per pixel, lane owns channel pairs {2*lane + 64*j}
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ vec,
+                                                        int vec_ld, const float* __restrict__ g,
+                                                        const float* __restrict__ beta, bf16* __restrict__ out,
+                                                        int HW, int C, size_t npix) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
+    const int nj = C >> 6;
+    for (size_t pix = warp; pix < npix; pix += nwarps) {
+        const int b = static_cast<int>(pix / HW);
+        const uint32_t* xp = reinterpret_cast<const uint32_t*>(x + pix * C);
+        const float* vp = vec + static_cast<size_t>(b) * vec_ld;
+        float2 val[8];
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < nj) {
+                const int c = 2 * lane + 64 * j;
+                float2 f = unpack_bf16(__ldg(xp + (c >> 1)));
+                f.x += vp[c]; f.y += vp[c + 1];
+                val[j] = f;
+                sum += f.x + f.y;
+            }
+        }
+        const float mean = warp_sum(sum) / C;
+        float sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < nj) {
+                const float dx = val[j].x - mean, dy = val[j].y - mean;
+                sq += dx * dx + dy * dy;
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(sq) / C + 1e-5f);
+        uint32_t* op = reinterpret_cast<uint32_t*>(out + pix * C);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j < nj) {
+                const int c = 2 * lane + 64 * j;
+                op[c >> 1] = pack_bf16((val[j].x - mean) * rstd * g[c] + beta[c],
+                                       (val[j].y - mean) * rstd * g[c + 1] + beta[c + 1]);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// shot_mlp1.fc1: cat[clean, x] (8) -> C, GELU.  thread = (pixel, 8 output channels)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) shot_in_kernel(const float4* __restrict__ clean, const float4* __restrict__ x,
+                                                      const float* __restrict__ w, const float* __restrict__ bias,
+                                                      bf16* __restrict__ out, size_t npix, int C) {
+    extern __shared__ float sw[];  // [C][8] weights then [C] bias
+    for (int i = threadIdx.x; i < C * 8; i += blockDim.x) sw[i] = w[i];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sw[C * 8 + i] = bias[i];
+    __syncthreads();
+    const int cv = C >> 3;
+    const size_t total = npix * cv;
+    for (size_t v = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < total;
+         v += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t pix = v / cv;
+        const int c0 = static_cast<int>(v % cv) * 8;
+        const float4 a = __ldg(clean + pix), bq = __ldg(x + pix);
+        const float in[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float acc = sw[C * 8 + c0 + j];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc += sw[(c0 + j) * 8 + k] * in[k];
+            f[j] = gelu_erf(acc);
+        }
+        reinterpret_cast<uint4*>(out)[v] = pack8(f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// init_conv 7x7 pad 3, 4 -> C(=64), fp32.  block = 16x16 pixels; thread = 1 pixel x 64 outputs
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kIcTile = 16, kIcHalo = kIcTile + 6;
+
+__global__ void __launch_bounds__(256) init_conv7_kernel(const float4* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, bf16* __restrict__ out, int H,
+                                                         int W) {
+    extern __shared__ float4 sm4[];
+    float4* sx = sm4;                                               // [22*22]
+    float4* swt = sm4 + kIcHalo * kIcHalo;                          // [49][4 ci][16 float4 of co]
+    const int b = blockIdx.z, y0 = blockIdx.y * kIcTile, x0 = blockIdx.x * kIcTile;
+    for (int i = threadIdx.x; i < 49 * 4 * 16; i += 256) swt[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
+    for (int i = threadIdx.x; i < kIcHalo * kIcHalo; i += 256) {
+        const int yy = y0 + i / kIcHalo - 3, xx = x0 + i % kIcHalo - 3;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(x + (static_cast<size_t>(b) * H + yy) * W + xx);
+        sx[i] = v;
+    }
+    __syncthreads();
+    const int ly = threadIdx.x >> 4, lx = threadIdx.x & 15;
+    float acc[64];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) acc[c] = __ldg(bias + c);
+#pragma unroll 1
+    for (int ky = 0; ky < 7; ++ky) {
+#pragma unroll 1
+        for (int kx = 0; kx < 7; ++kx) {
+            const float4 xi = sx[(ly + ky) * kIcHalo + lx + kx];
+            const float4* wt = swt + (ky * 7 + kx) * 64;
+#pragma unroll
+            for (int c4 = 0; c4 < 16; ++c4) {
+                const float4 w0 = wt[c4], w1 = wt[16 + c4], w2 = wt[32 + c4], w3 = wt[48 + c4];
+                acc[c4 * 4 + 0] += xi.x * w0.x + xi.y * w1.x + xi.z * w2.x + xi.w * w3.x;
+                acc[c4 * 4 + 1] += xi.x * w0.y + xi.y * w1.y + xi.z * w2.y + xi.w * w3.y;
+                acc[c4 * 4 + 2] += xi.x * w0.z + xi.y * w1.z + xi.z * w2.z + xi.w * w3.z;
+                acc[c4 * 4 + 3] += xi.x * w0.w + xi.y * w1.w + xi.z * w2.w + xi.w * w3.w;
+            }
+        }
+    }
+    const int yy = y0 + ly, xx = x0 + lx;
+    if (yy < H && xx < W) {
+        uint4* op = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(b) * H + yy) * W + xx) * 64);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            uint4 u;
+            u.x = pack_bf16(acc[j * 8 + 0], acc[j * 8 + 1]); u.y = pack_bf16(acc[j * 8 + 2], acc[j * 8 + 3]);
+            u.z = pack_bf16(acc[j * 8 + 4], acc[j * 8 + 5]); u.w = pack_bf16(acc[j * 8 + 6], acc[j * 8 + 7]);
+            op[j] = u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int H,
+                                                         int W, int cv, size_t total) {
+    // H, W = INPUT size; out is [B, 2H, 2W, C]
+    for (size_t v = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < total;
+         v += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(v % cv);
+        size_t p = v / cv;
+        const int ox = static_cast<int>(p % (2 * W)); p /= (2 * W);
+        const int oy = static_cast<int>(p % (2 * H));
+        const size_t b = p / (2 * H);
+        out[v] = __ldg(in + ((b * H + (oy >> 1)) * W + (ox >> 1)) * cv + c);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Philox4x32-10 -> 4 standard normals (Box-Muller)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+__device__ __forceinline__ float4 philox_normal4(unsigned long long seed, unsigned long long stream_id,
+                                                 unsigned long long idx) {
+    const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(idx), static_cast<uint32_t>(idx >> 32),
+                                             static_cast<uint32_t>(stream_id), static_cast<uint32_t>(stream_id >> 32)),
+                                  make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+    // (0,1] uniforms with 32 random bits (bottom bits lost to fp32 rounding; never 0)
+    const float k = 2.3283064365386963e-10f;  // 2^-32
+    const float u0 = (static_cast<float>(r.x) + 1.0f) * k, u1 = static_cast<float>(r.y) * k;
+    const float u2 = (static_cast<float>(r.z) + 1.0f) * k, u3 = static_cast<float>(r.w) * k;
+    const float ra = sqrtf(-2.0f * logf(fminf(u0, 1.0f))), rb = sqrtf(-2.0f * logf(fminf(u2, 1.0f)));
+    float s0, c0, s1, c1;
+    sincospif(2.0f * u1, &s0, &c0);
+    sincospif(2.0f * u3, &s1, &c1);
+    return make_float4(ra * c0, ra * s0, rb * c1, rb * s1);
+}
+
+__global__ void __launch_bounds__(256) philox_normal_kernel(float4* out, size_t n4, unsigned long long seed,
+                                                            unsigned long long stream_id) {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        out[i] = philox_normal4(seed, stream_id, i);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// final 1x1 heads + posterior update.  8 lanes per pixel, each lane 8 channels of both feature maps.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) final_kernel(const FinalArgs a) {
+    extern __shared__ float sw[];  // wf[4][C], ws[4][C]
+    const int C = a.C;
+    for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) { sw[i] = a.wf[i]; sw[4 * C + i] = a.ws[i]; }
+    __syncthreads();
+    const int lanes = C >> 3;                                  // lanes cooperating on one pixel (8 for C = 64)
+    const int sub = threadIdx.x % lanes;
+    const size_t pix = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) / lanes;
+    const bool live = pix < static_cast<size_t>(a.npix);
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    if (live) {
+        float f[8], g[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(a.xf) + pix * lanes + sub), f);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(a.sf) + pix * lanes + sub), g);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc += f[j] * sw[k * C + sub * 8 + j] + g[j] * sw[4 * C + k * C + sub * 8 + j];
+            o[k] = acc;
+        }
+    }
+    for (int off = lanes >> 1; off > 0; off >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] += __shfl_xor_sync(0xffffffffu, o[k], off);
+    }
+    if (!live || sub != 0) return;
+    // reference order: shot_noise (= fc2 out + bias) + read_noise (= final_conv out + bias)
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = o[k] + (a.bs[k] + a.bfin[k]);
+    if (a.v_out) reinterpret_cast<float4*>(a.v_out)[pix] = make_float4(v[0], v[1], v[2], v[3]);
+    if (!a.chain) return;
+
+    const StepParams sp = a.chain->cur;
+    const int step = a.chain->step;
+    const int rel = step - a.chain->base_step;                 // index into this run's noise / snapshot arrays
+    const float* noise = a.chain->noise;
+    float* snap = a.chain->snap;
+    const size_t HW = a.HW, bimg = pix / HW, hw = pix % HW;
+    const size_t nB = static_cast<size_t>(a.npix) / HW;
+    const size_t plane0 = ((static_cast<size_t>(rel) * nB + bimg) * 4) * HW + hw;   // NCHW offset of channel 0
+    const float4 xi4 = reinterpret_cast<const float4*>(a.x)[pix];
+    const float xi[4] = {xi4.x, xi4.y, xi4.z, xi4.w};
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+    if (sp.sigma != 0.f) {
+        if (noise) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) z[k] = __ldg(noise + plane0 + k * HW);
+        } else {
+            const float4 z4 = philox_normal4(a.chain->seed, static_cast<unsigned long long>(step) + 1ull, pix);
+            z[0] = z4.x; z[1] = z4.y; z[2] = z4.z; z[3] = z4.w;
+        }
+    }
+    float xn[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        // separate roundings (no FMA contraction) to follow the reference's elementwise torch ops
+        float x0 = __fadd_rn(__fmul_rn(sp.p, xi[k]), __fmul_rn(sp.q, v[k]));
+        if (sp.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+        float m = __fadd_rn(__fmul_rn(sp.a, x0), __fmul_rn(sp.b, xi[k]));
+        if (sp.c != 0.f) {
+            const float eps = __fdiv_rn(__fadd_rn(__fmul_rn(sp.r1, xi[k]), -x0), sp.r2);
+            m = __fadd_rn(m, __fmul_rn(sp.c, eps));
+        }
+        xn[k] = sp.sigma != 0.f ? __fadd_rn(m, __fmul_rn(sp.sigma, z[k])) : m;
+    }
+    reinterpret_cast<float4*>(a.x)[pix] = make_float4(xn[0], xn[1], xn[2], xn[3]);
+    if (snap) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) snap[plane0 + k * HW] = xn[k];
+    }
+}
+
+__global__ void chain_advance_kernel(ChainState* chain) { chain->step += 1; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// time path
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) time_mlp_kernel(const int* __restrict__ t, int t_stride, int dim,
+                                                       const float* __restrict__ w1, const float* __restrict__ b1,
+                                                       const float* __restrict__ w2, const float* __restrict__ b2,
+                                                       float* __restrict__ st_out) {
+    __shared__ float emb[128], h[512];
+    const int n = blockIdx.x, td = dim * 4, half = dim / 2;
+    const float tv = static_cast<float>(t[n * t_stride]);
+    if (threadIdx.x < half) {
+        const float f = expf(static_cast<float>(threadIdx.x) * -(logf(10000.0f) / static_cast<float>(half - 1)));
+        emb[threadIdx.x] = sinf(tv * f);
+        emb[half + threadIdx.x] = cosf(tv * f);
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < td; o += blockDim.x) {
+        float acc = b1[o];
+        for (int k = 0; k < dim; ++k) acc += w1[o * dim + k] * emb[k];
+        h[o] = gelu_erf(acc);
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < td; o += blockDim.x) {
+        float acc = b2[o];
+        for (int k = 0; k < td; ++k) acc += w2[o * td + k] * h[k];
+        st_out[static_cast<size_t>(n) * td + o] = acc / (1.0f + expf(-acc));   // SiLU feeding every ResnetBlock.mlp
+    }
+}
+
+__global__ void __launch_bounds__(256) rows_gemv_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                                        const float* __restrict__ in, float* __restrict__ out, int rows,
+                                                        int K) {
+    const int n = blockIdx.y;
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* wr = W + static_cast<size_t>(row) * K;
+    const float* x = in + static_cast<size_t>(n) * K;
+    float acc = 0.f;
+    for (int k = lane * 4; k < K; k += 128) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + k));
+        const float4 x4 = __ldg(reinterpret_cast<const float4*>(x + k));
+        acc += w4.x * x4.x + w4.y * x4.y + w4.z * x4.z + w4.w * x4.w;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[static_cast<size_t>(n) * rows + row] = acc + bias[row];
+}
+
+__global__ void __launch_bounds__(128) iso_vec_kernel(const float* __restrict__ emb_table,
+                                                      const long long* __restrict__ idx, const float* __restrict__ wv,
+                                                      const float* __restrict__ wo, const float* __restrict__ bo,
+                                                      float* __restrict__ out, int out_ld, int out_off, int C) {
+    __shared__ float v[128];
+    const int b = blockIdx.x;
+    const float* e = emb_table + idx[b] * 16;
+    {
+        float acc = 0.f;
+        for (int k = 0; k < 16; ++k) acc += wv[threadIdx.x * 16 + k] * e[k];
+        v[threadIdx.x] = acc;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 128) {
+        float acc = bo[c];
+        for (int k = 0; k < 128; ++k) acc += wo[c * 128 + k] * v[k];
+        out[static_cast<size_t>(b) * out_ld + out_off + c] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// positional path (runs once per condition)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) pos_maps_kernel(const PosArgs a) {
+    extern __shared__ float sw[];
+    const int C2 = 2 * a.C;
+    float* wm1 = sw;                 // [2C][8]
+    float* wm2 = wm1 + C2 * 8;
+    float* bm1 = wm2 + C2 * 8;       // [2C]
+    float* bm2 = bm1 + C2;
+    float* small = bm2 + C2;         // we[16] be[8] w1[384] b1[16] w2[128] b2[8]
+    for (int i = threadIdx.x; i < C2 * 8; i += blockDim.x) { wm1[i] = a.wm1[i]; wm2[i] = a.wm2[i]; }
+    for (int i = threadIdx.x; i < C2; i += blockDim.x) { bm1[i] = a.bm1[i]; bm2[i] = a.bm2[i]; }
+    for (int i = threadIdx.x; i < 16; i += blockDim.x) small[i] = a.we[i];
+    for (int i = threadIdx.x; i < 8; i += blockDim.x) small[16 + i] = a.be[i];
+    for (int i = threadIdx.x; i < 384; i += blockDim.x) small[24 + i] = a.w1[i];
+    for (int i = threadIdx.x; i < 16; i += blockDim.x) small[408 + i] = a.b1[i];
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) small[424 + i] = a.w2[i];
+    for (int i = threadIdx.x; i < 8; i += blockDim.x) small[552 + i] = a.b2[i];
+    __syncthreads();
+    const size_t pix = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (pix >= static_cast<size_t>(a.B) * a.HW) return;
+    const size_t b = pix / a.HW, hw = pix % a.HW;
+    const float p0 = a.position[(b * 2 + 0) * a.HW + hw], p1 = a.position[(b * 2 + 1) * a.HW + hw];
+    float feat[24];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float w = small[j * 2] * p0 + small[j * 2 + 1] * p1 + small[16 + j];
+        const float fr = w * 2.0f * 3.14159265358979323846f;
+        feat[j] = w; feat[8 + j] = sinf(fr); feat[16 + j] = cosf(fr);
+    }
+    float h[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+        float acc = small[408 + o];
+#pragma unroll
+        for (int k = 0; k < 24; ++k) acc += small[24 + o * 24 + k] * feat[k];
+        h[o] = gelu_erf(acc);
+    }
+    float pe[8], ps[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+        float acc = small[552 + o];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc += small[424 + o * 16 + k] * h[k];
+        pe[o] = acc;
+        ps[o] = acc / (1.0f + expf(-acc));
+    }
+    if (a.pos_emb) {
+#pragma unroll
+        for (int o = 0; o < 8; ++o) a.pos_emb[pix * 8 + o] = pe[o];
+    }
+    for (int which = 0; which < 2; ++which) {
+        const float* wm = which ? wm2 : wm1;
+        const float* bm = which ? bm2 : bm1;
+        uint4* mp = reinterpret_cast<uint4*>((which ? a.map2 : a.map1) + pix * C2);
+        for (int c0 = 0; c0 < C2; c0 += 8) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float acc = bm[c0 + j];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc += wm[(c0 + j) * 8 + k] * ps[k];
+                f[j] = acc;
+            }
+            mp[c0 >> 3] = pack8(f);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) nchw_to_nhwc4_kernel(const float* __restrict__ in, float4* __restrict__ out,
+                                                            int HW, size_t npix) {
+    const size_t pix = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    const size_t b = pix / HW, hw = pix % HW;
+    const float* p = in + b * 4 * HW + hw;
+    out[pix] = make_float4(p[0], p[HW], p[2 * static_cast<size_t>(HW)], p[3 * static_cast<size_t>(HW)]);
+}
+__global__ void __launch_bounds__(256) nhwc4_to_nchw_kernel(const float4* __restrict__ in, float* __restrict__ out,
+                                                            int HW, size_t npix) {
+    const size_t pix = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    const size_t b = pix / HW, hw = pix % HW;
+    const float4 v = in[pix];
+    float* p = out + b * 4 * HW + hw;
+    p[0] = v.x; p[HW] = v.y; p[2 * static_cast<size_t>(HW)] = v.z; p[3 * static_cast<size_t>(HW)] = v.w;
+}
+
+inline int blocks_for(size_t n, int per_block, int cap = 1 << 20) {
+    size_t b = (n + per_block - 1) / per_block;
+    return static_cast<int>(b < static_cast<size_t>(cap) ? (b ? b : 1) : cap);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------------------
+int gn_apply_launch(const GnApplyArgs& a, cudaStream_t s) {
+    NDIFF_REQUIRE(a.C % 8 == 0 && a.C <= 512 && a.C % a.G == 0, "GroupNorm apply: unsupported channel count");
+    const size_t nvec = static_cast<size_t>(a.HW) * (a.C / 8);
+    dim3 grid(blocks_for(nvec, kGnThreads * kGnVecPerThread), a.B);
+    gn_apply_kernel<<<grid, kGnThreads, 0, s>>>(a);
+    NDIFF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int layernorm_launch(const bf16* x, const float* vec, int vec_ld, const float* g, const float* beta, bf16* out, int B,
+                     int HW, int C, cudaStream_t s) {
+    NDIFF_REQUIRE(C % 64 == 0 && C <= 512, "LayerNorm: C must be a multiple of 64, at most 512");
+    const size_t npix = static_cast<size_t>(B) * HW;
+    layernorm_kernel<<<blocks_for(npix, 8 * 4, 148 * 16), 256, 0, s>>>(x, vec, vec_ld, g, beta, out, HW, C, npix);
+    NDIFF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int shot_in_launch(const float* clean, const float* x, const float* w, const float* bias, bf16* out, int npix, int C,
+                   cudaStream_t s) {
+    const size_t total = static_cast<size_t>(npix) * (C / 8);
+    shot_in_kernel<<<blocks_for(total, 256 * 4, 148 * 16), 256, (C * 9) * sizeof(float), s>>>(
+        reinterpret_cast<const float4*>(clean), reinterpret_cast<const float4*>(x), w, bias, out, npix, C);
+    NDIFF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int pointwise_init() {
+    const int smem = (kIcHalo * kIcHalo + 49 * 4 * 16) * sizeof(float4);
+    NDIFF_CUDA_OK(cudaFuncSetAttribute(init_conv7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    return 0;
+}
+
+int init_conv7_launch(const float* x, const float* w, const float* bias, bf16* out, int B, int H, int W, int C,
+                      cudaStream_t s) {
+    NDIFF_REQUIRE(C == 64, "init_conv kernel is specialised for dim = 64");
+    const int smem = (kIcHalo * kIcHalo + 49 * 4 * 16) * sizeof(float4);
+    dim3 grid((W + kIcTile - 1) / kIcTile, (H + kIcTile - 1) / kIcTile, B);
+    init_conv7_kernel<<<grid, 256, smem, s>>>(reinterpret_cast<const float4*>(x), w, bias, out, H, W);
+    NDIFF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int upsample2x_launch(const bf16* in, bf16* out, int B, int H, int W, int C, cudaStream_t s) {
+    const int cv = C / 8;
+    const size_t total = static_cast<size_t>(B) * 4 * H * W * cv;
+    upsample2x_kernel<<<blocks_for(total, 256 * 4, 148 * 16), 256, 0, s>>>(
+        reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), H, W, cv, total);
+    NDIFF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int final_launch(const FinalArgs& a, cudaStream_t s) {
+    NDIFF_REQUIRE(a.C == 64 || a.C == 128 || a.C == 256, "final heads: C/8 must be a power of two <= 32");
+    const size_t threads = static_cast<size_t>(a.npix) * (a.C / 8);
+    final_kernel<<<blocks_for(threads, 256), 256, 8 * a.C * sizeof(float), s>>>(a);
+    NDIFF_CUDA_OK(cudaGetLastError());
+    if (a.chain) {
+        chain_advance_kernel<<<1, 1, 0, s>>>(a.chain);
+        NDIFF_CUDA_OK(cudaGetLastError());
+    }
+    return 0;
+}
+
+int time_mlp_launch(const int* t, int t_stride, int n, int dim, const float* w1, const float* b1, const float* w2,
+                    const float* b2, float* st_out, cudaStream_t s) {
+    NDIFF_REQUIRE(dim <= 128 && dim % 2 == 0, "time embedding: dim must be even and <= 128");
+    time_mlp_kernel<<<n, 256, 0, s>>>(t, t_stride, dim, w1, b1, w2, b2, st_out);
+    NDIFF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int rows_gemv_launch(const float* W, const float* bias, const float* in, float* out, int n, int rows, int K,
+                     cudaStream_t s) {
+    NDIFF_REQUIRE(K % 128 == 0, "gemv: K must be a multiple of 128");
+    dim3 grid((rows + 7) / 8, n);
+    rows_gemv_kernel<<<grid, 256, 0, s>>>(W, bias, in, out, rows, K);
+    NDIFF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int iso_vec_launch(const float* emb_table, const long long* idx, const float* wv, const float* wo, const float* bo,
+                   float* out, int out_ld, int out_off, int B, int C, cudaStream_t s) {
+    iso_vec_kernel<<<B, 128, 0, s>>>(emb_table, idx, wv, wo, bo, out, out_ld, out_off, C);
+    NDIFF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int pos_maps_launch(const PosArgs& a, cudaStream_t s) {
+    const int C2 = 2 * a.C;
+    const int smem = (2 * C2 * 8 + 2 * C2 + 560) * sizeof(float);
+    const size_t npix = static_cast<size_t>(a.B) * a.HW;
+    pos_maps_kernel<<<blocks_for(npix, 128), 128, smem, s>>>(a);
+    NDIFF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int nchw_to_nhwc4_launch(const float* in, float* out, int B, int HW, cudaStream_t s) {
+    const size_t npix = static_cast<size_t>(B) * HW;
+    nchw_to_nhwc4_kernel<<<blocks_for(npix, 256), 256, 0, s>>>(in, reinterpret_cast<float4*>(out), HW, npix);
+    NDIFF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int nhwc4_to_nchw_launch(const float* in, float* out, int B, int HW, cudaStream_t s) {
+    const size_t npix = static_cast<size_t>(B) * HW;
+    nhwc4_to_nchw_kernel<<<blocks_for(npix, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(in), out, HW, npix);
+    NDIFF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int philox_normal_launch(float* out, size_t n4, unsigned long long seed, unsigned long long stream_id, cudaStream_t s) {
+    philox_normal_kernel<<<blocks_for(n4, 256 * 4, 148 * 16), 256, 0, s>>>(reinterpret_cast<float4*>(out), n4, seed,
+                                                                           stream_id);
+    NDIFF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace ndiff
