@@ -95,6 +95,10 @@ NDIFF_API int32_t ndiff_chain_begin(ndiff_engine* e, const ndiff_step* steps_hos
 NDIFF_API int32_t ndiff_chain_run(ndiff_engine* e, int32_t n, const float* noise_dev, const float* teacher_dev,
                         float* snapshots_dev, void* stream);
 NDIFF_API int32_t ndiff_chain_read(ndiff_engine* e, float* out_dev, void* stream);
+/*   seek  : re-positions the chain at `step` with state x_dev (fp32 NCHW) — lets ONE engine advance several
+ *           micro-batches of a larger batch in lock-step (their states are swapped in and out between chunks);
+ *           `seed` is that micro-batch's Philox seed. */
+NDIFF_API int32_t ndiff_chain_seek(ndiff_engine* e, int32_t step, const float* x_dev, uint64_t seed, void* stream);
 
 /* End-to-end convenience with HOST buffers (what Trainer.test() does per batch, models/trainer_diffusion.py:256-317:
  * host->device copies, full chain, device->host copy).  Synchronous. */

@@ -822,6 +822,19 @@ int32_t ndiff_chain_read(ndiff_engine* e, float* out_dev, void* stream) {
     return nhwc4_to_nchw_launch(e->x, out_dev, e->B, e->H * e->W, as_stream(stream));
 }
 
+int32_t ndiff_chain_seek(ndiff_engine* e, int32_t step, const float* x_dev, uint64_t seed, void* stream) {
+    NDIFF_REQUIRE(e && e->n_steps > 0 && x_dev, "ndiff_chain_begin has not been called / null state");
+    NDIFF_REQUIRE(step >= 0 && step <= e->n_steps, "step out of range");
+    NDIFF_CUDA_OK(cudaSetDevice(e->cfg.device));
+    cudaStream_t s = as_stream(stream);
+    const unsigned long long sd = seed;
+    NDIFF_CUDA_OK(cudaMemcpyAsync(&e->chain->step, &step, sizeof(int), cudaMemcpyHostToDevice, s));
+    NDIFF_CUDA_OK(cudaMemcpyAsync(&e->chain->seed, &sd, sizeof(sd), cudaMemcpyHostToDevice, s));
+    NDIFF_CUDA_OK(cudaStreamSynchronize(s));   // `step` / `sd` are stack variables
+    e->steps_done = step;
+    return nchw_to_nhwc4_launch(x_dev, e->x, e->B, e->H * e->W, s);
+}
+
 int32_t ndiff_sample_host(ndiff_engine* e, const float* clean_host, const float* position_host,
                           const int64_t* iso_idx_host, const ndiff_step* steps_host, int32_t n_steps, uint64_t seed,
                           float* out_host) {

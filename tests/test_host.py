@@ -1,0 +1,124 @@
+"""CPU: host-side mirror of the reference interface (no compute on the library without a GPU)."""
+import ctypes
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+import noisediff_b200 as nd
+from noisediff_b200 import _lib
+from tests.util import load, net_args, seeded_net
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    names = _lib.declared_symbols()
+    assert len(names) >= 20 and "ndiff_forward" in names and "ndiff_chain_run" in names
+    l = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(l, n), f"{n} declared in include/noisediff_b200.h but not exported"
+    assert set(names) == set(_lib._SIGS), "ctypes signature table out of sync with the header"
+    assert _lib.lib().ndiff_abi_version() == 1
+
+
+def test_abi_struct_layouts():
+    assert ctypes.sizeof(_lib.Step) == 48 and ctypes.sizeof(_lib.Config) == 24
+
+
+def test_engine_create_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        nd.Engine(dim=64, batch=1, height=64, width=64)
+    net = seeded_net()
+    cond = {"clean_img": torch.zeros(1, 4, 8, 8), "position": torch.zeros(1, 2, 8, 8),
+            "iso_ratio_idx": torch.zeros(1, dtype=torch.long)}
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(torch.zeros(1, 4, 8, 8), torch.zeros(1, dtype=torch.long), cond)
+    gd = nd.GaussianDiffusion(net, image_size=8, timesteps=4, beta_schedule="sigmoid2")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        gd.sample(batch_size=1, condition=cond)
+
+
+def test_net_attributes_and_state_dict_names():
+    net = seeded_net()
+    assert (net.channels, net.out_dim, net.self_condition, net.random_or_learned_sinusoidal_cond) == (4, 4, False, False)
+    sd = net.state_dict()
+    assert len(sd) == 416
+    for k, shp in {"init_conv.weight": (64, 4, 7, 7), "iso_embed.weight": (100, 16), "time_mlp.1.weight": (256, 64),
+                   "downs.0.0.mlp.1.weight": (128, 256), "downs.0.2.attn.to_q.weight": (128, 64),
+                   "downs.0.2.ff.net.0.0.weight": (128, 64), "downs.0.2.ff.net.2.weight": (64, 128),
+                   "downs.0.3.1.weight": (64, 256, 1, 1), "downs.3.3.weight": (512, 256, 3, 3),
+                   "ups.0.0.res_conv.weight": (512, 768, 1, 1), "ups.0.3.1.weight": (256, 512, 3, 3),
+                   "ups.3.3.weight": (64, 64, 3, 3), "pos_enc.weights.weight": (8, 2, 1, 1),
+                   "pos_block1.mlp.1.weight": (128, 8, 1, 1), "shot_mlp3.fc2.weight": (4, 64, 1, 1),
+                   "final_conv.weight": (4, 64, 1, 1)}.items():
+        assert tuple(sd[k].shape) == shp, k
+    # survives the reference's wrapping (models/modules.py:81) and strict reload (trainer_diffusion.py:333-349)
+    wrapped = nn.DataParallel(net)
+    clone = nd.NoiseDiffNet(net_args())
+    clone.load_state_dict({("module." + k)[7:]: v for k, v in wrapped.module.state_dict().items()}, strict=True)
+    with pytest.raises(AssertionError):
+        net(torch.zeros(1, 4, 12, 12), torch.zeros(1, dtype=torch.long), {})
+
+
+@pytest.mark.parametrize("name", ["linear", "cosine", "sigmoid1", "sigmoid2", "sigmoid3"])
+def test_schedule_buffers_match_reference(name):
+    z = load("schedules.npz")
+    for T in (1000, 50):
+        gd = nd.GaussianDiffusion(seeded_net(), image_size=64, timesteps=T, beta_schedule=name)
+        bufs = dict(gd.named_buffers(recurse=False))
+        assert len(bufs) == 13
+        for k, v in bufs.items():
+            assert v.dtype == torch.float32 and np.array_equal(v.numpy(), z[f"{name}/{T}/{k}"]), (name, T, k)
+
+
+def test_ctor_contract():
+    net = seeded_net()
+    with pytest.raises(ValueError):
+        nd.GaussianDiffusion(net, image_size=64)                      # default 'sigmoid' raises as in the reference
+    with pytest.raises(AssertionError):
+        nd.GaussianDiffusion(net, image_size=64, beta_schedule="linear", objective="nope")
+    gd = nd.GaussianDiffusion(nn.DataParallel(net), image_size=64, timesteps=100, sampling_timesteps=10,
+                              beta_schedule="sigmoid2", ddim_sampling_eta=1.0)
+    assert gd.is_ddim_sampling and gd.channels == 4 and gd.num_timesteps == 100
+    assert gd.ddim_time_pairs()[0] == (99, 89) and gd.ddim_time_pairs()[-1][1] == -1
+    assert nd.GaussianDiffusion(net, image_size=64, timesteps=10, beta_schedule="linear", auto_normalize=True) \
+        .unnormalize(torch.zeros(1)).item() == 0.5
+
+
+def test_step_tables_follow_the_buffers():
+    gd = nd.GaussianDiffusion(seeded_net(), image_size=64, timesteps=1000, beta_schedule="sigmoid2", objective="pred_v")
+    steps = gd.ddpm_steps()
+    assert [s.t for s in steps[:3]] == [999, 998, 997] and steps[-1].t == 0 and len(steps) == 1000
+    s = steps[500]
+    t = s.t
+    assert s.p == pytest.approx(float(gd.sqrt_alphas_cumprod[t])) and s.q == pytest.approx(-float(gd.sqrt_one_minus_alphas_cumprod[t]))
+    assert s.a == pytest.approx(float(gd.posterior_mean_coef1[t])) and s.b == pytest.approx(float(gd.posterior_mean_coef2[t]))
+    assert s.sigma == pytest.approx(float((0.5 * gd.posterior_log_variance_clipped[t]).exp())) and s.c == 0.0 and s.clip == 1
+    assert steps[-1].sigma == 0.0                                     # no noise at t == 0 (ref :371)
+    g2 = nd.GaussianDiffusion(seeded_net(), image_size=64, timesteps=50, sampling_timesteps=5, ddim_sampling_eta=0.5,
+                              beta_schedule="sigmoid2")
+    d = g2.ddim_steps()
+    assert len(d) == 5 and d[-1].a == 1.0 and d[-1].sigma == 0.0 and d[0].b == 0.0 and d[0].sigma > 0.0
+    g3 = nd.GaussianDiffusion(seeded_net(), image_size=64, timesteps=4, beta_schedule="linear", objective="pred_x0")
+    assert (g3.ddpm_steps()[0].p, g3.ddpm_steps()[0].q) == (0.0, 1.0)
+
+
+def test_elementwise_helpers_match_oracle():
+    from oracle import noisediff_oracle as O
+    gd = nd.GaussianDiffusion(seeded_net(), image_size=8, timesteps=20, beta_schedule="sigmoid2")
+    tab = O.schedule_tables("sigmoid2", 20)
+    g = torch.Generator().manual_seed(0)
+    x, v, z = (torch.randn(2, 4, 8, 8, generator=g) for _ in range(3))
+    t = torch.tensor([7, 7])
+    x0 = gd.predict_start_from_v(x, t, v)
+    assert torch.equal(x0, tab["sqrt_alphas_cumprod"][7] * x - tab["sqrt_one_minus_alphas_cumprod"][7] * v)
+    ref, _ = O.ddpm_step(tab, "pred_v", x, 7, v, z)
+    mean, _, logvar = gd.q_posterior(x0.clamp(-1, 1), x, t)
+    assert torch.allclose(mean + (0.5 * logvar).exp() * z, ref, atol=0, rtol=0)
+    assert torch.equal(gd.q_sample(x, t, z), tab["sqrt_alphas_cumprod"][7] * x + tab["sqrt_one_minus_alphas_cumprod"][7] * z)
+    with pytest.raises(NotImplementedError):
+        gd(torch.zeros(1, 4, 8, 8), {})
