@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int lane = threadIdx.x & 31;
     const int CB = a.cb0 + a.cb1;
     const int TAPS = a.taps_y * a.taps_x;
-    const bool halo = a.mode == kHalo3;
+    const bool halo1 = a.mode == kHalo1 || a.mode == kHalo1BaseOff;
+    const bool halo = a.mode == kHalo3 || halo1;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&a.tmA0);
@@ -79,10 +80,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     const int c0 = (cb < a.cb0 ? cb : cb - a.cb0) * 64;
                     if (halo) {
                         mbar_wait(&tail->emptyA[sa], pa ^ 1);
-                        mbar_expect_tx(&tail->fullA[sa], 3 * a.a_copy_bytes);
                         uint8_t* dst = ringA + sa * a.a_stage_bytes;
-                        for (int kx = 0; kx < 3; ++kx)
-                            tma_load_4d(dst + kx * a.a_copy_bytes, tm, &tail->fullA[sa], c0, x0 + kx - 1, y0 - 1, b);
+                        if (halo1) {
+                            mbar_expect_tx(&tail->fullA[sa], a.a_copy_bytes);
+                            tma_load_4d(dst, tm, &tail->fullA[sa], c0, x0 - 1, y0 - 1, b);
+                        } else {
+                            mbar_expect_tx(&tail->fullA[sa], 3 * a.a_copy_bytes);
+                            for (int kx = 0; kx < 3; ++kx)
+                                tma_load_4d(dst + kx * a.a_copy_bytes, tm, &tail->fullA[sa], c0, x0 + kx - 1, y0 - 1, b);
+                        }
                         if (++sa == a.a_stages) { sa = 0; pa ^= 1; }
                     }
                     for (int tap = 0; tap < TAPS; ++tap) {
@@ -122,15 +128,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                         mbar_wait(&tail->fullB[sb], pb);
                         tc_fence_after();
                         uint32_t a_addr = smem_u32(ringA + sa * a.a_stage_bytes);
-                        if (halo) {
+                        uint32_t a_sbo = 1024, a_boff = 0;
+                        if (halo1) {
+                            const int ky = tap / 3, kx = tap - ky * 3;
+                            a_addr += (ky * (a.TW + 2) + kx) * 128;
+                            a_sbo = (a.TW + 2) * 128;
+                            if (a.mode == kHalo1BaseOff) a_boff = (a_addr >> 7) & 7;
+                        } else if (halo) {
                             const int ky = tap / 3, kx = tap - ky * 3;
                             a_addr += kx * a.a_copy_bytes + ky * a.TW * 128;
                         }
                         const uint32_t b_addr = smem_u32(ringB + sb * kBStage);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                                      first ? 0u : 1u);
+                            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32, a_boff, a_sbo),
+                                      umma_desc_sw128(b_addr + k * 32), idesc, first ? 0u : 1u);
                             first = 0;
                         }
                         umma_commit(&tail->emptyB[sb]);
@@ -332,7 +344,8 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     a.B = d.B; a.H = d.H; a.W = d.W;
     int TW = d.TW;
     if (TW == 0) {
-        if (d.mode == kHalo3) TW = d.H >= 16 ? 8 : 16;
+        if (d.mode == kHalo1 || d.mode == kHalo1BaseOff) TW = 8;
+        else if (d.mode == kHalo3) TW = d.H >= 16 ? 8 : 16;
         else TW = d.W >= 64 ? 64 : (d.W >= 32 ? 32 : (d.W >= 16 ? 16 : 8));
     }
     NDIFF_REQUIRE(TW >= 8 && TW <= 128 && (TW & (TW - 1)) == 0, "tile width must be a power of two in [8,128]");
@@ -340,13 +353,20 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     a.tiles_x = (d.W + a.TW - 1) / a.TW;
     a.tiles_y = (d.H + a.TH - 1) / a.TH;
     a.cb0 = d.C0 / 64; a.cb1 = d.C1 / 64;
-    if (d.mode == kHalo3) { a.taps_y = 3; a.taps_x = 3; a.pad_y = 1; a.pad_x = 1; }
+    const bool halo1 = d.mode == kHalo1 || d.mode == kHalo1BaseOff;
+    NDIFF_REQUIRE(!halo1 || TW == 8, "single-copy halo mode needs TW == 8 (one 8-row UMMA group per output row)");
+    if (d.mode == kHalo3 || halo1) { a.taps_y = 3; a.taps_x = 3; a.pad_y = 1; a.pad_x = 1; }
     else if (d.mode == kS2D) { a.taps_y = 2; a.taps_x = 2; a.pad_y = 0; a.pad_x = 0; }
     else { a.taps_y = d.taps_y; a.taps_x = d.taps_x; a.pad_y = d.pad_y; a.pad_x = d.pad_x; }
     a.n_tiles = d.Cout / NT;
     a.total_tiles = d.B * a.tiles_y * a.tiles_x * a.n_tiles;
     const int b_stage = NT * 128;
-    if (d.mode == kHalo3) {
+    if (halo1) {
+        a.a_copy_bytes = (a.TH + 2) * (a.TW + 2) * 128;
+        a.a_stage_bytes = (a.a_copy_bytes + 1023) / 1024 * 1024;
+        a.a_stages = 3;
+        a.b_stages = NT == 128 ? 6 : 8;
+    } else if (d.mode == kHalo3) {
         a.a_copy_bytes = (a.TH + 2) * a.TW * 128;
         a.a_stage_bytes = 3 * a.a_copy_bytes;
         a.a_stages = 2;
@@ -357,7 +377,8 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
         a.a_stages = NT == 128 ? 6 : 8;
         a.b_stages = a.a_stages;
     }
-    NDIFF_REQUIRE(a.a_stage_bytes % 1024 == 0 && a.a_copy_bytes % 1024 == 0, "operand stages must stay 1024-B aligned");
+    NDIFF_REQUIRE(a.a_stage_bytes % 1024 == 0 && (halo1 || a.a_copy_bytes % 1024 == 0),
+                  "operand stages must stay 1024-B aligned");
     plan->smem_bytes = 1024 + a.a_stages * a.a_stage_bytes + a.b_stages * b_stage + static_cast<int>(sizeof(SmemTail));
     NDIFF_REQUIRE(plan->smem_bytes <= 227 * 1024, "shared-memory budget exceeded");
     plan->grid = a.total_tiles < num_sms ? a.total_tiles : num_sms;
@@ -386,8 +407,8 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
                                 static_cast<uint64_t>(d.B)};
             uint64_t str[3] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(Win) * C * 2,
                                static_cast<uint64_t>(Hin) * Win * C * 2};
-            uint32_t box[4] = {64, static_cast<uint32_t>(a.TW),
-                               static_cast<uint32_t>(d.mode == kHalo3 ? a.TH + 2 : a.TH), 1};
+            uint32_t box[4] = {64, static_cast<uint32_t>(halo1 ? a.TW + 2 : a.TW),
+                               static_cast<uint32_t>(d.mode == kHalo3 || halo1 ? a.TH + 2 : a.TH), 1};
             if (encode_tensor_map(tm, src, 4, dims, str, box, true)) return 1;
         }
     }

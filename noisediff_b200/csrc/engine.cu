@@ -386,7 +386,7 @@ struct Builder {
         d.stats = stats; d.groups = groups;
         auto plan = std::make_shared<ConvGemmPlan>();
         if (conv_gemm_plan(d, e->num_sms, plan.get())) { err = 1; return out; }
-        const int taps = mode == kHalo3 ? 9 : (mode == kS2D ? 4 : 1);
+        const int taps = (mode == kHalo3 || mode == kHalo1 || mode == kHalo1BaseOff) ? 9 : (mode == kS2D ? 4 : 1);
         Op op;
         op.name = wname;
         op.flops = 2.0 * e->B * Ho * Wo * Cout * static_cast<double>(taps) * (s0.C + (s1 ? s1->C : 0));

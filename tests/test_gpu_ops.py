@@ -1,0 +1,182 @@
+"""GPU parity of the individual sm_100a kernels against plain fp32 torch ops on the same (bf16-rounded) inputs.
+All calls go through the C ABI (include/noisediff_b200.h)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from noisediff_b200 import _lib
+from tests import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _fp32_reference_math():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, generator=g, device="cuda") * scale).to(torch.bfloat16).float()
+
+
+def _check(out_nhwc, ref_nchw, tol=1.5e-2):
+    got = G.from_nhwc(out_nhwc)
+    err = (got - ref_nchw).abs().max().item()
+    scale = ref_nchw.abs().max().item()
+    rel = ((got - ref_nchw).norm() / ref_nchw.norm()).item()
+    assert rel < 4e-3 and err <= tol * max(scale, 1.0), f"rel-L2 {rel:.3e}, max abs {err:.3e} (scale {scale:.3e})"
+
+
+# (B, H, W, Cin0, Cin1, Cout)
+GEMM_CASES = [(2, 16, 16, 64, 0, 64), (1, 32, 32, 128, 0, 256), (2, 8, 8, 256, 128, 128), (1, 64, 64, 64, 64, 64),
+              (3, 24, 40, 64, 0, 128), (1, 8, 8, 512, 0, 512)]
+
+
+@pytest.mark.parametrize("case", GEMM_CASES)
+def test_gemm_1x1(case):
+    B, H, W, c0, c1, co = case
+    x0 = _rand((B, c0, H, W), 1)
+    x1 = _rand((B, c1, H, W), 2) if c1 else None
+    w = _rand((co, c0 + c1, 1, 1), 3, 1.0 / math.sqrt(c0 + c1))
+    bias = torch.randn(co, device="cuda")
+    ref = F.conv2d(torch.cat([x0, x1], 1) if c1 else x0, w, bias)
+    out = G.conv(G.MODE_DIRECT, G.to_nhwc_bf16(x0), G.pack_weight(w), co, src1=G.to_nhwc_bf16(x1) if c1 else None,
+                 bias=bias)
+    _check(out, ref)
+
+
+def test_gemm_epilogue_gelu_residual_vector():
+    B, H, W, c, co = 2, 16, 16, 128, 64
+    x = _rand((B, c, H, W), 4)
+    w = _rand((co, c, 1, 1), 5, 1.0 / math.sqrt(c))
+    bias = torch.randn(co, device="cuda")
+    res = _rand((B, co, H, W), 6)
+    vec = torch.randn(B, 96, device="cuda")            # leading dimension larger than Cout on purpose
+    ref = F.gelu(F.conv2d(x, w, bias)) + vec[:, :co, None, None] + res
+    out = G.conv(G.MODE_DIRECT, G.to_nhwc_bf16(x), G.pack_weight(w), co, bias=bias, vec=vec, res=G.to_nhwc_bf16(res), act=1)
+    _check(out, ref)
+
+
+CONV3_CASES = [(2, 32, 32, 64, 0, 64), (1, 16, 16, 128, 64, 128), (1, 8, 8, 256, 0, 256), (2, 24, 40, 64, 64, 64),
+               (1, 64, 64, 64, 0, 64), (1, 8, 8, 512, 256, 512), (4, 128, 128, 64, 0, 64)]
+
+
+@pytest.mark.parametrize("mode", ["halo", "direct"])
+@pytest.mark.parametrize("case", CONV3_CASES)
+def test_conv3x3(case, mode):
+    B, H, W, c0, c1, co = case
+    x0 = _rand((B, c0, H, W), 7)
+    x1 = _rand((B, c1, H, W), 8) if c1 else None
+    w = _rand((co, c0 + c1, 3, 3), 9, 1.0 / math.sqrt(9 * (c0 + c1)))
+    bias = torch.randn(co, device="cuda")
+    ref = F.conv2d(torch.cat([x0, x1], 1) if c1 else x0, w, bias, padding=1)
+    kw = dict(src1=G.to_nhwc_bf16(x1) if c1 else None, bias=bias)
+    if mode == "halo":
+        out = G.conv(G.MODE_HALO3, G.to_nhwc_bf16(x0), G.pack_weight(w), co, **kw)
+    else:
+        out = G.conv(G.MODE_DIRECT, G.to_nhwc_bf16(x0), G.pack_weight(w), co, taps=(3, 3), pad=(1, 1), **kw)
+    _check(out, ref)
+
+
+@pytest.mark.parametrize("tile_w", [8, 16, 32])
+def test_conv3x3_tile_shapes(tile_w):
+    B, H, W, c, co = 1, 32, 32, 64, 128
+    x = _rand((B, c, H, W), 10)
+    w = _rand((co, c, 3, 3), 11, 1.0 / math.sqrt(9 * c))
+    out = G.conv(G.MODE_HALO3, G.to_nhwc_bf16(x), G.pack_weight(w), co, tile_w=tile_w)
+    _check(out, F.conv2d(x, w, None, padding=1))
+
+
+@pytest.mark.parametrize("case", [(2, 32, 32, 64, 64), (1, 16, 16, 128, 256), (1, 64, 64, 64, 128)])
+def test_downsample_space_to_depth(case):
+    B, H, W, c, co = case                                 # H, W = input size
+    x = _rand((B, c, H, W), 12)
+    w = _rand((co, 4 * c, 1, 1), 13, 1.0 / math.sqrt(4 * c))
+    bias = torch.randn(co, device="cuda")
+    s2d = x.reshape(B, c, H // 2, 2, W // 2, 2).permute(0, 1, 3, 5, 2, 4).reshape(B, 4 * c, H // 2, W // 2)
+    ref = F.conv2d(s2d, w, bias)
+    out = G.conv(G.MODE_S2D, G.to_nhwc_bf16(x), G.pack_weight(w, s2d=True), co, bias=bias, out_hw=(H // 2, W // 2))
+    _check(out, ref)
+
+
+@pytest.mark.parametrize("case", [(2, 32, 32, 64, 8), (2, 16, 16, 128, 8), (1, 8, 8, 512, 8), (2, 32, 32, 64, 2)])
+def test_groupnorm_stats_and_apply(case):
+    B, H, W, c, groups = case
+    x = _rand((B, c, H, W), 14)
+    w = _rand((c, c, 3, 3), 15, 1.0 / math.sqrt(9 * c))
+    bias = torch.randn(c, device="cuda")
+    gamma, beta = torch.randn(c, device="cuda"), torch.randn(c, device="cuda")
+    ss = torch.randn(B, 3 * c, device="cuda") * 0.5
+    res = _rand((B, c, H, W), 16)
+    stats = torch.zeros(B, groups, 2, device="cuda")
+    y = G.conv(G.MODE_HALO3, G.to_nhwc_bf16(x), G.pack_weight(w), c, bias=bias, stats=stats, groups=groups)
+    conv_ref = F.conv2d(x, w, bias, padding=1)
+    grp = conv_ref.reshape(B, groups, -1)
+    assert torch.allclose(stats[..., 0], grp.sum(-1), rtol=2e-3, atol=2e-2 * math.sqrt(grp.shape[-1]))
+    assert torch.allclose(stats[..., 1], (grp ** 2).sum(-1), rtol=2e-3)
+    out = torch.empty_like(y)
+    _lib.check(_lib.lib().ndiff_op_gn_apply(G.P(y), G.P(out), G.P(stats), G.P(gamma), G.P(beta), G.P(ss), 3 * c, c // 2,
+                                            None, G.P(G.to_nhwc_bf16(res)), None, B, H * W, c, groups, G.stream()))
+    torch.cuda.synchronize()
+    sc, sh = ss[:, c // 2:c // 2 + c, None, None], ss[:, c // 2 + c:c // 2 + 2 * c, None, None]
+    ref = F.silu(F.group_norm(conv_ref, groups, gamma, beta, eps=1e-5) * (sc + 1) + sh) + res
+    _check(out, ref, tol=3e-2)
+
+
+def test_groupnorm_apply_with_pixel_maps():
+    B, H, W, c, groups = 2, 16, 16, 64, 2
+    y = _rand((B, c, H, W), 17)
+    maps = _rand((B, 2 * c, H, W), 18, 0.5)
+    gamma, beta = torch.randn(c, device="cuda"), torch.randn(c, device="cuda")
+    grp = y.reshape(B, groups, -1)
+    stats = torch.stack([grp.sum(-1), (grp ** 2).sum(-1)], dim=-1).contiguous()
+    yb = G.to_nhwc_bf16(y)
+    out = torch.empty_like(yb)
+    _lib.check(_lib.lib().ndiff_op_gn_apply(G.P(yb), G.P(out), G.P(stats), G.P(gamma), G.P(beta), None, 0, 0,
+                                            G.P(G.to_nhwc_bf16(maps)), None, None, B, H * W, c, groups, G.stream()))
+    torch.cuda.synchronize()
+    ref = F.silu(F.group_norm(y, groups, gamma, beta, eps=1e-5) * (maps[:, :c] + 1) + maps[:, c:])
+    _check(out, ref, tol=3e-2)
+
+
+@pytest.mark.parametrize("c", [64, 128, 512])
+def test_layernorm_with_sample_vector(c):
+    B, H, W = 2, 16, 8
+    x = _rand((B, c, H, W), 19)
+    vec = torch.randn(B, c + 32, device="cuda")
+    g, b = torch.randn(c, device="cuda"), torch.randn(c, device="cuda")
+    xb = G.to_nhwc_bf16(x)
+    out = torch.empty_like(xb)
+    _lib.check(_lib.lib().ndiff_op_layernorm(G.P(xb), G.P(vec), c + 32, G.P(g), G.P(b), G.P(out), B, H * W, c, G.stream()))
+    torch.cuda.synchronize()
+    tok = x.permute(0, 2, 3, 1) + vec[:, None, None, :c]
+    ref = F.layer_norm(tok, (c,), g, b, eps=1e-5).permute(0, 3, 1, 2)
+    _check(out, ref, tol=3e-2)
+
+
+def test_philox_normals_are_standard_normal_and_counter_based():
+    n4 = 1 << 18
+    a = torch.empty(n4 * 4, device="cuda")
+    b = torch.empty(n4 * 4, device="cuda")
+    lib = _lib.lib()
+    _lib.check(lib.ndiff_op_philox_normal(G.P(a), n4, 42, 7, G.stream()))
+    _lib.check(lib.ndiff_op_philox_normal(G.P(b), n4, 42, 7, G.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)                                                 # deterministic in (seed, stream, index)
+    _lib.check(lib.ndiff_op_philox_normal(G.P(b), n4, 42, 8, G.stream()))
+    torch.cuda.synchronize()
+    assert abs(float((a * b).mean())) < 5e-3                                 # streams are uncorrelated
+    n = a.numel()
+    assert abs(float(a.mean())) < 4 / math.sqrt(n) and abs(float(a.var()) - 1) < 6 * math.sqrt(2 / n)
+    assert abs(float((a ** 3).mean())) < 0.02 and abs(float((a ** 4).mean()) - 3) < 0.05
+    # Kolmogorov-Smirnov distance to the normal CDF on a subsample
+    s = a[:: 64].double().sort().values
+    cdf = 0.5 * (1 + torch.erf(s / math.sqrt(2)))
+    emp = (torch.arange(1, s.numel() + 1, device="cuda", dtype=torch.float64)) / s.numel()
+    assert float((cdf - emp).abs().max()) < 1.63 / math.sqrt(s.numel())      # 1% critical value
+    assert float(a.abs().max()) < 7 and float((a.reshape(-1, 4)[:, 0] * a.reshape(-1, 4)[:, 1]).mean()) < 5e-3
