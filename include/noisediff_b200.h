@@ -46,6 +46,8 @@ typedef struct ndiff_config {
 
 #define NDIFF_FLAG_CONV_DIRECT 1   /* debug: 3x3 convs load every tap from L2 instead of the halo layout */
 #define NDIFF_FLAG_NO_GRAPH    2   /* debug: launch kernels eagerly instead of replaying a CUDA graph */
+#define NDIFF_FLAG_KEEP_ACTS   4   /* debug: never recycle activation buffers (ndiff_debug_tensor sees every layer) */
+#define NDIFF_FLAG_CONV_HALO3  8   /* debug: 3x3 convs use three kx-shifted halo copies instead of one */
 
 /* One reverse step's scalars; the caller derives them from GaussianDiffusion's fp32 buffers
  * (models/denoising_diffusion_pytorch.py:240-266) so the arithmetic constants are the reference's own:
@@ -114,12 +116,12 @@ NDIFF_API int32_t ndiff_time_layers(ndiff_engine* e, int32_t iters, float* ms_ou
                           int32_t* n_out, void* stream);
 
 /* Single-operator entry points (parity tests of the individual kernels; pointers are device pointers, activations
- * bf16 NHWC). */
+ * bf16 NHWC).  GroupNorm statistics are uint64 [B][groups][2] = (sum, sum of squares) in 2^-24 fixed point. */
 NDIFF_API int32_t ndiff_op_conv(int32_t mode, int32_t B, int32_t H, int32_t W, const void* src0, int32_t C0, const void* src1,
                       int32_t C1, int32_t taps_y, int32_t taps_x, int32_t pad_y, int32_t pad_x, const void* weight_packed,
                       int32_t Cout, const float* bias, const float* vec, int32_t vec_ld, const void* res, int32_t act,
-                      float* stats, int32_t groups, void* out, int32_t force_nt, int32_t tile_w, void* stream);
-NDIFF_API int32_t ndiff_op_gn_apply(const void* x, void* out, const float* stats, const float* gamma, const float* beta,
+                      void* stats, int32_t groups, void* out, int32_t force_nt, int32_t tile_w, void* stream);
+NDIFF_API int32_t ndiff_op_gn_apply(const void* x, void* out, const void* stats, const float* gamma, const float* beta,
                           const float* ss, int32_t ss_ld, int32_t ss_off, const void* maps, const void* res1,
                           const void* res2, int32_t B, int32_t HW, int32_t C, int32_t G, void* stream);
 NDIFF_API int32_t ndiff_op_layernorm(const void* x, const float* vec, int32_t vec_ld, const float* g, const float* beta, void* out,

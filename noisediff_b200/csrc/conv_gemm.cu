@@ -26,7 +26,8 @@ struct SmemTail {  // lives after the operand rings
     uint64_t fullA[8], emptyA[8], fullB[16], emptyB[16];
     uint64_t tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
-    float stats[32];
+    uint32_t pad_;
+    unsigned long long stats[32];
 };
 
 template <int NT>
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<2 * NT>(&tail->tmem_base);
-    if (threadIdx.x < 32) tail->stats[threadIdx.x] = 0.f;
+    if (threadIdx.x < 32) tail->stats[threadIdx.x] = 0ull;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -236,8 +237,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             const int gl = (ch * 32 + g * 8) >> a.lgs;
-                            atomicAdd(&tail->stats[gl * 2], s[g]);
-                            atomicAdd(&tail->stats[gl * 2 + 1], sq[g]);
+                            atomicAdd(&tail->stats[gl * 2], static_cast<unsigned long long>(__float2ll_rn(s[g] * kStatScale)));
+                            atomicAdd(&tail->stats[gl * 2 + 1],
+                                      static_cast<unsigned long long>(__float2ll_rn(sq[g] * kStatScale)));
                         }
                     }
                 }
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 if (ethread < ng * 2) {
                     const int g = (n0 >> a.lgs) + (ethread >> 1);
                     atomicAdd(&a.stats[(static_cast<size_t>(b) * a.G + g) * 2 + (ethread & 1)], tail->stats[ethread]);
-                    tail->stats[ethread] = 0.f;
+                    tail->stats[ethread] = 0ull;
                 }
                 named_bar_sync(1, 128);
             }
@@ -333,6 +335,12 @@ int encode_tensor_map(CUtensorMap* map, const void* base, int rank, const uint64
 }
 
 int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
+    {   // opt in to > 48 KB dynamic shared memory once per process (plans are never built under stream capture)
+        static std::once_flag once;
+        static int init_rc = 0;
+        std::call_once(once, [] { init_rc = conv_gemm_init(); });
+        if (init_rc) return 1;
+    }
     ConvGemmArgs& a = plan->args;
     memset(&a, 0, sizeof(a));
     NDIFF_REQUIRE(d.C0 > 0 && d.C0 % 64 == 0 && d.C1 % 64 == 0, "channel counts must be multiples of 64");

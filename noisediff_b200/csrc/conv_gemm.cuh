@@ -14,6 +14,7 @@ enum ConvMode : int {
     kHalo1BaseOff = 4,
 };
 enum ConvAct : int { kActNone = 0, kActGelu = 1 };
+constexpr float kStatScale = 16777216.0f;   // 2^24
 
 // Kernel arguments (one struct, passed as a __grid_constant__ so the three tensor maps stay in param space).
 struct ConvGemmArgs {
@@ -37,7 +38,8 @@ struct ConvGemmArgs {
     __nv_bfloat16* out;          // [B,H,W,out_ld]
     int out_ld;
     int act;
-    float* stats;                // GroupNorm partial sums [B][G][2] (sum, sum of squares) or null
+    unsigned long long* stats;   // GroupNorm sums [B][G][2] (sum, sum of squares) in 2^-24 fixed point, or null
+                                 // (integer atomics are associative: the result does not depend on tile order)
     int lgs;                     // log2(channels per group)
     int G;
 };
@@ -67,7 +69,7 @@ struct ConvGemmDesc {
     const __nv_bfloat16* res = nullptr; int res_ld = 0;
     __nv_bfloat16* out = nullptr; int out_ld = 0;
     int act = kActNone;
-    float* stats = nullptr; int groups = 0;
+    unsigned long long* stats = nullptr; int groups = 0;
     int force_nt = 0;                    // 0 = auto
     int TW = 0;                          // 0 = auto
 };

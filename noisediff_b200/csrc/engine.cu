@@ -146,7 +146,7 @@ struct ndiff_engine {
     float* pos_emb = nullptr;
     float* x = nullptr;            // fp32 NHWC4 chain state / network input
     float* v_out = nullptr;        // fp32 NHWC4 network output
-    float* stats = nullptr; int n_stats = 0; size_t stats_bytes = 0;
+    unsigned long long* stats = nullptr; int n_stats = 0; size_t stats_bytes = 0;
     ChainState* chain = nullptr;
     StepParams* step_table = nullptr; int n_steps = 0; int steps_done = 0;
     // plan
@@ -350,9 +350,10 @@ struct Builder {
     ndiff_engine* e;
     int err = 0;
     int stats_slot = 0;
-    bool direct3;
+    bool direct3, halo3;
 
-    explicit Builder(ndiff_engine* eng) : e(eng), direct3((eng->cfg.flags & NDIFF_FLAG_CONV_DIRECT) != 0) {}
+    explicit Builder(ndiff_engine* eng)
+        : e(eng), direct3((eng->cfg.flags & NDIFF_FLAG_CONV_DIRECT) != 0), halo3((eng->cfg.flags & NDIFF_FLAG_CONV_HALO3) != 0) {}
 
     Act make(int C, int H, int W) {
         Act a; a.C = C; a.H = H; a.W = W;
@@ -362,17 +363,18 @@ struct Builder {
     }
     void drop(const Act& a) { e->pool_put(a.p); }
     void name(const std::string& n, const Act& a) { e->named[n] = a; }
-    float* next_stats() { return e->stats + static_cast<size_t>(stats_slot++) * e->B * 8 * 2; }
+    unsigned long long* next_stats() { return e->stats + static_cast<size_t>(stats_slot++) * e->B * 8 * 2; }
 
     // generic conv / GEMM launch -> new activation
     Act conv(const std::string& wname, int mode, const Act& s0, const Act* s1, int Cout, int act, const float* vec,
-             int vec_ld, const Act* res, float* stats, int groups) {
+             int vec_ld, const Act* res, unsigned long long* stats, int groups) {
         const int Ho = mode == kS2D ? s0.H / 2 : s0.H, Wo = mode == kS2D ? s0.W / 2 : s0.W;
         Act out = make(Cout, Ho, Wo);
         if (err) return out;
         ConvGemmDesc d;
         d.mode = mode;
         if (mode == kHalo3 && direct3) { d.mode = kDirect; d.taps_y = 3; d.taps_x = 3; d.pad_y = 1; d.pad_x = 1; }
+        else if (mode == kHalo3 && !halo3) d.mode = kHalo1;
         d.B = e->B; d.H = Ho; d.W = Wo;
         d.src0 = s0.p; d.C0 = s0.C;
         if (s1) { d.src1 = s1->p; d.C1 = s1->C; }
@@ -396,7 +398,7 @@ struct Builder {
         return out;
     }
 
-    void gn(const std::string& nname, const Act& xio, float* stats, int groups, int ss_off, const bf16* maps,
+    void gn(const std::string& nname, const Act& xio, unsigned long long* stats, int groups, int ss_off, const bf16* maps,
             const Act* r1, const Act* r2) {
         GnApplyArgs g{};
         g.x = xio.p; g.out = xio.p; g.stats = stats;
@@ -414,10 +416,10 @@ struct Builder {
     Act resblock(const std::string& n, const Act& s0, const Act* s1, int Cout, int groups, const bf16* maps,
                  const Act* extra_res) {
         const int Cin = s0.C + (s1 ? s1->C : 0);
-        float* st1 = next_stats();
+        unsigned long long* st1 = next_stats();
         Act h = conv(n + ".block1.proj", kHalo3, s0, s1, Cout, kActNone, nullptr, 0, nullptr, st1, groups);
         gn(n + ".block1.norm", h, st1, groups, maps ? -1 : e->ss_off.at(n), maps, nullptr, nullptr);
-        float* st2 = next_stats();
+        unsigned long long* st2 = next_stats();
         Act h2 = conv(n + ".block2.proj", kHalo3, h, nullptr, Cout, kActNone, nullptr, 0, nullptr, st2, groups);
         drop(h);
         if (Cin != Cout) {
@@ -658,14 +660,14 @@ int32_t ndiff_engine_create(const ndiff_config* cfg, ndiff_engine** out) {
     e->cfg = *cfg;
     e->num_sms = prop.multiProcessorCount;
     e->B = cfg->batch; e->H = cfg->height; e->W = cfg->width; e->dim = cfg->dim;
-    e->keep_all = (cfg->flags & 4) != 0;
+    e->keep_all = (cfg->flags & NDIFF_FLAG_KEEP_ACTS) != 0;
     const size_t npix = static_cast<size_t>(e->B) * e->H * e->W;
     if (e->alloc(&e->clean, npix * 4) || e->alloc(&e->x, npix * 4) || e->alloc(&e->v_out, npix * 4)) return 1;
     if (e->alloc(&e->map1, npix * 2 * e->dim) || e->alloc(&e->map2, npix * 2 * e->dim)) return 1;
     if (e->alloc(&e->pos_emb, npix * 8)) return 1;
     e->n_stats = 64;
-    e->stats_bytes = static_cast<size_t>(e->n_stats) * e->B * 8 * 2 * sizeof(float);
-    if (e->alloc(&e->stats, e->stats_bytes / sizeof(float))) return 1;
+    e->stats_bytes = static_cast<size_t>(e->n_stats) * e->B * 8 * 2 * sizeof(unsigned long long);
+    if (e->alloc(&e->stats, e->stats_bytes / sizeof(unsigned long long))) return 1;
     if (e->alloc(&e->chain, 1)) return 1;
     NDIFF_CUDA_OK(cudaMemset(e->chain, 0, sizeof(ChainState)));
     *out = e.release();
@@ -955,7 +957,7 @@ int32_t ndiff_time_layers(ndiff_engine* e, int32_t iters, float* ms_out, char* n
 int32_t ndiff_op_conv(int32_t mode, int32_t B, int32_t H, int32_t W, const void* src0, int32_t C0, const void* src1,
                       int32_t C1, int32_t taps_y, int32_t taps_x, int32_t pad_y, int32_t pad_x, const void* weight_packed,
                       int32_t Cout, const float* bias, const float* vec, int32_t vec_ld, const void* res, int32_t act,
-                      float* stats, int32_t groups, void* out, int32_t force_nt, int32_t tile_w, void* stream) {
+                      void* stats, int32_t groups, void* out, int32_t force_nt, int32_t tile_w, void* stream) {
     int dev = 0;
     NDIFF_CUDA_OK(cudaGetDevice(&dev));
     cudaDeviceProp prop;
@@ -970,19 +972,19 @@ int32_t ndiff_op_conv(int32_t mode, int32_t B, int32_t H, int32_t W, const void*
     d.bias = bias; d.vec = vec; d.vec_ld = vec_ld;
     d.res = static_cast<const bf16*>(res); d.res_ld = Cout;
     d.out = static_cast<bf16*>(out); d.out_ld = Cout;
-    d.act = act; d.stats = stats; d.groups = groups;
+    d.act = act; d.stats = static_cast<unsigned long long*>(stats); d.groups = groups;
     d.force_nt = force_nt; d.TW = tile_w;
     ConvGemmPlan plan;
     if (conv_gemm_plan(d, prop.multiProcessorCount, &plan)) return 1;
     return conv_gemm_launch(plan, as_stream(stream));
 }
 
-int32_t ndiff_op_gn_apply(const void* x, void* out, const float* stats, const float* gamma, const float* beta,
+int32_t ndiff_op_gn_apply(const void* x, void* out, const void* stats, const float* gamma, const float* beta,
                           const float* ss, int32_t ss_ld, int32_t ss_off, const void* maps, const void* res1,
                           const void* res2, int32_t B, int32_t HW, int32_t C, int32_t G, void* stream) {
     GnApplyArgs g{};
     g.x = static_cast<const bf16*>(x); g.out = static_cast<bf16*>(out);
-    g.stats = stats; g.gamma = gamma; g.beta = beta;
+    g.stats = static_cast<const unsigned long long*>(stats); g.gamma = gamma; g.beta = beta;
     g.ss = ss; g.ss_ld = ss_ld; g.ss_off = ss_off;
     g.maps = static_cast<const bf16*>(maps);
     g.res1 = static_cast<const bf16*>(res1); g.res2 = static_cast<const bf16*>(res2);

@@ -30,12 +30,14 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnApplyArgs 
     __shared__ float sA[512], sB[512];
     const int b = blockIdx.y;
     const int C = a.C, gs = C / a.G;
-    const float inv_n = 1.0f / (static_cast<float>(a.HW) * gs);
+    const double inv_n = 1.0 / (static_cast<double>(a.HW) * gs);
     for (int c = threadIdx.x; c < C; c += kGnThreads) {
         const int g = c / gs;
-        const float s = a.stats[(b * a.G + g) * 2], ss = a.stats[(b * a.G + g) * 2 + 1];
-        const float mean = s * inv_n;
-        const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
+        const double s = static_cast<double>(static_cast<long long>(a.stats[(b * a.G + g) * 2])) * (1.0 / 16777216.0);
+        const double ss = static_cast<double>(static_cast<long long>(a.stats[(b * a.G + g) * 2 + 1])) * (1.0 / 16777216.0);
+        const double meand = s * inv_n;
+        const float mean = static_cast<float>(meand);
+        const float var = fmaxf(static_cast<float>(ss * inv_n - meand * meand), 0.f);
         const float rstd = rsqrtf(var + a.eps);
         float A = rstd * a.gamma[c];
         float Bc = a.beta[c] - mean * A;

@@ -35,7 +35,8 @@ struct ChainState {      // device-resident, advanced by the last kernel of ever
 // per-(sample, group) sums were accumulated by the conv epilogue.  ref Block.forward, Diffusion_arch.py:135-144.
 struct GnApplyArgs {
     const bf16* x; bf16* out;
-    const float* stats; const float* gamma; const float* beta;
+    const unsigned long long* stats;               // 2^-24 fixed-point sums from the conv epilogue
+    const float* gamma; const float* beta;
     const float* ss; int ss_ld; int ss_off;       // per-sample [scale C | shift C] at ss[b*ss_ld + ss_off], or null
     const bf16* maps;                              // per-pixel [scale C | shift C] bf16 [B,HW,2C], or null
     const bf16* res1; const bf16* res2;            // optional residuals added after SiLU

@@ -27,7 +27,8 @@ def _cond(z, dev="cuda"):
 
 @pytest.fixture(scope="module")
 def net():
-    return seeded_net().cuda()
+    import copy
+    return copy.deepcopy(seeded_net()).cuda()
 
 
 def layer_report(flags=0):
@@ -57,14 +58,16 @@ def test_forward_matches_reference_layer_by_layer():
     rows, out, ref = layer_report()
     for n, e in rows:
         print(f"{n:20s} {e:.3e}")
-    assert torch.equal(ref, torch.from_numpy(load("fwd_64.npz")["out"]))      # oracle == reference (golden)
+    # oracle (run on this box's CPU) == reference output minted in the build container, up to MKLDNN kernel choice
+    assert rel_l2(ref, torch.from_numpy(load("fwd_64.npz")["out"])) < 1e-5
     bad = [(n, e) for n, e in rows if not (e < 3e-2)]
     assert not bad, f"layers off: {bad}"
     assert dict(rows)["pos_emb"] < 1e-5 and dict(rows)["out(v)"] < 2.5e-2
 
 
-def test_forward_direct_conv_mode_agrees():
-    rows, _, _ = layer_report(flags=_lib.FLAG_CONV_DIRECT | _lib.FLAG_NO_GRAPH)
+@pytest.mark.parametrize("flags", [_lib.FLAG_CONV_DIRECT | _lib.FLAG_NO_GRAPH, _lib.FLAG_CONV_HALO3])
+def test_forward_other_conv_staging_modes_agree(flags):
+    rows, _, _ = layer_report(flags=flags)
     assert all(e < 3e-2 for _, e in rows), rows
 
 
@@ -84,7 +87,7 @@ def test_forward_through_dataparallel_wrapper_and_graph_replay(net):
         a = wrapped(x, t, cond)
         b = wrapped(x, t, cond)                       # second call replays the captured graph
     ref = torch.from_numpy(z["out"])
-    assert rel_l2(a, ref) < 2.5e-2 and rel_l2(b, a.cpu()) < 5e-3
+    assert rel_l2(a, ref) < 2.5e-2 and torch.equal(a, b)       # deterministic: fixed-point GroupNorm sums
 
 
 def _teacher_forced(gd, net, steps, x_in, cond, noises):
@@ -180,7 +183,7 @@ def test_micro_batches_in_lockstep_equal_one_batch(net):
     gd.micro_batch, gd.chunk_steps = 2, 2              # 2 + 1(padded) patches, state swapped every 2 steps
     two = gd._run_chain(gd.ddpm_steps(), (3, 4, 32, 32), cond, x_T, False, noises=noises)
     assert one.shape == two.shape == (3, 4, 32, 32)
-    assert rel_l2(two, one) < 5e-3                     # only GroupNorm's atomic summation order differs
+    assert torch.equal(two, one)                       # per-sample math only; integer GroupNorm sums are order-free
 
 
 def test_sample_public_api_torch_rng_and_philox(net):
@@ -191,17 +194,17 @@ def test_sample_public_api_torch_rng_and_philox(net):
     a = gd.sample(batch_size=2, condition=cond)
     torch.manual_seed(5)
     b = gd.sample(batch_size=2, condition=cond)
-    assert a.shape == (2, 4, 32, 32) and torch.isfinite(a).all() and rel_l2(b, a) < 5e-3
+    assert a.shape == (2, 4, 32, 32) and torch.isfinite(a).all() and torch.equal(a, b)
     # the torch-RNG stream is the reference's: x_T then one draw per noisy step
     torch.manual_seed(5)
     x_T = torch.randn(2, 4, 32, 32, device="cuda")
     zs = [torch.randn(2, 4, 32, 32, device="cuda") for _ in range(4)] + [torch.zeros(2, 4, 32, 32, device="cuda")]
     c = gd._run_chain(gd.ddpm_steps(), (2, 4, 32, 32), cond, x_T, False, noises=torch.stack(zs))
-    assert rel_l2(c, a) < 5e-3
+    assert torch.equal(c, a)
     stack = None
     torch.manual_seed(5)
     stack = gd.sample(batch_size=2, condition=cond, return_all_timesteps=True)
-    assert stack.shape == (2, 6, 4, 32, 32) and rel_l2(stack[:, -1], a) < 5e-3 and torch.equal(stack[:, 0], x_T)
+    assert stack.shape == (2, 6, 4, 32, 32) and torch.equal(stack[:, -1], a) and torch.equal(stack[:, 0], x_T)
     gd.noise_source = "philox"
     torch.manual_seed(7)
     p1 = gd.sample(batch_size=2, condition=cond)
@@ -209,7 +212,7 @@ def test_sample_public_api_torch_rng_and_philox(net):
     p2 = gd.sample(batch_size=2, condition=cond)
     torch.manual_seed(8)
     p3 = gd.sample(batch_size=2, condition=cond)
-    assert rel_l2(p2, p1) < 5e-3 and rel_l2(p3, p1) > 0.1 and torch.isfinite(p1).all()
+    assert torch.equal(p2, p1) and rel_l2(p3, p1) > 0.1 and torch.isfinite(p1).all()
 
 
 def test_p_sample_api_matches_oracle(net):
@@ -232,5 +235,5 @@ def test_end_to_end_host_buffers(net):
     out = eng.sample_host(cond["clean_img"], cond["position"], cond["iso_ratio_idx"], gd.ddpm_steps(), seed=99)
     out2 = eng.sample_host(cond["clean_img"], cond["position"], cond["iso_ratio_idx"], gd.ddpm_steps(), seed=99)
     assert out.device.type == "cpu" and out.shape == (2, 4, 32, 32) and torch.isfinite(out).all()
-    assert rel_l2(out2, out) < 5e-3 and float(out.std()) > 1e-3
+    assert torch.equal(out2, out) and float(out.std()) > 1e-3
     assert eng.launches_per_step > 100 and eng.conv_flops_per_step > 1e9

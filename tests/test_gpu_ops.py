@@ -66,7 +66,7 @@ CONV3_CASES = [(2, 32, 32, 64, 0, 64), (1, 16, 16, 128, 64, 128), (1, 8, 8, 256,
                (1, 64, 64, 64, 0, 64), (1, 8, 8, 512, 256, 512), (4, 128, 128, 64, 0, 64)]
 
 
-@pytest.mark.parametrize("mode", ["halo", "direct"])
+@pytest.mark.parametrize("mode", ["halo1", "halo3", "direct"])
 @pytest.mark.parametrize("case", CONV3_CASES)
 def test_conv3x3(case, mode):
     B, H, W, c0, c1, co = case
@@ -76,8 +76,8 @@ def test_conv3x3(case, mode):
     bias = torch.randn(co, device="cuda")
     ref = F.conv2d(torch.cat([x0, x1], 1) if c1 else x0, w, bias, padding=1)
     kw = dict(src1=G.to_nhwc_bf16(x1) if c1 else None, bias=bias)
-    if mode == "halo":
-        out = G.conv(G.MODE_HALO3, G.to_nhwc_bf16(x0), G.pack_weight(w), co, **kw)
+    if mode != "direct":
+        out = G.conv(G.MODE_HALO1 if mode == "halo1" else G.MODE_HALO3, G.to_nhwc_bf16(x0), G.pack_weight(w), co, **kw)
     else:
         out = G.conv(G.MODE_DIRECT, G.to_nhwc_bf16(x0), G.pack_weight(w), co, taps=(3, 3), pad=(1, 1), **kw)
     _check(out, ref)
@@ -113,12 +113,16 @@ def test_groupnorm_stats_and_apply(case):
     gamma, beta = torch.randn(c, device="cuda"), torch.randn(c, device="cuda")
     ss = torch.randn(B, 3 * c, device="cuda") * 0.5
     res = _rand((B, c, H, W), 16)
-    stats = torch.zeros(B, groups, 2, device="cuda")
-    y = G.conv(G.MODE_HALO3, G.to_nhwc_bf16(x), G.pack_weight(w), c, bias=bias, stats=stats, groups=groups)
+    stats = torch.zeros(B, groups, 2, device="cuda", dtype=torch.int64)       # 2^-24 fixed point
+    y = G.conv(G.MODE_HALO1, G.to_nhwc_bf16(x), G.pack_weight(w), c, bias=bias, stats=stats, groups=groups)
+    stats2 = torch.zeros_like(stats)
+    G.conv(G.MODE_HALO3, G.to_nhwc_bf16(x), G.pack_weight(w), c, bias=bias, stats=stats2, groups=groups, tile_w=16)
     conv_ref = F.conv2d(x, w, bias, padding=1)
     grp = conv_ref.reshape(B, groups, -1)
-    assert torch.allclose(stats[..., 0], grp.sum(-1), rtol=2e-3, atol=2e-2 * math.sqrt(grp.shape[-1]))
-    assert torch.allclose(stats[..., 1], (grp ** 2).sum(-1), rtol=2e-3)
+    sums = stats.double() / 2 ** 24
+    assert torch.allclose(sums[..., 0], grp.sum(-1).double(), rtol=2e-3, atol=2e-2 * math.sqrt(grp.shape[-1]))
+    assert torch.allclose(sums[..., 1], (grp ** 2).sum(-1).double(), rtol=2e-3)
+    assert (stats - stats2).abs().max().item() <= 2 ** 24 * 1e-2              # tiling changes only fp32 partial rounding
     out = torch.empty_like(y)
     _lib.check(_lib.lib().ndiff_op_gn_apply(G.P(y), G.P(out), G.P(stats), G.P(gamma), G.P(beta), G.P(ss), 3 * c, c // 2,
                                             None, G.P(G.to_nhwc_bf16(res)), None, B, H * W, c, groups, G.stream()))
@@ -134,7 +138,7 @@ def test_groupnorm_apply_with_pixel_maps():
     maps = _rand((B, 2 * c, H, W), 18, 0.5)
     gamma, beta = torch.randn(c, device="cuda"), torch.randn(c, device="cuda")
     grp = y.reshape(B, groups, -1)
-    stats = torch.stack([grp.sum(-1), (grp ** 2).sum(-1)], dim=-1).contiguous()
+    stats = (torch.stack([grp.sum(-1), (grp ** 2).sum(-1)], dim=-1).double() * 2 ** 24).round().to(torch.int64).contiguous()
     yb = G.to_nhwc_bf16(y)
     out = torch.empty_like(yb)
     _lib.check(_lib.lib().ndiff_op_gn_apply(G.P(yb), G.P(out), G.P(stats), G.P(gamma), G.P(beta), None, 0, 0,

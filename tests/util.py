@@ -43,7 +43,8 @@ def seeded_net(dim=64, seed=0):
 
 
 def seeded_sd(dim=64, seed=0):
-    return {k: v.detach() for k, v in seeded_net(dim, seed).state_dict().items()}
+    """CPU fp32 state_dict (the oracle runs on the host even when the module was moved to the GPU)."""
+    return {k: v.detach().cpu() for k, v in seeded_net(dim, seed).state_dict().items()}
 
 
 def load(name):

@@ -87,7 +87,8 @@ def main():
     if "net" in which:
         from tests.util import seeded_net
         from oracle import noisediff_oracle as O
-        net = seeded_net().cuda()
+        import copy
+        net = copy.deepcopy(seeded_net()).cuda()
         for B in (2, 4, 8):
             def run(B=B):
                 gd = nd.GaussianDiffusion(net, image_size=256, timesteps=1000, beta_schedule="sigmoid2").cuda()
