@@ -47,7 +47,6 @@ typedef struct ndiff_config {
 #define NDIFF_FLAG_CONV_DIRECT 1   /* debug: 3x3 convs load every tap from L2 instead of the halo layout */
 #define NDIFF_FLAG_NO_GRAPH    2   /* debug: launch kernels eagerly instead of replaying a CUDA graph */
 #define NDIFF_FLAG_KEEP_ACTS   4   /* debug: never recycle activation buffers (ndiff_debug_tensor sees every layer) */
-#define NDIFF_FLAG_CONV_HALO3  8   /* debug: 3x3 convs use three kx-shifted halo copies instead of one */
 
 /* One reverse step's scalars; the caller derives them from GaussianDiffusion's fp32 buffers
  * (models/denoising_diffusion_pytorch.py:240-266) so the arithmetic constants are the reference's own:

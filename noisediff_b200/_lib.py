@@ -14,7 +14,6 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "noisediff_b200.h"
 FLAG_CONV_DIRECT = 1
 FLAG_NO_GRAPH = 2
 FLAG_KEEP_ACTIVATIONS = 4
-FLAG_CONV_HALO3 = 8
 
 
 class Config(C.Structure):

@@ -30,22 +30,32 @@ struct SmemTail {  // lives after the operand rings
     unsigned long long stats[32];
 };
 
-template <int NT>
+// Tap geometry of the single-copy halo mode (compile-time: TW = 8 so that one 8-row UMMA group == one output row).
+constexpr int kHaloTW = 8, kHaloTH = 16;
+constexpr int kHaloPitch = (kHaloTW + 2) * 128;                          // bytes between halo rows
+constexpr int kHaloCopy = (kHaloTH + 2) * kHaloPitch;                    // 23040 B landed by one TMA box
+constexpr int kHaloStage = (kHaloCopy + 1023) / 1024 * 1024;
+
+template <int NT, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem is only guaranteed 16-B aligned by the ABI; SWIZZLE_128B wants 1024
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr bool kHalo = MODE == kHalo1;
     constexpr int kBStage = NT * 128;
-    uint8_t* ringA = smem;
-    uint8_t* ringB = ringA + a.a_stages * a.a_stage_bytes;
-    SmemTail* tail = reinterpret_cast<SmemTail*>(ringB + a.b_stages * kBStage);
+    constexpr int kAStage = kHalo ? kHaloStage : 128 * 128;
+    const int a_stages = a.a_stages, b_stages = a.b_stages;
+    const uint32_t ringA = smem_u32(smem);
+    const uint32_t ringB = ringA + a_stages * kAStage;
+    SmemTail* tail = reinterpret_cast<SmemTail*>(smem + a_stages * kAStage + b_stages * kBStage);
+    const uint32_t bar_fullA = smem_u32(&tail->fullA[0]), bar_emptyA = smem_u32(&tail->emptyA[0]);
+    const uint32_t bar_fullB = smem_u32(&tail->fullB[0]), bar_emptyB = smem_u32(&tail->emptyB[0]);
+    const uint32_t bar_tfull = smem_u32(&tail->tmem_full[0]), bar_tempty = smem_u32(&tail->tmem_empty[0]);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int CB = a.cb0 + a.cb1;
-    const int TAPS = a.taps_y * a.taps_x;
-    const bool halo1 = a.mode == kHalo1 || a.mode == kHalo1BaseOff;
-    const bool halo = a.mode == kHalo3 || halo1;
+    const int TAPS = kHalo ? 9 : a.taps_y * a.taps_x;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&a.tmA0);
@@ -53,8 +63,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         tma_prefetch_desc(&a.tmB);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < a.a_stages; ++i) { mbar_init(&tail->fullA[i], 1); mbar_init(&tail->emptyA[i], 1); }
-        for (int i = 0; i < a.b_stages; ++i) { mbar_init(&tail->fullB[i], 1); mbar_init(&tail->emptyB[i], 1); }
+        for (int i = 0; i < a_stages; ++i) { mbar_init(&tail->fullA[i], 1); mbar_init(&tail->emptyA[i], 1); }
+        for (int i = 0; i < b_stages; ++i) { mbar_init(&tail->fullB[i], 1); mbar_init(&tail->emptyB[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tail->tmem_full[i], 1); mbar_init(&tail->tmem_empty[i], 4); }
         fence_mbar_init();
     }
@@ -66,101 +76,116 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const uint32_t tmem_base = tail->tmem_base;
 
     if (warp == 0) {
-        // ================================ TMA producer =========================================================
-        if (lane == 0) {
-            int sa = 0, pa = 0, sb = 0, pb = 0;
-            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-                const int nt = tile % a.n_tiles;
-                int m = tile / a.n_tiles;
-                const int tx = m % a.tiles_x; m /= a.tiles_x;
-                const int ty = m % a.tiles_y;
-                const int b = m / a.tiles_y;
-                const int x0 = tx * a.TW, y0 = ty * a.TH;
-                for (int cb = 0; cb < CB; ++cb) {
-                    const CUtensorMap* tm = cb < a.cb0 ? &a.tmA0 : &a.tmA1;
-                    const int c0 = (cb < a.cb0 ? cb : cb - a.cb0) * 64;
-                    if (halo) {
-                        mbar_wait(&tail->emptyA[sa], pa ^ 1);
-                        uint8_t* dst = ringA + sa * a.a_stage_bytes;
-                        if (halo1) {
-                            mbar_expect_tx(&tail->fullA[sa], a.a_copy_bytes);
-                            tma_load_4d(dst, tm, &tail->fullA[sa], c0, x0 - 1, y0 - 1, b);
-                        } else {
-                            mbar_expect_tx(&tail->fullA[sa], 3 * a.a_copy_bytes);
-                            for (int kx = 0; kx < 3; ++kx)
-                                tma_load_4d(dst + kx * a.a_copy_bytes, tm, &tail->fullA[sa], c0, x0 + kx - 1, y0 - 1, b);
-                        }
-                        if (++sa == a.a_stages) { sa = 0; pa ^= 1; }
+        // ================================ TMA producer (whole warp walks the loop, one elected lane issues) ========
+        int sa = 0, pa = 0, sb = 0, pb = 0;
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+            const int nt = tile % a.n_tiles;
+            int m = tile / a.n_tiles;
+            const int tx = m % a.tiles_x; m /= a.tiles_x;
+            const int ty = m % a.tiles_y;
+            const int b = m / a.tiles_y;
+            const int x0 = tx * a.TW, y0 = ty * a.TH;
+            int kcol = 0;
+            for (int cb = 0; cb < CB; ++cb) {
+                const CUtensorMap* tm = cb < a.cb0 ? &a.tmA0 : &a.tmA1;
+                const int c0 = (cb < a.cb0 ? cb : cb - a.cb0) * 64;
+                if constexpr (kHalo) {
+                    mbar_wait(bar_emptyA + sa * 8, pa ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(bar_fullA + sa * 8, kHaloCopy);
+                        tma_load_4d(ringA + sa * kAStage, tm, bar_fullA + sa * 8, c0, x0 - 1, y0 - 1, b);
                     }
-                    for (int tap = 0; tap < TAPS; ++tap) {
-                        if (!halo) {
-                            mbar_wait(&tail->emptyA[sa], pa ^ 1);
-                            mbar_expect_tx(&tail->fullA[sa], 128 * 128);
-                            uint8_t* dst = ringA + sa * a.a_stage_bytes;
-                            const int ky = tap / a.taps_x, kx = tap - ky * a.taps_x;
-                            if (a.mode == kS2D)
-                                tma_load_5d(dst, tm, &tail->fullA[sa], c0, kx, x0, ky, b * a.H + y0);
+                    __syncwarp();
+                    if (++sa == a_stages) { sa = 0; pa ^= 1; }
+                }
+                int ky = 0, kx = 0;
+                for (int tap = 0; tap < TAPS; ++tap) {
+                    if constexpr (!kHalo) {
+                        mbar_wait(bar_emptyA + sa * 8, pa ^ 1);
+                        if (elect_one()) {
+                            mbar_expect_tx(bar_fullA + sa * 8, 128 * 128);
+                            if constexpr (MODE == kS2D)
+                                tma_load_5d(ringA + sa * kAStage, tm, bar_fullA + sa * 8, c0, kx, x0, ky, b * a.H + y0);
                             else
-                                tma_load_4d(dst, tm, &tail->fullA[sa], c0, x0 + kx - a.pad_x, y0 + ky - a.pad_y, b);
-                            if (++sa == a.a_stages) { sa = 0; pa ^= 1; }
+                                tma_load_4d(ringA + sa * kAStage, tm, bar_fullA + sa * 8, c0, x0 + kx - a.pad_x,
+                                            y0 + ky - a.pad_y, b);
                         }
-                        mbar_wait(&tail->emptyB[sb], pb ^ 1);
-                        mbar_expect_tx(&tail->fullB[sb], kBStage);
-                        tma_load_2d(ringB + sb * kBStage, &a.tmB, &tail->fullB[sb], (cb * TAPS + tap) * 64, nt * NT);
-                        if (++sb == a.b_stages) { sb = 0; pb ^= 1; }
+                        __syncwarp();
+                        if (++sa == a_stages) { sa = 0; pa ^= 1; }
+                        if (++kx == a.taps_x) { kx = 0; ++ky; }
                     }
+                    mbar_wait(bar_emptyB + sb * 8, pb ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(bar_fullB + sb * 8, kBStage);
+                        tma_load_2d(ringB + sb * kBStage, &a.tmB, bar_fullB + sb * 8, kcol, nt * NT);
+                    }
+                    __syncwarp();
+                    kcol += 64;
+                    if (++sb == b_stages) { sb = 0; pb ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================================ MMA issuer ===========================================================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(128, NT);
-            int sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
-            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-                mbar_wait(&tail->tmem_empty[acc], pacc ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * NT;
-                uint32_t first = 1;
-                for (int cb = 0; cb < CB; ++cb) {
-                    if (halo) { mbar_wait(&tail->fullA[sa], pa); }
-                    for (int tap = 0; tap < TAPS; ++tap) {
-                        if (!halo) { mbar_wait(&tail->fullA[sa], pa); }
-                        mbar_wait(&tail->fullB[sb], pb);
-                        tc_fence_after();
-                        uint32_t a_addr = smem_u32(ringA + sa * a.a_stage_bytes);
-                        uint32_t a_sbo = 1024, a_boff = 0;
-                        if (halo1) {
-                            const int ky = tap / 3, kx = tap - ky * 3;
-                            a_addr += (ky * (a.TW + 2) + kx) * 128;
-                            a_sbo = (a.TW + 2) * 128;
-                            if (a.mode == kHalo1BaseOff) a_boff = (a_addr >> 7) & 7;
-                        } else if (halo) {
-                            const int ky = tap / 3, kx = tap - ky * 3;
-                            a_addr += kx * a.a_copy_bytes + ky * a.TW * 128;
-                        }
-                        const uint32_t b_addr = smem_u32(ringB + sb * kBStage);
+        // ================================ MMA issuer (warp-uniform loop, one elected lane issues tcgen05.mma) =======
+        constexpr uint32_t idesc = umma_idesc_bf16(128, NT);
+        constexpr uint32_t hiB = umma_desc_hi(1024);
+        constexpr uint32_t hiA = umma_desc_hi(kHalo ? kHaloPitch : 1024);
+        int sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+            mbar_wait(bar_tempty + acc * 8, pacc ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * NT;
+            bool first = true;
+            for (int cb = 0; cb < CB; ++cb) {
+                if constexpr (kHalo) {
+                    mbar_wait(bar_fullA + sa * 8, pa);
+                    const uint32_t a_base = umma_desc_lo(ringA + sa * kAStage);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32, a_boff, a_sbo),
-                                      umma_desc_sw128(b_addr + k * 32), idesc, first ? 0u : 1u);
-                            first = 0;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(bar_fullB + sb * 8, pb);
+                        tc_fence_after();
+                        const uint32_t a_lo = a_base + (((tap / 3) * kHaloPitch + (tap % 3) * 128) >> 4);
+                        const uint32_t b_lo = umma_desc_lo(ringB + sb * kBStage);
+                        if (elect_one()) {
+                            if (first) umma_bf16_lohi<false>(d_tmem, a_lo, hiA, b_lo, hiB, idesc);
+                            else umma_bf16_lohi<true>(d_tmem, a_lo, hiA, b_lo, hiB, idesc);
+                            umma_bf16_lohi<true>(d_tmem, a_lo + 2, hiA, b_lo + 2, hiB, idesc);
+                            umma_bf16_lohi<true>(d_tmem, a_lo + 4, hiA, b_lo + 4, hiB, idesc);
+                            umma_bf16_lohi<true>(d_tmem, a_lo + 6, hiA, b_lo + 6, hiB, idesc);
+                            umma_commit(bar_emptyB + sb * 8);
+                            if (tap == 8) umma_commit(bar_emptyA + sa * 8);
                         }
-                        umma_commit(&tail->emptyB[sb]);
-                        if (++sb == a.b_stages) { sb = 0; pb ^= 1; }
-                        if (!halo) {
-                            umma_commit(&tail->emptyA[sa]);
-                            if (++sa == a.a_stages) { sa = 0; pa ^= 1; }
-                        }
+                        __syncwarp();
+                        first = false;
+                        if (++sb == b_stages) { sb = 0; pb ^= 1; }
                     }
-                    if (halo) {
-                        umma_commit(&tail->emptyA[sa]);
-                        if (++sa == a.a_stages) { sa = 0; pa ^= 1; }
+                    if (++sa == a_stages) { sa = 0; pa ^= 1; }
+                } else {
+                    for (int tap = 0; tap < TAPS; ++tap) {
+                        mbar_wait(bar_fullA + sa * 8, pa);
+                        mbar_wait(bar_fullB + sb * 8, pb);
+                        tc_fence_after();
+                        const uint32_t a_lo = umma_desc_lo(ringA + sa * kAStage);
+                        const uint32_t b_lo = umma_desc_lo(ringB + sb * kBStage);
+                        if (elect_one()) {
+                            if (first) umma_bf16_lohi<false>(d_tmem, a_lo, hiA, b_lo, hiB, idesc);
+                            else umma_bf16_lohi<true>(d_tmem, a_lo, hiA, b_lo, hiB, idesc);
+                            umma_bf16_lohi<true>(d_tmem, a_lo + 2, hiA, b_lo + 2, hiB, idesc);
+                            umma_bf16_lohi<true>(d_tmem, a_lo + 4, hiA, b_lo + 4, hiB, idesc);
+                            umma_bf16_lohi<true>(d_tmem, a_lo + 6, hiA, b_lo + 6, hiB, idesc);
+                            umma_commit(bar_emptyB + sb * 8);
+                            umma_commit(bar_emptyA + sa * 8);
+                        }
+                        __syncwarp();
+                        first = false;
+                        if (++sb == b_stages) { sb = 0; pb ^= 1; }
+                        if (++sa == a_stages) { sa = 0; pa ^= 1; }
                     }
                 }
-                umma_commit(&tail->tmem_full[acc]);
-                if (++acc == 2) { acc = 0; pacc ^= 1; }
             }
+            if (elect_one()) umma_commit(bar_tfull + acc * 8);
+            __syncwarp();
+            if (++acc == 2) { acc = 0; pacc ^= 1; }
         }
     } else if (warp >= kEpiWarp0) {
         // ================================ epilogue =============================================================
@@ -179,7 +204,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const size_t pix = (static_cast<size_t>(b) * a.H + y) * a.W + x;
             const int n0 = nt * NT;
 
-            mbar_wait(&tail->tmem_full[acc], pacc);
+            mbar_wait(bar_tfull + acc * 8, pacc);
             tc_fence_after();
 #pragma unroll 1
             for (int ch = 0; ch < NT / 32; ++ch) {
@@ -259,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             // accumulator drained: hand the TMEM stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tail->tmem_empty[acc]);
+            if (lane == 0) mbar_arrive(bar_tempty + acc * 8);
             if (++acc == 2) { acc = 0; pacc ^= 1; }
 
             if (a.stats) {
@@ -352,8 +377,7 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     a.B = d.B; a.H = d.H; a.W = d.W;
     int TW = d.TW;
     if (TW == 0) {
-        if (d.mode == kHalo1 || d.mode == kHalo1BaseOff) TW = 8;
-        else if (d.mode == kHalo3) TW = d.H >= 16 ? 8 : 16;
+        if (d.mode == kHalo1) TW = kHaloTW;
         else TW = d.W >= 64 ? 64 : (d.W >= 32 ? 32 : (d.W >= 16 ? 16 : 8));
     }
     NDIFF_REQUIRE(TW >= 8 && TW <= 128 && (TW & (TW - 1)) == 0, "tile width must be a power of two in [8,128]");
@@ -361,32 +385,27 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     a.tiles_x = (d.W + a.TW - 1) / a.TW;
     a.tiles_y = (d.H + a.TH - 1) / a.TH;
     a.cb0 = d.C0 / 64; a.cb1 = d.C1 / 64;
-    const bool halo1 = d.mode == kHalo1 || d.mode == kHalo1BaseOff;
-    NDIFF_REQUIRE(!halo1 || TW == 8, "single-copy halo mode needs TW == 8 (one 8-row UMMA group per output row)");
-    if (d.mode == kHalo3 || halo1) { a.taps_y = 3; a.taps_x = 3; a.pad_y = 1; a.pad_x = 1; }
+    const bool halo1 = d.mode == kHalo1;
+    NDIFF_REQUIRE(d.mode == kDirect || d.mode == kS2D || d.mode == kHalo1, "unknown convolution mode");
+    NDIFF_REQUIRE(!halo1 || TW == kHaloTW, "halo mode needs TW == 8 (one 8-row UMMA group per output row)");
+    if (halo1) { a.taps_y = 3; a.taps_x = 3; a.pad_y = 1; a.pad_x = 1; }
     else if (d.mode == kS2D) { a.taps_y = 2; a.taps_x = 2; a.pad_y = 0; a.pad_x = 0; }
     else { a.taps_y = d.taps_y; a.taps_x = d.taps_x; a.pad_y = d.pad_y; a.pad_x = d.pad_x; }
     a.n_tiles = d.Cout / NT;
     a.total_tiles = d.B * a.tiles_y * a.tiles_x * a.n_tiles;
     const int b_stage = NT * 128;
     if (halo1) {
-        a.a_copy_bytes = (a.TH + 2) * (a.TW + 2) * 128;
-        a.a_stage_bytes = (a.a_copy_bytes + 1023) / 1024 * 1024;
+        a.a_copy_bytes = kHaloCopy;
+        a.a_stage_bytes = kHaloStage;
         a.a_stages = 3;
-        a.b_stages = NT == 128 ? 6 : 8;
-    } else if (d.mode == kHalo3) {
-        a.a_copy_bytes = (a.TH + 2) * a.TW * 128;
-        a.a_stage_bytes = 3 * a.a_copy_bytes;
-        a.a_stages = 2;
-        a.b_stages = NT == 128 ? 5 : 8;
+        a.b_stages = NT == 128 ? 8 : 12;
     } else {
         a.a_copy_bytes = 128 * 128;
         a.a_stage_bytes = 128 * 128;
         a.a_stages = NT == 128 ? 6 : 8;
         a.b_stages = a.a_stages;
     }
-    NDIFF_REQUIRE(a.a_stage_bytes % 1024 == 0 && (halo1 || a.a_copy_bytes % 1024 == 0),
-                  "operand stages must stay 1024-B aligned");
+    NDIFF_REQUIRE(a.a_stage_bytes % 1024 == 0, "operand stages must stay 1024-B aligned");
     plan->smem_bytes = 1024 + a.a_stages * a.a_stage_bytes + a.b_stages * b_stage + static_cast<int>(sizeof(SmemTail));
     NDIFF_REQUIRE(plan->smem_bytes <= 227 * 1024, "shared-memory budget exceeded");
     plan->grid = a.total_tiles < num_sms ? a.total_tiles : num_sms;
@@ -416,7 +435,7 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
             uint64_t str[3] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(Win) * C * 2,
                                static_cast<uint64_t>(Hin) * Win * C * 2};
             uint32_t box[4] = {64, static_cast<uint32_t>(halo1 ? a.TW + 2 : a.TW),
-                               static_cast<uint32_t>(d.mode == kHalo3 || halo1 ? a.TH + 2 : a.TH), 1};
+                               static_cast<uint32_t>(halo1 ? a.TH + 2 : a.TH), 1};
             if (encode_tensor_map(tm, src, 4, dims, str, box, true)) return 1;
         }
     }
@@ -440,19 +459,39 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     return 0;
 }
 
+namespace {
+template <int NT, int MODE>
+int launch_one(const ConvGemmPlan& plan, cudaStream_t stream) {
+    conv_gemm_kernel<NT, MODE><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.args);
+    NDIFF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+template <int NT, int MODE>
+cudaError_t opt_in() {
+    return cudaFuncSetAttribute(conv_gemm_kernel<NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+}  // namespace
+
 int conv_gemm_init() {
-    NDIFF_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    NDIFF_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    NDIFF_CUDA_OK((opt_in<64, kDirect>()));
+    NDIFF_CUDA_OK((opt_in<128, kDirect>()));
+    NDIFF_CUDA_OK((opt_in<64, kS2D>()));
+    NDIFF_CUDA_OK((opt_in<128, kS2D>()));
+    NDIFF_CUDA_OK((opt_in<64, kHalo1>()));
+    NDIFF_CUDA_OK((opt_in<128, kHalo1>()));
     return 0;
 }
 
 int conv_gemm_launch(const ConvGemmPlan& plan, cudaStream_t stream) {
-    if (plan.NT == 64)
-        conv_gemm_kernel<64><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.args);
-    else
-        conv_gemm_kernel<128><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.args);
-    NDIFF_CUDA_OK(cudaGetLastError());
-    return 0;
+    const int mode = plan.args.mode;
+    if (plan.NT == 64) {
+        if (mode == kHalo1) return launch_one<64, kHalo1>(plan, stream);
+        if (mode == kS2D) return launch_one<64, kS2D>(plan, stream);
+        return launch_one<64, kDirect>(plan, stream);
+    }
+    if (mode == kHalo1) return launch_one<128, kHalo1>(plan, stream);
+    if (mode == kS2D) return launch_one<128, kS2D>(plan, stream);
+    return launch_one<128, kDirect>(plan, stream);
 }
 
 }  // namespace ndiff

@@ -6,12 +6,11 @@ namespace ndiff {
 
 enum ConvMode : int {
     kDirect = 0,  // every (channel-block, tap) k-block loads its own shifted 128-pixel box (1x1, 7x7-row trick, debug 3x3)
-    kHalo3 = 1,   // 3x3 pad 1: per channel block three kx-shifted (TH+2)xTW halo boxes; 9 taps are row offsets into them
     kS2D = 2,     // 2x2 stride-2 (space-to-depth + 1x1) through a 5-D view of the input
-    kHalo1 = 3,   // 3x3 pad 1, ONE (TH+2)x(TW+2) halo box per channel block (TW = 8); taps are 128-B row shifts of the
-                  // UMMA start address with SBO = (TW+2)*128 (relies on address-based swizzling; base-offset variants
-                  // selectable with mode 4 = kHalo1 | base_offset from the start address)
-    kHalo1BaseOff = 4,
+    kHalo1 = 3,   // 3x3 pad 1: ONE (TH+2)x(TW+2) = 18x10-pixel halo box per 64-channel block (TH x TW = 16 x 8); the nine
+                  // taps are 128-byte row shifts of the UMMA start address with SBO = (TW+2)*128.  Works because the
+                  // 128-B swizzle is a function of the absolute shared-memory address for both TMA and UMMA
+                  // (verified on B200: tests/test_gpu_ops.py::test_conv3x3).
 };
 enum ConvAct : int { kActNone = 0, kActGelu = 1 };
 constexpr float kStatScale = 16777216.0f;   // 2^24

@@ -350,10 +350,9 @@ struct Builder {
     ndiff_engine* e;
     int err = 0;
     int stats_slot = 0;
-    bool direct3, halo3;
+    bool direct3;
 
-    explicit Builder(ndiff_engine* eng)
-        : e(eng), direct3((eng->cfg.flags & NDIFF_FLAG_CONV_DIRECT) != 0), halo3((eng->cfg.flags & NDIFF_FLAG_CONV_HALO3) != 0) {}
+    explicit Builder(ndiff_engine* eng) : e(eng), direct3((eng->cfg.flags & NDIFF_FLAG_CONV_DIRECT) != 0) {}
 
     Act make(int C, int H, int W) {
         Act a; a.C = C; a.H = H; a.W = W;
@@ -373,8 +372,7 @@ struct Builder {
         if (err) return out;
         ConvGemmDesc d;
         d.mode = mode;
-        if (mode == kHalo3 && direct3) { d.mode = kDirect; d.taps_y = 3; d.taps_x = 3; d.pad_y = 1; d.pad_x = 1; }
-        else if (mode == kHalo3 && !halo3) d.mode = kHalo1;
+        if (mode == kHalo1 && direct3) { d.mode = kDirect; d.taps_y = 3; d.taps_x = 3; d.pad_y = 1; d.pad_x = 1; }
         d.B = e->B; d.H = Ho; d.W = Wo;
         d.src0 = s0.p; d.C0 = s0.C;
         if (s1) { d.src1 = s1->p; d.C1 = s1->C; }
@@ -388,7 +386,7 @@ struct Builder {
         d.stats = stats; d.groups = groups;
         auto plan = std::make_shared<ConvGemmPlan>();
         if (conv_gemm_plan(d, e->num_sms, plan.get())) { err = 1; return out; }
-        const int taps = (mode == kHalo3 || mode == kHalo1 || mode == kHalo1BaseOff) ? 9 : (mode == kS2D ? 4 : 1);
+        const int taps = mode == kHalo1 ? 9 : (mode == kS2D ? 4 : 1);
         Op op;
         op.name = wname;
         op.flops = 2.0 * e->B * Ho * Wo * Cout * static_cast<double>(taps) * (s0.C + (s1 ? s1->C : 0));
@@ -417,10 +415,10 @@ struct Builder {
                  const Act* extra_res) {
         const int Cin = s0.C + (s1 ? s1->C : 0);
         unsigned long long* st1 = next_stats();
-        Act h = conv(n + ".block1.proj", kHalo3, s0, s1, Cout, kActNone, nullptr, 0, nullptr, st1, groups);
+        Act h = conv(n + ".block1.proj", kHalo1, s0, s1, Cout, kActNone, nullptr, 0, nullptr, st1, groups);
         gn(n + ".block1.norm", h, st1, groups, maps ? -1 : e->ss_off.at(n), maps, nullptr, nullptr);
         unsigned long long* st2 = next_stats();
-        Act h2 = conv(n + ".block2.proj", kHalo3, h, nullptr, Cout, kActNone, nullptr, 0, nullptr, st2, groups);
+        Act h2 = conv(n + ".block2.proj", kHalo1, h, nullptr, Cout, kActNone, nullptr, 0, nullptr, st2, groups);
         drop(h);
         if (Cin != Cout) {
             Act r = conv(n + ".res_conv", kDirect, s0, s1, Cout, kActNone, nullptr, 0, nullptr, nullptr, 0);
@@ -520,7 +518,7 @@ int build_plan(ndiff_engine* e) {
         if (i < 3) {
             cur = b.conv(p + ".3.1", kS2D, a3, nullptr, d[i + 1], kActNone, nullptr, 0, nullptr, nullptr, 0);
         } else {
-            cur = b.conv(p + ".3", kHalo3, a3, nullptr, d[i + 1], kActNone, nullptr, 0, nullptr, nullptr, 0);
+            cur = b.conv(p + ".3", kHalo1, a3, nullptr, d[i + 1], kActNone, nullptr, 0, nullptr, nullptr, 0);
         }
         b.drop(a3);
         b.name(p + ".3", cur);
@@ -553,10 +551,10 @@ int build_plan(ndiff_engine* e) {
                 e->net_ops.push_back(op);
             }
             b.drop(a3);
-            cur = b.conv(p + ".3.1", kHalo3, up, nullptr, ci, kActNone, nullptr, 0, nullptr, nullptr, 0);
+            cur = b.conv(p + ".3.1", kHalo1, up, nullptr, ci, kActNone, nullptr, 0, nullptr, nullptr, 0);
             b.drop(up);
         } else {
-            cur = b.conv(p + ".3", kHalo3, a3, nullptr, ci, kActNone, nullptr, 0, nullptr, nullptr, 0);
+            cur = b.conv(p + ".3", kHalo1, a3, nullptr, ci, kActNone, nullptr, 0, nullptr, nullptr, 0);
             b.drop(a3);
         }
         b.name(p + ".3", cur);

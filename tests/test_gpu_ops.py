@@ -66,7 +66,7 @@ CONV3_CASES = [(2, 32, 32, 64, 0, 64), (1, 16, 16, 128, 64, 128), (1, 8, 8, 256,
                (1, 64, 64, 64, 0, 64), (1, 8, 8, 512, 256, 512), (4, 128, 128, 64, 0, 64)]
 
 
-@pytest.mark.parametrize("mode", ["halo1", "halo3", "direct"])
+@pytest.mark.parametrize("mode", ["halo", "direct"])
 @pytest.mark.parametrize("case", CONV3_CASES)
 def test_conv3x3(case, mode):
     B, H, W, c0, c1, co = case
@@ -77,18 +77,18 @@ def test_conv3x3(case, mode):
     ref = F.conv2d(torch.cat([x0, x1], 1) if c1 else x0, w, bias, padding=1)
     kw = dict(src1=G.to_nhwc_bf16(x1) if c1 else None, bias=bias)
     if mode != "direct":
-        out = G.conv(G.MODE_HALO1 if mode == "halo1" else G.MODE_HALO3, G.to_nhwc_bf16(x0), G.pack_weight(w), co, **kw)
+        out = G.conv(G.MODE_HALO1, G.to_nhwc_bf16(x0), G.pack_weight(w), co, **kw)
     else:
         out = G.conv(G.MODE_DIRECT, G.to_nhwc_bf16(x0), G.pack_weight(w), co, taps=(3, 3), pad=(1, 1), **kw)
     _check(out, ref)
 
 
-@pytest.mark.parametrize("tile_w", [8, 16, 32])
-def test_conv3x3_tile_shapes(tile_w):
-    B, H, W, c, co = 1, 32, 32, 64, 128
+@pytest.mark.parametrize("tile_w", [8, 16, 32, 64])
+def test_direct_conv_tile_shapes(tile_w):
+    B, H, W, c, co = 1, 32, 64, 64, 128
     x = _rand((B, c, H, W), 10)
     w = _rand((co, c, 3, 3), 11, 1.0 / math.sqrt(9 * c))
-    out = G.conv(G.MODE_HALO3, G.to_nhwc_bf16(x), G.pack_weight(w), co, tile_w=tile_w)
+    out = G.conv(G.MODE_DIRECT, G.to_nhwc_bf16(x), G.pack_weight(w), co, taps=(3, 3), pad=(1, 1), tile_w=tile_w)
     _check(out, F.conv2d(x, w, None, padding=1))
 
 
@@ -116,7 +116,8 @@ def test_groupnorm_stats_and_apply(case):
     stats = torch.zeros(B, groups, 2, device="cuda", dtype=torch.int64)       # 2^-24 fixed point
     y = G.conv(G.MODE_HALO1, G.to_nhwc_bf16(x), G.pack_weight(w), c, bias=bias, stats=stats, groups=groups)
     stats2 = torch.zeros_like(stats)
-    G.conv(G.MODE_HALO3, G.to_nhwc_bf16(x), G.pack_weight(w), c, bias=bias, stats=stats2, groups=groups, tile_w=16)
+    G.conv(G.MODE_DIRECT, G.to_nhwc_bf16(x), G.pack_weight(w), c, bias=bias, stats=stats2, groups=groups, tile_w=16,
+           taps=(3, 3), pad=(1, 1))
     conv_ref = F.conv2d(x, w, bias, padding=1)
     grp = conv_ref.reshape(B, groups, -1)
     sums = stats.double() / 2 ** 24

@@ -30,7 +30,7 @@ def rnd(shape, seed, scale=1.0):
 
 def conv_case(mode, B, H, W, c0, co, tile_w=0, force_nt=0, check=True, iters=20, taps=(1, 1), pad=(0, 0)):
     x = rnd((B, c0, H, W), 1)
-    k = 3 if mode in (1, 3, 4) or taps == (3, 3) else 1
+    k = 3 if mode == 3 or taps == (3, 3) else 1
     w = rnd((co, c0, k, k), 2, 1.0 / math.sqrt(k * k * c0))
     xb, wp = G.to_nhwc_bf16(x), G.pack_weight(w)
     out = G.conv(mode, xb, wp, co, tile_w=tile_w, force_nt=force_nt, taps=taps, pad=pad)
