@@ -8,7 +8,7 @@ Both call the C-ABI CUDA library in ``noisediff_b200/csrc`` (see ``include/noise
 from .arch import NoiseDiffNet
 from .diffusion import GaussianDiffusion, ModelPrediction, make_betas
 from .engine import Engine
-from . import _lib
+from . import _lib, tiles
 
 __all__ = ["NoiseDiffNet", "GaussianDiffusion", "ModelPrediction", "make_betas", "Engine"]
 __version__ = "0.1.0"
