@@ -19,8 +19,9 @@ namespace ndiff {
 
 namespace {
 
-constexpr int kThreads = 256;
 constexpr int kEpiWarp0 = 4;
+constexpr int kEpiWarps = 8;                    // two warps per TMEM lane quarter, each takes every other 32-column chunk
+constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;
 
 struct SmemTail {  // lives after the operand rings
     uint64_t fullA[8], emptyA[8], fullB[16], emptyB[16];
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int a_stages = a.a_stages, b_stages = a.b_stages;
     const uint32_t ringA = smem_u32(smem);
     const uint32_t ringB = ringA + a_stages * kAStage;
-    SmemTail* tail = reinterpret_cast<SmemTail*>(smem + a_stages * kAStage + b_stages * kBStage);
+    SmemTail* tail = reinterpret_cast<SmemTail*>(smem + a_stages * kAStage + a.b_region_bytes);
     const uint32_t bar_fullA = smem_u32(&tail->fullA[0]), bar_emptyA = smem_u32(&tail->emptyA[0]);
     const uint32_t bar_fullB = smem_u32(&tail->fullB[0]), bar_emptyB = smem_u32(&tail->emptyB[0]);
     const uint32_t bar_tfull = smem_u32(&tail->tmem_full[0]), bar_tempty = smem_u32(&tail->tmem_empty[0]);
@@ -56,6 +57,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int lane = threadIdx.x & 31;
     const int CB = a.cb0 + a.cb1;
     const int TAPS = kHalo ? 9 : a.taps_y * a.taps_x;
+    const int nt = blockIdx.x % a.n_tiles;                       // this CTA's N tile for its whole life
+    const int m_first = blockIdx.x / a.n_tiles, m_step = gridDim.x / a.n_tiles;
+    const int m_total = a.total_tiles / a.n_tiles;
+    const bool resident = a.b_resident != 0;                     // whole weight slice of this N tile lives in smem
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&a.tmA0);
@@ -65,7 +70,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < a_stages; ++i) { mbar_init(&tail->fullA[i], 1); mbar_init(&tail->emptyA[i], 1); }
         for (int i = 0; i < b_stages; ++i) { mbar_init(&tail->fullB[i], 1); mbar_init(&tail->emptyB[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tail->tmem_full[i], 1); mbar_init(&tail->tmem_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tail->tmem_full[i], 1); mbar_init(&tail->tmem_empty[i], kEpiWarps); }
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<2 * NT>(&tail->tmem_base);
@@ -78,9 +83,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     if (warp == 0) {
         // ================================ TMA producer (whole warp walks the loop, one elected lane issues) ========
         int sa = 0, pa = 0, sb = 0, pb = 0;
-        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-            const int nt = tile % a.n_tiles;
-            int m = tile / a.n_tiles;
+        if (resident) {
+            if (elect_one()) {
+                const int nkb = CB * TAPS;
+                mbar_expect_tx(bar_fullB, nkb * kBStage);
+                for (int kb = 0; kb < nkb; ++kb) tma_load_2d(ringB + kb * kBStage, &a.tmB, bar_fullB, kb * 64, nt * NT);
+            }
+            __syncwarp();
+        }
+        for (int mt = m_first; mt < m_total; mt += m_step) {
+            int m = mt;
             const int tx = m % a.tiles_x; m /= a.tiles_x;
             const int ty = m % a.tiles_y;
             const int b = m / a.tiles_y;
@@ -114,14 +126,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                         if (++sa == a_stages) { sa = 0; pa ^= 1; }
                         if (++kx == a.taps_x) { kx = 0; ++ky; }
                     }
-                    mbar_wait(bar_emptyB + sb * 8, pb ^ 1);
-                    if (elect_one()) {
-                        mbar_expect_tx(bar_fullB + sb * 8, kBStage);
-                        tma_load_2d(ringB + sb * kBStage, &a.tmB, bar_fullB + sb * 8, kcol, nt * NT);
+                    if (!resident) {
+                        mbar_wait(bar_emptyB + sb * 8, pb ^ 1);
+                        if (elect_one()) {
+                            mbar_expect_tx(bar_fullB + sb * 8, kBStage);
+                            tma_load_2d(ringB + sb * kBStage, &a.tmB, bar_fullB + sb * 8, kcol, nt * NT);
+                        }
+                        __syncwarp();
+                        kcol += 64;
+                        if (++sb == b_stages) { sb = 0; pb ^= 1; }
                     }
-                    __syncwarp();
-                    kcol += 64;
-                    if (++sb == b_stages) { sb = 0; pb ^= 1; }
                 }
             }
         }
@@ -131,7 +145,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         constexpr uint32_t hiB = umma_desc_hi(1024);
         constexpr uint32_t hiA = umma_desc_hi(kHalo ? kHaloPitch : 1024);
         int sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
-        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        if (resident) mbar_wait(bar_fullB, 0);
+        for (int mt = m_first; mt < m_total; mt += m_step) {
             mbar_wait(bar_tempty + acc * 8, pacc ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * NT;
@@ -142,43 +157,43 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     const uint32_t a_base = umma_desc_lo(ringA + sa * kAStage);
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
-                        mbar_wait(bar_fullB + sb * 8, pb);
+                        if (!resident) mbar_wait(bar_fullB + sb * 8, pb);
                         tc_fence_after();
                         const uint32_t a_lo = a_base + (((tap / 3) * kHaloPitch + (tap % 3) * 128) >> 4);
-                        const uint32_t b_lo = umma_desc_lo(ringB + sb * kBStage);
+                        const uint32_t b_lo = umma_desc_lo(ringB + (resident ? cb * 9 + tap : sb) * kBStage);
                         if (elect_one()) {
                             if (first) umma_bf16_lohi<false>(d_tmem, a_lo, hiA, b_lo, hiB, idesc);
                             else umma_bf16_lohi<true>(d_tmem, a_lo, hiA, b_lo, hiB, idesc);
                             umma_bf16_lohi<true>(d_tmem, a_lo + 2, hiA, b_lo + 2, hiB, idesc);
                             umma_bf16_lohi<true>(d_tmem, a_lo + 4, hiA, b_lo + 4, hiB, idesc);
                             umma_bf16_lohi<true>(d_tmem, a_lo + 6, hiA, b_lo + 6, hiB, idesc);
-                            umma_commit(bar_emptyB + sb * 8);
+                            if (!resident) umma_commit(bar_emptyB + sb * 8);
                             if (tap == 8) umma_commit(bar_emptyA + sa * 8);
                         }
                         __syncwarp();
                         first = false;
-                        if (++sb == b_stages) { sb = 0; pb ^= 1; }
+                        if (!resident && ++sb == b_stages) { sb = 0; pb ^= 1; }
                     }
                     if (++sa == a_stages) { sa = 0; pa ^= 1; }
                 } else {
                     for (int tap = 0; tap < TAPS; ++tap) {
                         mbar_wait(bar_fullA + sa * 8, pa);
-                        mbar_wait(bar_fullB + sb * 8, pb);
+                        if (!resident) mbar_wait(bar_fullB + sb * 8, pb);
                         tc_fence_after();
                         const uint32_t a_lo = umma_desc_lo(ringA + sa * kAStage);
-                        const uint32_t b_lo = umma_desc_lo(ringB + sb * kBStage);
+                        const uint32_t b_lo = umma_desc_lo(ringB + (resident ? cb * TAPS + tap : sb) * kBStage);
                         if (elect_one()) {
                             if (first) umma_bf16_lohi<false>(d_tmem, a_lo, hiA, b_lo, hiB, idesc);
                             else umma_bf16_lohi<true>(d_tmem, a_lo, hiA, b_lo, hiB, idesc);
                             umma_bf16_lohi<true>(d_tmem, a_lo + 2, hiA, b_lo + 2, hiB, idesc);
                             umma_bf16_lohi<true>(d_tmem, a_lo + 4, hiA, b_lo + 4, hiB, idesc);
                             umma_bf16_lohi<true>(d_tmem, a_lo + 6, hiA, b_lo + 6, hiB, idesc);
-                            umma_commit(bar_emptyB + sb * 8);
+                            if (!resident) umma_commit(bar_emptyB + sb * 8);
                             umma_commit(bar_emptyA + sa * 8);
                         }
                         __syncwarp();
                         first = false;
-                        if (++sb == b_stages) { sb = 0; pb ^= 1; }
+                        if (!resident && ++sb == b_stages) { sb = 0; pb ^= 1; }
                         if (++sa == a_stages) { sa = 0; pa ^= 1; }
                     }
                 }
@@ -190,11 +205,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     } else if (warp >= kEpiWarp0) {
         // ================================ epilogue =============================================================
         const int q = warp & 3;              // TMEM lane quarter this warp may read
+        const int cset = (warp - kEpiWarp0) >> 2;   // which interleaved set of 32-column chunks this warp drains
         const int ethread = threadIdx.x - kEpiWarp0 * 32;
         int acc = 0, pacc = 0;
-        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-            const int nt = tile % a.n_tiles;
-            int m = tile / a.n_tiles;
+        for (int mt = m_first; mt < m_total; mt += m_step) {
+            int m = mt;
             const int tx = m % a.tiles_x; m /= a.tiles_x;
             const int ty = m % a.tiles_y;
             const int b = m / a.tiles_y;
@@ -207,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             mbar_wait(bar_tfull + acc * 8, pacc);
             tc_fence_after();
 #pragma unroll 1
-            for (int ch = 0; ch < NT / 32; ++ch) {
+            for (int ch = cset; ch < NT / 32; ch += kEpiWarps / 4) {
                 uint32_t raw[32];
                 tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * NT + ch * 32, raw);
                 tmem_ld_wait();
@@ -288,14 +303,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             if (++acc == 2) { acc = 0; pacc ^= 1; }
 
             if (a.stats) {
-                named_bar_sync(1, 128);
+                named_bar_sync(1, kEpiWarps * 32);
                 const int ng = NT >> a.lgs;
                 if (ethread < ng * 2) {
                     const int g = (n0 >> a.lgs) + (ethread >> 1);
                     atomicAdd(&a.stats[(static_cast<size_t>(b) * a.G + g) * 2 + (ethread & 1)], tail->stats[ethread]);
                     tail->stats[ethread] = 0ull;
                 }
-                named_bar_sync(1, 128);
+                named_bar_sync(1, kEpiWarps * 32);
             }
         }
     }
@@ -406,9 +421,27 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
         a.b_stages = a.a_stages;
     }
     NDIFF_REQUIRE(a.a_stage_bytes % 1024 == 0, "operand stages must stay 1024-B aligned");
-    plan->smem_bytes = 1024 + a.a_stages * a.a_stage_bytes + a.b_stages * b_stage + static_cast<int>(sizeof(SmemTail));
+    // grid: persistent CTAs, a multiple of n_tiles so that every CTA keeps one N tile for its whole life
+    int grid = a.total_tiles < num_sms ? a.total_tiles : num_sms;
+    grid = grid / a.n_tiles * a.n_tiles;
+    if (grid == 0) grid = a.n_tiles;
+    plan->grid = grid;
+    // weights resident in shared memory when this CTA's slice fits next to >= 2 activation stages and is reused
+    const int budget = 227 * 1024 - 1024 - static_cast<int>(sizeof(SmemTail));
+    const int n_kb = (a.cb0 + a.cb1) * a.taps_y * a.taps_x;
+    const int slice = n_kb * b_stage;
+    const int m_per_cta = (a.total_tiles / a.n_tiles + grid / a.n_tiles - 1) / (grid / a.n_tiles);
+    a.b_resident = (slice + 2 * a.a_stage_bytes <= budget && m_per_cta >= 2 && slice < (1 << 20)) ? 1 : 0;
+    if (a.b_resident) {
+        int st = (budget - slice) / a.a_stage_bytes;
+        a.a_stages = st > 8 ? 8 : st;
+        a.b_stages = 1;
+        a.b_region_bytes = slice;
+    } else {
+        a.b_region_bytes = a.b_stages * b_stage;
+    }
+    plan->smem_bytes = 1024 + a.a_stages * a.a_stage_bytes + a.b_region_bytes + static_cast<int>(sizeof(SmemTail));
     NDIFF_REQUIRE(plan->smem_bytes <= 227 * 1024, "shared-memory budget exceeded");
-    plan->grid = a.total_tiles < num_sms ? a.total_tiles : num_sms;
 
     // ---- tensor maps -------------------------------------------------------------------------------------
     const int Hin = d.mode == kS2D ? 2 * d.H : d.H, Win = d.mode == kS2D ? 2 * d.W : d.W;

@@ -27,6 +27,8 @@ struct ConvGemmArgs {
     int n_tiles;           // Cout / NT
     int total_tiles;
     int a_stages, b_stages;
+    int b_region_bytes;    // bytes of shared memory holding B (ring, or the whole resident slice)
+    int b_resident;        // 1: the CTA's whole [NT x Ktot] weight slice is loaded once and stays in shared memory
     int a_stage_bytes, a_copy_bytes;
     // epilogue
     const float* bias;           // [Cout] or null

@@ -21,10 +21,11 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// GroupNorm apply
+// GroupNorm apply.  grid = (blocks per sample, B); every block derives the per-channel affine once (stats are 2^-24
+// fixed-point sums from the conv epilogue) and then streams its share of the sample, 4 vectors in flight per thread.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kGnThreads = 256;
-constexpr int kGnVecPerThread = 8;
+constexpr int kGnBatch = 4;
 
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnApplyArgs a) {
     __shared__ float sA[512], sB[512];
@@ -58,86 +59,109 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnApplyArgs 
     const uint4* r1 = a.res1 ? reinterpret_cast<const uint4*>(a.res1) + base : nullptr;
     const uint4* r2 = a.res2 ? reinterpret_cast<const uint4*>(a.res2) + base : nullptr;
     const uint4* mp = a.maps ? reinterpret_cast<const uint4*>(a.maps) + base * 2 : nullptr;
-    const size_t v0 = static_cast<size_t>(blockIdx.x) * (kGnThreads * kGnVecPerThread) + threadIdx.x;
+    const size_t span = static_cast<size_t>(kGnThreads) * kGnBatch;
+    for (size_t v0 = static_cast<size_t>(blockIdx.x) * span + threadIdx.x; v0 < nvec; v0 += static_cast<size_t>(gridDim.x) * span) {
+        uint4 xv[kGnBatch], rv1[kGnBatch], rv2[kGnBatch];
 #pragma unroll
-    for (int i = 0; i < kGnVecPerThread; ++i) {
-        const size_t v = v0 + static_cast<size_t>(i) * kGnThreads;
-        if (v >= nvec) break;
-        const int c0 = static_cast<int>(v % cv) * 8;
-        float f[8];
-        unpack8(__ldg(xin + v), f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = f[j] * sA[c0 + j] + sB[c0 + j];
-        if (mp) {
-            const size_t pix = v / cv;
-            float sc[8], sh[8];
-            unpack8(__ldg(mp + pix * (2 * cv) + (c0 >> 3)), sc);
-            unpack8(__ldg(mp + pix * (2 * cv) + cv + (c0 >> 3)), sh);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = f[j] * (sc[j] + 1.0f) + sh[j];
+        for (int i = 0; i < kGnBatch; ++i) {
+            const size_t v = v0 + static_cast<size_t>(i) * kGnThreads;
+            if (v < nvec) {
+                xv[i] = __ldg(xin + v);
+                if (r1) rv1[i] = __ldg(r1 + v);
+                if (r2) rv2[i] = __ldg(r2 + v);
+            }
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = silu(f[j]);
-        if (r1) {
-            float r[8];
-            unpack8(__ldg(r1 + v), r);
+        for (int i = 0; i < kGnBatch; ++i) {
+            const size_t v = v0 + static_cast<size_t>(i) * kGnThreads;
+            if (v >= nvec) break;
+            const int c0 = static_cast<int>(v % cv) * 8;
+            float f[8];
+            unpack8(xv[i], f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] += r[j];
-        }
-        if (r2) {
-            float r[8];
-            unpack8(__ldg(r2 + v), r);
+            for (int j = 0; j < 8; ++j) f[j] = f[j] * sA[c0 + j] + sB[c0 + j];
+            if (mp) {
+                const size_t pix = v / cv;
+                float sc[8], sh[8];
+                unpack8(__ldg(mp + pix * (2 * cv) + (c0 >> 3)), sc);
+                unpack8(__ldg(mp + pix * (2 * cv) + cv + (c0 >> 3)), sh);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] += r[j];
+                for (int j = 0; j < 8; ++j) f[j] = f[j] * (sc[j] + 1.0f) + sh[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = silu(f[j]);
+            if (r1) {
+                float r[8];
+                unpack8(rv1[i], r);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] += r[j];
+            }
+            if (r2) {
+                float r[8];
+                unpack8(rv2[i], r);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] += r[j];
+            }
+            xout[v] = pack8(f);
         }
-        xout[v] = pack8(f);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// LayerNorm over channels of (x + vec[b]); one warp per pixel, lane owns channel pairs {2*lane + 64*j}
+// LayerNorm over channels of (x + vec[b]).  L = min(32, C/8) lanes share one pixel, each lane owns VPL 16-byte vectors.
 // ---------------------------------------------------------------------------------------------------------------
+template <int VPL>
 __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ vec,
                                                         int vec_ld, const float* __restrict__ g,
                                                         const float* __restrict__ beta, bf16* __restrict__ out,
-                                                        int HW, int C, size_t npix) {
+                                                        int HW, int C, int L, size_t npix) {
     const int lane = threadIdx.x & 31;
+    const int sub = lane % L, slot = lane / L, ppw = 32 / L;
     const size_t warp = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const size_t nwarps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
-    const int nj = C >> 6;
-    for (size_t pix = warp; pix < npix; pix += nwarps) {
-        const int b = static_cast<int>(pix / HW);
-        const uint32_t* xp = reinterpret_cast<const uint32_t*>(x + pix * C);
-        const float* vp = vec + static_cast<size_t>(b) * vec_ld;
-        float2 val[8];
+    const int cv = C >> 3;
+    float gg[VPL][8], bb[VPL][8];
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+        const int c = (sub + j * L) * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { gg[j][k] = g[c + k]; bb[j][k] = beta[c + k]; }
+    }
+    const float inv_c = 1.0f / static_cast<float>(C);
+    for (size_t p0 = warp * ppw; p0 < npix; p0 += nwarps * ppw) {
+        const size_t pix = p0 + slot;
+        const bool live = pix < npix;
+        const size_t pp = live ? pix : npix - 1;
+        const float* vp = vec + (pp / HW) * static_cast<size_t>(vec_ld);
+        float f[VPL][8];
         float sum = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (j < nj) {
-                const int c = 2 * lane + 64 * j;
-                float2 f = unpack_bf16(__ldg(xp + (c >> 1)));
-                f.x += vp[c]; f.y += vp[c + 1];
-                val[j] = f;
-                sum += f.x + f.y;
-            }
+        for (int j = 0; j < VPL; ++j) {
+            const int cvi = sub + j * L;
+            unpack8(__ldg(reinterpret_cast<const uint4*>(x) + pp * cv + cvi), f[j]);
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(vp + cvi * 8));
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(vp + cvi * 8 + 4));
+            f[j][0] += v0.x; f[j][1] += v0.y; f[j][2] += v0.z; f[j][3] += v0.w;
+            f[j][4] += v1.x; f[j][5] += v1.y; f[j][6] += v1.z; f[j][7] += v1.w;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sum += f[j][k];
         }
-        const float mean = warp_sum(sum) / C;
+        for (int o = L >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum * inv_c;
         float sq = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (j < nj) {
-                const float dx = val[j].x - mean, dy = val[j].y - mean;
-                sq += dx * dx + dy * dy;
-            }
-        }
-        const float rstd = rsqrtf(warp_sum(sq) / C + 1e-5f);
-        uint32_t* op = reinterpret_cast<uint32_t*>(out + pix * C);
+        for (int j = 0; j < VPL; ++j)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (j < nj) {
-                const int c = 2 * lane + 64 * j;
-                op[c >> 1] = pack_bf16((val[j].x - mean) * rstd * g[c] + beta[c],
-                                       (val[j].y - mean) * rstd * g[c + 1] + beta[c + 1]);
+            for (int k = 0; k < 8; ++k) { const float d = f[j][k] - mean; sq += d * d; }
+        for (int o = L >> 1; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const float rstd = rsqrtf(sq * inv_c + 1e-5f);
+        if (live) {
+#pragma unroll
+            for (int j = 0; j < VPL; ++j) {
+                float o8[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o8[k] = (f[j][k] - mean) * rstd * gg[j][k] + bb[j][k];
+                reinterpret_cast<uint4*>(out)[pix * cv + sub + j * L] = pack8(o8);
             }
         }
     }
@@ -149,26 +173,36 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
 __global__ void __launch_bounds__(256) shot_in_kernel(const float4* __restrict__ clean, const float4* __restrict__ x,
                                                       const float* __restrict__ w, const float* __restrict__ bias,
                                                       bf16* __restrict__ out, size_t npix, int C) {
-    extern __shared__ float sw[];  // [C][8] weights then [C] bias
-    for (int i = threadIdx.x; i < C * 8; i += blockDim.x) sw[i] = w[i];
-    for (int i = threadIdx.x; i < C; i += blockDim.x) sw[C * 8 + i] = bias[i];
-    __syncthreads();
+    // weights regrouped per 8-channel output group as [group][k][j] with a 68-float group pitch: the 8 lanes that
+    // share a pixel read float4s from disjoint bank quads (no conflicts), lanes of other pixels broadcast
+    extern __shared__ float sw[];
     const int cv = C >> 3;
+    float* sbias = sw + cv * 68;
+    for (int i = threadIdx.x; i < C * 8; i += blockDim.x) {
+        const int c = i >> 3, k = i & 7;
+        sw[(c >> 3) * 68 + k * 8 + (c & 7)] = w[i];
+    }
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sbias[i] = bias[i];
+    __syncthreads();
     const size_t total = npix * cv;
     for (size_t v = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < total;
          v += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const size_t pix = v / cv;
-        const int c0 = static_cast<int>(v % cv) * 8;
+        const int cg = static_cast<int>(v % cv);
         const float4 a = __ldg(clean + pix), bq = __ldg(x + pix);
         const float in[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
         float f[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float acc = sw[C * 8 + c0 + j];
+        for (int j = 0; j < 8; ++j) f[j] = sbias[cg * 8 + j];
+        const float4* wg = reinterpret_cast<const float4*>(sw + cg * 68);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc += sw[(c0 + j) * 8 + k] * in[k];
-            f[j] = gelu_erf(acc);
+        for (int k = 0; k < 8; ++k) {
+            const float4 w0 = wg[k * 2], w1 = wg[k * 2 + 1];
+            f[0] += w0.x * in[k]; f[1] += w0.y * in[k]; f[2] += w0.z * in[k]; f[3] += w0.w * in[k];
+            f[4] += w1.x * in[k]; f[5] += w1.y * in[k]; f[6] += w1.z * in[k]; f[7] += w1.w * in[k];
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = gelu_erf(f[j]);
         reinterpret_cast<uint4*>(out)[v] = pack8(f);
     }
 }
@@ -524,7 +558,9 @@ inline int blocks_for(size_t n, int per_block, int cap = 1 << 20) {
 int gn_apply_launch(const GnApplyArgs& a, cudaStream_t s) {
     NDIFF_REQUIRE(a.C % 8 == 0 && a.C <= 512 && a.C % a.G == 0, "GroupNorm apply: unsupported channel count");
     const size_t nvec = static_cast<size_t>(a.HW) * (a.C / 8);
-    dim3 grid(blocks_for(nvec, kGnThreads * kGnVecPerThread), a.B);
+    const int want = blocks_for(nvec, kGnThreads * kGnBatch);
+    const int cap = (148 * 8 + a.B - 1) / a.B;                     // ~8 resident blocks per SM over the whole batch
+    dim3 grid(want < cap ? want : cap, a.B);
     gn_apply_kernel<<<grid, kGnThreads, 0, s>>>(a);
     NDIFF_CUDA_OK(cudaGetLastError());
     return 0;
@@ -532,9 +568,16 @@ int gn_apply_launch(const GnApplyArgs& a, cudaStream_t s) {
 
 int layernorm_launch(const bf16* x, const float* vec, int vec_ld, const float* g, const float* beta, bf16* out, int B,
                      int HW, int C, cudaStream_t s) {
-    NDIFF_REQUIRE(C % 64 == 0 && C <= 512, "LayerNorm: C must be a multiple of 64, at most 512");
+    NDIFF_REQUIRE(C == 64 || C == 128 || C == 256 || C == 512, "LayerNorm: C must be 64, 128, 256 or 512");
+    NDIFF_REQUIRE(vec_ld % 4 == 0, "LayerNorm: per-sample vector stride must keep 16-byte alignment");
     const size_t npix = static_cast<size_t>(B) * HW;
-    layernorm_kernel<<<blocks_for(npix, 8 * 4, 148 * 16), 256, 0, s>>>(x, vec, vec_ld, g, beta, out, HW, C, npix);
+    const int L = C / 8 > 32 ? 32 : C / 8;
+    const int ppw = 32 / L;
+    const int grid = blocks_for(npix, 8 * ppw * 4, 148 * 8);
+    if (C == 512)
+        layernorm_kernel<2><<<grid, 256, 0, s>>>(x, vec, vec_ld, g, beta, out, HW, C, L, npix);
+    else
+        layernorm_kernel<1><<<grid, 256, 0, s>>>(x, vec, vec_ld, g, beta, out, HW, C, L, npix);
     NDIFF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -542,7 +585,7 @@ int layernorm_launch(const bf16* x, const float* vec, int vec_ld, const float* g
 int shot_in_launch(const float* clean, const float* x, const float* w, const float* bias, bf16* out, int npix, int C,
                    cudaStream_t s) {
     const size_t total = static_cast<size_t>(npix) * (C / 8);
-    shot_in_kernel<<<blocks_for(total, 256 * 4, 148 * 16), 256, (C * 9) * sizeof(float), s>>>(
+    shot_in_kernel<<<blocks_for(total, 256 * 4, 148 * 8), 256, ((C / 8) * 68 + C) * sizeof(float), s>>>(
         reinterpret_cast<const float4*>(clean), reinterpret_cast<const float4*>(x), w, bias, out, npix, C);
     NDIFF_CUDA_OK(cudaGetLastError());
     return 0;

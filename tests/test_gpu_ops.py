@@ -34,7 +34,9 @@ def _check(out_nhwc, ref_nchw, tol=1.5e-2):
 
 # (B, H, W, Cin0, Cin1, Cout)
 GEMM_CASES = [(2, 16, 16, 64, 0, 64), (1, 32, 32, 128, 0, 256), (2, 8, 8, 256, 128, 128), (1, 64, 64, 64, 64, 64),
-              (3, 24, 40, 64, 0, 128), (1, 8, 8, 512, 0, 512)]
+              (3, 24, 40, 64, 0, 128), (1, 8, 8, 512, 0, 512),
+              # many tiles per CTA: the weight slice stays resident in shared memory
+              (4, 128, 128, 64, 0, 64), (2, 128, 128, 128, 0, 64), (2, 128, 128, 64, 64, 128), (8, 64, 64, 256, 0, 512)]
 
 
 @pytest.mark.parametrize("case", GEMM_CASES)
@@ -63,7 +65,8 @@ def test_gemm_epilogue_gelu_residual_vector():
 
 
 CONV3_CASES = [(2, 32, 32, 64, 0, 64), (1, 16, 16, 128, 64, 128), (1, 8, 8, 256, 0, 256), (2, 24, 40, 64, 64, 64),
-               (1, 64, 64, 64, 0, 64), (1, 8, 8, 512, 256, 512), (4, 128, 128, 64, 0, 64)]
+               (1, 64, 64, 64, 0, 64), (1, 8, 8, 512, 256, 512), (4, 128, 128, 64, 0, 64), (2, 128, 128, 64, 64, 64),
+               (1, 256, 256, 64, 0, 64), (1, 256, 256, 64, 64, 64)]
 
 
 @pytest.mark.parametrize("mode", ["halo", "direct"])
@@ -92,7 +95,7 @@ def test_direct_conv_tile_shapes(tile_w):
     _check(out, F.conv2d(x, w, None, padding=1))
 
 
-@pytest.mark.parametrize("case", [(2, 32, 32, 64, 64), (1, 16, 16, 128, 256), (1, 64, 64, 64, 128)])
+@pytest.mark.parametrize("case", [(2, 32, 32, 64, 64), (1, 16, 16, 128, 256), (1, 64, 64, 64, 128), (4, 256, 256, 64, 64)])
 def test_downsample_space_to_depth(case):
     B, H, W, c, co = case                                 # H, W = input size
     x = _rand((B, c, H, W), 12)
@@ -104,7 +107,8 @@ def test_downsample_space_to_depth(case):
     _check(out, ref)
 
 
-@pytest.mark.parametrize("case", [(2, 32, 32, 64, 8), (2, 16, 16, 128, 8), (1, 8, 8, 512, 8), (2, 32, 32, 64, 2)])
+@pytest.mark.parametrize("case", [(2, 32, 32, 64, 8), (2, 16, 16, 128, 8), (1, 8, 8, 512, 8), (2, 32, 32, 64, 2),
+                                  (1, 256, 256, 64, 2), (2, 256, 256, 64, 8), (4, 64, 64, 128, 8)])
 def test_groupnorm_stats_and_apply(case):
     B, H, W, c, groups = case
     x = _rand((B, c, H, W), 14)
