@@ -46,6 +46,7 @@ typedef struct ndiff_config {
 
 #define NDIFF_FLAG_CONV_DIRECT 1   /* debug: 3x3 convs load every tap from L2 instead of the halo layout */
 #define NDIFF_FLAG_NO_GRAPH    2   /* debug: launch kernels eagerly instead of replaying a CUDA graph */
+#define NDIFF_FLAG_INIT_SIMT   8   /* debug: 7x7 init_conv on CUDA cores instead of the tensor-core window trick */
 #define NDIFF_FLAG_KEEP_ACTS   4   /* debug: never recycle activation buffers (ndiff_debug_tensor sees every layer) */
 
 /* One reverse step's scalars; the caller derives them from GaussianDiffusion's fp32 buffers

@@ -14,6 +14,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "noisediff_b200.h"
 FLAG_CONV_DIRECT = 1
 FLAG_NO_GRAPH = 2
 FLAG_KEEP_ACTIVATIONS = 4
+FLAG_INIT_SIMT = 8
 
 
 class Config(C.Structure):

@@ -74,6 +74,31 @@ __global__ void init_conv_pack_kernel(const float* __restrict__ src, float* __re
     }
 }
 
+// init_conv on tensor cores: x_t is re-laid as bf16 [B][H+6][W+8][8] (3-pixel zero border, channels 4..7 zero) so that the
+// 7 taps of one kernel row are ONE contiguous 128-byte window (8 pixels x 8 channels) -> one SWIZZLE_128B operand row.
+__global__ void xpad_pack_kernel(const float4* __restrict__ x, uint4* __restrict__ xpad, int H, int W, size_t npix) {
+    const size_t pix = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    const int xx = static_cast<int>(pix % W);
+    const size_t r = pix / W;
+    const int yy = static_cast<int>(r % H);
+    const size_t b = r / H;
+    const float4 v = x[pix];
+    uint4 o;
+    o.x = pack_bf16(v.x, v.y); o.y = pack_bf16(v.z, v.w); o.z = 0u; o.w = 0u;
+    xpad[(b * (H + 6) + yy + 3) * (W + 8) + xx + 3] = o;
+}
+
+__global__ void init_conv_pack_tc_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int Cout) {
+    // dst[co][ky(7)][kxw(8)][ci(8)]  <-  src[co][ci(4)][7][7]; zero where ci >= 4 or kxw == 7
+    const int total = Cout * 7 * 64;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int ci = i & 7, kxw = (i >> 3) & 7, ky = (i >> 6) % 7, co = i / (7 * 64);
+        const float v = (ci < 4 && kxw < 7) ? src[((co * 4 + ci) * 7 + ky) * 7 + kxw] : 0.f;
+        dst[i] = __float2bfloat16_rn(v);
+    }
+}
+
 __global__ void i64_to_i32_kernel(const long long* in, int* out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = static_cast<int>(in[i]);
@@ -130,6 +155,7 @@ struct ndiff_engine {
 
     std::map<std::string, bf16*> packed;
     float* init_w = nullptr;
+    bf16* init_w_tc = nullptr; bf16* xpad = nullptr;
     // time path
     float* ss_w = nullptr; float* ss_b = nullptr; int ss_total = 0;
     std::map<std::string, int> ss_off;
@@ -311,6 +337,9 @@ int finalize(ndiff_engine* e, cudaStream_t s) {
     }
     if (!e->init_w && e->alloc(&e->init_w, static_cast<size_t>(dim) * 4 * 49)) return 1;
     init_conv_pack_kernel<<<64, 256, 0, s>>>(e->pf("init_conv.weight"), e->init_w, dim);
+    NDIFF_CUDA_OK(cudaGetLastError());
+    if (!e->init_w_tc && e->alloc(&e->init_w_tc, static_cast<size_t>(dim) * 7 * 64)) return 1;
+    init_conv_pack_tc_kernel<<<64, 256, 0, s>>>(e->pf("init_conv.weight"), e->init_w_tc, dim);
     NDIFF_CUDA_OK(cudaGetLastError());
     // --- stacked time-MLP heads: rows [scale C | shift C] per ResnetBlock, in plan order
     e->ss_total = 0;
@@ -498,11 +527,39 @@ int build_plan(ndiff_engine* e) {
     Act x0 = b.make(dim, H, W);
     if (b.err) return 1;
     {
-        Op op; op.name = "init_conv";
-        const float* x = e->x; const float* w = e->init_w; const float* bs = e->pf("init_conv.bias"); bf16* o = x0.p;
-        op.fn = [=](cudaStream_t st) { return init_conv7_launch(x, w, bs, o, B, H, W, dim, st); };
-        op.flops = 2.0 * npix * dim * 196.0;
-        e->net_ops.push_back(op);
+        // tensor-core path: pack x_t to the padded bf16 layout, then a 7-tap "direct" GEMM whose A rows are overlapping
+        // 128-byte windows (tensor-map stride 16 B < row length 128 B); CUDA-core kernel only if the driver rejects the map
+        ConvGemmDesc d;
+        d.mode = kDirect; d.B = B; d.H = H; d.W = W;
+        d.src0 = e->xpad; d.C0 = 64;
+        d.taps_y = 7; d.taps_x = 1; d.pad_y = 0; d.pad_x = 0;
+        d.custom_src0 = true;
+        d.cdim[0] = 64; d.cdim[1] = static_cast<uint64_t>(W); d.cdim[2] = static_cast<uint64_t>(H + 6); d.cdim[3] = static_cast<uint64_t>(B);
+        d.cstride[0] = 16; d.cstride[1] = static_cast<uint64_t>(W + 8) * 16; d.cstride[2] = static_cast<uint64_t>(H + 6) * (W + 8) * 16;
+        d.weight = e->init_w_tc; d.Cout = dim; d.bias = e->pf("init_conv.bias");
+        d.out = x0.p; d.out_ld = dim;
+        auto plan = std::make_shared<ConvGemmPlan>();
+        const bool tc_ok = (e->cfg.flags & NDIFF_FLAG_INIT_SIMT) == 0 && conv_gemm_plan(d, e->num_sms, plan.get()) == 0;
+        if (tc_ok) {
+            Op pk; pk.name = "init_conv.pack";
+            const float4* xs = reinterpret_cast<const float4*>(e->x); uint4* xp = reinterpret_cast<uint4*>(e->xpad);
+            pk.fn = [=](cudaStream_t st) {
+                xpad_pack_kernel<<<(npix + 255) / 256, 256, 0, st>>>(xs, xp, H, W, static_cast<size_t>(npix));
+                NDIFF_CUDA_OK(cudaGetLastError());
+                return 0;
+            };
+            e->net_ops.push_back(pk);
+            Op op; op.name = "init_conv";
+            op.flops = 2.0 * npix * dim * 196.0;
+            op.fn = [plan](cudaStream_t st) { return conv_gemm_launch(*plan, st); };
+            e->net_ops.push_back(op);
+            e->conv_flops += op.flops;
+        } else {
+            Op op; op.name = "init_conv(simt)";
+            const float* x = e->x; const float* w = e->init_w; const float* bs = e->pf("init_conv.bias"); bf16* o = x0.p;
+            op.fn = [=](cudaStream_t st) { return init_conv7_launch(x, w, bs, o, B, H, W, dim, st); };
+            e->net_ops.push_back(op);
+        }
     }
     b.name("init_conv", x0);
     Act cur = b.resblock("pos_block1", x0, nullptr, dim, 2, e->map1, nullptr);
@@ -663,6 +720,11 @@ int32_t ndiff_engine_create(const ndiff_config* cfg, ndiff_engine** out) {
     if (e->alloc(&e->clean, npix * 4) || e->alloc(&e->x, npix * 4) || e->alloc(&e->v_out, npix * 4)) return 1;
     if (e->alloc(&e->map1, npix * 2 * e->dim) || e->alloc(&e->map2, npix * 2 * e->dim)) return 1;
     if (e->alloc(&e->pos_emb, npix * 8)) return 1;
+    {
+        const size_t n = static_cast<size_t>(e->B) * (e->H + 6) * (e->W + 8) * 8;
+        if (e->alloc(&e->xpad, n)) return 1;
+        NDIFF_CUDA_OK(cudaMemset(e->xpad, 0, n * sizeof(bf16)));
+    }
     e->n_stats = 64;
     e->stats_bytes = static_cast<size_t>(e->n_stats) * e->B * 8 * 2 * sizeof(unsigned long long);
     if (e->alloc(&e->stats, e->stats_bytes / sizeof(unsigned long long))) return 1;

@@ -28,7 +28,7 @@ constexpr int kGnThreads = 256;
 constexpr int kGnBatch = 4;
 
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnApplyArgs a) {
-    __shared__ float sA[512], sB[512];
+    __shared__ __align__(16) float sA[512], sB[512];
     const int b = blockIdx.y;
     const int C = a.C, gs = C / a.G;
     const double inv_n = 1.0 / (static_cast<double>(a.HW) * gs);
@@ -78,8 +78,12 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnApplyArgs 
             const int c0 = static_cast<int>(v % cv) * 8;
             float f[8];
             unpack8(xv[i], f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = f[j] * sA[c0 + j] + sB[c0 + j];
+            {
+                const float4 a0 = *reinterpret_cast<const float4*>(sA + c0), a1 = *reinterpret_cast<const float4*>(sA + c0 + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(sB + c0), b1 = *reinterpret_cast<const float4*>(sB + c0 + 4);
+                f[0] = fmaf(f[0], a0.x, b0.x); f[1] = fmaf(f[1], a0.y, b0.y); f[2] = fmaf(f[2], a0.z, b0.z); f[3] = fmaf(f[3], a0.w, b0.w);
+                f[4] = fmaf(f[4], a1.x, b1.x); f[5] = fmaf(f[5], a1.y, b1.y); f[6] = fmaf(f[6], a1.z, b1.z); f[7] = fmaf(f[7], a1.w, b1.w);
+            }
             if (mp) {
                 const size_t pix = v / cv;
                 float sc[8], sh[8];
