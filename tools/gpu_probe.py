@@ -109,7 +109,7 @@ def main():
                 r = {"ms_per_step": ms, "us_per_patch_step": ms * 1e3 / B, "patches_per_s_1000steps": B / ms,
                      "finite": bool(torch.isfinite(x).all()), "launches": eng.launches_per_step,
                      "conv_tflops": eng.conv_flops_per_step / ms / 1e9}
-                if B == 4:
+                if B in (4, 8):
                     rows = eng.time_layers(5)
                     r["layers"] = [(n, round(t * 1e3, 1), round(f / max(t, 1e-9) / 1e9, 1)) for n, t, f in rows]
                     r["sum_layers_ms"] = sum(t for _, t, _ in rows)
