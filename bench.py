@@ -225,9 +225,10 @@ def main():
     # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv): live CUDA-event timing of every conv launch -------
     peaks = _peaks()
     rows = eng.time_layers(3)
-    conv_ms = sum(t_ for n, t_, f in rows if f > 0 and n != "init_conv")
-    conv_fl = sum(f for n, t_, f in rows if f > 0 and n != "init_conv")
-    n_conv = sum(1 for n, t_, f in rows if f > 0 and n != "init_conv")
+    is_conv = lambda n, f: f > 0 and n != "init_conv" and "fused chain" not in n
+    conv_ms = sum(t_ for n, t_, f in rows if is_conv(n, f))
+    conv_fl = sum(f for n, t_, f in rows if is_conv(n, f))
+    n_conv = sum(1 for n, t_, f in rows if is_conv(n, f))
     c3_ms = sum(t_ for n, t_, f in rows if f > 0 and (".proj" in n and "block" in n or n.endswith(".3.1") and n.startswith("ups") or n in ("downs.3.3", "ups.3.3")))
     achieved = conv_fl / (conv_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],

@@ -48,6 +48,7 @@ typedef struct ndiff_config {
 #define NDIFF_FLAG_NO_GRAPH    2   /* debug: launch kernels eagerly instead of replaying a CUDA graph */
 #define NDIFF_FLAG_INIT_SIMT   8   /* debug: 7x7 init_conv on CUDA cores instead of the tensor-core window trick */
 #define NDIFF_FLAG_KEEP_ACTS   4   /* debug: never recycle activation buffers (ndiff_debug_tensor sees every layer) */
+#define NDIFF_FLAG_UNFUSED     16  /* debug: run the per-pixel 1x1 chains layer by layer instead of as fused tensor-core chains */
 
 /* One reverse step's scalars; the caller derives them from GaussianDiffusion's fp32 buffers
  * (models/denoising_diffusion_pytorch.py:240-266) so the arithmetic constants are the reference's own:
@@ -127,6 +128,14 @@ NDIFF_API int32_t ndiff_op_gn_apply(const void* x, void* out, const void* stats,
 NDIFF_API int32_t ndiff_op_layernorm(const void* x, const float* vec, int32_t vec_ld, const float* g, const float* beta, void* out,
                            int32_t B, int32_t HW, int32_t C, void* stream);
 NDIFF_API int32_t ndiff_op_philox_normal(float* out, int64_t n4, uint64_t seed, uint64_t stream_id, void* stream);
+
+/* Fused per-pixel chain (prog 0: AttnBlock with the 1-token cross attention collapsed, Diffusion_arch.py:425-443;
+ * prog 1: shot_mlp1 -> shot_attn -> shot_mlp2, :598-601).  x/out/out2: bf16 [npix][64]; clean/xt: fp32 [npix][4];
+ * weights_blob: bf16 [rows][64] K-blocked rows and fvec: fp32 parameter block in the order documented in
+ * noisediff_b200/csrc/pixel_chain.cuh; cvec: per-sample collapsed attention vector [npix/HW][cvec_ld]. */
+NDIFF_API int32_t ndiff_op_pixel_chain(int32_t prog, int32_t npix, int32_t HW, const void* x, const float* clean_nhwc4,
+                             const float* xt_nhwc4, const void* weights_blob, const float* fvec, const float* cvec,
+                             int32_t cvec_ld, void* out, void* out2, void* stream);
 
 #ifdef __cplusplus
 }

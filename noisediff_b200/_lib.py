@@ -15,6 +15,7 @@ FLAG_CONV_DIRECT = 1
 FLAG_NO_GRAPH = 2
 FLAG_KEEP_ACTIVATIONS = 4
 FLAG_INIT_SIMT = 8
+FLAG_UNFUSED = 16
 
 
 class Config(C.Structure):
@@ -52,6 +53,7 @@ _SIGS = {
                       [_P, C.c_int32, _P, _P, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P, C.c_int32, C.c_int32, _P]),
     "ndiff_op_gn_apply": (C.c_int32, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P] + [C.c_int32] * 4 + [_P]),
     "ndiff_op_layernorm": (C.c_int32, [_P, _P, C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "ndiff_op_pixel_chain": (C.c_int32, [C.c_int32] * 3 + [_P] * 6 + [C.c_int32, _P, _P, _P]),
     "ndiff_op_philox_normal": (C.c_int32, [_P, C.c_int64, C.c_uint64, C.c_uint64, _P]),
 }
 

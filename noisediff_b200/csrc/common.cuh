@@ -159,6 +159,26 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, 
         : "memory");
 }
 
+// ---- TMA stores, proxy fence, raw shared-memory vector access ------------------------------------------------
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk stores of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // ---- tcgen05 / TMEM ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -268,21 +288,31 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
     __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
     return __bfloat1622float2(v);
 }
-// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of every consumer): two MUFU ops and
-// a degree-5 polynomial instead of libdevice's branchy erff.  GELU is the exact-erf form the reference uses (nn.GELU()).
-__device__ __forceinline__ float erf_fast(float x) {
-    const float z = fabsf(x);
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    const float r = 1.0f - p * t * __expf(-z * z);
-    return copysignf(r, x);
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752440f)); }
-// SiLU with the fast exponential / reciprocal (relative error ~1e-6; outputs are rounded to bf16 anyway)
-__device__ __forceinline__ float silu(float x) { return x * __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// GELU (the reference's exact-erf nn.GELU()) as x * Phi(x) with Phi(x) = sigmoid(x * (a0 + a1 x^2 + a2 x^4)), x^2 clamped
+// where the odd polynomial peaks.  Minimax fit against 0.5 x (1 + erf(x / sqrt 2)): max |error| 2.5e-5 over all x
+// (tests/test_host.py pins the coefficients against scipy/torch erf) — an order of magnitude below the bf16 rounding of
+// every consumer.  9 FP32 instructions + 2 MUFU per element instead of ~30 for a polynomial erf.
+__device__ __forceinline__ float gelu_erf(float x) {
+    constexpr float kL2e = 1.4426950408889634f;
+    const float x2 = fminf(x * x, 52.6f);
+    float p = fmaf(7.03035067e-04f * kL2e, x2, -7.40113019e-02f * kL2e);
+    p = fmaf(p, x2, -1.59501576f * kL2e);                       // -(a0 + a1 x2 + a2 x2^2) * log2(e)
+    return x * rcp_approx(1.0f + ex2_approx(x * p));
+}
+// libdevice erf for the run-once kernels (time MLP, positional path) whose outputs stay in fp32
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// SiLU = x * sigmoid(x) with the MUFU exponential / reciprocal (relative error ~1e-6; outputs are rounded to bf16 anyway)
+__device__ __forceinline__ float silu(float x) { return x * rcp_approx(1.0f + ex2_approx(x * -1.4426950408889634f)); }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -28,7 +28,7 @@ struct SmemTail {  // lives after the operand rings
     uint64_t tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
     uint32_t pad_;
-    unsigned long long stats[32];
+    alignas(16) float bias[128];   // this CTA's N-tile slice of the bias (zeros when the layer has none)
 };
 
 // Tap geometry of the single-copy halo mode (compile-time: TW = 8 so that one 8-row UMMA group == one output row).
@@ -58,8 +58,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int CB = a.cb0 + a.cb1;
     const int TAPS = kHalo ? 9 : a.taps_y * a.taps_x;
     const int nt = blockIdx.x % a.n_tiles;                       // this CTA's N tile for its whole life
-    const int m_first = blockIdx.x / a.n_tiles, m_step = gridDim.x / a.n_tiles;
+    // contiguous range of M tiles per CTA: consecutive tiles share halo rows in L2 and (almost always) the sample index,
+    // which lets the epilogue keep GroupNorm partial sums in registers across tiles
     const int m_total = a.total_tiles / a.n_tiles;
+    const int cta_m = blockIdx.x / a.n_tiles, n_cta_m = gridDim.x / a.n_tiles;
+    const int m_begin = static_cast<int>(static_cast<long long>(m_total) * cta_m / n_cta_m);
+    const int m_end = static_cast<int>(static_cast<long long>(m_total) * (cta_m + 1) / n_cta_m);
     const bool resident = a.b_resident != 0;                     // whole weight slice of this N tile lives in smem
 
     if (warp == 0 && lane == 0) {
@@ -74,7 +78,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc<2 * NT>(&tail->tmem_base);
-    if (threadIdx.x < 32) tail->stats[threadIdx.x] = 0ull;
+    if (threadIdx.x < NT) tail->bias[threadIdx.x] = a.bias ? __ldg(a.bias + nt * NT + threadIdx.x) : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -91,7 +95,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
             __syncwarp();
         }
-        for (int mt = m_first; mt < m_total; mt += m_step) {
+        for (int mt = m_begin; mt < m_end; ++mt) {
             int m = mt;
             const int tx = m % a.tiles_x; m /= a.tiles_x;
             const int ty = m % a.tiles_y;
@@ -146,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         constexpr uint32_t hiA = umma_desc_hi(kHalo ? kHaloPitch : 1024);
         int sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
         if (resident) mbar_wait(bar_fullB, 0);
-        for (int mt = m_first; mt < m_total; mt += m_step) {
+        for (int mt = m_begin; mt < m_end; ++mt) {
             mbar_wait(bar_tempty + acc * 8, pacc ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * NT;
@@ -204,11 +208,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         }
     } else if (warp >= kEpiWarp0) {
         // ================================ epilogue =============================================================
-        const int q = warp & 3;              // TMEM lane quarter this warp may read
-        const int cset = (warp - kEpiWarp0) >> 2;   // which interleaved set of 32-column chunks this warp drains
-        const int ethread = threadIdx.x - kEpiWarp0 * 32;
+        // Warp w may read TMEM lanes 32*(w%4)..+31 (= 32 pixels of the tile); the two warps of a lane quarter split the
+        // tile's 32-column chunks.  GroupNorm partial sums (per 8 columns) stay in registers across tiles and are flushed
+        // as fixed-point atomics only when the sample index changes — no per-tile shuffles, barriers or atomics.
+        constexpr int kSlots = NT / 64;         // chunks per warp per tile
+        const int q = warp & 3;
+        const int cset = (warp - kEpiWarp0) >> 2;
+        const int n0 = nt * NT;
+        float sacc[kSlots][4], qacc[kSlots][4];
+#pragma unroll
+        for (int k = 0; k < kSlots; ++k)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) { sacc[k][g] = 0.f; qacc[k][g] = 0.f; }
+        int stat_b = -1;
+        auto flush_stats = [&](int bb) {
+#pragma unroll
+            for (int k = 0; k < kSlots; ++k) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const float s_ = warp_sum(sacc[k][g]), q_ = warp_sum(qacc[k][g]);
+                    if (lane == 0) {
+                        const int gl = (n0 + (cset + 2 * k) * 32 + g * 8) >> a.lgs;
+                        unsigned long long* dst = a.stats + (static_cast<size_t>(bb) * a.G + gl) * 2;
+                        atomicAdd(dst, static_cast<unsigned long long>(__float2ll_rn(s_ * kStatScale)));
+                        atomicAdd(dst + 1, static_cast<unsigned long long>(__float2ll_rn(q_ * kStatScale)));
+                    }
+                    sacc[k][g] = 0.f; qacc[k][g] = 0.f;
+                }
+            }
+        };
         int acc = 0, pacc = 0;
-        for (int mt = m_first; mt < m_total; mt += m_step) {
+        for (int mt = m_begin; mt < m_end; ++mt) {
             int m = mt;
             const int tx = m % a.tiles_x; m /= a.tiles_x;
             const int ty = m % a.tiles_y;
@@ -217,25 +247,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const int y = ty * a.TH + (r >> a.lgTW), x = tx * a.TW + (r & (a.TW - 1));
             const bool valid = (y < a.H) && (x < a.W);
             const size_t pix = (static_cast<size_t>(b) * a.H + y) * a.W + x;
-            const int n0 = nt * NT;
+            if (a.stats && b != stat_b) {
+                if (stat_b >= 0) flush_stats(stat_b);
+                stat_b = b;
+            }
 
             mbar_wait(bar_tfull + acc * 8, pacc);
             tc_fence_after();
-#pragma unroll 1
-            for (int ch = cset; ch < NT / 32; ch += kEpiWarps / 4) {
-                uint32_t raw[32];
-                tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * NT + ch * 32, raw);
-                tmem_ld_wait();
+            uint32_t raw[kSlots][32];
+#pragma unroll
+            for (int k = 0; k < kSlots; ++k)
+                tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * NT + (cset + 2 * k) * 32, raw[k]);
+            tmem_ld_wait();
+            // everything this warp needs from the accumulator is in registers: hand the TMEM stage back right away
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + acc * 8);
+#pragma unroll
+            for (int k = 0; k < kSlots; ++k) {
+                const int ch = cset + 2 * k;
                 const int nbase = n0 + ch * 32;
                 float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-                if (a.bias) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + nbase + j));
-                        v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
-                    }
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 bv = *reinterpret_cast<const float4*>(&tail->bias[ch * 32 + j]);
+                    v[j] = __uint_as_float(raw[k][j]) + bv.x; v[j + 1] = __uint_as_float(raw[k][j + 1]) + bv.y;
+                    v[j + 2] = __uint_as_float(raw[k][j + 2]) + bv.z; v[j + 3] = __uint_as_float(raw[k][j + 3]) + bv.w;
                 }
                 if (a.act == kActGelu) {
 #pragma unroll
@@ -261,26 +298,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                         f = unpack_bf16(u.w); v[j * 8 + 6] += f.x; v[j * 8 + 7] += f.y;
                     }
                 }
-                if (a.stats) {
-                    float s[4], sq[4];
-                    const float msk = valid ? 1.f : 0.f;
+                if (a.stats && valid) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         float t0 = 0.f, t1 = 0.f;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) { const float w = v[g * 8 + j]; t0 += w; t1 += w * w; }
-                        s[g] = t0 * msk; sq[g] = t1 * msk;
-                    }
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) { s[g] = warp_sum(s[g]); sq[g] = warp_sum(sq[g]); }
-                    if (lane == 0) {
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const int gl = (ch * 32 + g * 8) >> a.lgs;
-                            atomicAdd(&tail->stats[gl * 2], static_cast<unsigned long long>(__float2ll_rn(s[g] * kStatScale)));
-                            atomicAdd(&tail->stats[gl * 2 + 1],
-                                      static_cast<unsigned long long>(__float2ll_rn(sq[g] * kStatScale)));
-                        }
+                        for (int j = 0; j < 8; ++j) { const float w = v[g * 8 + j]; t0 += w; t1 = fmaf(w, w, t1); }
+                        sacc[k][g] += t0; qacc[k][g] += t1;
                     }
                 }
                 if (valid) {
@@ -296,23 +320,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     }
                 }
             }
-            // accumulator drained: hand the TMEM stage back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + acc * 8);
             if (++acc == 2) { acc = 0; pacc ^= 1; }
-
-            if (a.stats) {
-                named_bar_sync(1, kEpiWarps * 32);
-                const int ng = NT >> a.lgs;
-                if (ethread < ng * 2) {
-                    const int g = (n0 >> a.lgs) + (ethread >> 1);
-                    atomicAdd(&a.stats[(static_cast<size_t>(b) * a.G + g) * 2 + (ethread & 1)], tail->stats[ethread]);
-                    tail->stats[ethread] = 0ull;
-                }
-                named_bar_sync(1, kEpiWarps * 32);
-            }
         }
+        if (a.stats && stat_b >= 0) flush_stats(stat_b);
     }
 
     tc_fence_before();

@@ -19,6 +19,7 @@
 #include "../../include/noisediff_b200.h"
 #include "conv_gemm.cuh"
 #include "pointwise.cuh"
+#include "pixel_chain.cuh"
 
 namespace ndiff {
 
@@ -44,6 +45,7 @@ struct Op {
     std::function<int(cudaStream_t)> fn;
     double flops = 0.0;
     int launches = 1;
+    bool chain = false;   // fused per-pixel chain (its FLOPs are not convolution FLOPs)
 };
 
 __global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int Cout, int Cin, int KH,
@@ -154,6 +156,8 @@ struct ndiff_engine {
     bool keep_all = false;
 
     std::map<std::string, bf16*> packed;
+    std::map<std::string, bf16*> chain_w;      // fused per-pixel chains: weight blob / parameter block per chain
+    std::map<std::string, float*> chain_f;
     float* init_w = nullptr;
     bf16* init_w_tc = nullptr; bf16* xpad = nullptr;
     // time path
@@ -310,6 +314,45 @@ int finalize(ndiff_engine* e, cudaStream_t s) {
         if (check_shape(e, ab.name + ".norm2.weight", {ab.C})) return 1;
         if (check_shape(e, ab.name + ".norm2.bias", {ab.C})) return 1;
     }
+    // --- fused per-pixel chains (pixel_chain.cuh): K-blocked weight blobs + fp32 parameter blocks
+    auto pack_attn_chain = [&](const std::string& n, bf16* w, float* f) -> int {
+        if (pack_chain_weight_launch(e->pf(n + ".ff.net.0.0.weight"), w, 128, 64, s)) return 1;
+        if (pack_chain_weight_launch(e->pf(n + ".ff.net.2.weight"), w + 128 * 64, 64, 128, s)) return 1;
+        if (pack_chain_weight_launch(e->pf(n + ".proj_out.weight"), w + 256 * 64, 64, 64, s)) return 1;
+        const char* names[5] = {".norm2.weight", ".norm2.bias", ".ff.net.0.0.bias", ".ff.net.2.bias", ".proj_out.bias"};
+        const int lens[5] = {64, 64, 128, 64, 64};
+        int off = 0;
+        for (int i = 0; i < 5; ++i) {
+            NDIFF_CUDA_OK(cudaMemcpyAsync(f + off, e->pf(n + names[i]), sizeof(float) * lens[i], cudaMemcpyDeviceToDevice, s));
+            off += lens[i];
+        }
+        return 0;
+    };
+    if (dim == 64) {
+        for (const AttnSpec& ab : attnblocks(dim)) {
+            if (ab.C != 64 || ab.name == "shot_attn") continue;
+            if (!e->chain_w.count(ab.name)) {
+                if (e->alloc(&e->chain_w[ab.name], static_cast<size_t>(kChainAttnRows) * 64)) return 1;
+                if (e->alloc(&e->chain_f[ab.name], kChainAttnFloats)) return 1;
+            }
+            if (pack_attn_chain(ab.name, e->chain_w[ab.name], e->chain_f[ab.name])) return 1;
+        }
+        if (!e->chain_w.count("shot")) {
+            if (e->alloc(&e->chain_w["shot"], static_cast<size_t>(kChainShotRows) * 64)) return 1;
+            if (e->alloc(&e->chain_f["shot"], kChainShotFloats)) return 1;
+        }
+        bf16* w = e->chain_w["shot"];
+        float* f = e->chain_f["shot"];
+        if (pack_chain_weight_launch(e->pf("shot_mlp1.fc1.weight"), w, 64, 8, s)) return 1;
+        if (pack_chain_weight_launch(e->pf("shot_mlp1.fc2.weight"), w + 64 * 64, 64, 64, s)) return 1;
+        if (pack_attn_chain("shot_attn", w + 128 * 64, f + 128)) return 1;
+        if (pack_chain_weight_launch(e->pf("shot_mlp2.fc1.weight"), w + 448 * 64, 64, 64, s)) return 1;
+        if (pack_chain_weight_launch(e->pf("shot_mlp2.fc2.weight"), w + 512 * 64, 64, 64, s)) return 1;
+        NDIFF_CUDA_OK(cudaMemcpyAsync(f, e->pf("shot_mlp1.fc1.bias"), sizeof(float) * 64, cudaMemcpyDeviceToDevice, s));
+        NDIFF_CUDA_OK(cudaMemcpyAsync(f + 64, e->pf("shot_mlp1.fc2.bias"), sizeof(float) * 64, cudaMemcpyDeviceToDevice, s));
+        NDIFF_CUDA_OK(cudaMemcpyAsync(f + 512, e->pf("shot_mlp2.fc1.bias"), sizeof(float) * 64, cudaMemcpyDeviceToDevice, s));
+        NDIFF_CUDA_OK(cudaMemcpyAsync(f + 576, e->pf("shot_mlp2.fc2.bias"), sizeof(float) * 64, cudaMemcpyDeviceToDevice, s));
+    }
     for (int i = 0; i < 3; ++i) {
         if (pack_conv(e, "downs." + std::to_string(i) + ".3.1", d[i + 1], d[i], 1, true, s)) return 1;
         if (pack_conv(e, "ups." + std::to_string(i) + ".3.1", d[3 - i], d[4 - i], 3, false, s)) return 1;
@@ -380,8 +423,11 @@ struct Builder {
     int err = 0;
     int stats_slot = 0;
     bool direct3;
+    bool fused;       // per-pixel 1x1 chains run as one kernel (pixel_chain.cuh)
 
-    explicit Builder(ndiff_engine* eng) : e(eng), direct3((eng->cfg.flags & NDIFF_FLAG_CONV_DIRECT) != 0) {}
+    explicit Builder(ndiff_engine* eng)
+        : e(eng), direct3((eng->cfg.flags & NDIFF_FLAG_CONV_DIRECT) != 0),
+          fused((eng->cfg.flags & NDIFF_FLAG_UNFUSED) == 0 && eng->dim == 64) {}
 
     Act make(int C, int H, int W) {
         Act a; a.C = C; a.H = H; a.W = W;
@@ -464,6 +510,25 @@ struct Builder {
     Act attn(const std::string& n, const Act& xin) {
         const int C = xin.C;
         const float* cv = e->cvec + e->cv_off.at(n);
+        if (fused && C == 64) {
+            Act o = make(C, xin.H, xin.W);
+            if (err) return o;
+            ChainDesc d;
+            d.prog = kProgAttn;
+            d.npix = e->B * xin.H * xin.W; d.HW = xin.H * xin.W;
+            d.x = xin.p; d.weights = e->chain_w.at(n); d.fvec = e->chain_f.at(n);
+            d.cvec = cv; d.cvec_ld = e->cv_total;
+            d.out = o.p;
+            auto plan = std::make_shared<ChainPlan>();
+            if (pixel_chain_plan(d, e->num_sms, plan.get())) { err = 1; return o; }
+            Op op; op.name = n + "(fused chain)";
+            op.flops = 2.0 * d.npix * (64.0 * 128 + 128.0 * 64 + 64.0 * 64);
+            op.chain = true;
+            op.fn = [plan](cudaStream_t st) { return pixel_chain_launch(*plan, st); };
+            e->net_ops.push_back(op);
+            name(n, o);
+            return o;
+        }
         Act u = make(C, xin.H, xin.W);
         if (err) return u;
         {
@@ -499,24 +564,47 @@ int build_plan(ndiff_engine* e) {
     const int npix = B * H * W;
 
     // ---- shot-noise branch (ref :598-604)
-    Act s0 = b.make(dim, H, W);
-    if (b.err) return 1;
-    {
-        Op op; op.name = "shot_mlp1.fc1";
-        const float* cl = e->clean; const float* x = e->x; bf16* o = s0.p;
-        const float* w = e->pf("shot_mlp1.fc1.weight"); const float* bs = e->pf("shot_mlp1.fc1.bias");
-        op.fn = [=](cudaStream_t st) { return shot_in_launch(cl, x, w, bs, o, npix, dim, st); };
+    Act s1, s4;
+    if (b.fused) {
+        s1 = b.make(dim, H, W);
+        s4 = b.make(dim, H, W);
+        if (b.err) return 1;
+        ChainDesc d;
+        d.prog = kProgShot;
+        d.npix = npix; d.HW = H * W;
+        d.weights = e->chain_w.at("shot"); d.fvec = e->chain_f.at("shot");
+        d.cvec = e->cvec + e->cv_off.at("shot_attn"); d.cvec_ld = e->cv_total;
+        d.clean = e->clean; d.xt = e->x;
+        d.out = s4.p; d.out2 = s1.p;
+        auto plan = std::make_shared<ChainPlan>();
+        if (pixel_chain_plan(d, e->num_sms, plan.get())) return 1;
+        Op op; op.name = "shot_mlp1+shot_attn+shot_mlp2(fused chain)";
+        op.flops = 2.0 * npix * (8.0 * 64 + 64.0 * 64 * 4 + 64.0 * 128 * 2);
+        op.chain = true;
+        op.fn = [plan](cudaStream_t st) { return pixel_chain_launch(*plan, st); };
         e->net_ops.push_back(op);
+        b.name("shot_mlp1", s1);
+        b.name("shot_mlp2", s4);
+    } else {
+        Act s0 = b.make(dim, H, W);
+        if (b.err) return 1;
+        {
+            Op op; op.name = "shot_mlp1.fc1";
+            const float* cl = e->clean; const float* x = e->x; bf16* o = s0.p;
+            const float* w = e->pf("shot_mlp1.fc1.weight"); const float* bs = e->pf("shot_mlp1.fc1.bias");
+            op.fn = [=](cudaStream_t st) { return shot_in_launch(cl, x, w, bs, o, npix, dim, st); };
+            e->net_ops.push_back(op);
+        }
+        s1 = b.gemm("shot_mlp1.fc2", s0, dim, kActNone);
+        b.drop(s0);
+        b.name("shot_mlp1", s1);
+        Act s2 = b.attn("shot_attn", s1);
+        Act s3 = b.gemm("shot_mlp2.fc1", s2, dim, kActGelu);
+        b.drop(s2);
+        s4 = b.gemm("shot_mlp2.fc2", s3, dim, kActNone);
+        b.drop(s3);
+        b.name("shot_mlp2", s4);
     }
-    Act s1 = b.gemm("shot_mlp1.fc2", s0, dim, kActNone);
-    b.drop(s0);
-    b.name("shot_mlp1", s1);
-    Act s2 = b.attn("shot_attn", s1);
-    Act s3 = b.gemm("shot_mlp2.fc1", s2, dim, kActGelu);
-    b.drop(s2);
-    Act s4 = b.gemm("shot_mlp2.fc2", s3, dim, kActNone);
-    b.drop(s3);
-    b.name("shot_mlp2", s4);
     Act s5 = b.resblock("shot_time", s4, nullptr, dim, 2, nullptr, &s1);   // + r (ref :603) folded into the apply pass
     b.drop(s4); b.drop(s1);
     Act s6 = b.gemm("shot_mlp3.fc1", s5, dim, kActGelu);
@@ -709,7 +797,7 @@ int32_t ndiff_engine_create(const ndiff_config* cfg, ndiff_engine** out) {
     NDIFF_CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
     NDIFF_REQUIRE(prop.major == 10, "noisediff_b200 needs an sm_100a GPU (B200); found sm_" + std::to_string(prop.major) +
                                         std::to_string(prop.minor));
-    if (conv_gemm_init() || pointwise_init()) return 1;
+    if (conv_gemm_init() || pointwise_init() || pixel_chain_init()) return 1;
     std::unique_ptr<ndiff_engine> e(new ndiff_engine());
     NDIFF_CUDA_OK(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
     e->cfg = *cfg;
@@ -1060,6 +1148,24 @@ int32_t ndiff_op_layernorm(const void* x, const float* vec, int32_t vec_ld, cons
 
 int32_t ndiff_op_philox_normal(float* out, int64_t n4, uint64_t seed, uint64_t stream_id, void* stream) {
     return philox_normal_launch(out, static_cast<size_t>(n4), seed, stream_id, as_stream(stream));
+}
+
+int32_t ndiff_op_pixel_chain(int32_t prog, int32_t npix, int32_t HW, const void* x, const float* clean_nhwc4,
+                             const float* xt_nhwc4, const void* weights_blob, const float* fvec, const float* cvec,
+                             int32_t cvec_ld, void* out, void* out2, void* stream) {
+    int dev = 0;
+    NDIFF_CUDA_OK(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    NDIFF_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+    NDIFF_REQUIRE(prop.major == 10, "noisediff_b200 needs an sm_100a GPU (B200)");
+    ChainDesc d;
+    d.prog = prog; d.npix = npix; d.HW = HW;
+    d.x = static_cast<const bf16*>(x); d.clean = clean_nhwc4; d.xt = xt_nhwc4;
+    d.weights = static_cast<const bf16*>(weights_blob); d.fvec = fvec; d.cvec = cvec; d.cvec_ld = cvec_ld;
+    d.out = static_cast<bf16*>(out); d.out2 = static_cast<bf16*>(out2);
+    ChainPlan plan;
+    if (pixel_chain_plan(d, prop.multiProcessorCount, &plan)) return 1;
+    return pixel_chain_launch(plan, as_stream(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,417 @@
+// noisediff_b200 — fused per-pixel MLP chains on tensor cores (sm_100a).  See pixel_chain.cuh.
+//
+// One CTA = two independent warpgroups of 128 threads.  Each warpgroup walks its own sequence of 128-pixel tiles; thread r
+// owns pixel r of the tile (= TMEM lane r), so LayerNorm over channels and all epilogue math are thread-local.  A GEMM
+// stage is: the 128 threads write the bf16 A operand [128 x K] into shared memory in the SWIZZLE_128B K-major layout,
+// fence.proxy.async + named barrier, ONE thread issues the tcgen05.mma's against the layer's weights (resident in shared
+// memory for the whole kernel, loaded once by TMA) and commits to an mbarrier, everyone waits and drains the fp32
+// accumulator from TMEM with tcgen05.ld.  Stages of one tile are strictly sequential; the two warpgroups interleave, so one
+// group's tensor-core work and TMEM/shared traffic overlaps the other group's epilogue arithmetic.
+// Input tiles arrive by TMA (attn) or as coalesced float4 loads (shot); outputs leave by TMA store from a staging block.
+#include "pixel_chain.cuh"
+#include "conv_gemm.cuh"
+
+#include <cstring>
+#include <mutex>
+
+namespace ndiff {
+
+namespace {
+
+constexpr int kTile = 128;                 // pixels per tile = TMEM lanes
+constexpr int kBlk = kTile * 128;          // bytes of one [128 x 64] bf16 operand block
+constexpr int kWgBytes = 4 * kBlk;         // per warpgroup: X / staging | A0 | A1 (two K blocks)
+
+struct ChainTail {
+    uint64_t bar_w, bar_x[2], bar_mma[2];
+    uint32_t tmem_base;
+    uint32_t pad_;
+    float fvec[kChainShotFloats];
+};
+
+__device__ __forceinline__ uint32_t swz(uint32_t blk, int r, int j) {   // 16-byte chunk j of row r in a SWIZZLE_128B block
+    return blk + r * 128 + ((j ^ (r & 7)) << 4);
+}
+__device__ __forceinline__ void store_half(uint32_t blk, int r, int h, const float (&v)[32]) {
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        uint4 u;
+        u.x = pack_bf16(v[jj * 8 + 0], v[jj * 8 + 1]); u.y = pack_bf16(v[jj * 8 + 2], v[jj * 8 + 3]);
+        u.z = pack_bf16(v[jj * 8 + 4], v[jj * 8 + 5]); u.w = pack_bf16(v[jj * 8 + 6], v[jj * 8 + 7]);
+        sts128(swz(blk, r, h * 4 + jj), u);
+    }
+}
+// D[tmem] = A[128 x (kblocks*64)] * W[N x (kblocks*64)]^T ; k16 = MMAs per K block (4, or 1 when only K = 16 is live)
+template <int N>
+__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_blk, uint32_t w_blk, int kblocks, int k16) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, N);
+    constexpr uint32_t hi = umma_desc_hi(1024);
+    bool first = true;
+    for (int kb = 0; kb < kblocks; ++kb) {
+        const uint32_t a_lo = umma_desc_lo(a_blk + kb * kBlk), b_lo = umma_desc_lo(w_blk + kb * N * 128);
+        for (int k = 0; k < k16; ++k) {
+            if (first) umma_bf16_lohi<false>(d_tmem, a_lo + 2 * k, hi, b_lo + 2 * k, hi, idesc);
+            else umma_bf16_lohi<true>(d_tmem, a_lo + 2 * k, hi, b_lo + 2 * k, hi, idesc);
+            first = false;
+        }
+    }
+}
+
+template <int PROG>
+__global__ void __launch_bounds__(256, 1) pixel_chain_kernel(const __grid_constant__ ChainArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr bool kShot = PROG == kProgShot;
+    constexpr int kWRows = kShot ? kChainShotRows : kChainAttnRows;
+    constexpr int kNF = kShot ? kChainShotFloats : kChainAttnFloats;
+    constexpr int kWBytes = kWRows * 128;
+    ChainTail* tail = reinterpret_cast<ChainTail*>(smem + kWBytes + 2 * kWgBytes);
+
+    const int tid = threadIdx.x, wg = tid >> 7, r = tid & 127, q = (tid >> 5) & 3;
+    const uint32_t sW = smem_u32(smem);
+    const uint32_t sX = sW + kWBytes + wg * kWgBytes, sA0 = sX + kBlk, sA1 = sA0 + kBlk;
+    // weight blocks (row offsets of pixel_chain.cuh's blob layout, 128 B per row)
+    const uint32_t sWattn = sW + (kShot ? 128 * 128 : 0);
+    const uint32_t sW1 = sWattn, sW2 = sW1 + 128 * 128, sWp = sW2 + 128 * 128, sWm1 = sWp + 64 * 128, sWm2 = sWm1 + 64 * 128;
+    const float* fA = tail->fvec + (kShot ? 128 : 0);
+    const float* f_lng = fA, *f_lnb = fA + 64, *f_b1 = fA + 128, *f_b2 = fA + 256, *f_bp = fA + 320, *f_bm1 = fA + 384,
+               *f_bm2 = fA + 448;
+    const uint32_t bar_w = smem_u32(&tail->bar_w), bar_x = smem_u32(&tail->bar_x[wg]), bar_mma = smem_u32(&tail->bar_mma[wg]);
+
+    if (tid == 0) {
+        tma_prefetch_desc(&a.tmW);
+        tma_prefetch_desc(&a.tmOut);
+        if (kShot) tma_prefetch_desc(&a.tmOut2); else tma_prefetch_desc(&a.tmX);
+        mbar_init(&tail->bar_w, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&tail->bar_x[i], 1); mbar_init(&tail->bar_mma[i], 1); }
+        fence_mbar_init();
+    }
+    if (tid < 32) tmem_alloc<256>(&tail->tmem_base);
+    for (int i = tid; i < kNF; i += 256) tail->fvec[i] = __ldg(a.fvec + i);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tail->tmem_base + wg * 128;                          // this warpgroup's 128 accumulator columns
+    const uint32_t tmem_rd = tmem_d + (static_cast<uint32_t>(q * 32) << 16);     // + this warp's lane quarter
+
+    if (tid == 0) {   // the whole weight blob, once
+        mbar_expect_tx(bar_w, kWBytes);
+        for (int i = 0; i < kWRows / 64; ++i) tma_load_2d(sW + i * 64 * 128, &a.tmW, bar_w, 0, i * 64);
+    }
+    const int tile0 = blockIdx.x * 2 + wg, tile_step = gridDim.x * 2;
+    if (!kShot && r == 0 && tile0 < a.n_tiles) {
+        mbar_expect_tx(bar_x, kBlk);
+        tma_load_2d(sX, &a.tmX, bar_x, 0, tile0 * kTile);
+    }
+    uint32_t xph = 0, mph = 0;
+    bool w_ready = false;
+
+    // one GEMM stage: publish my operand writes, one thread issues, everybody waits for the accumulator
+#define NDIFF_STAGE(ISSUE)                                                   \
+    do {                                                                     \
+        fence_proxy_async();                                                 \
+        tc_fence_before();                                                   \
+        named_bar_sync(1 + wg, 128);                                         \
+        if (r == 0) {                                                        \
+            if (!w_ready) { mbar_wait(bar_w, 0); w_ready = true; }           \
+            tc_fence_after();                                                \
+            ISSUE;                                                           \
+            umma_commit(bar_mma);                                            \
+        }                                                                    \
+        mbar_wait(bar_mma, mph);                                             \
+        mph ^= 1;                                                            \
+        tc_fence_after();                                                    \
+    } while (0)
+
+    for (int tile = tile0; tile < a.n_tiles; tile += tile_step) {
+        const int p = tile * kTile + r;
+        const int pc = p < a.npix ? p : a.npix - 1;
+        const float* cvp = a.cvec + static_cast<size_t>(pc / a.HW) * a.cvec_ld;
+        uint32_t xr[32];                      // this pixel's 64-channel attention-block input, packed bf16
+        float y[64];
+
+        // staging blocks (X slot, A1 block 0) are read by the previous tile's TMA stores: wait before anyone rewrites them
+        if (r == 0) tma_store_wait_read();
+
+        if constexpr (kShot) {
+            // ---- shot_mlp1.fc1 on cat[clean, x_t] (ref Diffusion_arch.py:598; clean first) --------------------------
+            float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f), x4 = c4;
+            if (p < a.npix) { c4 = __ldg(a.clean + p); x4 = a.x[p]; }
+            uint4 u;
+            u.x = pack_bf16(c4.x, c4.y); u.y = pack_bf16(c4.z, c4.w); u.z = pack_bf16(x4.x, x4.y); u.w = pack_bf16(x4.z, x4.w);
+            sts128(swz(sA0, r, 0), u);
+            sts128(swz(sA0, r, 1), make_uint4(0u, 0u, 0u, 0u));
+            NDIFF_STAGE(issue_gemm<64>(tmem_d, sA0, sW, 1, 1));
+            {
+                uint32_t raw[2][32];
+                tmem_ld32(tmem_rd, raw[0]);
+                tmem_ld32(tmem_rd + 32, raw[1]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(__uint_as_float(raw[h][j]) + tail->fvec[h * 32 + j]);
+                    store_half(sA0, r, h, v);
+                }
+            }
+            // ---- shot_mlp1.fc2 -> s1 (stored: it is the branch's residual r_s, ref :599) ------------------------------
+            NDIFF_STAGE(issue_gemm<64>(tmem_d, sA0, sW + 64 * 128, 1, 4));
+            {
+                uint32_t raw[2][32];
+                tmem_ld32(tmem_rd, raw[0]);
+                tmem_ld32(tmem_rd + 32, raw[1]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const float v0 = __uint_as_float(raw[h][j]) + tail->fvec[64 + h * 32 + j];
+                        const float v1 = __uint_as_float(raw[h][j + 1]) + tail->fvec[64 + h * 32 + j + 1];
+                        xr[h * 16 + j / 2] = pack_bf16(v0, v1);
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+                        sts128(swz(sX, r, h * 4 + jj), make_uint4(xr[h * 16 + jj * 4], xr[h * 16 + jj * 4 + 1],
+                                                                   xr[h * 16 + jj * 4 + 2], xr[h * 16 + jj * 4 + 3]));
+                }
+            }
+        } else {
+            mbar_wait(bar_x, xph);
+            xph ^= 1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint4 u = lds128(swz(sX, r, j));
+                xr[j * 4] = u.x; xr[j * 4 + 1] = u.y; xr[j * 4 + 2] = u.z; xr[j * 4 + 3] = u.w;
+            }
+        }
+
+        // ---- y = x + c ; A0 = LayerNorm_C(y) * g + b   (AttnBlock.norm2 on the collapsed attention, ref :438-439) ------
+        {
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; j += 4) {
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(cvp + j));
+                const float2 f0 = unpack_bf16(xr[j / 2]), f1 = unpack_bf16(xr[j / 2 + 1]);
+                y[j] = f0.x + c4.x; y[j + 1] = f0.y + c4.y; y[j + 2] = f1.x + c4.z; y[j + 3] = f1.y + c4.w;
+                sum += (y[j] + y[j + 1]) + (y[j + 2] + y[j + 3]);
+            }
+            const float mean = sum * (1.0f / 64.0f);
+            float sq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 64; ++j) { const float d = y[j] - mean; sq = fmaf(d, d, sq); }
+            const float rstd = rsqrtf(sq * (1.0f / 64.0f) + 1e-5f);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaf((y[h * 32 + j] - mean) * rstd, f_lng[h * 32 + j], f_lnb[h * 32 + j]);
+                store_half(sA0, r, h, v);
+            }
+        }
+        // ---- FeedForward.net.0: Linear(C, 2C) + GELU   (ref :405-422) -----------------------------------------------------
+        fence_proxy_async();
+        tc_fence_before();
+        named_bar_sync(1 + wg, 128);
+        if (r == 0) {
+            if (kShot) {                       // s1 staged in the X slot by every thread before this barrier
+                tma_store_2d(&a.tmOut2, sX, 0, tile * kTile);
+                tma_store_commit();
+            } else if (tile + tile_step < a.n_tiles) {   // everybody has copied its X row to registers: prefetch the next tile
+                mbar_expect_tx(bar_x, kBlk);
+                tma_load_2d(sX, &a.tmX, bar_x, 0, (tile + tile_step) * kTile);
+            }
+            if (!w_ready) { mbar_wait(bar_w, 0); w_ready = true; }
+            tc_fence_after();
+            issue_gemm<128>(tmem_d, sA0, sW1, 1, 4);
+            umma_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, mph);
+        mph ^= 1;
+        tc_fence_after();
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {       // hidden K block hh = accumulator columns [64 hh, 64 hh + 64)
+            uint32_t raw[2][32];
+            tmem_ld32(tmem_rd + hh * 64, raw[0]);
+            tmem_ld32(tmem_rd + hh * 64 + 32, raw[1]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = gelu_erf(__uint_as_float(raw[h][j]) + f_b1[hh * 64 + h * 32 + j]);
+                store_half(sA1 + hh * kBlk, r, h, v);
+            }
+        }
+        // ---- FeedForward.net.2: Linear(2C, C); z = ff + y --------------------------------------------------------------
+        NDIFF_STAGE(issue_gemm<64>(tmem_d, sA1, sW2, 2, 4));
+        {
+            uint32_t raw[2][32];
+            tmem_ld32(tmem_rd, raw[0]);
+            tmem_ld32(tmem_rd + 32, raw[1]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 c4 = __ldg(reinterpret_cast<const float4*>(cvp + h * 32 + j));
+                    const float2 f0 = unpack_bf16(xr[(h * 32 + j) / 2]), f1 = unpack_bf16(xr[(h * 32 + j) / 2 + 1]);
+                    v[j] = __uint_as_float(raw[h][j]) + f_b2[h * 32 + j] + (f0.x + c4.x);
+                    v[j + 1] = __uint_as_float(raw[h][j + 1]) + f_b2[h * 32 + j + 1] + (f0.y + c4.y);
+                    v[j + 2] = __uint_as_float(raw[h][j + 2]) + f_b2[h * 32 + j + 2] + (f1.x + c4.z);
+                    v[j + 3] = __uint_as_float(raw[h][j + 3]) + f_b2[h * 32 + j + 3] + (f1.y + c4.w);
+                }
+                store_half(sA0, r, h, v);
+            }
+        }
+        // ---- proj_out (1x1 conv) + x_in   (ref :441-443) -------------------------------------------------------------------
+        NDIFF_STAGE(issue_gemm<64>(tmem_d, sA0, sWp, 1, 4));
+        {
+            uint32_t raw[2][32];
+            tmem_ld32(tmem_rd, raw[0]);
+            tmem_ld32(tmem_rd + 32, raw[1]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const float2 f = unpack_bf16(xr[(h * 32 + j) / 2]);
+                    v[j] = __uint_as_float(raw[h][j]) + f_bp[h * 32 + j] + f.x;
+                    v[j + 1] = __uint_as_float(raw[h][j + 1]) + f_bp[h * 32 + j + 1] + f.y;
+                }
+                store_half(kShot ? sA0 : sA1, r, h, v);      // attn: staging for the TMA store; shot: operand of shot_mlp2.fc1
+            }
+        }
+        if constexpr (kShot) {
+            // ---- shot_mlp2: fc1 + GELU, fc2   (ref :601) ---------------------------------------------------------------------
+            NDIFF_STAGE(issue_gemm<64>(tmem_d, sA0, sWm1, 1, 4));
+            {
+                uint32_t raw[2][32];
+                tmem_ld32(tmem_rd, raw[0]);
+                tmem_ld32(tmem_rd + 32, raw[1]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(__uint_as_float(raw[h][j]) + f_bm1[h * 32 + j]);
+                    store_half(sA0, r, h, v);
+                }
+            }
+            NDIFF_STAGE(issue_gemm<64>(tmem_d, sA0, sWm2, 1, 4));
+            {
+                uint32_t raw[2][32];
+                tmem_ld32(tmem_rd, raw[0]);
+                tmem_ld32(tmem_rd + 32, raw[1]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[h][j]) + f_bm2[h * 32 + j];
+                    store_half(sA1, r, h, v);
+                }
+            }
+        }
+        // ---- output tile: staged in A1 block 0, stored by TMA (rows beyond npix are clipped by the tensor map) ------------
+        fence_proxy_async();
+        tc_fence_before();
+        named_bar_sync(1 + wg, 128);
+        if (r == 0) {
+            tma_store_2d(&a.tmOut, sA1, 0, tile * kTile);
+            tma_store_commit();
+        }
+    }
+#undef NDIFF_STAGE
+    if (r == 0) tma_store_wait_all();
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) {
+        tc_fence_after();
+        tmem_dealloc<256>(tail->tmem_base);
+    }
+}
+
+__global__ void pack_chain_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N, int K, int KB) {
+    const int total = KB * N * 64;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int kk = i & 63, n = (i >> 6) % N, kb = (i >> 6) / N;
+        const int k = kb * 64 + kk;
+        dst[i] = __float2bfloat16_rn(k < K ? src[static_cast<size_t>(n) * K + k] : 0.f);
+    }
+}
+
+}  // namespace
+
+int pack_chain_weight_launch(const float* src, __nv_bfloat16* dst, int N, int K, cudaStream_t s) {
+    const int KB = (K + 63) / 64;
+    pack_chain_weight_kernel<<<(KB * N * 64 + 255) / 256, 256, 0, s>>>(src, dst, N, K, KB);
+    NDIFF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int chain_smem_bytes(int prog) {
+    const int rows = prog == kProgShot ? kChainShotRows : kChainAttnRows;
+    return 1024 + rows * 128 + 2 * kWgBytes + static_cast<int>(sizeof(ChainTail));
+}
+
+int pixel_chain_init() {
+    NDIFF_CUDA_OK(cudaFuncSetAttribute(pixel_chain_kernel<kProgAttn>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       chain_smem_bytes(kProgAttn)));
+    NDIFF_CUDA_OK(cudaFuncSetAttribute(pixel_chain_kernel<kProgShot>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       chain_smem_bytes(kProgShot)));
+    return 0;
+}
+
+int pixel_chain_plan(const ChainDesc& d, int num_sms, ChainPlan* plan) {
+    {
+        static std::once_flag once;
+        static int init_rc = 0;
+        std::call_once(once, [] { init_rc = pixel_chain_init(); });
+        if (init_rc) return 1;
+    }
+    ChainArgs& a = plan->args;
+    memset(&a, 0, sizeof(a));
+    NDIFF_REQUIRE(d.prog == kProgAttn || d.prog == kProgShot, "unknown pixel-chain program");
+    NDIFF_REQUIRE(d.npix > 0 && d.HW > 0 && d.weights && d.fvec && d.cvec && d.out, "pixel chain: null argument");
+    NDIFF_REQUIRE(d.cvec_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(d.cvec) & 15) == 0,
+                  "pixel chain: the per-sample attention vector must be 16-byte aligned");
+    plan->prog = d.prog;
+    a.npix = d.npix; a.HW = d.HW; a.n_tiles = (d.npix + kTile - 1) / kTile;
+    a.fvec = d.fvec; a.cvec = d.cvec; a.cvec_ld = d.cvec_ld;
+    const uint64_t adims[2] = {64, static_cast<uint64_t>(d.npix)};
+    const uint64_t astr[1] = {128};
+    const uint32_t abox[2] = {64, kTile};
+    if (d.prog == kProgAttn) {
+        NDIFF_REQUIRE(d.x != nullptr, "pixel chain: null input");
+        if (encode_tensor_map(&a.tmX, d.x, 2, adims, astr, abox, true)) return 1;
+    } else {
+        NDIFF_REQUIRE(d.clean && d.xt && d.out2, "pixel chain (shot): null input");
+        a.clean = reinterpret_cast<const float4*>(d.clean);
+        a.x = reinterpret_cast<const float4*>(d.xt);
+        if (encode_tensor_map(&a.tmOut2, d.out2, 2, adims, astr, abox, true)) return 1;
+    }
+    if (encode_tensor_map(&a.tmOut, d.out, 2, adims, astr, abox, true)) return 1;
+    const int rows = d.prog == kProgShot ? kChainShotRows : kChainAttnRows;
+    const uint64_t wdims[2] = {64, static_cast<uint64_t>(rows)};
+    const uint32_t wbox[2] = {64, 64};
+    if (encode_tensor_map(&a.tmW, d.weights, 2, wdims, astr, wbox, true)) return 1;
+    const int want = (a.n_tiles + 1) / 2;
+    plan->grid = want < num_sms ? want : num_sms;
+    plan->smem_bytes = chain_smem_bytes(d.prog);
+    NDIFF_REQUIRE(plan->smem_bytes <= 227 * 1024, "pixel chain: shared-memory budget exceeded");
+    return 0;
+}
+
+int pixel_chain_launch(const ChainPlan& plan, cudaStream_t stream) {
+    if (plan.prog == kProgShot)
+        pixel_chain_kernel<kProgShot><<<plan.grid, 256, plan.smem_bytes, stream>>>(plan.args);
+    else
+        pixel_chain_kernel<kProgAttn><<<plan.grid, 256, plan.smem_bytes, stream>>>(plan.args);
+    NDIFF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace ndiff

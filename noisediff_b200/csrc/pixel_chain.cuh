@@ -1,0 +1,66 @@
+// noisediff_b200 — fused per-pixel MLP chains on tensor cores (declarations).
+//
+// NoiseDiffNet has long runs of 1x1 layers where every pixel is processed independently: AttnBlock with its 1-token cross
+// attention collapsed (LayerNorm -> Linear -> GELU -> Linear -> +res -> 1x1 conv -> +res, Diffusion_arch.py:425-443), and
+// the head of the shot-noise branch (shot_mlp1 -> shot_attn -> shot_mlp2, :598-601).  Run layer by layer these are
+// HBM-bound round trips of a 64-channel activation per layer; here a CTA keeps a 128-pixel tile on chip for the whole
+// chain: operands in shared memory (SWIZZLE_128B rows), accumulators in TMEM, epilogues write the next layer's operand.
+#pragma once
+#include "common.cuh"
+
+namespace ndiff {
+
+enum ChainProg : int {
+    kProgAttn = 0,   // out = AttnBlock(x)                                   (C = 64)
+    kProgShot = 1,   // s1 = shot_mlp1(cat[clean, x_t]); out = shot_mlp2(shot_attn(s1))   (dim = 64)
+};
+
+// rows of the bf16 weight blob ([rows][64], one 128-byte row per output channel per 64-wide K block) and floats of the
+// parameter block, in program order:
+//   attn : W1 (ff.net.0.0, 128 rows) | W2 kblock 0, 1 (ff.net.2, 64 + 64) | Wp (proj_out, 64)            = 320 rows
+//          [ln_g 64][ln_b 64][b1 128][b2 64][bp 64]                                                         = 384 floats
+//   shot : W0 (shot_mlp1.fc1, K = 8 zero-padded, 64) | Wfc2 (shot_mlp1.fc2, 64) | attn 320 | Wm1 | Wm2 (64 + 64) = 576 rows
+//          [b0 64][bfc2 64] + attn 384 + [bm1 64][bm2 64]                                                  = 640 floats
+constexpr int kChainAttnRows = 320, kChainAttnFloats = 384;
+constexpr int kChainShotRows = 576, kChainShotFloats = 640;
+
+struct ChainArgs {
+    CUtensorMap tmX;      // attn: input activation viewed as [npix][64] bf16, box {64, 128}
+    CUtensorMap tmW;      // weight blob [rows][64] bf16, box {64, 64}
+    CUtensorMap tmOut;    // output activation [npix][64]
+    CUtensorMap tmOut2;   // shot: shot_mlp1 output (kept as the branch's residual r_s)
+    int npix, HW, n_tiles;
+    const float* fvec;    // parameter block (see above)
+    const float* cvec;    // collapsed cross-attention vector of this block, per sample: cvec[b * cvec_ld + c]
+    int cvec_ld;
+    const float4* clean;  // shot: fp32 NHWC4 clean image and chain state
+    const float4* x;
+};
+
+struct ChainPlan {
+    ChainArgs args;
+    int prog;
+    int grid;
+    int smem_bytes;
+};
+
+struct ChainDesc {
+    int prog = kProgAttn;
+    int npix = 0, HW = 0;
+    const __nv_bfloat16* x = nullptr;       // attn input [npix][64]
+    const __nv_bfloat16* weights = nullptr; // blob
+    const float* fvec = nullptr;
+    const float* cvec = nullptr; int cvec_ld = 0;
+    const float* clean = nullptr; const float* xt = nullptr;   // shot inputs (fp32 NHWC4)
+    __nv_bfloat16* out = nullptr;
+    __nv_bfloat16* out2 = nullptr;
+};
+
+int pixel_chain_plan(const ChainDesc& d, int num_sms, ChainPlan* plan);
+int pixel_chain_launch(const ChainPlan& plan, cudaStream_t stream);
+int pixel_chain_init();
+
+// dst[(kb * N + n) * 64 + kk] = src[n * K + kb * 64 + kk] (zero beyond K): fp32 [N][K] -> bf16 K-blocked rows
+int pack_chain_weight_launch(const float* src, __nv_bfloat16* dst, int N, int K, cudaStream_t s);
+
+}  // namespace ndiff

@@ -21,92 +21,95 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// GroupNorm apply.  grid = (blocks per sample, B); every block derives the per-channel affine once (stats are 2^-24
-// fixed-point sums from the conv epilogue) and then streams its share of the sample, 4 vectors in flight per thread.
+// GroupNorm apply.  grid = (blocks per sample, B).  A thread owns ONE 16-byte channel vector (8 channels, always inside
+// one group because groups are >= 8 channels wide) for its whole life, so the folded affine
+//     y = x * A + B,  A = rstd*gamma*(scale+1),  B = (beta - mean*rstd*gamma)*(scale+1) + shift
+// lives in 16 registers and the streaming loop is: 16-B loads (kGnUnroll pixels in flight per stream) -> fma -> SiLU ->
+// (+ residuals) -> 16-B store.  Statistics are the 2^-24 fixed-point sums written by the conv epilogue.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kGnThreads = 256;
-constexpr int kGnBatch = 4;
+constexpr int kGnUnroll = 4;
 
+template <bool kMaps, int kRes>
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnApplyArgs a) {
-    __shared__ __align__(16) float sA[512], sB[512];
     const int b = blockIdx.y;
-    const int C = a.C, gs = C / a.G;
-    const double inv_n = 1.0 / (static_cast<double>(a.HW) * gs);
-    for (int c = threadIdx.x; c < C; c += kGnThreads) {
-        const int g = c / gs;
+    const int C = a.C, cv = C >> 3, gs = C / a.G;
+    const int cvi = threadIdx.x % cv;                  // this thread's channel vector (blockDim.x % cv == 0)
+    const int c0 = cvi * 8;
+    float A[8], Bc[8];
+    {
+        const int g = c0 / gs;
+        const double inv_n = 1.0 / (static_cast<double>(a.HW) * gs);
         const double s = static_cast<double>(static_cast<long long>(a.stats[(b * a.G + g) * 2])) * (1.0 / 16777216.0);
         const double ss = static_cast<double>(static_cast<long long>(a.stats[(b * a.G + g) * 2 + 1])) * (1.0 / 16777216.0);
         const double meand = s * inv_n;
         const float mean = static_cast<float>(meand);
         const float var = fmaxf(static_cast<float>(ss * inv_n - meand * meand), 0.f);
         const float rstd = rsqrtf(var + a.eps);
-        float A = rstd * a.gamma[c];
-        float Bc = a.beta[c] - mean * A;
-        if (a.ss) {
-            const float sc = a.ss[static_cast<size_t>(b) * a.ss_ld + a.ss_off + c] + 1.0f;
-            const float sh = a.ss[static_cast<size_t>(b) * a.ss_ld + a.ss_off + C + c];
-            A *= sc;
-            Bc = Bc * sc + sh;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float Aj = rstd * __ldg(a.gamma + c0 + j);
+            float Bj = __ldg(a.beta + c0 + j) - mean * Aj;
+            if (a.ss) {
+                const float sc = a.ss[static_cast<size_t>(b) * a.ss_ld + a.ss_off + c0 + j] + 1.0f;
+                const float sh = a.ss[static_cast<size_t>(b) * a.ss_ld + a.ss_off + C + c0 + j];
+                Aj *= sc;
+                Bj = Bj * sc + sh;
+            }
+            A[j] = Aj; Bc[j] = Bj;
         }
-        sA[c] = A; sB[c] = Bc;
     }
-    __syncthreads();
-    const int cv = C >> 3;                                   // 16-B vectors per pixel
-    const size_t nvec = static_cast<size_t>(a.HW) * cv;      // per sample
-    const size_t base = static_cast<size_t>(b) * nvec;
+    const int ppb = kGnThreads / cv;                                   // pixels per block per pass
+    const int pstride = gridDim.x * ppb;
+    const size_t base = static_cast<size_t>(b) * a.HW * cv + cvi;      // vector index of (b, pixel 0, cvi)
     const uint4* xin = reinterpret_cast<const uint4*>(a.x) + base;
     uint4* xout = reinterpret_cast<uint4*>(a.out) + base;
-    const uint4* r1 = a.res1 ? reinterpret_cast<const uint4*>(a.res1) + base : nullptr;
-    const uint4* r2 = a.res2 ? reinterpret_cast<const uint4*>(a.res2) + base : nullptr;
-    const uint4* mp = a.maps ? reinterpret_cast<const uint4*>(a.maps) + base * 2 : nullptr;
-    const size_t span = static_cast<size_t>(kGnThreads) * kGnBatch;
-    for (size_t v0 = static_cast<size_t>(blockIdx.x) * span + threadIdx.x; v0 < nvec; v0 += static_cast<size_t>(gridDim.x) * span) {
-        uint4 xv[kGnBatch], rv1[kGnBatch], rv2[kGnBatch];
+    const uint4* r1 = kRes >= 1 ? reinterpret_cast<const uint4*>(a.res1) + base : nullptr;
+    const uint4* r2 = kRes >= 2 ? reinterpret_cast<const uint4*>(a.res2) + base : nullptr;
+    const uint4* mp = kMaps ? reinterpret_cast<const uint4*>(a.maps) + (base - cvi) * 2 : nullptr;   // (b, pixel 0, 0) of [2C]
+    for (int p0 = blockIdx.x * ppb + threadIdx.x / cv; p0 < a.HW; p0 += pstride * kGnUnroll) {
+        uint4 xv[kGnUnroll], rv1[kGnUnroll], rv2[kGnUnroll], ms[kGnUnroll], mh[kGnUnroll];
 #pragma unroll
-        for (int i = 0; i < kGnBatch; ++i) {
-            const size_t v = v0 + static_cast<size_t>(i) * kGnThreads;
-            if (v < nvec) {
-                xv[i] = __ldg(xin + v);
-                if (r1) rv1[i] = __ldg(r1 + v);
-                if (r2) rv2[i] = __ldg(r2 + v);
+        for (int i = 0; i < kGnUnroll; ++i) {
+            const int p = p0 + i * pstride;
+            if (p < a.HW) {
+                const size_t o = static_cast<size_t>(p) * cv;
+                xv[i] = __ldg(xin + o);
+                if (kRes >= 1) rv1[i] = __ldg(r1 + o);
+                if (kRes >= 2) rv2[i] = __ldg(r2 + o);
+                if (kMaps) { ms[i] = __ldg(mp + o * 2 + cvi); mh[i] = __ldg(mp + o * 2 + cv + cvi); }
             }
         }
 #pragma unroll
-        for (int i = 0; i < kGnBatch; ++i) {
-            const size_t v = v0 + static_cast<size_t>(i) * kGnThreads;
-            if (v >= nvec) break;
-            const int c0 = static_cast<int>(v % cv) * 8;
+        for (int i = 0; i < kGnUnroll; ++i) {
+            const int p = p0 + i * pstride;
+            if (p >= a.HW) break;
             float f[8];
             unpack8(xv[i], f);
-            {
-                const float4 a0 = *reinterpret_cast<const float4*>(sA + c0), a1 = *reinterpret_cast<const float4*>(sA + c0 + 4);
-                const float4 b0 = *reinterpret_cast<const float4*>(sB + c0), b1 = *reinterpret_cast<const float4*>(sB + c0 + 4);
-                f[0] = fmaf(f[0], a0.x, b0.x); f[1] = fmaf(f[1], a0.y, b0.y); f[2] = fmaf(f[2], a0.z, b0.z); f[3] = fmaf(f[3], a0.w, b0.w);
-                f[4] = fmaf(f[4], a1.x, b1.x); f[5] = fmaf(f[5], a1.y, b1.y); f[6] = fmaf(f[6], a1.z, b1.z); f[7] = fmaf(f[7], a1.w, b1.w);
-            }
-            if (mp) {
-                const size_t pix = v / cv;
-                float sc[8], sh[8];
-                unpack8(__ldg(mp + pix * (2 * cv) + (c0 >> 3)), sc);
-                unpack8(__ldg(mp + pix * (2 * cv) + cv + (c0 >> 3)), sh);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = f[j] * (sc[j] + 1.0f) + sh[j];
+            for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], A[j], Bc[j]);
+            if (kMaps) {
+                float sc[8], sh[8];
+                unpack8(ms[i], sc);
+                unpack8(mh[i], sh);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j] + 1.0f, sh[j]);
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = silu(f[j]);
-            if (r1) {
+            if (kRes >= 1) {
                 float r[8];
                 unpack8(rv1[i], r);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] += r[j];
             }
-            if (r2) {
+            if (kRes >= 2) {
                 float r[8];
                 unpack8(rv2[i], r);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] += r[j];
             }
-            xout[v] = pack8(f);
+            xout[static_cast<size_t>(p) * cv] = pack8(f);
         }
     }
 }
@@ -413,7 +416,7 @@ __global__ void __launch_bounds__(256) time_mlp_kernel(const int* __restrict__ t
     for (int o = threadIdx.x; o < td; o += blockDim.x) {
         float acc = b1[o];
         for (int k = 0; k < dim; ++k) acc += w1[o * dim + k] * emb[k];
-        h[o] = gelu_erf(acc);
+        h[o] = gelu_exact(acc);
     }
     __syncthreads();
     for (int o = threadIdx.x; o < td; o += blockDim.x) {
@@ -498,7 +501,7 @@ __global__ void __launch_bounds__(128) pos_maps_kernel(const PosArgs a) {
         float acc = small[408 + o];
 #pragma unroll
         for (int k = 0; k < 24; ++k) acc += small[24 + o * 24 + k] * feat[k];
-        h[o] = gelu_erf(acc);
+        h[o] = gelu_exact(acc);
     }
     float pe[8], ps[8];
 #pragma unroll
@@ -560,12 +563,23 @@ inline int blocks_for(size_t n, int per_block, int cap = 1 << 20) {
 // launchers
 // ---------------------------------------------------------------------------------------------------------------
 int gn_apply_launch(const GnApplyArgs& a, cudaStream_t s) {
-    NDIFF_REQUIRE(a.C % 8 == 0 && a.C <= 512 && a.C % a.G == 0, "GroupNorm apply: unsupported channel count");
-    const size_t nvec = static_cast<size_t>(a.HW) * (a.C / 8);
-    const int want = blocks_for(nvec, kGnThreads * kGnBatch);
-    const int cap = (148 * 8 + a.B - 1) / a.B;                     // ~8 resident blocks per SM over the whole batch
+    NDIFF_REQUIRE(a.C % 64 == 0 && a.C <= 512 && a.C % a.G == 0 && (a.C / a.G) % 8 == 0,
+                  "GroupNorm apply: channels must be a multiple of 64 (<= 512) in groups of >= 8");
+    NDIFF_REQUIRE(!(a.res2 && !a.res1), "GroupNorm apply: res2 without res1");
+    const int cv = a.C / 8, ppb = kGnThreads / cv;
+    const int want = (a.HW + ppb * kGnUnroll - 1) / (ppb * kGnUnroll);
+    const int cap = (148 * 6 + a.B - 1) / a.B;                     // a few resident blocks per SM over the whole batch
     dim3 grid(want < cap ? want : cap, a.B);
-    gn_apply_kernel<<<grid, kGnThreads, 0, s>>>(a);
+    const int nres = a.res2 ? 2 : (a.res1 ? 1 : 0);
+    if (a.maps) {
+        if (nres == 0) gn_apply_kernel<true, 0><<<grid, kGnThreads, 0, s>>>(a);
+        else if (nres == 1) gn_apply_kernel<true, 1><<<grid, kGnThreads, 0, s>>>(a);
+        else gn_apply_kernel<true, 2><<<grid, kGnThreads, 0, s>>>(a);
+    } else {
+        if (nres == 0) gn_apply_kernel<false, 0><<<grid, kGnThreads, 0, s>>>(a);
+        else if (nres == 1) gn_apply_kernel<false, 1><<<grid, kGnThreads, 0, s>>>(a);
+        else gn_apply_kernel<false, 2><<<grid, kGnThreads, 0, s>>>(a);
+    }
     NDIFF_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -189,3 +189,88 @@ def test_philox_normals_are_standard_normal_and_counter_based():
     emp = (torch.arange(1, s.numel() + 1, device="cuda", dtype=torch.float64)) / s.numel()
     assert float((cdf - emp).abs().max()) < 1.63 / math.sqrt(s.numel())      # 1% critical value
     assert float(a.abs().max()) < 7 and float((a.reshape(-1, 4)[:, 0] * a.reshape(-1, 4)[:, 1]).mean()) < 5e-3
+
+
+# ---- fused per-pixel chains (pixel_chain.cu) ---------------------------------------------------------------------------
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def _blob(w):
+    """fp32 [N][K] -> bf16 [ceil(K/64)][N][64] rows (the chain kernels' K-blocked weight layout)."""
+    n, k = w.shape
+    kb = (k + 63) // 64
+    wp = torch.zeros(n, kb * 64, device=w.device)
+    wp[:, :k] = w
+    return wp.reshape(n, kb, 64).permute(1, 0, 2).reshape(kb * n, 64).to(torch.bfloat16)
+
+
+def _attn_params(seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    rn = lambda *s, sc=1.0: torch.randn(*s, generator=g, device="cuda") * sc
+    p = dict(ln_g=1 + 0.3 * rn(64), ln_b=0.2 * rn(64), W1=_bf(rn(128, 64, sc=0.125)), b1=0.3 * rn(128),
+             W2=_bf(rn(64, 128, sc=0.09)), b2=0.3 * rn(64), Wp=_bf(rn(64, 64, sc=0.125)), bp=0.3 * rn(64))
+    blob = torch.cat([_blob(p["W1"]), _blob(p["W2"]), _blob(p["Wp"])])
+    fvec = torch.cat([p["ln_g"], p["ln_b"], p["b1"], p["b2"], p["bp"]])
+    return p, blob, fvec
+
+
+def _attn_ref(tok, cv, p):
+    """tok: [npix, 64] fp32 (bf16-representable), cv: [npix, 64].  Rounds to bf16 where the kernel stores bf16."""
+    y = tok + cv
+    u = _bf(F.layer_norm(y, (64,), p["ln_g"], p["ln_b"], eps=1e-5))
+    h = _bf(F.gelu(u @ p["W1"].T + p["b1"]))
+    z = _bf(h @ p["W2"].T + p["b2"] + y)
+    return z @ p["Wp"].T + p["bp"] + tok
+
+
+def _rel(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+@pytest.mark.parametrize("case", [(2, 16, 16), (3, 8, 8), (1, 8, 24), (4, 128, 128)])
+def test_attn_chain(case):
+    B, H, W = case
+    npix, HW = B * H * W, H * W
+    x = _rand((npix, 64), 31)
+    cvec = torch.randn(B, 96, device="cuda")                    # leading dimension larger than C on purpose
+    p, blob, fvec = _attn_params(32)
+    out = torch.zeros((npix, 64), dtype=torch.bfloat16, device="cuda")
+    xb = x.to(torch.bfloat16)
+    _lib.check(_lib.lib().ndiff_op_pixel_chain(0, npix, HW, G.P(xb), None, None, G.P(blob), G.P(fvec), G.P(cvec), 96,
+                                               G.P(out), None, G.stream()))
+    torch.cuda.synchronize()
+    ref = _attn_ref(x, cvec[:, :64].repeat_interleave(HW, dim=0), p)
+    assert _rel(out.float(), ref) < 5e-3, _rel(out.float(), ref)
+    assert (out.float() - ref).abs().max().item() < 3e-2 * max(ref.abs().max().item(), 1.0)
+
+
+@pytest.mark.parametrize("case", [(2, 16, 16), (3, 8, 8), (2, 256, 256)])
+def test_shot_chain(case):
+    B, H, W = case
+    npix, HW = B * H * W, H * W
+    g = torch.Generator(device="cuda").manual_seed(41)
+    clean = torch.rand((npix, 4), generator=g, device="cuda") * 0.3
+    xt = torch.randn((npix, 4), generator=g, device="cuda")
+    cvec = torch.randn(B, 64, device="cuda")
+    p, ablob, afvec = _attn_params(42)
+    rn = lambda *s, sc=1.0: torch.randn(*s, generator=g, device="cuda") * sc
+    W0, b0 = _bf(rn(64, 8, sc=0.35)), 0.3 * rn(64)
+    Wf, bf_ = _bf(rn(64, 64, sc=0.125)), 0.3 * rn(64)
+    Wm1, bm1, Wm2, bm2 = _bf(rn(64, 64, sc=0.125)), 0.3 * rn(64), _bf(rn(64, 64, sc=0.125)), 0.3 * rn(64)
+    blob = torch.cat([_blob(W0), _blob(Wf), ablob, _blob(Wm1), _blob(Wm2)])
+    fvec = torch.cat([b0, bf_, afvec, bm1, bm2])
+    assert blob.shape == (576, 64) and fvec.numel() == 640
+    out = torch.zeros((npix, 64), dtype=torch.bfloat16, device="cuda")
+    out2 = torch.zeros_like(out)
+    _lib.check(_lib.lib().ndiff_op_pixel_chain(1, npix, HW, None, G.P(clean), G.P(xt), G.P(blob), G.P(fvec), G.P(cvec), 64,
+                                               G.P(out), G.P(out2), G.stream()))
+    torch.cuda.synchronize()
+    a0 = _bf(torch.cat([clean, xt], dim=1))
+    h0 = _bf(F.gelu(a0 @ W0.T + b0))
+    s1 = _bf(h0 @ Wf.T + bf_)
+    s2 = _bf(_attn_ref(s1, cvec.repeat_interleave(HW, dim=0), p))
+    h5 = _bf(F.gelu(s2 @ Wm1.T + bm1))
+    ref = h5 @ Wm2.T + bm2
+    assert _rel(out2.float(), s1) < 4e-3, _rel(out2.float(), s1)
+    assert _rel(out.float(), ref) < 8e-3, _rel(out.float(), ref)

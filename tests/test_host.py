@@ -10,7 +10,7 @@ from torch import nn
 
 import noisediff_b200 as nd
 from noisediff_b200 import _lib
-from tests.util import load, net_args, seeded_net
+from tests.util import ROOT, load, net_args, seeded_net
 
 
 def test_library_loads_and_exports_every_declared_symbol():
@@ -122,3 +122,20 @@ def test_elementwise_helpers_match_oracle():
     assert torch.equal(gd.q_sample(x, t, z), tab["sqrt_alphas_cumprod"][7] * x + tab["sqrt_one_minus_alphas_cumprod"][7] * z)
     with pytest.raises(NotImplementedError):
         gd(torch.zeros(1, 4, 8, 8), {})
+
+
+def test_fast_gelu_coefficients_track_exact_erf_gelu():
+    """The CUDA kernels evaluate nn.GELU() (exact erf, ref Diffusion_arch.py:345,412) as x * sigmoid(x * P(x^2)) with the
+    coefficients below (noisediff_b200/csrc/common.cuh::gelu_erf); pin their error against torch's erf GELU."""
+    import re
+    src = open(os.path.join(ROOT, "noisediff_b200", "csrc", "common.cuh")).read()
+    body = src[src.index("float gelu_erf(float x)"):]
+    body = body[:body.index("}")]
+    a2, a1, a0 = [float(v) for v in re.findall(r"(-?\d\.\d+e?-?\d*)f \* kL2e", body)]
+    x = torch.linspace(-12, 12, 480001, dtype=torch.float64)
+    x2 = (x * x).clamp(max=52.6)
+    L2E = 1.4426950408889634
+    p = ((a2 * x2 + a1) * x2 + a0) * 1.0              # = -(P) / ... : the kernel folds the minus sign and log2(e) into the constants
+    approx = x / (1 + torch.exp(x * p))               # the kernel's ex2(x * p * log2 e) == exp(x * p)
+    exact = 0.5 * x * (1 + torch.erf(x / 2 ** 0.5))
+    assert float((approx - exact).abs().max()) < 4e-5

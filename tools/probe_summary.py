@@ -5,7 +5,8 @@ L=r[key]['layers']
 print('sum layers ms', r[key]['sum_layers_ms'], 'step', r[key]['ms_per_step'])
 cats={}
 for n,t,f in L:
-    if 'proj' in n and 'block' in n: c='conv3x3(RB)'
+    if 'chain' in n: c='fused chain'
+    elif 'proj' in n and 'block' in n: c='conv3x3(RB)'
     elif n.endswith('.norm') : c='gn_apply'
     elif 'norm2' in n: c='layernorm'
     elif 'ff.net' in n or 'proj_out' in n: c='attn gemm'
