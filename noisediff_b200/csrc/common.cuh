@@ -228,6 +228,33 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, u
             : "memory");
     }
 }
+// Same with a run-time accumulate flag (first MMA of a tile clears the accumulator).
+__device__ __forceinline__ void umma_bf16_lohi_pred(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                    uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "setp.ne.u32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Running-descriptor form: bumps both descriptor address words by compile-time increments and issues an accumulating
+// MMA.  The in-place "+r" operands chain consecutive calls, so ptxas emits add / add / UTCHMMA per MMA instead of
+// materialising (and spilling) a long list of independent descriptors.
+template <int kAInc, int kBInc>
+__device__ __forceinline__ void umma_bf16_step(uint32_t d_tmem, uint32_t& a_lo, uint32_t a_hi, uint32_t& b_lo, uint32_t b_hi,
+                                               uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"
+        "add.u32 %0, %0, %6;\n\tadd.u32 %1, %1, %7;\n\t"
+        "mov.b64 da, {%0, %2};\n\tmov.b64 db, {%1, %3};\n\t"
+        "setp.eq.u32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%4], da, db, %5, p;\n\t}"
+        : "+r"(a_lo), "+r"(b_lo)
+        : "r"(a_hi), "r"(b_hi), "r"(d_tmem), "r"(idesc), "n"(kAInc), "n"(kBInc)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }

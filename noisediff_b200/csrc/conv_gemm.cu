@@ -37,13 +37,14 @@ constexpr int kHaloPitch = (kHaloTW + 2) * 128;                          // byte
 constexpr int kHaloCopy = (kHaloTH + 2) * kHaloPitch;                    // 23040 B landed by one TMA box
 constexpr int kHaloStage = (kHaloCopy + 1023) / 1024 * 1024;
 
-template <int NT, int MODE>
+template <int NT, int MODE, bool RES>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem is only guaranteed 16-B aligned by the ABI; SWIZZLE_128B wants 1024
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr bool kHalo = MODE == kHalo1;
-    constexpr int kBStage = NT * 128;
+    constexpr int kBTap = NT * 128;                              // one [NT x 64] weight block (one tap of one channel block)
+    constexpr int kBStage = (kHalo ? 3 : 1) * kBTap;             // streamed weights: one stage = one kernel row of taps
     constexpr int kAStage = kHalo ? kHaloStage : 128 * 128;
     const int a_stages = a.a_stages, b_stages = a.b_stages;
     const uint32_t ringA = smem_u32(smem);
@@ -64,7 +65,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int cta_m = blockIdx.x / a.n_tiles, n_cta_m = gridDim.x / a.n_tiles;
     const int m_begin = static_cast<int>(static_cast<long long>(m_total) * cta_m / n_cta_m);
     const int m_end = static_cast<int>(static_cast<long long>(m_total) * (cta_m + 1) / n_cta_m);
-    const bool resident = a.b_resident != 0;                     // whole weight slice of this N tile lives in smem
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&a.tmA0);
@@ -87,11 +87,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     if (warp == 0) {
         // ================================ TMA producer (whole warp walks the loop, one elected lane issues) ========
         int sa = 0, pa = 0, sb = 0, pb = 0;
-        if (resident) {
+        if constexpr (RES) {
             if (elect_one()) {
                 const int nkb = CB * TAPS;
-                mbar_expect_tx(bar_fullB, nkb * kBStage);
-                for (int kb = 0; kb < nkb; ++kb) tma_load_2d(ringB + kb * kBStage, &a.tmB, bar_fullB, kb * 64, nt * NT);
+                mbar_expect_tx(bar_fullB, nkb * kBTap);
+                for (int kb = 0; kb < nkb; ++kb) tma_load_2d(ringB + kb * kBTap, &a.tmB, bar_fullB, kb * 64, nt * NT);
             }
             __syncwarp();
         }
@@ -113,10 +113,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     }
                     __syncwarp();
                     if (++sa == a_stages) { sa = 0; pa ^= 1; }
-                }
-                int ky = 0, kx = 0;
-                for (int tap = 0; tap < TAPS; ++tap) {
-                    if constexpr (!kHalo) {
+                    if constexpr (!RES) {
+                        // weights stream in groups of one kernel row (3 taps = 3 x [NT x 64]) per stage
+#pragma unroll 1
+                        for (int g = 0; g < 3; ++g) {
+                            mbar_wait(bar_emptyB + sb * 8, pb ^ 1);
+                            if (elect_one()) {
+                                mbar_expect_tx(bar_fullB + sb * 8, kBStage);
+#pragma unroll
+                                for (int t = 0; t < 3; ++t)
+                                    tma_load_2d(ringB + sb * kBStage + t * kBTap, &a.tmB, bar_fullB + sb * 8, kcol + t * 64,
+                                                nt * NT);
+                            }
+                            __syncwarp();
+                            kcol += 192;
+                            if (++sb == b_stages) { sb = 0; pb ^= 1; }
+                        }
+                    }
+                } else {
+                    int ky = 0, kx = 0;
+                    for (int tap = 0; tap < TAPS; ++tap) {
                         mbar_wait(bar_emptyA + sa * 8, pa ^ 1);
                         if (elect_one()) {
                             mbar_expect_tx(bar_fullA + sa * 8, 128 * 128);
@@ -129,75 +145,105 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                         __syncwarp();
                         if (++sa == a_stages) { sa = 0; pa ^= 1; }
                         if (++kx == a.taps_x) { kx = 0; ++ky; }
-                    }
-                    if (!resident) {
-                        mbar_wait(bar_emptyB + sb * 8, pb ^ 1);
-                        if (elect_one()) {
-                            mbar_expect_tx(bar_fullB + sb * 8, kBStage);
-                            tma_load_2d(ringB + sb * kBStage, &a.tmB, bar_fullB + sb * 8, kcol, nt * NT);
+                        if constexpr (!RES) {
+                            mbar_wait(bar_emptyB + sb * 8, pb ^ 1);
+                            if (elect_one()) {
+                                mbar_expect_tx(bar_fullB + sb * 8, kBStage);
+                                tma_load_2d(ringB + sb * kBStage, &a.tmB, bar_fullB + sb * 8, kcol, nt * NT);
+                            }
+                            __syncwarp();
+                            kcol += 64;
+                            if (++sb == b_stages) { sb = 0; pb ^= 1; }
                         }
-                        __syncwarp();
-                        kcol += 64;
-                        if (++sb == b_stages) { sb = 0; pb ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================================ MMA issuer (warp-uniform loop, one elected lane issues tcgen05.mma) =======
+        // ================================ MMA issuer ================================================================
+        // The issuing warp is a serial instruction stream: every barrier wait, election and descriptor fix-up between two
+        // tcgen05.mma's is dead time for the tensor pipe.  So one election covers a whole group of MMAs (36 for a resident
+        // 64-channel block, 12 per streamed kernel row) whose descriptors differ from a base by compile-time immediates.
         constexpr uint32_t idesc = umma_idesc_bf16(128, NT);
         constexpr uint32_t hiB = umma_desc_hi(1024);
         constexpr uint32_t hiA = umma_desc_hi(kHalo ? kHaloPitch : 1024);
         int sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
-        if (resident) mbar_wait(bar_fullB, 0);
+        if constexpr (RES) mbar_wait(bar_fullB, 0);
         for (int mt = m_begin; mt < m_end; ++mt) {
             mbar_wait(bar_tempty + acc * 8, pacc ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * NT;
-            bool first = true;
             for (int cb = 0; cb < CB; ++cb) {
                 if constexpr (kHalo) {
                     mbar_wait(bar_fullA + sa * 8, pa);
+                    tc_fence_after();
                     const uint32_t a_base = umma_desc_lo(ringA + sa * kAStage);
-#pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        if (!resident) mbar_wait(bar_fullB + sb * 8, pb);
-                        tc_fence_after();
-                        const uint32_t a_lo = a_base + (((tap / 3) * kHaloPitch + (tap % 3) * 128) >> 4);
-                        const uint32_t b_lo = umma_desc_lo(ringB + (resident ? cb * 9 + tap : sb) * kBStage);
+                    if constexpr (RES) {
+                        const uint32_t b_base = umma_desc_lo(ringB + cb * 9 * kBTap);
                         if (elect_one()) {
-                            if (first) umma_bf16_lohi<false>(d_tmem, a_lo, hiA, b_lo, hiB, idesc);
-                            else umma_bf16_lohi<true>(d_tmem, a_lo, hiA, b_lo, hiB, idesc);
-                            umma_bf16_lohi<true>(d_tmem, a_lo + 2, hiA, b_lo + 2, hiB, idesc);
-                            umma_bf16_lohi<true>(d_tmem, a_lo + 4, hiA, b_lo + 4, hiB, idesc);
-                            umma_bf16_lohi<true>(d_tmem, a_lo + 6, hiA, b_lo + 6, hiB, idesc);
-                            if (!resident) umma_commit(bar_emptyB + sb * 8);
-                            if (tap == 8) umma_commit(bar_emptyA + sa * 8);
+                            uint32_t a_cur = a_base, b_cur = b_base;
+                            umma_bf16_lohi_pred(d_tmem, a_cur, hiA, b_cur, hiB, idesc, cb > 0 ? 1u : 0u);
+                            umma_bf16_step<2, 2>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
+                            umma_bf16_step<2, 2>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
+                            umma_bf16_step<2, 2>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
+#pragma unroll
+                            for (int tap = 1; tap < 9; ++tap) {
+                                // from (previous tap, k = 3) to (this tap, k = 0)
+                                constexpr int kRow = kHaloPitch >> 4, kPix = 128 >> 4, kTapB = kBTap >> 4;
+                                if (tap % 3 == 0) umma_bf16_step<kRow - 2 * kPix - 6, kTapB - 6>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
+                                else umma_bf16_step<kPix - 6, kTapB - 6>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
+                                umma_bf16_step<2, 2>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
+                                umma_bf16_step<2, 2>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
+                                umma_bf16_step<2, 2>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
+                            }
+                            umma_commit(bar_emptyA + sa * 8);
                         }
                         __syncwarp();
-                        first = false;
-                        if (!resident && ++sb == b_stages) { sb = 0; pb ^= 1; }
+                    } else {
+#pragma unroll 1
+                        for (int g = 0; g < 3; ++g) {
+                            mbar_wait(bar_fullB + sb * 8, pb);
+                            tc_fence_after();
+                            const uint32_t a_row = a_base + ((g * kHaloPitch) >> 4);
+                            const uint32_t b_base = umma_desc_lo(ringB + sb * kBStage);
+                            if (elect_one()) {
+                                uint32_t a_cur = a_row, b_cur = b_base;
+                                umma_bf16_lohi_pred(d_tmem, a_cur, hiA, b_cur, hiB, idesc, (cb > 0 || g > 0) ? 1u : 0u);
+                                umma_bf16_step<2, 2>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
+                                umma_bf16_step<2, 2>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
+                                umma_bf16_step<2, 2>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
+#pragma unroll
+                                for (int t = 1; t < 3; ++t) {
+                                    umma_bf16_step<(128 >> 4) - 6, (kBTap >> 4) - 6>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
+                                    umma_bf16_step<2, 2>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
+                                    umma_bf16_step<2, 2>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
+                                    umma_bf16_step<2, 2>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
+                                }
+                                umma_commit(bar_emptyB + sb * 8);
+                                if (g == 2) umma_commit(bar_emptyA + sa * 8);
+                            }
+                            __syncwarp();
+                            if (++sb == b_stages) { sb = 0; pb ^= 1; }
+                        }
                     }
                     if (++sa == a_stages) { sa = 0; pa ^= 1; }
                 } else {
                     for (int tap = 0; tap < TAPS; ++tap) {
                         mbar_wait(bar_fullA + sa * 8, pa);
-                        if (!resident) mbar_wait(bar_fullB + sb * 8, pb);
+                        if constexpr (!RES) mbar_wait(bar_fullB + sb * 8, pb);
                         tc_fence_after();
                         const uint32_t a_lo = umma_desc_lo(ringA + sa * kAStage);
-                        const uint32_t b_lo = umma_desc_lo(ringB + (resident ? cb * TAPS + tap : sb) * kBStage);
+                        const uint32_t b_lo = umma_desc_lo(ringB + (RES ? (cb * TAPS + tap) * kBTap : sb * kBStage));
                         if (elect_one()) {
-                            if (first) umma_bf16_lohi<false>(d_tmem, a_lo, hiA, b_lo, hiB, idesc);
-                            else umma_bf16_lohi<true>(d_tmem, a_lo, hiA, b_lo, hiB, idesc);
+                            umma_bf16_lohi_pred(d_tmem, a_lo, hiA, b_lo, hiB, idesc, (cb > 0 || tap > 0) ? 1u : 0u);
                             umma_bf16_lohi<true>(d_tmem, a_lo + 2, hiA, b_lo + 2, hiB, idesc);
                             umma_bf16_lohi<true>(d_tmem, a_lo + 4, hiA, b_lo + 4, hiB, idesc);
                             umma_bf16_lohi<true>(d_tmem, a_lo + 6, hiA, b_lo + 6, hiB, idesc);
-                            if (!resident) umma_commit(bar_emptyB + sb * 8);
+                            if constexpr (!RES) umma_commit(bar_emptyB + sb * 8);
                             umma_commit(bar_emptyA + sa * 8);
                         }
                         __syncwarp();
-                        first = false;
-                        if (!resident && ++sb == b_stages) { sb = 0; pb ^= 1; }
+                        if constexpr (!RES) { if (++sb == b_stages) { sb = 0; pb ^= 1; } }
                         if (++sa == a_stages) { sa = 0; pa ^= 1; }
                     }
                 }
@@ -418,12 +464,13 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     else { a.taps_y = d.taps_y; a.taps_x = d.taps_x; a.pad_y = d.pad_y; a.pad_x = d.pad_x; }
     a.n_tiles = d.Cout / NT;
     a.total_tiles = d.B * a.tiles_y * a.tiles_x * a.n_tiles;
-    const int b_stage = NT * 128;
+    const int b_tap = NT * 128;                          // one [NT x 64] weight block
+    const int b_stage = (halo1 ? 3 : 1) * b_tap;         // streamed weights: halo mode moves one kernel row of taps per stage
     if (halo1) {
         a.a_copy_bytes = kHaloCopy;
         a.a_stage_bytes = kHaloStage;
         a.a_stages = 3;
-        a.b_stages = NT == 128 ? 8 : 12;
+        a.b_stages = NT == 128 ? 3 : 5;
     } else {
         a.a_copy_bytes = 128 * 128;
         a.a_stage_bytes = 128 * 128;
@@ -439,7 +486,7 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     // weights resident in shared memory when this CTA's slice fits next to >= 2 activation stages and is reused
     const int budget = 227 * 1024 - 1024 - static_cast<int>(sizeof(SmemTail));
     const int n_kb = (a.cb0 + a.cb1) * a.taps_y * a.taps_x;
-    const int slice = n_kb * b_stage;
+    const int slice = n_kb * b_tap;
     const int m_per_cta = (a.total_tiles / a.n_tiles + grid / a.n_tiles - 1) / (grid / a.n_tiles);
     a.b_resident = (slice + 2 * a.a_stage_bytes <= budget && m_per_cta >= 2 && slice < (1 << 20)) ? 1 : 0;
     if (a.b_resident) {
@@ -503,15 +550,21 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
 }
 
 namespace {
-template <int NT, int MODE>
+template <int NT, int MODE, bool RES>
 int launch_one(const ConvGemmPlan& plan, cudaStream_t stream) {
-    conv_gemm_kernel<NT, MODE><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.args);
+    conv_gemm_kernel<NT, MODE, RES><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.args);
     NDIFF_CUDA_OK(cudaGetLastError());
     return 0;
 }
 template <int NT, int MODE>
+int launch_res(const ConvGemmPlan& plan, cudaStream_t stream) {
+    return plan.args.b_resident ? launch_one<NT, MODE, true>(plan, stream) : launch_one<NT, MODE, false>(plan, stream);
+}
+template <int NT, int MODE>
 cudaError_t opt_in() {
-    return cudaFuncSetAttribute(conv_gemm_kernel<NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<NT, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(conv_gemm_kernel<NT, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 }  // namespace
 
@@ -528,13 +581,13 @@ int conv_gemm_init() {
 int conv_gemm_launch(const ConvGemmPlan& plan, cudaStream_t stream) {
     const int mode = plan.args.mode;
     if (plan.NT == 64) {
-        if (mode == kHalo1) return launch_one<64, kHalo1>(plan, stream);
-        if (mode == kS2D) return launch_one<64, kS2D>(plan, stream);
-        return launch_one<64, kDirect>(plan, stream);
+        if (mode == kHalo1) return launch_res<64, kHalo1>(plan, stream);
+        if (mode == kS2D) return launch_res<64, kS2D>(plan, stream);
+        return launch_res<64, kDirect>(plan, stream);
     }
-    if (mode == kHalo1) return launch_one<128, kHalo1>(plan, stream);
-    if (mode == kS2D) return launch_one<128, kS2D>(plan, stream);
-    return launch_one<128, kDirect>(plan, stream);
+    if (mode == kHalo1) return launch_res<128, kHalo1>(plan, stream);
+    if (mode == kS2D) return launch_res<128, kS2D>(plan, stream);
+    return launch_res<128, kDirect>(plan, stream);
 }
 
 }  // namespace ndiff
