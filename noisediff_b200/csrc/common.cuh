@@ -4,6 +4,7 @@
 
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -302,6 +303,10 @@ __host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+// Same with A = B = fp16 (format code 0 in bits 7 and 10).
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
+    return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 
 // ---- misc --------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
@@ -335,6 +340,22 @@ __device__ __forceinline__ float gelu_erf(float x) {
     float p = fmaf(7.03035067e-04f * kL2e, x2, -7.40113019e-02f * kL2e);
     p = fmaf(p, x2, -1.59501576f * kL2e);                       // -(a0 + a1 x2 + a2 x2^2) * log2(e)
     return x * rcp_approx(1.0f + ex2_approx(x * p));
+}
+// Two GELUs per instruction stream in packed fp16: 0.5 x (1 + tanh(x (c0 + c1 x^2))), the tanh form of the same sigmoid
+// fit truncated to two coefficients (max |error| vs exact-erf GELU 2.7e-4 in exact arithmetic; fp16 evaluation adds
+// ~5e-4 relative).  Used where the result is the fp16 A operand of the next tensor-core GEMM inside a fused chain.
+// 6 HFMA2-class instructions + 1 MUFU per PAIR of elements.
+__device__ __forceinline__ uint32_t gelu_f16x2(float a, float b) {
+    const __half2 x = __floats2half2_rn(a, b);
+    const __half2 c0 = __float2half2_rn(0.80015698f), c1 = __float2half2_rn(0.034700935f), half = __float2half2_rn(0.5f);
+    const __half2 x2 = __hmul2(x, x);
+    const __half2 u = __hmul2(x, __hfma2(c1, x2, c0));
+    uint32_t ui = *reinterpret_cast<const uint32_t*>(&u), ti;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(ui));
+    const __half2 th = *reinterpret_cast<const __half2*>(&ti);
+    const __half2 hx = __hmul2(x, half);
+    const __half2 o = __hfma2(hx, th, hx);
+    return *reinterpret_cast<const uint32_t*>(&o);
 }
 // libdevice erf for the run-once kernels (time MLP, positional path) whose outputs stay in fp32
 __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }

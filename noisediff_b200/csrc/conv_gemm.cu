@@ -181,20 +181,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     if constexpr (RES) {
                         const uint32_t b_base = umma_desc_lo(ringB + cb * 9 * kBTap);
                         if (elect_one()) {
-                            uint32_t a_cur = a_base, b_cur = b_base;
-                            umma_bf16_lohi_pred(d_tmem, a_cur, hiA, b_cur, hiB, idesc, cb > 0 ? 1u : 0u);
-                            umma_bf16_step<2, 2>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
-                            umma_bf16_step<2, 2>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
-                            umma_bf16_step<2, 2>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
-#pragma unroll
-                            for (int tap = 1; tap < 9; ++tap) {
-                                // from (previous tap, k = 3) to (this tap, k = 0)
-                                constexpr int kRow = kHaloPitch >> 4, kPix = 128 >> 4, kTapB = kBTap >> 4;
-                                if (tap % 3 == 0) umma_bf16_step<kRow - 2 * kPix - 6, kTapB - 6>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
-                                else umma_bf16_step<kPix - 6, kTapB - 6>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
-                                umma_bf16_step<2, 2>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
-                                umma_bf16_step<2, 2>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
-                                umma_bf16_step<2, 2>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
+                            // rolled tap loops on purpose: unrolled, ptxas hoists all 72 descriptor updates ahead of the
+                            // first MMA (spilling uniform registers) and the tensor pipe idles meanwhile
+                            uint32_t a_row = a_base, b_cur = b_base, accum = cb > 0 ? 1u : 0u;
+#pragma unroll 1
+                            for (int ky = 0; ky < 3; ++ky) {
+                                uint32_t a_cur = a_row;
+#pragma unroll 1
+                                for (int kx = 0; kx < 3; ++kx) {
+                                    umma_bf16_lohi_pred(d_tmem, a_cur, hiA, b_cur, hiB, idesc, accum);
+                                    umma_bf16_lohi<true>(d_tmem, a_cur + 2, hiA, b_cur + 2, hiB, idesc);
+                                    umma_bf16_lohi<true>(d_tmem, a_cur + 4, hiA, b_cur + 4, hiB, idesc);
+                                    umma_bf16_lohi<true>(d_tmem, a_cur + 6, hiA, b_cur + 6, hiB, idesc);
+                                    accum = 1u;
+                                    a_cur += 128 >> 4;
+                                    b_cur += kBTap >> 4;
+                                }
+                                a_row += kHaloPitch >> 4;
                             }
                             umma_commit(bar_emptyA + sa * 8);
                         }
@@ -207,17 +210,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                             const uint32_t a_row = a_base + ((g * kHaloPitch) >> 4);
                             const uint32_t b_base = umma_desc_lo(ringB + sb * kBStage);
                             if (elect_one()) {
-                                uint32_t a_cur = a_row, b_cur = b_base;
-                                umma_bf16_lohi_pred(d_tmem, a_cur, hiA, b_cur, hiB, idesc, (cb > 0 || g > 0) ? 1u : 0u);
-                                umma_bf16_step<2, 2>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
-                                umma_bf16_step<2, 2>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
-                                umma_bf16_step<2, 2>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
-#pragma unroll
-                                for (int t = 1; t < 3; ++t) {
-                                    umma_bf16_step<(128 >> 4) - 6, (kBTap >> 4) - 6>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
-                                    umma_bf16_step<2, 2>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
-                                    umma_bf16_step<2, 2>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
-                                    umma_bf16_step<2, 2>(d_tmem, a_cur, hiA, b_cur, hiB, idesc);
+                                uint32_t a_cur = a_row, b_cur = b_base, accum = (cb > 0 || g > 0) ? 1u : 0u;
+#pragma unroll 1
+                                for (int t = 0; t < 3; ++t) {
+                                    umma_bf16_lohi_pred(d_tmem, a_cur, hiA, b_cur, hiB, idesc, accum);
+                                    umma_bf16_lohi<true>(d_tmem, a_cur + 2, hiA, b_cur + 2, hiB, idesc);
+                                    umma_bf16_lohi<true>(d_tmem, a_cur + 4, hiA, b_cur + 4, hiB, idesc);
+                                    umma_bf16_lohi<true>(d_tmem, a_cur + 6, hiA, b_cur + 6, hiB, idesc);
+                                    accum = 1u;
+                                    a_cur += 128 >> 4;
+                                    b_cur += kBTap >> 4;
                                 }
                                 umma_commit(bar_emptyB + sb * 8);
                                 if (g == 2) umma_commit(bar_emptyA + sa * 8);

@@ -316,9 +316,9 @@ int finalize(ndiff_engine* e, cudaStream_t s) {
     }
     // --- fused per-pixel chains (pixel_chain.cuh): K-blocked weight blobs + fp32 parameter blocks
     auto pack_attn_chain = [&](const std::string& n, bf16* w, float* f) -> int {
-        if (pack_chain_weight_launch(e->pf(n + ".ff.net.0.0.weight"), w, 128, 64, s)) return 1;
-        if (pack_chain_weight_launch(e->pf(n + ".ff.net.2.weight"), w + 128 * 64, 64, 128, s)) return 1;
-        if (pack_chain_weight_launch(e->pf(n + ".proj_out.weight"), w + 256 * 64, 64, 64, s)) return 1;
+        if (pack_chain_weight_launch(e->pf(n + ".ff.net.0.0.weight"), w, 128, 64, false, s)) return 1;
+        if (pack_chain_weight_launch(e->pf(n + ".ff.net.2.weight"), w + 128 * 64, 64, 128, true, s)) return 1;
+        if (pack_chain_weight_launch(e->pf(n + ".proj_out.weight"), w + 256 * 64, 64, 64, false, s)) return 1;
         const char* names[5] = {".norm2.weight", ".norm2.bias", ".ff.net.0.0.bias", ".ff.net.2.bias", ".proj_out.bias"};
         const int lens[5] = {64, 64, 128, 64, 64};
         int off = 0;
@@ -343,11 +343,11 @@ int finalize(ndiff_engine* e, cudaStream_t s) {
         }
         bf16* w = e->chain_w["shot"];
         float* f = e->chain_f["shot"];
-        if (pack_chain_weight_launch(e->pf("shot_mlp1.fc1.weight"), w, 64, 8, s)) return 1;
-        if (pack_chain_weight_launch(e->pf("shot_mlp1.fc2.weight"), w + 64 * 64, 64, 64, s)) return 1;
+        if (pack_chain_weight_launch(e->pf("shot_mlp1.fc1.weight"), w, 64, 8, false, s)) return 1;
+        if (pack_chain_weight_launch(e->pf("shot_mlp1.fc2.weight"), w + 64 * 64, 64, 64, true, s)) return 1;
         if (pack_attn_chain("shot_attn", w + 128 * 64, f + 128)) return 1;
-        if (pack_chain_weight_launch(e->pf("shot_mlp2.fc1.weight"), w + 448 * 64, 64, 64, s)) return 1;
-        if (pack_chain_weight_launch(e->pf("shot_mlp2.fc2.weight"), w + 512 * 64, 64, 64, s)) return 1;
+        if (pack_chain_weight_launch(e->pf("shot_mlp2.fc1.weight"), w + 448 * 64, 64, 64, false, s)) return 1;
+        if (pack_chain_weight_launch(e->pf("shot_mlp2.fc2.weight"), w + 512 * 64, 64, 64, true, s)) return 1;
         NDIFF_CUDA_OK(cudaMemcpyAsync(f, e->pf("shot_mlp1.fc1.bias"), sizeof(float) * 64, cudaMemcpyDeviceToDevice, s));
         NDIFF_CUDA_OK(cudaMemcpyAsync(f + 64, e->pf("shot_mlp1.fc2.bias"), sizeof(float) * 64, cudaMemcpyDeviceToDevice, s));
         NDIFF_CUDA_OK(cudaMemcpyAsync(f + 512, e->pf("shot_mlp2.fc1.bias"), sizeof(float) * 64, cudaMemcpyDeviceToDevice, s));

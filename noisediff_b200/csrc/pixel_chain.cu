@@ -41,10 +41,22 @@ __device__ __forceinline__ void store_half(uint32_t blk, int r, int h, const flo
         sts128(swz(blk, r, h * 4 + jj), u);
     }
 }
+// GELU(acc + bias) of 32 accumulator columns -> fp16 operand half (the consuming GEMM runs with fp16 A and B)
+__device__ __forceinline__ void store_half_gelu_f16(uint32_t blk, int r, int h, const uint32_t (&raw)[32], const float* bias) {
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        uint4 u;
+        u.x = gelu_f16x2(__uint_as_float(raw[jj * 8 + 0]) + bias[jj * 8 + 0], __uint_as_float(raw[jj * 8 + 1]) + bias[jj * 8 + 1]);
+        u.y = gelu_f16x2(__uint_as_float(raw[jj * 8 + 2]) + bias[jj * 8 + 2], __uint_as_float(raw[jj * 8 + 3]) + bias[jj * 8 + 3]);
+        u.z = gelu_f16x2(__uint_as_float(raw[jj * 8 + 4]) + bias[jj * 8 + 4], __uint_as_float(raw[jj * 8 + 5]) + bias[jj * 8 + 5]);
+        u.w = gelu_f16x2(__uint_as_float(raw[jj * 8 + 6]) + bias[jj * 8 + 6], __uint_as_float(raw[jj * 8 + 7]) + bias[jj * 8 + 7]);
+        sts128(swz(blk, r, h * 4 + jj), u);
+    }
+}
 // D[tmem] = A[128 x (kblocks*64)] * W[N x (kblocks*64)]^T ; k16 = MMAs per K block (4, or 1 when only K = 16 is live)
-template <int N>
+template <int N, bool F16 = false>
 __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_blk, uint32_t w_blk, int kblocks, int k16) {
-    constexpr uint32_t idesc = umma_idesc_bf16(128, N);
+    constexpr uint32_t idesc = F16 ? umma_idesc_f16(128, N) : umma_idesc_bf16(128, N);
     constexpr uint32_t hi = umma_desc_hi(1024);
     bool first = true;
     for (int kb = 0; kb < kblocks; ++kb) {
@@ -148,15 +160,10 @@ __global__ void __launch_bounds__(256, 1) pixel_chain_kernel(const __grid_consta
                 tmem_ld32(tmem_rd + 32, raw[1]);
                 tmem_ld_wait();
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(__uint_as_float(raw[h][j]) + tail->fvec[h * 32 + j]);
-                    store_half(sA0, r, h, v);
-                }
+                for (int h = 0; h < 2; ++h) store_half_gelu_f16(sA0, r, h, raw[h], tail->fvec + h * 32);
             }
             // ---- shot_mlp1.fc2 -> s1 (stored: it is the branch's residual r_s, ref :599) ------------------------------
-            NDIFF_STAGE(issue_gemm<64>(tmem_d, sA0, sW + 64 * 128, 1, 4));
+            NDIFF_STAGE((issue_gemm<64, true>(tmem_d, sA0, sW + 64 * 128, 1, 4)));
             {
                 uint32_t raw[2][32];
                 tmem_ld32(tmem_rd, raw[0]);
@@ -236,15 +243,10 @@ __global__ void __launch_bounds__(256, 1) pixel_chain_kernel(const __grid_consta
             tmem_ld32(tmem_rd + hh * 64 + 32, raw[1]);
             tmem_ld_wait();
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = gelu_erf(__uint_as_float(raw[h][j]) + f_b1[hh * 64 + h * 32 + j]);
-                store_half(sA1 + hh * kBlk, r, h, v);
-            }
+            for (int h = 0; h < 2; ++h) store_half_gelu_f16(sA1 + hh * kBlk, r, h, raw[h], f_b1 + hh * 64 + h * 32);
         }
         // ---- FeedForward.net.2: Linear(2C, C); z = ff + y --------------------------------------------------------------
-        NDIFF_STAGE(issue_gemm<64>(tmem_d, sA1, sW2, 2, 4));
+        NDIFF_STAGE((issue_gemm<64, true>(tmem_d, sA1, sW2, 2, 4)));
         {
             uint32_t raw[2][32];
             tmem_ld32(tmem_rd, raw[0]);
@@ -293,14 +295,9 @@ __global__ void __launch_bounds__(256, 1) pixel_chain_kernel(const __grid_consta
                 tmem_ld32(tmem_rd + 32, raw[1]);
                 tmem_ld_wait();
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(__uint_as_float(raw[h][j]) + f_bm1[h * 32 + j]);
-                    store_half(sA0, r, h, v);
-                }
+                for (int h = 0; h < 2; ++h) store_half_gelu_f16(sA0, r, h, raw[h], f_bm1 + h * 32);
             }
-            NDIFF_STAGE(issue_gemm<64>(tmem_d, sA0, sWm2, 1, 4));
+            NDIFF_STAGE((issue_gemm<64, true>(tmem_d, sA0, sWm2, 1, 4)));
             {
                 uint32_t raw[2][32];
                 tmem_ld32(tmem_rd, raw[0]);
@@ -334,20 +331,23 @@ __global__ void __launch_bounds__(256, 1) pixel_chain_kernel(const __grid_consta
     }
 }
 
-__global__ void pack_chain_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N, int K, int KB) {
+__global__ void pack_chain_weight_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int N, int K, int KB,
+                                         int f16) {
     const int total = KB * N * 64;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int kk = i & 63, n = (i >> 6) % N, kb = (i >> 6) / N;
         const int k = kb * 64 + kk;
-        dst[i] = __float2bfloat16_rn(k < K ? src[static_cast<size_t>(n) * K + k] : 0.f);
+        const float v = k < K ? src[static_cast<size_t>(n) * K + k] : 0.f;
+        dst[i] = f16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
     }
 }
 
 }  // namespace
 
-int pack_chain_weight_launch(const float* src, __nv_bfloat16* dst, int N, int K, cudaStream_t s) {
+int pack_chain_weight_launch(const float* src, __nv_bfloat16* dst, int N, int K, bool f16, cudaStream_t s) {
     const int KB = (K + 63) / 64;
-    pack_chain_weight_kernel<<<(KB * N * 64 + 255) / 256, 256, 0, s>>>(src, dst, N, K, KB);
+    pack_chain_weight_kernel<<<(KB * N * 64 + 255) / 256, 256, 0, s>>>(src, reinterpret_cast<uint16_t*>(dst), N, K, KB,
+                                                                       f16 ? 1 : 0);
     NDIFF_CUDA_OK(cudaGetLastError());
     return 0;
 }

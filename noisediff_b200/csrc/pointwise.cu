@@ -562,15 +562,20 @@ inline int blocks_for(size_t n, int per_block, int cap = 1 << 20) {
 // ---------------------------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------------------------
+static int g_gn_occ[2][3] = {{0, 0, 0}, {0, 0, 0}};   // resident blocks per SM of each gn_apply variant (pointwise_init)
+static int g_num_sms = 148;
+
 int gn_apply_launch(const GnApplyArgs& a, cudaStream_t s) {
     NDIFF_REQUIRE(a.C % 64 == 0 && a.C <= 512 && a.C % a.G == 0 && (a.C / a.G) % 8 == 0,
                   "GroupNorm apply: channels must be a multiple of 64 (<= 512) in groups of >= 8");
     NDIFF_REQUIRE(!(a.res2 && !a.res1), "GroupNorm apply: res2 without res1");
+    const int nres = a.res2 ? 2 : (a.res1 ? 1 : 0);
     const int cv = a.C / 8, ppb = kGnThreads / cv;
     const int want = (a.HW + ppb * kGnUnroll - 1) / (ppb * kGnUnroll);
-    const int cap = (148 * 6 + a.B - 1) / a.B;                     // a few resident blocks per SM over the whole batch
+    // exactly one wave: (resident blocks per SM) x SMs blocks over the whole batch, each looping over its share
+    const int occ = g_gn_occ[a.maps ? 1 : 0][nres] > 0 ? g_gn_occ[a.maps ? 1 : 0][nres] : 2;
+    const int cap = (g_num_sms * occ) / a.B > 0 ? (g_num_sms * occ) / a.B : 1;
     dim3 grid(want < cap ? want : cap, a.B);
-    const int nres = a.res2 ? 2 : (a.res1 ? 1 : 0);
     if (a.maps) {
         if (nres == 0) gn_apply_kernel<true, 0><<<grid, kGnThreads, 0, s>>>(a);
         else if (nres == 1) gn_apply_kernel<true, 1><<<grid, kGnThreads, 0, s>>>(a);
@@ -610,6 +615,17 @@ int shot_in_launch(const float* clean, const float* x, const float* w, const flo
 }
 
 int pointwise_init() {
+    {
+        int dev = 0;
+        NDIFF_CUDA_OK(cudaGetDevice(&dev));
+        NDIFF_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+        NDIFF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_gn_occ[0][0], gn_apply_kernel<false, 0>, kGnThreads, 0));
+        NDIFF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_gn_occ[0][1], gn_apply_kernel<false, 1>, kGnThreads, 0));
+        NDIFF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_gn_occ[0][2], gn_apply_kernel<false, 2>, kGnThreads, 0));
+        NDIFF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_gn_occ[1][0], gn_apply_kernel<true, 0>, kGnThreads, 0));
+        NDIFF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_gn_occ[1][1], gn_apply_kernel<true, 1>, kGnThreads, 0));
+        NDIFF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_gn_occ[1][2], gn_apply_kernel<true, 2>, kGnThreads, 0));
+    }
     const int smem = (kIcHalo * kIcHalo + 49 * 4 * 16) * sizeof(float4);
     NDIFF_CUDA_OK(cudaFuncSetAttribute(init_conv7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     return 0;

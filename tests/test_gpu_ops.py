@@ -196,13 +196,19 @@ def _bf(t):
     return t.to(torch.bfloat16).float()
 
 
-def _blob(w):
-    """fp32 [N][K] -> bf16 [ceil(K/64)][N][64] rows (the chain kernels' K-blocked weight layout)."""
+def _hf(t):
+    return t.to(torch.float16).float()
+
+
+def _blob(w, f16=False):
+    """fp32 [N][K] -> 16-bit [ceil(K/64)][N][64] rows (the chain kernels' K-blocked weight layout); f16 rows (layers fed
+    by an on-chip fp16 GELU output) are returned as their bit pattern in a bf16-typed tensor."""
     n, k = w.shape
     kb = (k + 63) // 64
     wp = torch.zeros(n, kb * 64, device=w.device)
     wp[:, :k] = w
-    return wp.reshape(n, kb, 64).permute(1, 0, 2).reshape(kb * n, 64).to(torch.bfloat16)
+    rows = wp.reshape(n, kb, 64).permute(1, 0, 2).reshape(kb * n, 64).contiguous()
+    return rows.to(torch.float16).view(torch.bfloat16) if f16 else rows.to(torch.bfloat16)
 
 
 def _attn_params(seed):
@@ -210,7 +216,7 @@ def _attn_params(seed):
     rn = lambda *s, sc=1.0: torch.randn(*s, generator=g, device="cuda") * sc
     p = dict(ln_g=1 + 0.3 * rn(64), ln_b=0.2 * rn(64), W1=_bf(rn(128, 64, sc=0.125)), b1=0.3 * rn(128),
              W2=_bf(rn(64, 128, sc=0.09)), b2=0.3 * rn(64), Wp=_bf(rn(64, 64, sc=0.125)), bp=0.3 * rn(64))
-    blob = torch.cat([_blob(p["W1"]), _blob(p["W2"]), _blob(p["Wp"])])
+    blob = torch.cat([_blob(p["W1"]), _blob(p["W2"], f16=True), _blob(p["Wp"])])
     fvec = torch.cat([p["ln_g"], p["ln_b"], p["b1"], p["b2"], p["bp"]])
     return p, blob, fvec
 
@@ -219,7 +225,7 @@ def _attn_ref(tok, cv, p):
     """tok: [npix, 64] fp32 (bf16-representable), cv: [npix, 64].  Rounds to bf16 where the kernel stores bf16."""
     y = tok + cv
     u = _bf(F.layer_norm(y, (64,), p["ln_g"], p["ln_b"], eps=1e-5))
-    h = _bf(F.gelu(u @ p["W1"].T + p["b1"]))
+    h = _hf(F.gelu(u @ p["W1"].T + p["b1"]))              # hidden activations stay on chip in fp16
     z = _bf(h @ p["W2"].T + p["b2"] + y)
     return z @ p["Wp"].T + p["bp"] + tok
 
@@ -258,7 +264,7 @@ def test_shot_chain(case):
     W0, b0 = _bf(rn(64, 8, sc=0.35)), 0.3 * rn(64)
     Wf, bf_ = _bf(rn(64, 64, sc=0.125)), 0.3 * rn(64)
     Wm1, bm1, Wm2, bm2 = _bf(rn(64, 64, sc=0.125)), 0.3 * rn(64), _bf(rn(64, 64, sc=0.125)), 0.3 * rn(64)
-    blob = torch.cat([_blob(W0), _blob(Wf), ablob, _blob(Wm1), _blob(Wm2)])
+    blob = torch.cat([_blob(W0), _blob(Wf, f16=True), ablob, _blob(Wm1), _blob(Wm2, f16=True)])
     fvec = torch.cat([b0, bf_, afvec, bm1, bm2])
     assert blob.shape == (576, 64) and fvec.numel() == 640
     out = torch.zeros((npix, 64), dtype=torch.bfloat16, device="cuda")
@@ -267,10 +273,10 @@ def test_shot_chain(case):
                                                G.P(out), G.P(out2), G.stream()))
     torch.cuda.synchronize()
     a0 = _bf(torch.cat([clean, xt], dim=1))
-    h0 = _bf(F.gelu(a0 @ W0.T + b0))
+    h0 = _hf(F.gelu(a0 @ W0.T + b0))
     s1 = _bf(h0 @ Wf.T + bf_)
     s2 = _bf(_attn_ref(s1, cvec.repeat_interleave(HW, dim=0), p))
-    h5 = _bf(F.gelu(s2 @ Wm1.T + bm1))
+    h5 = _hf(F.gelu(s2 @ Wm1.T + bm1))
     ref = h5 @ Wm2.T + bm2
     assert _rel(out2.float(), s1) < 4e-3, _rel(out2.float(), s1)
     assert _rel(out.float(), ref) < 8e-3, _rel(out.float(), ref)
