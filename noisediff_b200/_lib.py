@@ -16,6 +16,7 @@ FLAG_NO_GRAPH = 2
 FLAG_KEEP_ACTIVATIONS = 4
 FLAG_INIT_SIMT = 8
 FLAG_UNFUSED = 16
+FLAG_PDL = 32
 
 
 class Config(C.Structure):

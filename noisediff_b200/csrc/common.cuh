@@ -10,6 +10,7 @@
 
 #include <cstdio>
 #include <string>
+#include <utility>
 
 namespace ndiff {
 
@@ -38,6 +39,27 @@ const char* get_error();
         }                                                                            \
     } while (0)
 
+// Programmatic dependent launch: kernels of one reverse step are chained with programmatic edges, so a kernel's CTAs
+// start (barrier init, TMEM allocation, weight prefetch) as soon as SM resources free up, and block in pdl_wait() until the
+// previous kernel has completed and flushed.  g_use_pdl is process-wide (NDIFF_FLAG_PDL sets it; measured on B200 it
+// buys nothing inside a CUDA graph, so it is off by default).
+extern bool g_use_pdl;
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
+
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------------------------
 // device helpers
@@ -55,6 +77,12 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
+
+// ---- programmatic dependent launch -------------------------------------------------------------------------
+// wait: every memory operation of the prerequisite grids is complete and visible (no-op without a programmatic edge);
+// trigger: this thread no longer holds back the launch of the dependent grid.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- mbarrier ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tail->tmem_base;
+    pdl_trigger();
 
     if (warp == 0) {
         // ================================ TMA producer (whole warp walks the loop, one elected lane issues) ========
@@ -95,6 +96,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
             __syncwarp();
         }
+        // weights are constants; activations are the previous kernel's output.  Everything downstream of the first
+        // activation load (MMA, epilogue reads and writes) is ordered behind this wait by the mbarrier chain.
+        pdl_wait();
         for (int mt = m_begin; mt < m_end; ++mt) {
             int m = mt;
             const int tx = m % a.tiles_x; m /= a.tiles_x;
@@ -554,8 +558,7 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
 namespace {
 template <int NT, int MODE, bool RES>
 int launch_one(const ConvGemmPlan& plan, cudaStream_t stream) {
-    conv_gemm_kernel<NT, MODE, RES><<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.args);
-    NDIFF_CUDA_OK(cudaGetLastError());
+    NDIFF_CUDA_OK(launch_pdl(conv_gemm_kernel<NT, MODE, RES>, dim3(plan.grid), dim3(kThreads), plan.smem_bytes, stream, plan.args));
     return 0;
 }
 template <int NT, int MODE>

@@ -23,6 +23,7 @@
 
 namespace ndiff {
 
+bool g_use_pdl = false;
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 const char* get_error() { return g_error.c_str(); }
@@ -79,6 +80,8 @@ __global__ void init_conv_pack_kernel(const float* __restrict__ src, float* __re
 // init_conv on tensor cores: x_t is re-laid as bf16 [B][H+6][W+8][8] (3-pixel zero border, channels 4..7 zero) so that the
 // 7 taps of one kernel row are ONE contiguous 128-byte window (8 pixels x 8 channels) -> one SWIZZLE_128B operand row.
 __global__ void xpad_pack_kernel(const float4* __restrict__ x, uint4* __restrict__ xpad, int H, int W, size_t npix) {
+    pdl_trigger();
+    pdl_wait();
     const size_t pix = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (pix >= npix) return;
     const int xx = static_cast<int>(pix % W);
@@ -118,10 +121,16 @@ __global__ void bf16_nhwc_to_f32_nchw_kernel(const bf16* __restrict__ in, float*
 }
 
 // step prologue: publish this step's scalars + time vectors; optional teacher forcing of the state
+__global__ void zero_u64_kernel(unsigned long long* p, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0ull;
+}
+
 __global__ void __launch_bounds__(256) chain_step_begin_kernel(ChainState* chain, const StepParams* table,
                                                                const float* __restrict__ ss_table, int ss_len,
                                                                float* __restrict__ ss_cur, int B, int HW,
-                                                               float4* __restrict__ x) {
+                                                               float4* __restrict__ x, unsigned long long* stats,
+                                                               int n_stats_words) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_stats_words; i += gridDim.x * blockDim.x) stats[i] = 0ull;
     const int step = chain->step;
     if (blockIdx.x == 0 && threadIdx.x == 0) chain->cur = table[step];
     const float* row = ss_table + static_cast<size_t>(step) * ss_len;
@@ -632,8 +641,8 @@ int build_plan(ndiff_engine* e) {
             Op pk; pk.name = "init_conv.pack";
             const float4* xs = reinterpret_cast<const float4*>(e->x); uint4* xp = reinterpret_cast<uint4*>(e->xpad);
             pk.fn = [=](cudaStream_t st) {
-                xpad_pack_kernel<<<(npix + 255) / 256, 256, 0, st>>>(xs, xp, H, W, static_cast<size_t>(npix));
-                NDIFF_CUDA_OK(cudaGetLastError());
+                NDIFF_CUDA_OK(launch_pdl(xpad_pack_kernel, dim3((npix + 255) / 256), dim3(256), 0, st, xs, xp, H, W,
+                                         static_cast<size_t>(npix)));
                 return 0;
             };
             e->net_ops.push_back(pk);
@@ -715,8 +724,13 @@ int build_plan(ndiff_engine* e) {
     return 0;
 }
 
-int run_net(ndiff_engine* e, cudaStream_t s) {
-    NDIFF_CUDA_OK(cudaMemsetAsync(e->stats, 0, e->stats_bytes, s));
+int run_net(ndiff_engine* e, cudaStream_t s, bool zero_stats = true) {
+    // GroupNorm sums are accumulated with atomics: clear the arena first (a kernel, not a memset node, so that the first
+    // layer can hang off it with a programmatic edge)
+    if (zero_stats) {
+        zero_u64_kernel<<<32, 256, 0, s>>>(e->stats, static_cast<int>(e->stats_bytes / sizeof(unsigned long long)));
+        NDIFF_CUDA_OK(cudaGetLastError());
+    }
     for (Op& op : e->net_ops)
         if (op.fn(s)) return 1;
     return 0;
@@ -734,9 +748,10 @@ int final_args(ndiff_engine* e, bool chain, FinalArgs* f) {
 
 int run_step(ndiff_engine* e, cudaStream_t s) {
     chain_step_begin_kernel<<<32, 256, 0, s>>>(e->chain, e->step_table, e->ss_table, e->ss_total, e->ss_cur, e->B,
-                                               e->H * e->W, reinterpret_cast<float4*>(e->x));
+                                               e->H * e->W, reinterpret_cast<float4*>(e->x), e->stats,
+                                               static_cast<int>(e->stats_bytes / sizeof(unsigned long long)));
     NDIFF_CUDA_OK(cudaGetLastError());
-    if (run_net(e, s)) return 1;
+    if (run_net(e, s, false)) return 1;
     FinalArgs f;
     final_args(e, true, &f);
     return final_launch(f, s);
@@ -804,6 +819,7 @@ int32_t ndiff_engine_create(const ndiff_config* cfg, ndiff_engine** out) {
     e->num_sms = prop.multiProcessorCount;
     e->B = cfg->batch; e->H = cfg->height; e->W = cfg->width; e->dim = cfg->dim;
     e->keep_all = (cfg->flags & NDIFF_FLAG_KEEP_ACTS) != 0;
+    g_use_pdl = (cfg->flags & NDIFF_FLAG_PDL) != 0;
     const size_t npix = static_cast<size_t>(e->B) * e->H * e->W;
     if (e->alloc(&e->clean, npix * 4) || e->alloc(&e->x, npix * 4) || e->alloc(&e->v_out, npix * 4)) return 1;
     if (e->alloc(&e->map1, npix * 2 * e->dim) || e->alloc(&e->map2, npix * 2 * e->dim)) return 1;

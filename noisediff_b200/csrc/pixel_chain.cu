@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(256, 1) pixel_chain_kernel(const __grid_consta
         mbar_expect_tx(bar_w, kWBytes);
         for (int i = 0; i < kWRows / 64; ++i) tma_load_2d(sW + i * 64 * 128, &a.tmW, bar_w, 0, i * 64);
     }
+    pdl_trigger();
+    pdl_wait();          // weights / parameters above are constants; everything below touches the previous kernel's output
     const int tile0 = blockIdx.x * 2 + wg, tile_step = gridDim.x * 2;
     if (!kShot && r == 0 && tile0 < a.n_tiles) {
         mbar_expect_tx(bar_x, kBlk);
@@ -407,10 +409,9 @@ int pixel_chain_plan(const ChainDesc& d, int num_sms, ChainPlan* plan) {
 
 int pixel_chain_launch(const ChainPlan& plan, cudaStream_t stream) {
     if (plan.prog == kProgShot)
-        pixel_chain_kernel<kProgShot><<<plan.grid, 256, plan.smem_bytes, stream>>>(plan.args);
+        NDIFF_CUDA_OK(launch_pdl(pixel_chain_kernel<kProgShot>, dim3(plan.grid), dim3(256), plan.smem_bytes, stream, plan.args));
     else
-        pixel_chain_kernel<kProgAttn><<<plan.grid, 256, plan.smem_bytes, stream>>>(plan.args);
-    NDIFF_CUDA_OK(cudaGetLastError());
+        NDIFF_CUDA_OK(launch_pdl(pixel_chain_kernel<kProgAttn>, dim3(plan.grid), dim3(256), plan.smem_bytes, stream, plan.args));
     return 0;
 }
 

@@ -32,6 +32,8 @@ constexpr int kGnUnroll = 4;
 
 template <bool kMaps, int kRes>
 __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnApplyArgs a) {
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.y;
     const int C = a.C, cv = C >> 3, gs = C / a.G;
     const int cvi = threadIdx.x % cv;                  // this thread's channel vector (blockDim.x % cv == 0)
@@ -122,6 +124,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
                                                         int vec_ld, const float* __restrict__ g,
                                                         const float* __restrict__ beta, bf16* __restrict__ out,
                                                         int HW, int C, int L, size_t npix) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int sub = lane % L, slot = lane / L, ppw = 32 / L;
     const size_t warp = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -271,6 +275,8 @@ __global__ void __launch_bounds__(256) init_conv7_kernel(const float4* __restric
 __global__ void __launch_bounds__(256) upsample2x_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int H,
                                                          int W, int cv, size_t total) {
     // H, W = INPUT size; out is [B, 2H, 2W, C]
+    pdl_trigger();
+    pdl_wait();
     for (size_t v = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; v < total;
          v += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const int c = static_cast<int>(v % cv);
@@ -324,8 +330,10 @@ __global__ void __launch_bounds__(256) philox_normal_kernel(float4* out, size_t 
 __global__ void __launch_bounds__(256) final_kernel(const FinalArgs a) {
     extern __shared__ float sw[];  // wf[4][C], ws[4][C]
     const int C = a.C;
+    pdl_trigger();
     for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) { sw[i] = a.wf[i]; sw[4 * C + i] = a.ws[i]; }
     __syncthreads();
+    pdl_wait();
     const int lanes = C >> 3;                                  // lanes cooperating on one pixel (8 for C = 64)
     const int sub = threadIdx.x % lanes;
     const size_t pix = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) / lanes;
@@ -395,7 +403,10 @@ __global__ void __launch_bounds__(256) final_kernel(const FinalArgs a) {
     }
 }
 
-__global__ void chain_advance_kernel(ChainState* chain) { chain->step += 1; }
+__global__ void chain_advance_kernel(ChainState* chain) {
+    pdl_wait();
+    chain->step += 1;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // time path
@@ -577,13 +588,13 @@ int gn_apply_launch(const GnApplyArgs& a, cudaStream_t s) {
     const int cap = (g_num_sms * occ) / a.B > 0 ? (g_num_sms * occ) / a.B : 1;
     dim3 grid(want < cap ? want : cap, a.B);
     if (a.maps) {
-        if (nres == 0) gn_apply_kernel<true, 0><<<grid, kGnThreads, 0, s>>>(a);
-        else if (nres == 1) gn_apply_kernel<true, 1><<<grid, kGnThreads, 0, s>>>(a);
-        else gn_apply_kernel<true, 2><<<grid, kGnThreads, 0, s>>>(a);
+        if (nres == 0) NDIFF_CUDA_OK(launch_pdl(gn_apply_kernel<true, 0>, grid, dim3(kGnThreads), 0, s, a));
+        else if (nres == 1) NDIFF_CUDA_OK(launch_pdl(gn_apply_kernel<true, 1>, grid, dim3(kGnThreads), 0, s, a));
+        else NDIFF_CUDA_OK(launch_pdl(gn_apply_kernel<true, 2>, grid, dim3(kGnThreads), 0, s, a));
     } else {
-        if (nres == 0) gn_apply_kernel<false, 0><<<grid, kGnThreads, 0, s>>>(a);
-        else if (nres == 1) gn_apply_kernel<false, 1><<<grid, kGnThreads, 0, s>>>(a);
-        else gn_apply_kernel<false, 2><<<grid, kGnThreads, 0, s>>>(a);
+        if (nres == 0) NDIFF_CUDA_OK(launch_pdl(gn_apply_kernel<false, 0>, grid, dim3(kGnThreads), 0, s, a));
+        else if (nres == 1) NDIFF_CUDA_OK(launch_pdl(gn_apply_kernel<false, 1>, grid, dim3(kGnThreads), 0, s, a));
+        else NDIFF_CUDA_OK(launch_pdl(gn_apply_kernel<false, 2>, grid, dim3(kGnThreads), 0, s, a));
     }
     NDIFF_CUDA_OK(cudaGetLastError());
     return 0;
@@ -598,9 +609,9 @@ int layernorm_launch(const bf16* x, const float* vec, int vec_ld, const float* g
     const int ppw = 32 / L;
     const int grid = blocks_for(npix, 8 * ppw * 4, 148 * 8);
     if (C == 512)
-        layernorm_kernel<2><<<grid, 256, 0, s>>>(x, vec, vec_ld, g, beta, out, HW, C, L, npix);
+        NDIFF_CUDA_OK(launch_pdl(layernorm_kernel<2>, dim3(grid), dim3(256), 0, s, x, vec, vec_ld, g, beta, out, HW, C, L, npix));
     else
-        layernorm_kernel<1><<<grid, 256, 0, s>>>(x, vec, vec_ld, g, beta, out, HW, C, L, npix);
+        NDIFF_CUDA_OK(launch_pdl(layernorm_kernel<1>, dim3(grid), dim3(256), 0, s, x, vec, vec_ld, g, beta, out, HW, C, L, npix));
     NDIFF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -644,8 +655,8 @@ int init_conv7_launch(const float* x, const float* w, const float* bias, bf16* o
 int upsample2x_launch(const bf16* in, bf16* out, int B, int H, int W, int C, cudaStream_t s) {
     const int cv = C / 8;
     const size_t total = static_cast<size_t>(B) * 4 * H * W * cv;
-    upsample2x_kernel<<<blocks_for(total, 256 * 4, 148 * 16), 256, 0, s>>>(
-        reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), H, W, cv, total);
+    NDIFF_CUDA_OK(launch_pdl(upsample2x_kernel, dim3(blocks_for(total, 256 * 4, 148 * 16)), dim3(256), 0, s,
+                             reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), H, W, cv, total));
     NDIFF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -653,10 +664,10 @@ int upsample2x_launch(const bf16* in, bf16* out, int B, int H, int W, int C, cud
 int final_launch(const FinalArgs& a, cudaStream_t s) {
     NDIFF_REQUIRE(a.C == 64 || a.C == 128 || a.C == 256, "final heads: C/8 must be a power of two <= 32");
     const size_t threads = static_cast<size_t>(a.npix) * (a.C / 8);
-    final_kernel<<<blocks_for(threads, 256), 256, 8 * a.C * sizeof(float), s>>>(a);
+    NDIFF_CUDA_OK(launch_pdl(final_kernel, dim3(blocks_for(threads, 256)), dim3(256), 8 * a.C * sizeof(float), s, a));
     NDIFF_CUDA_OK(cudaGetLastError());
     if (a.chain) {
-        chain_advance_kernel<<<1, 1, 0, s>>>(a.chain);
+        NDIFF_CUDA_OK(launch_pdl(chain_advance_kernel, dim3(1), dim3(1), 0, s, a.chain));
         NDIFF_CUDA_OK(cudaGetLastError());
     }
     return 0;
