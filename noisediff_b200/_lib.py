@@ -17,6 +17,7 @@ FLAG_KEEP_ACTIVATIONS = 4
 FLAG_INIT_SIMT = 8
 FLAG_UNFUSED = 16
 FLAG_PDL = 32
+FLAG_HALO1 = 64
 
 
 class Config(C.Structure):

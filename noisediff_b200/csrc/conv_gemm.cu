@@ -36,16 +36,24 @@ constexpr int kHaloTW = 8, kHaloTH = 16;
 constexpr int kHaloPitch = (kHaloTW + 2) * 128;                          // bytes between halo rows
 constexpr int kHaloCopy = (kHaloTH + 2) * kHaloPitch;                    // 23040 B landed by one TMA box
 constexpr int kHaloStage = (kHaloCopy + 1023) / 1024 * 1024;
+constexpr int kHaloCopy2 = (2 * kHaloTH + 2) * kHaloPitch;                // 43520 B: halo of two stacked sub-tiles
+constexpr int kHaloStage2 = (kHaloCopy2 + 1023) / 1024 * 1024;
+constexpr int kSubStep = (kHaloTH * kHaloPitch) >> 4;                    // descriptor offset of the second sub-tile
+// taps per streamed weight stage in halo mode
+__host__ __device__ constexpr int halo_btaps(int nt, int sub) { return (sub == 2 && nt == 128) ? 1 : 3; }
 
 template <int NT, int MODE, bool RES>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem is only guaranteed 16-B aligned by the ABI; SWIZZLE_128B wants 1024
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    constexpr bool kHalo = MODE == kHalo1;
+    constexpr bool kHalo = MODE == kHalo1 || MODE == kHalo2;
+    constexpr int kSub = MODE == kHalo2 ? 2 : 1;                 // 128-pixel sub-tiles (TMEM accumulators) per CTA tile
+    constexpr int kBG = kHalo ? halo_btaps(NT, kSub) : 1;        // taps per streamed weight stage
     constexpr int kBTap = NT * 128;                              // one [NT x 64] weight block (one tap of one channel block)
-    constexpr int kBStage = (kHalo ? 3 : 1) * kBTap;             // streamed weights: one stage = one kernel row of taps
-    constexpr int kAStage = kHalo ? kHaloStage : 128 * 128;
+    constexpr int kBStage = kBG * kBTap;
+    constexpr int kAStage = MODE == kHalo2 ? kHaloStage2 : (kHalo ? kHaloStage : 128 * 128);
+    constexpr int kACopy = MODE == kHalo2 ? kHaloCopy2 : kHaloCopy;
     const int a_stages = a.a_stages, b_stages = a.b_stages;
     const uint32_t ringA = smem_u32(smem);
     const uint32_t ringB = ringA + a_stages * kAStage;
@@ -77,7 +85,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         for (int i = 0; i < 2; ++i) { mbar_init(&tail->tmem_full[i], 1); mbar_init(&tail->tmem_empty[i], kEpiWarps); }
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc<2 * NT>(&tail->tmem_base);
+    if (warp == 2) tmem_alloc<2 * kSub * NT>(&tail->tmem_base);
     if (threadIdx.x < NT) tail->bias[threadIdx.x] = a.bias ? __ldg(a.bias + nt * NT + threadIdx.x) : 0.f;
     tc_fence_before();
     __syncthreads();
@@ -112,25 +120,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 if constexpr (kHalo) {
                     mbar_wait(bar_emptyA + sa * 8, pa ^ 1);
                     if (elect_one()) {
-                        mbar_expect_tx(bar_fullA + sa * 8, kHaloCopy);
+                        mbar_expect_tx(bar_fullA + sa * 8, kACopy);
                         tma_load_4d(ringA + sa * kAStage, tm, bar_fullA + sa * 8, c0, x0 - 1, y0 - 1, b);
                     }
                     __syncwarp();
                     if (++sa == a_stages) { sa = 0; pa ^= 1; }
                     if constexpr (!RES) {
-                        // weights stream in groups of one kernel row (3 taps = 3 x [NT x 64]) per stage
+                        // weights stream in groups of kBG taps (kBG x [NT x 64]) per stage
 #pragma unroll 1
-                        for (int g = 0; g < 3; ++g) {
+                        for (int g = 0; g < 9 / kBG; ++g) {
                             mbar_wait(bar_emptyB + sb * 8, pb ^ 1);
                             if (elect_one()) {
                                 mbar_expect_tx(bar_fullB + sb * 8, kBStage);
 #pragma unroll
-                                for (int t = 0; t < 3; ++t)
+                                for (int t = 0; t < kBG; ++t)
                                     tma_load_2d(ringB + sb * kBStage + t * kBTap, &a.tmB, bar_fullB + sb * 8, kcol + t * 64,
                                                 nt * NT);
                             }
                             __syncwarp();
-                            kcol += 192;
+                            kcol += 64 * kBG;
                             if (++sb == b_stages) { sb = 0; pb ^= 1; }
                         }
                     }
@@ -176,7 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         for (int mt = m_begin; mt < m_end; ++mt) {
             mbar_wait(bar_tempty + acc * 8, pacc ^ 1);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * NT;
+            const uint32_t d_tmem = tmem_base + acc * kSub * NT;
             for (int cb = 0; cb < CB; ++cb) {
                 if constexpr (kHalo) {
                     mbar_wait(bar_fullA + sa * 8, pa);
@@ -193,10 +201,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                                 uint32_t a_cur = a_row;
 #pragma unroll 1
                                 for (int kx = 0; kx < 3; ++kx) {
-                                    umma_bf16_lohi_pred(d_tmem, a_cur, hiA, b_cur, hiB, idesc, accum);
-                                    umma_bf16_lohi<true>(d_tmem, a_cur + 2, hiA, b_cur + 2, hiB, idesc);
-                                    umma_bf16_lohi<true>(d_tmem, a_cur + 4, hiA, b_cur + 4, hiB, idesc);
-                                    umma_bf16_lohi<true>(d_tmem, a_cur + 6, hiA, b_cur + 6, hiB, idesc);
+#pragma unroll
+                                    for (int sub = 0; sub < kSub; ++sub) {
+                                        const uint32_t d = d_tmem + sub * NT, as = a_cur + sub * kSubStep;
+                                        umma_bf16_lohi_pred(d, as, hiA, b_cur, hiB, idesc, accum);
+                                        umma_bf16_lohi<true>(d, as + 2, hiA, b_cur + 2, hiB, idesc);
+                                        umma_bf16_lohi<true>(d, as + 4, hiA, b_cur + 4, hiB, idesc);
+                                        umma_bf16_lohi<true>(d, as + 6, hiA, b_cur + 6, hiB, idesc);
+                                    }
                                     accum = 1u;
                                     a_cur += 128 >> 4;
                                     b_cur += kBTap >> 4;
@@ -208,25 +220,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                         __syncwarp();
                     } else {
 #pragma unroll 1
-                        for (int g = 0; g < 3; ++g) {
+                        for (int g = 0; g < 9 / kBG; ++g) {
                             mbar_wait(bar_fullB + sb * 8, pb);
                             tc_fence_after();
-                            const uint32_t a_row = a_base + ((g * kHaloPitch) >> 4);
                             const uint32_t b_base = umma_desc_lo(ringB + sb * kBStage);
                             if (elect_one()) {
-                                uint32_t a_cur = a_row, b_cur = b_base, accum = (cb > 0 || g > 0) ? 1u : 0u;
+                                uint32_t b_cur = b_base, accum = (cb > 0 || g > 0) ? 1u : 0u;
 #pragma unroll 1
-                                for (int t = 0; t < 3; ++t) {
-                                    umma_bf16_lohi_pred(d_tmem, a_cur, hiA, b_cur, hiB, idesc, accum);
-                                    umma_bf16_lohi<true>(d_tmem, a_cur + 2, hiA, b_cur + 2, hiB, idesc);
-                                    umma_bf16_lohi<true>(d_tmem, a_cur + 4, hiA, b_cur + 4, hiB, idesc);
-                                    umma_bf16_lohi<true>(d_tmem, a_cur + 6, hiA, b_cur + 6, hiB, idesc);
+                                for (int t = 0; t < kBG; ++t) {
+                                    const int tap = g * kBG + t, ky = (tap * 11) >> 5, kx = tap - 3 * ky;
+                                    const uint32_t a_cur = a_base + ((ky * kHaloPitch + kx * 128) >> 4);
+#pragma unroll
+                                    for (int sub = 0; sub < kSub; ++sub) {
+                                        const uint32_t d = d_tmem + sub * NT, as = a_cur + sub * kSubStep;
+                                        umma_bf16_lohi_pred(d, as, hiA, b_cur, hiB, idesc, accum);
+                                        umma_bf16_lohi<true>(d, as + 2, hiA, b_cur + 2, hiB, idesc);
+                                        umma_bf16_lohi<true>(d, as + 4, hiA, b_cur + 4, hiB, idesc);
+                                        umma_bf16_lohi<true>(d, as + 6, hiA, b_cur + 6, hiB, idesc);
+                                    }
                                     accum = 1u;
-                                    a_cur += 128 >> 4;
                                     b_cur += kBTap >> 4;
                                 }
                                 umma_commit(bar_emptyB + sb * 8);
-                                if (g == 2) umma_commit(bar_emptyA + sa * 8);
+                                if (g == 9 / kBG - 1) umma_commit(bar_emptyA + sa * 8);
                             }
                             __syncwarp();
                             if (++sb == b_stages) { sb = 0; pb ^= 1; }
@@ -296,9 +312,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const int ty = m % a.tiles_y;
             const int b = m / a.tiles_y;
             const int r = q * 32 + lane;
-            const int y = ty * a.TH + (r >> a.lgTW), x = tx * a.TW + (r & (a.TW - 1));
-            const bool valid = (y < a.H) && (x < a.W);
-            const size_t pix = (static_cast<size_t>(b) * a.H + y) * a.W + x;
             if (a.stats && b != stat_b) {
                 if (stat_b >= 0) flush_stats(stat_b);
                 stat_b = b;
@@ -306,69 +319,78 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
             mbar_wait(bar_tfull + acc * 8, pacc);
             tc_fence_after();
-            uint32_t raw[kSlots][32];
+#pragma unroll 1
+            for (int sub = 0; sub < kSub; ++sub) {
+                const int y = ty * a.TH + sub * kHaloTH + (r >> a.lgTW), x = tx * a.TW + (r & (a.TW - 1));
+                const bool valid = (y < a.H) && (x < a.W);
+                const size_t pix = (static_cast<size_t>(b) * a.H + y) * a.W + x;
+                uint32_t raw[kSlots][32];
 #pragma unroll
-            for (int k = 0; k < kSlots; ++k)
-                tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * NT + (cset + 2 * k) * 32, raw[k]);
-            tmem_ld_wait();
-            // everything this warp needs from the accumulator is in registers: hand the TMEM stage back right away
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + acc * 8);
-#pragma unroll
-            for (int k = 0; k < kSlots; ++k) {
-                const int ch = cset + 2 * k;
-                const int nbase = n0 + ch * 32;
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 bv = *reinterpret_cast<const float4*>(&tail->bias[ch * 32 + j]);
-                    v[j] = __uint_as_float(raw[k][j]) + bv.x; v[j + 1] = __uint_as_float(raw[k][j + 1]) + bv.y;
-                    v[j + 2] = __uint_as_float(raw[k][j + 2]) + bv.z; v[j + 3] = __uint_as_float(raw[k][j + 3]) + bv.w;
+                for (int k = 0; k < kSlots; ++k)
+                    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (acc * kSub + sub) * NT + (cset + 2 * k) * 32,
+                              raw[k]);
+                tmem_ld_wait();
+                if (sub == kSub - 1) {
+                    // everything this warp needs from the accumulators is in registers: hand the TMEM stage back right away
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + acc * 8);
                 }
-                if (a.act == kActGelu) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-                }
-                if (a.vec) {
-                    const float* vp = a.vec + static_cast<size_t>(b) * a.vec_ld + nbase;
+                for (int k = 0; k < kSlots; ++k) {
+                    const int ch = cset + 2 * k;
+                    const int nbase = n0 + ch * 32;
+                    float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4*>(vp + j));
-                        v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+                        const float4 bv = *reinterpret_cast<const float4*>(&tail->bias[ch * 32 + j]);
+                        v[j] = __uint_as_float(raw[k][j]) + bv.x; v[j + 1] = __uint_as_float(raw[k][j + 1]) + bv.y;
+                        v[j + 2] = __uint_as_float(raw[k][j + 2]) + bv.z; v[j + 3] = __uint_as_float(raw[k][j + 3]) + bv.w;
                     }
-                }
-                if (a.res && valid) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(a.res + pix * a.res_ld + nbase);
+                    if (a.act == kActGelu) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint4 u = __ldg(rp + j);
-                        float2 f;
-                        f = unpack_bf16(u.x); v[j * 8 + 0] += f.x; v[j * 8 + 1] += f.y;
-                        f = unpack_bf16(u.y); v[j * 8 + 2] += f.x; v[j * 8 + 3] += f.y;
-                        f = unpack_bf16(u.z); v[j * 8 + 4] += f.x; v[j * 8 + 5] += f.y;
-                        f = unpack_bf16(u.w); v[j * 8 + 6] += f.x; v[j * 8 + 7] += f.y;
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
                     }
-                }
-                if (a.stats && valid) {
+                    if (a.vec) {
+                        const float* vp = a.vec + static_cast<size_t>(b) * a.vec_ld + nbase;
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        float t0 = 0.f, t1 = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) { const float w = v[g * 8 + j]; t0 += w; t1 = fmaf(w, w, t1); }
-                        sacc[k][g] += t0; qacc[k][g] += t1;
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 bv = __ldg(reinterpret_cast<const float4*>(vp + j));
+                            v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+                        }
                     }
-                }
-                if (valid) {
-                    uint4* op = reinterpret_cast<uint4*>(a.out + pix * a.out_ld + nbase);
+                    if (a.res && valid) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(a.res + pix * a.res_ld + nbase);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 u;
-                        u.x = pack_bf16(v[j * 8 + 0], v[j * 8 + 1]);
-                        u.y = pack_bf16(v[j * 8 + 2], v[j * 8 + 3]);
-                        u.z = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]);
-                        u.w = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
-                        op[j] = u;
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 u = __ldg(rp + j);
+                            float2 f;
+                            f = unpack_bf16(u.x); v[j * 8 + 0] += f.x; v[j * 8 + 1] += f.y;
+                            f = unpack_bf16(u.y); v[j * 8 + 2] += f.x; v[j * 8 + 3] += f.y;
+                            f = unpack_bf16(u.z); v[j * 8 + 4] += f.x; v[j * 8 + 5] += f.y;
+                            f = unpack_bf16(u.w); v[j * 8 + 6] += f.x; v[j * 8 + 7] += f.y;
+                        }
+                    }
+                    if (a.stats && valid) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) { const float w = v[g * 8 + j]; t0 += w; t1 = fmaf(w, w, t1); }
+                            sacc[k][g] += t0; qacc[k][g] += t1;
+                        }
+                    }
+                    if (valid) {
+                        uint4* op = reinterpret_cast<uint4*>(a.out + pix * a.out_ld + nbase);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 u;
+                            u.x = pack_bf16(v[j * 8 + 0], v[j * 8 + 1]);
+                            u.y = pack_bf16(v[j * 8 + 2], v[j * 8 + 3]);
+                            u.z = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]);
+                            u.w = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
+                            op[j] = u;
+                        }
                     }
                 }
             }
@@ -381,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc<2 * NT>(tmem_base);
+        tmem_dealloc<2 * kSub * NT>(tmem_base);
     }
 }
 
@@ -454,16 +476,17 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     a.B = d.B; a.H = d.H; a.W = d.W;
     int TW = d.TW;
     if (TW == 0) {
-        if (d.mode == kHalo1) TW = kHaloTW;
+        if (d.mode == kHalo1 || d.mode == kHalo2) TW = kHaloTW;
         else TW = d.W >= 64 ? 64 : (d.W >= 32 ? 32 : (d.W >= 16 ? 16 : 8));
     }
     NDIFF_REQUIRE(TW >= 8 && TW <= 128 && (TW & (TW - 1)) == 0, "tile width must be a power of two in [8,128]");
-    a.TW = TW; a.TH = 128 / TW; a.lgTW = ilog2(TW);
+    const int sub = d.mode == kHalo2 ? 2 : 1;
+    a.TW = TW; a.TH = sub * (128 / TW); a.lgTW = ilog2(TW);
     a.tiles_x = (d.W + a.TW - 1) / a.TW;
     a.tiles_y = (d.H + a.TH - 1) / a.TH;
     a.cb0 = d.C0 / 64; a.cb1 = d.C1 / 64;
-    const bool halo1 = d.mode == kHalo1;
-    NDIFF_REQUIRE(d.mode == kDirect || d.mode == kS2D || d.mode == kHalo1, "unknown convolution mode");
+    const bool halo1 = d.mode == kHalo1 || d.mode == kHalo2;
+    NDIFF_REQUIRE(d.mode == kDirect || d.mode == kS2D || halo1, "unknown convolution mode");
     NDIFF_REQUIRE(!halo1 || TW == kHaloTW, "halo mode needs TW == 8 (one 8-row UMMA group per output row)");
     if (halo1) { a.taps_y = 3; a.taps_x = 3; a.pad_y = 1; a.pad_x = 1; }
     else if (d.mode == kS2D) { a.taps_y = 2; a.taps_x = 2; a.pad_y = 0; a.pad_x = 0; }
@@ -471,8 +494,13 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     a.n_tiles = d.Cout / NT;
     a.total_tiles = d.B * a.tiles_y * a.tiles_x * a.n_tiles;
     const int b_tap = NT * 128;                          // one [NT x 64] weight block
-    const int b_stage = (halo1 ? 3 : 1) * b_tap;         // streamed weights: halo mode moves one kernel row of taps per stage
-    if (halo1) {
+    const int b_stage = (halo1 ? halo_btaps(NT, sub) : 1) * b_tap;   // streamed weights: bytes per ring stage
+    if (d.mode == kHalo2) {
+        a.a_copy_bytes = kHaloCopy2;
+        a.a_stage_bytes = kHaloStage2;
+        a.a_stages = NT == 128 ? 2 : 3;
+        a.b_stages = NT == 128 ? 8 : 3;
+    } else if (halo1) {
         a.a_copy_bytes = kHaloCopy;
         a.a_stage_bytes = kHaloStage;
         a.a_stages = 3;
@@ -497,7 +525,7 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     a.b_resident = (slice + 2 * a.a_stage_bytes <= budget && m_per_cta >= 2 && slice < (1 << 20)) ? 1 : 0;
     if (a.b_resident) {
         int st = (budget - slice) / a.a_stage_bytes;
-        a.a_stages = st > 8 ? 8 : st;
+        a.a_stages = st > 6 ? 6 : st;
         a.b_stages = 1;
         a.b_region_bytes = slice;
     } else {
@@ -580,16 +608,20 @@ int conv_gemm_init() {
     NDIFF_CUDA_OK((opt_in<128, kS2D>()));
     NDIFF_CUDA_OK((opt_in<64, kHalo1>()));
     NDIFF_CUDA_OK((opt_in<128, kHalo1>()));
+    NDIFF_CUDA_OK((opt_in<64, kHalo2>()));
+    NDIFF_CUDA_OK((opt_in<128, kHalo2>()));
     return 0;
 }
 
 int conv_gemm_launch(const ConvGemmPlan& plan, cudaStream_t stream) {
     const int mode = plan.args.mode;
     if (plan.NT == 64) {
+        if (mode == kHalo2) return launch_res<64, kHalo2>(plan, stream);
         if (mode == kHalo1) return launch_res<64, kHalo1>(plan, stream);
         if (mode == kS2D) return launch_res<64, kS2D>(plan, stream);
         return launch_res<64, kDirect>(plan, stream);
     }
+    if (mode == kHalo2) return launch_res<128, kHalo2>(plan, stream);
     if (mode == kHalo1) return launch_res<128, kHalo1>(plan, stream);
     if (mode == kS2D) return launch_res<128, kS2D>(plan, stream);
     return launch_res<128, kDirect>(plan, stream);

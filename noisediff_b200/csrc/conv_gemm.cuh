@@ -7,6 +7,8 @@ namespace ndiff {
 enum ConvMode : int {
     kDirect = 0,  // every (channel-block, tap) k-block loads its own shifted 128-pixel box (1x1, 7x7-row trick, debug 3x3)
     kS2D = 2,     // 2x2 stride-2 (space-to-depth + 1x1) through a 5-D view of the input
+    kHalo2 = 4,   // kHalo1 with TWO vertically stacked 16x8 sub-tiles per CTA tile (32x8 pixels, one 34x10 halo box, two TMEM
+                  // accumulators): every weight block read from shared memory / streamed from L2 feeds 256 pixels
     kHalo1 = 3,   // 3x3 pad 1: ONE (TH+2)x(TW+2) = 18x10-pixel halo box per 64-channel block (TH x TW = 16 x 8); the nine
                   // taps are 128-byte row shifts of the UMMA start address with SBO = (TW+2)*128.  Works because the
                   // 128-B swizzle is a function of the absolute shared-memory address for both TMA and UMMA

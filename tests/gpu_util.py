@@ -7,7 +7,7 @@ import torch
 
 from noisediff_b200 import _lib
 
-MODE_DIRECT, MODE_S2D, MODE_HALO1 = 0, 2, 3
+MODE_DIRECT, MODE_S2D, MODE_HALO1, MODE_HALO2 = 0, 2, 3, 4
 
 
 def P(t):

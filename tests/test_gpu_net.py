@@ -67,7 +67,7 @@ def test_forward_matches_reference_layer_by_layer():
     assert dict(rows)["pos_emb"] < 1e-5 and dict(rows)["out(v)"] < 2.5e-2
 
 
-@pytest.mark.parametrize("flags", [_lib.FLAG_CONV_DIRECT | _lib.FLAG_NO_GRAPH, _lib.FLAG_INIT_SIMT, _lib.FLAG_UNFUSED])
+@pytest.mark.parametrize("flags", [_lib.FLAG_CONV_DIRECT | _lib.FLAG_NO_GRAPH, _lib.FLAG_INIT_SIMT, _lib.FLAG_UNFUSED, _lib.FLAG_HALO1 | _lib.FLAG_PDL])
 def test_forward_other_conv_staging_modes_agree(flags):
     rows, _, _ = layer_report(flags=flags)
     assert all(e < 3e-2 for _, e in rows), rows

@@ -64,12 +64,12 @@ def test_gemm_epilogue_gelu_residual_vector():
     _check(out, ref)
 
 
-CONV3_CASES = [(2, 32, 32, 64, 0, 64), (1, 16, 16, 128, 64, 128), (1, 8, 8, 256, 0, 256), (2, 24, 40, 64, 64, 64),
+CONV3_CASES = [(8, 32, 32, 512, 256, 512), (8, 64, 64, 256, 0, 256), (2, 32, 32, 64, 0, 64), (1, 16, 16, 128, 64, 128), (1, 8, 8, 256, 0, 256), (2, 24, 40, 64, 64, 64),
                (1, 64, 64, 64, 0, 64), (1, 8, 8, 512, 256, 512), (4, 128, 128, 64, 0, 64), (2, 128, 128, 64, 64, 64),
                (1, 256, 256, 64, 0, 64), (1, 256, 256, 64, 64, 64)]
 
 
-@pytest.mark.parametrize("mode", ["halo", "direct"])
+@pytest.mark.parametrize("mode", ["halo", "halo2", "direct"])
 @pytest.mark.parametrize("case", CONV3_CASES)
 def test_conv3x3(case, mode):
     B, H, W, c0, c1, co = case
@@ -80,7 +80,7 @@ def test_conv3x3(case, mode):
     ref = F.conv2d(torch.cat([x0, x1], 1) if c1 else x0, w, bias, padding=1)
     kw = dict(src1=G.to_nhwc_bf16(x1) if c1 else None, bias=bias)
     if mode != "direct":
-        out = G.conv(G.MODE_HALO1, G.to_nhwc_bf16(x0), G.pack_weight(w), co, **kw)
+        out = G.conv(G.MODE_HALO2 if mode == "halo2" else G.MODE_HALO1, G.to_nhwc_bf16(x0), G.pack_weight(w), co, **kw)
     else:
         out = G.conv(G.MODE_DIRECT, G.to_nhwc_bf16(x0), G.pack_weight(w), co, taps=(3, 3), pad=(1, 1), **kw)
     _check(out, ref)
@@ -119,6 +119,10 @@ def test_groupnorm_stats_and_apply(case):
     res = _rand((B, c, H, W), 16)
     stats = torch.zeros(B, groups, 2, device="cuda", dtype=torch.int64)       # 2^-24 fixed point
     y = G.conv(G.MODE_HALO1, G.to_nhwc_bf16(x), G.pack_weight(w), c, bias=bias, stats=stats, groups=groups)
+    stats3 = torch.zeros_like(stats)
+    y3 = G.conv(G.MODE_HALO2, G.to_nhwc_bf16(x), G.pack_weight(w), c, bias=bias, stats=stats3, groups=groups)
+    assert torch.equal(y3, y)
+    assert ((stats - stats3).abs().double() <= 2 ** 24 * 1e-2 + 1e-7 * stats.abs().double()).all()
     stats2 = torch.zeros_like(stats)
     G.conv(G.MODE_DIRECT, G.to_nhwc_bf16(x), G.pack_weight(w), c, bias=bias, stats=stats2, groups=groups, tile_w=16,
            taps=(3, 3), pad=(1, 1))
