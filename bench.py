@@ -231,8 +231,14 @@ def main():
     n_conv = sum(1 for n, t_, f in rows if is_conv(n, f))
     c3_ms = sum(t_ for n, t_, f in rows if f > 0 and (".proj" in n and "block" in n or n.endswith(".3.1") and n.startswith("ups") or n in ("downs.3.3", "ups.3.3")))
     achieved = conv_fl / (conv_ms * 1e-3) / 1e12
+    traffic = None
+    try:     # dram__bytes_read.sum + dram__bytes_write.sum per conv_gemm launch from the committed ncu pass (profiles/)
+        with open(os.path.join(ROOT, "profiles", "ncu_r1_step_summary.json")) as f:
+            traffic = json.load(f)["conv_gemm"]["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                "traffic": None, "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, all 3x3/1x1/2x2s2 launches of one step)",
+                "traffic": traffic, "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, all 3x3/1x1/2x2s2 launches of one step)",
                 "launches_per_step": n_conv, "avg_launch_us": conv_ms * 1e3 / max(n_conv, 1),
                 "flops_per_launch_avg": conv_fl / max(n_conv, 1), "peak_source": peaks["source"],
                 "conv3x3_frac_of_burst_peak": CONV3_FLOPS_PER_PATCH_STEP * mb / (c3_ms * 1e-3) / 1e12 / peaks["burst"],

@@ -41,15 +41,18 @@ constexpr int kHaloStage2 = (kHaloCopy2 + 1023) / 1024 * 1024;
 constexpr int kSubStep = (kHaloTH * kHaloPitch) >> 4;                    // descriptor offset of the second sub-tile
 // taps per streamed weight stage in halo mode
 __host__ __device__ constexpr int halo_btaps(int nt, int sub) { return (sub == 2 && nt == 128) ? 1 : 3; }
+constexpr int kUpBTaps = 4;                                              // kHaloUp: one stage = the 4 taps of one phase
 
 template <int NT, int MODE, bool RES>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem is only guaranteed 16-B aligned by the ABI; SWIZZLE_128B wants 1024
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    constexpr bool kHalo = MODE == kHalo1 || MODE == kHalo2;
+    constexpr bool kHalo = MODE == kHalo1 || MODE == kHalo2 || MODE == kHaloUp;
+    constexpr bool kUp = MODE == kHaloUp;
     constexpr int kSub = MODE == kHalo2 ? 2 : 1;                 // 128-pixel sub-tiles (TMEM accumulators) per CTA tile
-    constexpr int kBG = kHalo ? halo_btaps(NT, kSub) : 1;        // taps per streamed weight stage
+    constexpr int kHTaps = kUp ? 4 : 9;                          // taps per (channel block[, phase]) in the halo modes
+    constexpr int kBG = kUp ? kUpBTaps : (kHalo ? halo_btaps(NT, kSub) : 1);   // taps per streamed weight stage
     constexpr int kBTap = NT * 128;                              // one [NT x 64] weight block (one tap of one channel block)
     constexpr int kBStage = kBG * kBTap;
     constexpr int kAStage = MODE == kHalo2 ? kHaloStage2 : (kHalo ? kHaloStage : 128 * 128);
@@ -65,7 +68,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int CB = a.cb0 + a.cb1;
-    const int TAPS = kHalo ? 9 : a.taps_y * a.taps_x;
+    const int TAPS = kUp ? 16 : (kHalo ? 9 : a.taps_y * a.taps_x);    // weight blocks per channel block
     const int nt = blockIdx.x % a.n_tiles;                       // this CTA's N tile for its whole life
     // contiguous range of M tiles per CTA: consecutive tiles share halo rows in L2 and (almost always) the sample index,
     // which lets the epilogue keep GroupNorm partial sums in registers across tiles
@@ -109,11 +112,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         pdl_wait();
         for (int mt = m_begin; mt < m_end; ++mt) {
             int m = mt;
+            const int phase = kUp ? (m & 3) : 0;
+            if (kUp) m >>= 2;
             const int tx = m % a.tiles_x; m /= a.tiles_x;
             const int ty = m % a.tiles_y;
             const int b = m / a.tiles_y;
             const int x0 = tx * a.TW, y0 = ty * a.TH;
-            int kcol = 0;
+            int kcol = kUp ? phase * 4 * 64 : 0;
             for (int cb = 0; cb < CB; ++cb) {
                 const CUtensorMap* tm = cb < a.cb0 ? &a.tmA0 : &a.tmA1;
                 const int c0 = (cb < a.cb0 ? cb : cb - a.cb0) * 64;
@@ -128,7 +133,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     if constexpr (!RES) {
                         // weights stream in groups of kBG taps (kBG x [NT x 64]) per stage
 #pragma unroll 1
-                        for (int g = 0; g < 9 / kBG; ++g) {
+                        for (int g = 0; g < kHTaps / kBG; ++g) {
                             mbar_wait(bar_emptyB + sb * 8, pb ^ 1);
                             if (elect_one()) {
                                 mbar_expect_tx(bar_fullB + sb * 8, kBStage);
@@ -141,6 +146,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                             kcol += 64 * kBG;
                             if (++sb == b_stages) { sb = 0; pb ^= 1; }
                         }
+                        if (kUp) kcol += 12 * 64;      // skip the other three phases of this channel block
                     }
                 } else {
                     int ky = 0, kx = 0;
@@ -182,6 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         int sa = 0, pa = 0, sb = 0, pb = 0, acc = 0, pacc = 0;
         if constexpr (RES) mbar_wait(bar_fullB, 0);
         for (int mt = m_begin; mt < m_end; ++mt) {
+            const int py = kUp ? ((mt >> 1) & 1) : 0, px = kUp ? (mt & 1) : 0;      // phase = mt & 3 = py * 2 + px
             mbar_wait(bar_tempty + acc * 8, pacc ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * kSub * NT;
@@ -190,7 +197,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     mbar_wait(bar_fullA + sa * 8, pa);
                     tc_fence_after();
                     const uint32_t a_base = umma_desc_lo(ringA + sa * kAStage);
-                    if constexpr (RES) {
+                    if constexpr (RES && kUp) {
+                        const uint32_t b_base = umma_desc_lo(ringB + (cb * 16 + (py * 2 + px) * 4) * kBTap);
+                        if (elect_one()) {
+                            uint32_t b_cur = b_base, accum = cb > 0 ? 1u : 0u;
+#pragma unroll 1
+                            for (int t = 0; t < 4; ++t) {
+                                const uint32_t a_cur = a_base + (((py + (t >> 1)) * kHaloPitch + (px + (t & 1)) * 128) >> 4);
+                                umma_bf16_lohi_pred(d_tmem, a_cur, hiA, b_cur, hiB, idesc, accum);
+                                umma_bf16_lohi<true>(d_tmem, a_cur + 2, hiA, b_cur + 2, hiB, idesc);
+                                umma_bf16_lohi<true>(d_tmem, a_cur + 4, hiA, b_cur + 4, hiB, idesc);
+                                umma_bf16_lohi<true>(d_tmem, a_cur + 6, hiA, b_cur + 6, hiB, idesc);
+                                accum = 1u;
+                                b_cur += kBTap >> 4;
+                            }
+                            umma_commit(bar_emptyA + sa * 8);
+                        }
+                        __syncwarp();
+                    } else if constexpr (RES) {
                         const uint32_t b_base = umma_desc_lo(ringB + cb * 9 * kBTap);
                         if (elect_one()) {
                             // rolled tap loops on purpose: unrolled, ptxas hoists all 72 descriptor updates ahead of the
@@ -220,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                         __syncwarp();
                     } else {
 #pragma unroll 1
-                        for (int g = 0; g < 9 / kBG; ++g) {
+                        for (int g = 0; g < kHTaps / kBG; ++g) {
                             mbar_wait(bar_fullB + sb * 8, pb);
                             tc_fence_after();
                             const uint32_t b_base = umma_desc_lo(ringB + sb * kBStage);
@@ -228,7 +252,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                                 uint32_t b_cur = b_base, accum = (cb > 0 || g > 0) ? 1u : 0u;
 #pragma unroll 1
                                 for (int t = 0; t < kBG; ++t) {
-                                    const int tap = g * kBG + t, ky = (tap * 11) >> 5, kx = tap - 3 * ky;
+                                    const int tap = g * kBG + t;
+                                    const int ky = kUp ? py + (tap >> 1) : (tap * 11) >> 5, kx = kUp ? px + (tap & 1) : tap - 3 * ky;
                                     const uint32_t a_cur = a_base + ((ky * kHaloPitch + kx * 128) >> 4);
 #pragma unroll
                                     for (int sub = 0; sub < kSub; ++sub) {
@@ -242,7 +267,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                                     b_cur += kBTap >> 4;
                                 }
                                 umma_commit(bar_emptyB + sb * 8);
-                                if (g == 9 / kBG - 1) umma_commit(bar_emptyA + sa * 8);
+                                if (g == kHTaps / kBG - 1) umma_commit(bar_emptyA + sa * 8);
                             }
                             __syncwarp();
                             if (++sb == b_stages) { sb = 0; pb ^= 1; }
@@ -308,6 +333,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         int acc = 0, pacc = 0;
         for (int mt = m_begin; mt < m_end; ++mt) {
             int m = mt;
+            const int phase = kUp ? (m & 3) : 0;
+            if (kUp) m >>= 2;
             const int tx = m % a.tiles_x; m /= a.tiles_x;
             const int ty = m % a.tiles_y;
             const int b = m / a.tiles_y;
@@ -323,7 +350,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             for (int sub = 0; sub < kSub; ++sub) {
                 const int y = ty * a.TH + sub * kHaloTH + (r >> a.lgTW), x = tx * a.TW + (r & (a.TW - 1));
                 const bool valid = (y < a.H) && (x < a.W);
-                const size_t pix = (static_cast<size_t>(b) * a.H + y) * a.W + x;
+                // kHaloUp writes output pixel (2y + py, 2x + px) of the [B, 2H, 2W] grid
+                const size_t pix = kUp ? (static_cast<size_t>(b) * 2 * a.H + 2 * y + (phase >> 1)) * (2 * a.W) + 2 * x + (phase & 1)
+                                       : (static_cast<size_t>(b) * a.H + y) * a.W + x;
                 uint32_t raw[kSlots][32];
 #pragma unroll
                 for (int k = 0; k < kSlots; ++k)
@@ -476,7 +505,7 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     a.B = d.B; a.H = d.H; a.W = d.W;
     int TW = d.TW;
     if (TW == 0) {
-        if (d.mode == kHalo1 || d.mode == kHalo2) TW = kHaloTW;
+        if (d.mode == kHalo1 || d.mode == kHalo2 || d.mode == kHaloUp) TW = kHaloTW;
         else TW = d.W >= 64 ? 64 : (d.W >= 32 ? 32 : (d.W >= 16 ? 16 : 8));
     }
     NDIFF_REQUIRE(TW >= 8 && TW <= 128 && (TW & (TW - 1)) == 0, "tile width must be a power of two in [8,128]");
@@ -485,21 +514,28 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     a.tiles_x = (d.W + a.TW - 1) / a.TW;
     a.tiles_y = (d.H + a.TH - 1) / a.TH;
     a.cb0 = d.C0 / 64; a.cb1 = d.C1 / 64;
-    const bool halo1 = d.mode == kHalo1 || d.mode == kHalo2;
+    const bool halo1 = d.mode == kHalo1 || d.mode == kHalo2 || d.mode == kHaloUp;
+    const bool up = d.mode == kHaloUp;
     NDIFF_REQUIRE(d.mode == kDirect || d.mode == kS2D || halo1, "unknown convolution mode");
     NDIFF_REQUIRE(!halo1 || TW == kHaloTW, "halo mode needs TW == 8 (one 8-row UMMA group per output row)");
-    if (halo1) { a.taps_y = 3; a.taps_x = 3; a.pad_y = 1; a.pad_x = 1; }
+    if (up) { a.taps_y = 4; a.taps_x = 4; a.pad_y = 1; a.pad_x = 1; }      // 16 weight blocks per channel block (4 phases x 4 taps)
+    else if (halo1) { a.taps_y = 3; a.taps_x = 3; a.pad_y = 1; a.pad_x = 1; }
     else if (d.mode == kS2D) { a.taps_y = 2; a.taps_x = 2; a.pad_y = 0; a.pad_x = 0; }
     else { a.taps_y = d.taps_y; a.taps_x = d.taps_x; a.pad_y = d.pad_y; a.pad_x = d.pad_x; }
     a.n_tiles = d.Cout / NT;
-    a.total_tiles = d.B * a.tiles_y * a.tiles_x * a.n_tiles;
+    a.total_tiles = d.B * a.tiles_y * a.tiles_x * a.n_tiles * (up ? 4 : 1);
     const int b_tap = NT * 128;                          // one [NT x 64] weight block
-    const int b_stage = (halo1 ? halo_btaps(NT, sub) : 1) * b_tap;   // streamed weights: bytes per ring stage
+    const int b_stage = (up ? kUpBTaps : (halo1 ? halo_btaps(NT, sub) : 1)) * b_tap;   // streamed weights: bytes per ring stage
     if (d.mode == kHalo2) {
         a.a_copy_bytes = kHaloCopy2;
         a.a_stage_bytes = kHaloStage2;
         a.a_stages = NT == 128 ? 2 : 3;
         a.b_stages = NT == 128 ? 8 : 3;
+    } else if (up) {
+        a.a_copy_bytes = kHaloCopy;
+        a.a_stage_bytes = kHaloStage;
+        a.a_stages = 3;
+        a.b_stages = NT == 128 ? 2 : 4;
     } else if (halo1) {
         a.a_copy_bytes = kHaloCopy;
         a.a_stage_bytes = kHaloStage;
@@ -610,17 +646,21 @@ int conv_gemm_init() {
     NDIFF_CUDA_OK((opt_in<128, kHalo1>()));
     NDIFF_CUDA_OK((opt_in<64, kHalo2>()));
     NDIFF_CUDA_OK((opt_in<128, kHalo2>()));
+    NDIFF_CUDA_OK((opt_in<64, kHaloUp>()));
+    NDIFF_CUDA_OK((opt_in<128, kHaloUp>()));
     return 0;
 }
 
 int conv_gemm_launch(const ConvGemmPlan& plan, cudaStream_t stream) {
     const int mode = plan.args.mode;
     if (plan.NT == 64) {
+        if (mode == kHaloUp) return launch_res<64, kHaloUp>(plan, stream);
         if (mode == kHalo2) return launch_res<64, kHalo2>(plan, stream);
         if (mode == kHalo1) return launch_res<64, kHalo1>(plan, stream);
         if (mode == kS2D) return launch_res<64, kS2D>(plan, stream);
         return launch_res<64, kDirect>(plan, stream);
     }
+    if (mode == kHaloUp) return launch_res<128, kHaloUp>(plan, stream);
     if (mode == kHalo2) return launch_res<128, kHalo2>(plan, stream);
     if (mode == kHalo1) return launch_res<128, kHalo1>(plan, stream);
     if (mode == kS2D) return launch_res<128, kS2D>(plan, stream);

@@ -7,6 +7,11 @@ namespace ndiff {
 enum ConvMode : int {
     kDirect = 0,  // every (channel-block, tap) k-block loads its own shifted 128-pixel box (1x1, 7x7-row trick, debug 3x3)
     kS2D = 2,     // 2x2 stride-2 (space-to-depth + 1x1) through a 5-D view of the input
+    kHaloUp = 5,  // nearest x2 upsample + 3x3 pad 1 (Upsample, Diffusion_arch.py:72-76) WITHOUT materialising the upsampled
+                  // tensor: output phase (py, px) of pixel (2y+py, 2x+px) is a 2x2 convolution of the low-resolution input
+                  // with pre-summed weights (rows {y-1: w0, y: w1+w2} for py = 0, {y: w0+w1, y+1: w2} for py = 1; same in x).
+                  // Tiles walk (low-res 16x8 tile, phase); the halo box is the kHalo1 one.  4/9 of the direct-form MACs.
+                  // Weights: [Cout][cblk][phase(4)][tap(4)][64].  H, W in the descriptor are the LOW-resolution size.
     kHalo2 = 4,   // kHalo1 with TWO vertically stacked 16x8 sub-tiles per CTA tile (32x8 pixels, one 34x10 halo box, two TMEM
                   // accumulators): every weight block read from shared memory / streamed from L2 feeds 256 pixels
     kHalo1 = 3,   // 3x3 pad 1: ONE (TH+2)x(TW+2) = 18x10-pixel halo box per 64-channel block (TH x TW = 16 x 8); the nine

@@ -68,6 +68,30 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restri
     }
 }
 
+// Upsample(nearest x2) + conv3x3 as four 2x2 phase convolutions (conv_gemm.cuh kHaloUp):
+// dst[co][cblk][phase = py*2+px][tap = dy*2+dx][64]; rows {w0 | w1+w2} for py = 0 and {w0+w1 | w2} for py = 1, same in x.
+__global__ void pack_upconv_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int Cout, int Cin) {
+    const size_t total = static_cast<size_t>(Cout) * Cin * 16;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int kk = static_cast<int>(i % 64);
+        size_t r = i / 64;
+        const int tap = static_cast<int>(r % 4); r /= 4;
+        const int phase = static_cast<int>(r % 4); r /= 4;
+        const int cb = static_cast<int>(r % (Cin / 64));
+        const int co = static_cast<int>(r / (Cin / 64));
+        const int ci = cb * 64 + kk, py = phase >> 1, px = phase & 1, dy = tap >> 1, dx = tap & 1;
+        // taps of the 3x3 kernel that read low-res row y - 1 + py + dy: py=0: {0},{1,2}; py=1: {0,1},{2}
+        const int ky0 = py == 0 ? (dy == 0 ? 0 : 1) : (dy == 0 ? 0 : 2), ky1 = py == 0 ? (dy == 0 ? 0 : 2) : (dy == 0 ? 1 : 2);
+        const int kx0 = px == 0 ? (dx == 0 ? 0 : 1) : (dx == 0 ? 0 : 2), kx1 = px == 0 ? (dx == 0 ? 0 : 2) : (dx == 0 ? 1 : 2);
+        const float* w = src + (static_cast<size_t>(co) * Cin + ci) * 9;
+        float acc = 0.f;
+        for (int ky = ky0; ky <= ky1; ++ky)
+            for (int kx = kx0; kx <= kx1; ++kx) acc += w[ky * 3 + kx];
+        dst[i] = __float2bfloat16_rn(acc);
+    }
+}
+
 __global__ void init_conv_pack_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout) {
     // dst[tap(49)][ci(4)][co]  <-  src[co][ci][7][7]
     const int total = Cout * 4 * 49;
@@ -365,6 +389,15 @@ int finalize(ndiff_engine* e, cudaStream_t s) {
     for (int i = 0; i < 3; ++i) {
         if (pack_conv(e, "downs." + std::to_string(i) + ".3.1", d[i + 1], d[i], 1, true, s)) return 1;
         if (pack_conv(e, "ups." + std::to_string(i) + ".3.1", d[3 - i], d[4 - i], 3, false, s)) return 1;
+        {   // the same layer in the fused nearest-x2 form (four 2x2 phase kernels)
+            const std::string n = "ups." + std::to_string(i) + ".3.1";
+            const int co = d[3 - i], ci = d[4 - i];
+            bf16* dst = e->packed.count(n + "#up") ? e->packed[n + "#up"] : nullptr;
+            if (!dst && e->alloc(&dst, static_cast<size_t>(co) * ci * 16)) return 1;
+            pack_upconv_weight_kernel<<<256, 256, 0, s>>>(e->pf(n + ".weight"), dst, co, ci);
+            NDIFF_CUDA_OK(cudaGetLastError());
+            e->packed[n + "#up"] = dst;
+        }
     }
     if (pack_conv(e, "downs.3.3", d[4], d[3], 3, false, s)) return 1;
     if (pack_conv(e, "ups.3.3", d[0], d[1], 3, false, s)) return 1;
@@ -698,7 +731,25 @@ int build_plan(ndiff_engine* e) {
         b.drop(a1); b.drop(sk);
         Act a3 = b.attn(p + ".2", a2);
         b.drop(a2);
-        if (i < 3) {
+        if (i < 3 && b.fused) {
+            // Upsample(nearest x2) + conv3x3 in one kernel: four 2x2 phase convolutions on the low-resolution tensor
+            Act out = b.make(ci, a3.H * 2, a3.W * 2);
+            if (b.err) return 1;
+            ConvGemmDesc d;
+            d.mode = kHaloUp; d.B = B; d.H = a3.H; d.W = a3.W;
+            d.src0 = a3.p; d.C0 = a3.C;
+            d.weight = e->packed.at(p + ".3.1#up"); d.Cout = ci; d.bias = e->pf(p + ".3.1.bias");
+            d.out = out.p; d.out_ld = ci;
+            auto plan = std::make_shared<ConvGemmPlan>();
+            if (conv_gemm_plan(d, e->num_sms, plan.get())) return 1;
+            Op op; op.name = p + ".3.1";
+            op.flops = 2.0 * B * (4.0 * a3.H * a3.W) * ci * 4.0 * a3.C;      // executed: 4 taps per output pixel
+            op.fn = [plan](cudaStream_t st) { return conv_gemm_launch(*plan, st); };
+            e->net_ops.push_back(op);
+            e->conv_flops += op.flops;
+            b.drop(a3);
+            cur = out;
+        } else if (i < 3) {
             Act up = b.make(co, a3.H * 2, a3.W * 2);
             if (b.err) return 1;
             {

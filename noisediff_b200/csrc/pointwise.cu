@@ -4,6 +4,8 @@
 
 namespace ndiff {
 
+static int g_num_sms = 148;
+
 namespace {
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
@@ -336,70 +338,80 @@ __global__ void __launch_bounds__(256) final_kernel(const FinalArgs a) {
     pdl_wait();
     const int lanes = C >> 3;                                  // lanes cooperating on one pixel (8 for C = 64)
     const int sub = threadIdx.x % lanes;
-    const size_t pix = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) / lanes;
-    const bool live = pix < static_cast<size_t>(a.npix);
-    float o[4] = {0.f, 0.f, 0.f, 0.f};
-    if (live) {
-        float f[8], g[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(a.xf) + pix * lanes + sub), f);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(a.sf) + pix * lanes + sub), g);
+    const float bsum[4] = {a.bs[0] + a.bfin[0], a.bs[1] + a.bfin[1], a.bs[2] + a.bfin[2], a.bs[3] + a.bfin[3]};
+    const size_t ppb = blockDim.x / lanes;                     // pixels per block per pass
+    const size_t npix = static_cast<size_t>(a.npix);
+    const size_t passes = (npix + ppb * gridDim.x - 1) / (ppb * gridDim.x);
+    StepParams sp{};
+    int step = 0, rel = 0;
+    const float* noise = nullptr;
+    float* snap = nullptr;
+    unsigned long long seed = 0ull;
+    if (a.chain) {
+        sp = a.chain->cur; step = a.chain->step; rel = step - a.chain->base_step;   // index into this run's noise / snapshot arrays
+        noise = a.chain->noise; snap = a.chain->snap; seed = a.chain->seed;
+    }
+    for (size_t it = 0; it < passes; ++it) {
+        const size_t pix = (it * gridDim.x + blockIdx.x) * ppb + threadIdx.x / lanes;
+        const bool live = pix < npix;
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        if (live) {
+            float f[8], g[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(a.xf) + pix * lanes + sub), f);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(a.sf) + pix * lanes + sub), g);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float acc = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc += f[j] * sw[k * C + sub * 8 + j] + g[j] * sw[4 * C + k * C + sub * 8 + j];
+                o[k] = acc;
+            }
+        }
+        for (int off = lanes >> 1; off > 0; off >>= 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] += __shfl_xor_sync(0xffffffffu, o[k], off);
+        }
+        if (!live || sub != 0) continue;
+        // reference order: shot_noise (= fc2 out + bias) + read_noise (= final_conv out + bias)
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = o[k] + bsum[k];
+        if (a.v_out) reinterpret_cast<float4*>(a.v_out)[pix] = make_float4(v[0], v[1], v[2], v[3]);
+        if (!a.chain) continue;
+
+        const size_t HW = a.HW, bimg = pix / HW, hw = pix % HW;
+        const size_t nB = npix / HW;
+        const size_t plane0 = ((static_cast<size_t>(rel) * nB + bimg) * 4) * HW + hw;   // NCHW offset of channel 0
+        const float4 xi4 = reinterpret_cast<const float4*>(a.x)[pix];
+        const float xi[4] = {xi4.x, xi4.y, xi4.z, xi4.w};
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        if (sp.sigma != 0.f) {
+            if (noise) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) z[k] = __ldg(noise + plane0 + k * HW);
+            } else {
+                const float4 z4 = philox_normal4(seed, static_cast<unsigned long long>(step) + 1ull, pix);
+                z[0] = z4.x; z[1] = z4.y; z[2] = z4.z; z[3] = z4.w;
+            }
+        }
+        float xn[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            float acc = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc += f[j] * sw[k * C + sub * 8 + j] + g[j] * sw[4 * C + k * C + sub * 8 + j];
-            o[k] = acc;
+            // separate roundings (no FMA contraction) to follow the reference's elementwise torch ops
+            float x0 = __fadd_rn(__fmul_rn(sp.p, xi[k]), __fmul_rn(sp.q, v[k]));
+            if (sp.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+            float m = __fadd_rn(__fmul_rn(sp.a, x0), __fmul_rn(sp.b, xi[k]));
+            if (sp.c != 0.f) {
+                const float eps = __fdiv_rn(__fadd_rn(__fmul_rn(sp.r1, xi[k]), -x0), sp.r2);
+                m = __fadd_rn(m, __fmul_rn(sp.c, eps));
+            }
+            xn[k] = sp.sigma != 0.f ? __fadd_rn(m, __fmul_rn(sp.sigma, z[k])) : m;
         }
-    }
-    for (int off = lanes >> 1; off > 0; off >>= 1) {
+        reinterpret_cast<float4*>(a.x)[pix] = make_float4(xn[0], xn[1], xn[2], xn[3]);
+        if (snap) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) o[k] += __shfl_xor_sync(0xffffffffu, o[k], off);
-    }
-    if (!live || sub != 0) return;
-    // reference order: shot_noise (= fc2 out + bias) + read_noise (= final_conv out + bias)
-    float v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = o[k] + (a.bs[k] + a.bfin[k]);
-    if (a.v_out) reinterpret_cast<float4*>(a.v_out)[pix] = make_float4(v[0], v[1], v[2], v[3]);
-    if (!a.chain) return;
-
-    const StepParams sp = a.chain->cur;
-    const int step = a.chain->step;
-    const int rel = step - a.chain->base_step;                 // index into this run's noise / snapshot arrays
-    const float* noise = a.chain->noise;
-    float* snap = a.chain->snap;
-    const size_t HW = a.HW, bimg = pix / HW, hw = pix % HW;
-    const size_t nB = static_cast<size_t>(a.npix) / HW;
-    const size_t plane0 = ((static_cast<size_t>(rel) * nB + bimg) * 4) * HW + hw;   // NCHW offset of channel 0
-    const float4 xi4 = reinterpret_cast<const float4*>(a.x)[pix];
-    const float xi[4] = {xi4.x, xi4.y, xi4.z, xi4.w};
-    float z[4] = {0.f, 0.f, 0.f, 0.f};
-    if (sp.sigma != 0.f) {
-        if (noise) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) z[k] = __ldg(noise + plane0 + k * HW);
-        } else {
-            const float4 z4 = philox_normal4(a.chain->seed, static_cast<unsigned long long>(step) + 1ull, pix);
-            z[0] = z4.x; z[1] = z4.y; z[2] = z4.z; z[3] = z4.w;
+            for (int k = 0; k < 4; ++k) snap[plane0 + k * HW] = xn[k];
         }
-    }
-    float xn[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        // separate roundings (no FMA contraction) to follow the reference's elementwise torch ops
-        float x0 = __fadd_rn(__fmul_rn(sp.p, xi[k]), __fmul_rn(sp.q, v[k]));
-        if (sp.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
-        float m = __fadd_rn(__fmul_rn(sp.a, x0), __fmul_rn(sp.b, xi[k]));
-        if (sp.c != 0.f) {
-            const float eps = __fdiv_rn(__fadd_rn(__fmul_rn(sp.r1, xi[k]), -x0), sp.r2);
-            m = __fadd_rn(m, __fmul_rn(sp.c, eps));
-        }
-        xn[k] = sp.sigma != 0.f ? __fadd_rn(m, __fmul_rn(sp.sigma, z[k])) : m;
-    }
-    reinterpret_cast<float4*>(a.x)[pix] = make_float4(xn[0], xn[1], xn[2], xn[3]);
-    if (snap) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) snap[plane0 + k * HW] = xn[k];
     }
 }
 
@@ -574,7 +586,6 @@ inline int blocks_for(size_t n, int per_block, int cap = 1 << 20) {
 // launchers
 // ---------------------------------------------------------------------------------------------------------------
 static int g_gn_occ[2][3] = {{0, 0, 0}, {0, 0, 0}};   // resident blocks per SM of each gn_apply variant (pointwise_init)
-static int g_num_sms = 148;
 
 int gn_apply_launch(const GnApplyArgs& a, cudaStream_t s) {
     NDIFF_REQUIRE(a.C % 64 == 0 && a.C <= 512 && a.C % a.G == 0 && (a.C / a.G) % 8 == 0,
@@ -664,7 +675,7 @@ int upsample2x_launch(const bf16* in, bf16* out, int B, int H, int W, int C, cud
 int final_launch(const FinalArgs& a, cudaStream_t s) {
     NDIFF_REQUIRE(a.C == 64 || a.C == 128 || a.C == 256, "final heads: C/8 must be a power of two <= 32");
     const size_t threads = static_cast<size_t>(a.npix) * (a.C / 8);
-    NDIFF_CUDA_OK(launch_pdl(final_kernel, dim3(blocks_for(threads, 256)), dim3(256), 8 * a.C * sizeof(float), s, a));
+    NDIFF_CUDA_OK(launch_pdl(final_kernel, dim3(blocks_for(threads, 256, g_num_sms * 4)), dim3(256), 8 * a.C * sizeof(float), s, a));
     NDIFF_CUDA_OK(cudaGetLastError());
     if (a.chain) {
         NDIFF_CUDA_OK(launch_pdl(chain_advance_kernel, dim3(1), dim3(1), 0, s, a.chain));

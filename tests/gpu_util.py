@@ -7,7 +7,7 @@ import torch
 
 from noisediff_b200 import _lib
 
-MODE_DIRECT, MODE_S2D, MODE_HALO1, MODE_HALO2 = 0, 2, 3, 4
+MODE_DIRECT, MODE_S2D, MODE_HALO1, MODE_HALO2, MODE_HALO_UP = 0, 2, 3, 4, 5
 
 
 def P(t):
@@ -39,12 +39,28 @@ def pack_weight(w: torch.Tensor, s2d: bool = False) -> torch.Tensor:
     return wt.contiguous().to(torch.bfloat16)
 
 
+def pack_upconv_weight(w: torch.Tensor) -> torch.Tensor:
+    """(Cout, Cin, 3, 3) fp32 -> bf16 [Cout][Cin/64][phase(4)][tap(4)][64]: nearest-x2 upsample + conv3x3 (ref
+    Diffusion_arch.py:72-76) as four 2x2 phase convolutions on the low-resolution input with pre-summed taps."""
+    co, ci = w.shape[:2]
+    sets = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
+    out = torch.zeros(co, ci // 64, 4, 4, 64, device=w.device)
+    for py in range(2):
+        for px in range(2):
+            for dy in range(2):
+                for dx in range(2):
+                    ws = w[:, :, sets[py][dy]][:, :, :, sets[px][dx]].sum((2, 3))
+                    out[:, :, py * 2 + px, dy * 2 + dx, :] = ws.reshape(co, ci // 64, 64)
+    return out.contiguous().to(torch.bfloat16)
+
+
 def conv(mode, src0, w_packed, cout, *, src1=None, taps=(1, 1), pad=(0, 0), bias=None, vec=None, res=None, act=0,
-         stats=None, groups=0, force_nt=0, tile_w=0, out_hw=None):
+         stats=None, groups=0, force_nt=0, tile_w=0, out_hw=None, alloc_hw=None):
     """src*: bf16 NHWC.  Returns bf16 NHWC output."""
     B, H, W, C0 = src0.shape
     Ho, Wo = out_hw if out_hw else (H, W)
-    out = torch.empty((B, Ho, Wo, cout), dtype=torch.bfloat16, device=src0.device)
+    Ha, Wa = alloc_hw if alloc_hw else (Ho, Wo)
+    out = torch.empty((B, Ha, Wa, cout), dtype=torch.bfloat16, device=src0.device)
     _lib.check(_lib.lib().ndiff_op_conv(
         mode, B, Ho, Wo, P(src0), C0, P(src1), src1.shape[3] if src1 is not None else 0, taps[0], taps[1], pad[0], pad[1],
         P(w_packed), cout, P(bias), P(vec), vec.shape[1] if vec is not None else 0, P(res), act, P(stats), groups,

@@ -107,6 +107,21 @@ def test_downsample_space_to_depth(case):
     _check(out, ref)
 
 
+@pytest.mark.parametrize("force_nt", [0, 64])
+@pytest.mark.parametrize("case", [(2, 16, 16, 128, 64), (1, 32, 32, 512, 256), (2, 64, 64, 256, 128), (2, 128, 128, 128, 64),
+                                  (1, 24, 40, 64, 64), (8, 32, 32, 512, 256)])
+def test_upsample_conv3x3_phase_form(case, force_nt):
+    """Upsample = nearest x2 then conv3x3 pad 1 (ref Diffusion_arch.py:72-76) as four 2x2 phase convolutions (kHaloUp)."""
+    B, H, W, c, co = case                                 # H, W = low-resolution input size
+    x = _rand((B, c, H, W), 30)
+    w = _rand((co, c, 3, 3), 31, 1.0 / math.sqrt(9 * c))
+    bias = torch.randn(co, device="cuda")
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, bias, padding=1)
+    out = G.conv(G.MODE_HALO_UP, G.to_nhwc_bf16(x), G.pack_upconv_weight(w), co, bias=bias, alloc_hw=(2 * H, 2 * W),
+                 force_nt=force_nt)
+    _check(out, ref)
+
+
 @pytest.mark.parametrize("case", [(2, 32, 32, 64, 8), (2, 16, 16, 128, 8), (1, 8, 8, 512, 8), (2, 32, 32, 64, 2),
                                   (1, 256, 256, 64, 2), (2, 256, 256, 64, 8), (4, 64, 64, 128, 8)])
 def test_groupnorm_stats_and_apply(case):
@@ -122,7 +137,7 @@ def test_groupnorm_stats_and_apply(case):
     stats3 = torch.zeros_like(stats)
     y3 = G.conv(G.MODE_HALO2, G.to_nhwc_bf16(x), G.pack_weight(w), c, bias=bias, stats=stats3, groups=groups)
     assert torch.equal(y3, y)
-    assert ((stats - stats3).abs().double() <= 2 ** 24 * 1e-2 + 1e-7 * stats.abs().double()).all()
+    assert ((stats - stats3).abs().double() <= 2 ** 24 * 1e-2 + 2e-6 * stats.abs().double()).all()   # fp32 partials
     stats2 = torch.zeros_like(stats)
     G.conv(G.MODE_DIRECT, G.to_nhwc_bf16(x), G.pack_weight(w), c, bias=bias, stats=stats2, groups=groups, tile_w=16,
            taps=(3, 3), pad=(1, 1))
@@ -131,7 +146,7 @@ def test_groupnorm_stats_and_apply(case):
     sums = stats.double() / 2 ** 24
     assert torch.allclose(sums[..., 0], grp.sum(-1).double(), rtol=2e-3, atol=2e-2 * math.sqrt(grp.shape[-1]))
     assert torch.allclose(sums[..., 1], (grp ** 2).sum(-1).double(), rtol=2e-3)
-    assert (stats - stats2).abs().max().item() <= 2 ** 24 * 1e-2              # tiling changes only fp32 partial rounding
+    assert ((stats - stats2).abs().double() <= 2 ** 24 * 1e-2 + 2e-6 * stats.abs().double()).all()   # tiling changes only fp32 partial rounding
     out = torch.empty_like(y)
     _lib.check(_lib.lib().ndiff_op_gn_apply(G.P(y), G.P(out), G.P(stats), G.P(gamma), G.P(beta), G.P(ss), 3 * c, c // 2,
                                             None, G.P(G.to_nhwc_bf16(res)), None, B, H * W, c, groups, G.stream()))
