@@ -146,7 +146,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="patches per GPU")
-    ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("NDIFF_MICRO_BATCH", "8")))
+    ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("NDIFF_MICRO_BATCH", "64")))
+    ap.add_argument("--dump-layers", default=None, help="write the per-layer CUDA-event table (name, ms, flops) to this JSON file")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=8)
@@ -225,6 +226,9 @@ def main():
     # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv): live CUDA-event timing of every conv launch -------
     peaks = _peaks()
     rows = eng.time_layers(3)
+    if args.dump_layers and rank == 0:
+        with open(args.dump_layers, "w") as f:
+            json.dump({"micro_batch": mb, "ms_per_step": ms_step, "layers": [(n, t_, f_) for n, t_, f_ in rows]}, f)
     is_conv = lambda n, f: f > 0 and n != "init_conv" and "fused chain" not in n
     conv_ms = sum(t_ for n, t_, f in rows if is_conv(n, f))
     conv_fl = sum(f for n, t_, f in rows if is_conv(n, f))

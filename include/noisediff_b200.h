@@ -125,6 +125,12 @@ NDIFF_API int32_t ndiff_op_conv(int32_t mode, int32_t B, int32_t H, int32_t W, c
                       int32_t C1, int32_t taps_y, int32_t taps_x, int32_t pad_y, int32_t pad_x, const void* weight_packed,
                       int32_t Cout, const float* bias, const float* vec, int32_t vec_ld, const void* res, int32_t act,
                       void* stats, int32_t groups, void* out, int32_t force_nt, int32_t tile_w, void* stream);
+/* Same operator, launched `iters` times back to back after 3 warm-up launches and timed with CUDA events on `stream`
+ * (kernel-variant selection experiments and the per-shape roofline table; blocks until done). */
+NDIFF_API int32_t ndiff_op_conv_time(int32_t mode, int32_t B, int32_t H, int32_t W, const void* src0, int32_t C0, const void* src1,
+                           int32_t C1, int32_t taps_y, int32_t taps_x, int32_t pad_y, int32_t pad_x,
+                           const void* weight_packed, int32_t Cout, const float* bias, void* stats, int32_t groups, void* out,
+                           int32_t force_nt, int32_t tile_w, int32_t iters, float* ms_per_launch, void* stream);
 NDIFF_API int32_t ndiff_op_gn_apply(const void* x, void* out, const void* stats, const float* gamma, const float* beta,
                           const float* ss, int32_t ss_ld, int32_t ss_off, const void* maps, const void* res1,
                           const void* res2, int32_t B, int32_t HW, int32_t C, int32_t G, void* stream);

@@ -53,6 +53,8 @@ _SIGS = {
                                       C.POINTER(C.c_int32), _P]),
     "ndiff_op_conv": (C.c_int32, [C.c_int32] * 4 + [_P, C.c_int32, _P, C.c_int32] + [C.c_int32] * 4 +
                       [_P, C.c_int32, _P, _P, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P, C.c_int32, C.c_int32, _P]),
+    "ndiff_op_conv_time": (C.c_int32, [C.c_int32] * 4 + [_P, C.c_int32, _P, C.c_int32] + [C.c_int32] * 4 +
+                           [_P, C.c_int32, _P, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), _P]),
     "ndiff_op_gn_apply": (C.c_int32, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P] + [C.c_int32] * 4 + [_P]),
     "ndiff_op_layernorm": (C.c_int32, [_P, _P, C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "ndiff_op_pixel_chain": (C.c_int32, [C.c_int32] * 3 + [_P] * 6 + [C.c_int32, _P, _P, _P]),

@@ -1172,10 +1172,10 @@ int32_t ndiff_time_layers(ndiff_engine* e, int32_t iters, float* ms_out, char* n
 }
 
 // ---- single-operator entry points ---------------------------------------------------------------------------
-int32_t ndiff_op_conv(int32_t mode, int32_t B, int32_t H, int32_t W, const void* src0, int32_t C0, const void* src1,
-                      int32_t C1, int32_t taps_y, int32_t taps_x, int32_t pad_y, int32_t pad_x, const void* weight_packed,
-                      int32_t Cout, const float* bias, const float* vec, int32_t vec_ld, const void* res, int32_t act,
-                      void* stats, int32_t groups, void* out, int32_t force_nt, int32_t tile_w, void* stream) {
+static int op_conv_plan(int32_t mode, int32_t B, int32_t H, int32_t W, const void* src0, int32_t C0, const void* src1,
+                        int32_t C1, int32_t taps_y, int32_t taps_x, int32_t pad_y, int32_t pad_x, const void* weight_packed,
+                        int32_t Cout, const float* bias, const float* vec, int32_t vec_ld, const void* res, int32_t act,
+                        void* stats, int32_t groups, void* out, int32_t force_nt, int32_t tile_w, ConvGemmPlan* plan) {
     int dev = 0;
     NDIFF_CUDA_OK(cudaGetDevice(&dev));
     cudaDeviceProp prop;
@@ -1192,9 +1192,43 @@ int32_t ndiff_op_conv(int32_t mode, int32_t B, int32_t H, int32_t W, const void*
     d.out = static_cast<bf16*>(out); d.out_ld = Cout;
     d.act = act; d.stats = static_cast<unsigned long long*>(stats); d.groups = groups;
     d.force_nt = force_nt; d.TW = tile_w;
+    return conv_gemm_plan(d, prop.multiProcessorCount, plan);
+}
+
+int32_t ndiff_op_conv(int32_t mode, int32_t B, int32_t H, int32_t W, const void* src0, int32_t C0, const void* src1,
+                      int32_t C1, int32_t taps_y, int32_t taps_x, int32_t pad_y, int32_t pad_x, const void* weight_packed,
+                      int32_t Cout, const float* bias, const float* vec, int32_t vec_ld, const void* res, int32_t act,
+                      void* stats, int32_t groups, void* out, int32_t force_nt, int32_t tile_w, void* stream) {
     ConvGemmPlan plan;
-    if (conv_gemm_plan(d, prop.multiProcessorCount, &plan)) return 1;
+    if (op_conv_plan(mode, B, H, W, src0, C0, src1, C1, taps_y, taps_x, pad_y, pad_x, weight_packed, Cout, bias, vec, vec_ld,
+                     res, act, stats, groups, out, force_nt, tile_w, &plan)) return 1;
     return conv_gemm_launch(plan, as_stream(stream));
+}
+
+int32_t ndiff_op_conv_time(int32_t mode, int32_t B, int32_t H, int32_t W, const void* src0, int32_t C0, const void* src1,
+                           int32_t C1, int32_t taps_y, int32_t taps_x, int32_t pad_y, int32_t pad_x,
+                           const void* weight_packed, int32_t Cout, const float* bias, void* stats, int32_t groups, void* out,
+                           int32_t force_nt, int32_t tile_w, int32_t iters, float* ms_per_launch, void* stream) {
+    ConvGemmPlan plan;
+    if (op_conv_plan(mode, B, H, W, src0, C0, src1, C1, taps_y, taps_x, pad_y, pad_x, weight_packed, Cout, bias, nullptr, 0,
+                     nullptr, 0, stats, groups, out, force_nt, tile_w, &plan)) return 1;
+    cudaStream_t s = as_stream(stream);
+    cudaEvent_t e0, e1;
+    NDIFF_CUDA_OK(cudaEventCreate(&e0));
+    NDIFF_CUDA_OK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i)
+        if (conv_gemm_launch(plan, s)) return 1;
+    NDIFF_CUDA_OK(cudaEventRecord(e0, s));
+    for (int i = 0; i < iters; ++i)
+        if (conv_gemm_launch(plan, s)) return 1;
+    NDIFF_CUDA_OK(cudaEventRecord(e1, s));
+    NDIFF_CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    NDIFF_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_per_launch = ms / static_cast<float>(iters > 0 ? iters : 1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return 0;
 }
 
 int32_t ndiff_op_gn_apply(const void* x, void* out, const void* stats, const float* gamma, const float* beta,

@@ -60,7 +60,7 @@ class GaussianDiffusion(nn.Module):
     #: steps per engine call; also the granularity at which torch-RNG noise is pre-drawn
     chunk_steps = 25
     #: patches processed together by one engine (L2-residency knob)
-    micro_batch = 8
+    micro_batch = 64
     #: "torch": draw x_T and every z_t from torch's global CUDA generator in the reference's order (ref :381,:371);
     #: "philox": in-kernel counter-based Philox4x32-10, seeded from torch's generator
     noise_source = "torch"
