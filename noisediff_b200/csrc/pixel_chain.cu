@@ -1,12 +1,12 @@
 // noisediff_b200 — fused per-pixel MLP chains on tensor cores (sm_100a).  See pixel_chain.cuh.
 //
-// One CTA = two independent warpgroups of 128 threads.  Each warpgroup walks its own sequence of 128-pixel tiles; thread r
+// One CTA = four independent warpgroups of 128 threads.  Each warpgroup walks its own sequence of 128-pixel tiles; thread r
 // owns pixel r of the tile (= TMEM lane r), so LayerNorm over channels and all epilogue math are thread-local.  A GEMM
 // stage is: the 128 threads write the bf16 A operand [128 x K] into shared memory in the SWIZZLE_128B K-major layout,
 // fence.proxy.async + named barrier, ONE thread issues the tcgen05.mma's against the layer's weights (resident in shared
 // memory for the whole kernel, loaded once by TMA) and commits to an mbarrier, everyone waits and drains the fp32
-// accumulator from TMEM with tcgen05.ld.  Stages of one tile are strictly sequential; the two warpgroups interleave, so one
-// group's tensor-core work and TMEM/shared traffic overlaps the other group's epilogue arithmetic.
+// accumulator from TMEM with tcgen05.ld.  Stages of one tile are strictly sequential; the warpgroups interleave, so one
+// group's tensor-core work and TMEM/shared traffic overlaps the other groups' epilogue arithmetic.
 // Input tiles arrive by TMA (attn) or as coalesced float4 loads (shot); outputs leave by TMA store from a staging block.
 #include "pixel_chain.cuh"
 #include "conv_gemm.cuh"
@@ -20,13 +20,20 @@ namespace {
 
 constexpr int kTile = 128;                 // pixels per tile = TMEM lanes
 constexpr int kBlk = kTile * 128;          // bytes of one [128 x 64] bf16 operand block
-constexpr int kWgBytes = 4 * kBlk;         // per warpgroup: X / staging | A0 | A1 (two K blocks)
+constexpr int kNWG = 3;                    // warpgroups per CTA (each owns 128 TMEM columns and two operand blocks)
+constexpr int kWgBytes = 3 * kBlk;         // per warpgroup: X (input tile by TMA / s1 staging) | A0 | A1 (A0, A1 = the two K
+                                           // blocks of the hidden layer; A1 doubles as the staging block of the output store)
+constexpr int kThreads = kNWG * 128;
+constexpr int kTmemCols = kNWG <= 2 ? 256 : 512;    // power of two >= kNWG * 128
 
 struct ChainTail {
-    uint64_t bar_w, bar_x[2], bar_mma[2];
+    uint64_t bar_w, bar_x[kNWG], bar_mma[kNWG];
     uint32_t tmem_base;
     uint32_t pad_;
     float fvec[kChainShotFloats];
+    // per warpgroup, per sample slot (a 128-pixel tile touches at most two samples): [0] the collapsed attention vector c,
+    // [1] b2 + c (bias of ff.net.2 plus the residual's per-sample part)
+    alignas(16) float ctab[kNWG][2][2][64];
 };
 
 __device__ __forceinline__ uint32_t swz(uint32_t blk, int r, int j) {   // 16-byte chunk j of row r in a SWIZZLE_128B block
@@ -69,15 +76,20 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_blk, uint
     }
 }
 
+// kNWG warpgroups keep that many independent tiles in flight per SM (the chain of one tile is strictly sequential: operand
+// write -> barrier -> MMA -> TMEM drain, six times for the shot program), so the tensor-core round trips and the epilogue
+// arithmetic of different tiles overlap.  384 threads cap the kernel at 168 registers: the pixel's input row stays packed
+// (xr, 32 registers), accumulators are drained 32 columns at a time, and LayerNorm re-derives y = x + c per pass instead of
+// holding 64 floats.
 template <int PROG>
-__global__ void __launch_bounds__(256, 1) pixel_chain_kernel(const __grid_constant__ ChainArgs a) {
+__global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_constant__ ChainArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr bool kShot = PROG == kProgShot;
     constexpr int kWRows = kShot ? kChainShotRows : kChainAttnRows;
     constexpr int kNF = kShot ? kChainShotFloats : kChainAttnFloats;
     constexpr int kWBytes = kWRows * 128;
-    ChainTail* tail = reinterpret_cast<ChainTail*>(smem + kWBytes + 2 * kWgBytes);
+    ChainTail* tail = reinterpret_cast<ChainTail*>(smem + kWBytes + kNWG * kWgBytes);
 
     const int tid = threadIdx.x, wg = tid >> 7, r = tid & 127, q = (tid >> 5) & 3;
     const uint32_t sW = smem_u32(smem);
@@ -86,8 +98,8 @@ __global__ void __launch_bounds__(256, 1) pixel_chain_kernel(const __grid_consta
     const uint32_t sWattn = sW + (kShot ? 128 * 128 : 0);
     const uint32_t sW1 = sWattn, sW2 = sW1 + 128 * 128, sWp = sW2 + 128 * 128, sWm1 = sWp + 64 * 128, sWm2 = sWm1 + 64 * 128;
     const float* fA = tail->fvec + (kShot ? 128 : 0);
-    const float* f_lng = fA, *f_lnb = fA + 64, *f_b1 = fA + 128, *f_b2 = fA + 256, *f_bp = fA + 320, *f_bm1 = fA + 384,
-               *f_bm2 = fA + 448;
+    // (the first 128 floats of the attention block are reserved: LayerNorm's affine is folded into W1 / b1 by the packer)
+    const float* f_b1 = fA + 128, *f_b2 = fA + 256, *f_bp = fA + 320, *f_bm1 = fA + 384, *f_bm2 = fA + 448;
     const uint32_t bar_w = smem_u32(&tail->bar_w), bar_x = smem_u32(&tail->bar_x[wg]), bar_mma = smem_u32(&tail->bar_mma[wg]);
 
     if (tid == 0) {
@@ -95,11 +107,11 @@ __global__ void __launch_bounds__(256, 1) pixel_chain_kernel(const __grid_consta
         tma_prefetch_desc(&a.tmOut);
         if (kShot) tma_prefetch_desc(&a.tmOut2); else tma_prefetch_desc(&a.tmX);
         mbar_init(&tail->bar_w, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&tail->bar_x[i], 1); mbar_init(&tail->bar_mma[i], 1); }
+        for (int i = 0; i < kNWG; ++i) { mbar_init(&tail->bar_x[i], 1); mbar_init(&tail->bar_mma[i], 1); }
         fence_mbar_init();
     }
-    if (tid < 32) tmem_alloc<256>(&tail->tmem_base);
-    for (int i = tid; i < kNF; i += 256) tail->fvec[i] = __ldg(a.fvec + i);
+    if (tid < 32) tmem_alloc<kTmemCols>(&tail->tmem_base);
+    for (int i = tid; i < kNF; i += kThreads) tail->fvec[i] = __ldg(a.fvec + i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -112,13 +124,14 @@ __global__ void __launch_bounds__(256, 1) pixel_chain_kernel(const __grid_consta
     }
     pdl_trigger();
     pdl_wait();          // weights / parameters above are constants; everything below touches the previous kernel's output
-    const int tile0 = blockIdx.x * 2 + wg, tile_step = gridDim.x * 2;
+    const int tile0 = blockIdx.x * kNWG + wg, tile_step = gridDim.x * kNWG;
     if (!kShot && r == 0 && tile0 < a.n_tiles) {
         mbar_expect_tx(bar_x, kBlk);
         tma_load_2d(sX, &a.tmX, bar_x, 0, tile0 * kTile);
     }
     uint32_t xph = 0, mph = 0;
     bool w_ready = false;
+    int tab_b0 = -1, tab_b1 = -1;            // samples currently held by this warpgroup's ctab slots
 
     // one GEMM stage: publish my operand writes, one thread issues, everybody waits for the accumulator
 #define NDIFF_STAGE(ISSUE)                                                   \
@@ -139,52 +152,63 @@ __global__ void __launch_bounds__(256, 1) pixel_chain_kernel(const __grid_consta
 
     for (int tile = tile0; tile < a.n_tiles; tile += tile_step) {
         const int p = tile * kTile + r;
-        const int pc = p < a.npix ? p : a.npix - 1;
-        const float* cvp = a.cvec + static_cast<size_t>(pc / a.HW) * a.cvec_ld;
+        const bool live = p < a.npix;
+        const int pc = live ? p : a.npix - 1;
         uint32_t xr[32];                      // this pixel's 64-channel attention-block input, packed bf16
-        float y[64];
+        // per-sample vectors of the tile's (at most two) samples -> shared memory; refreshed only when the samples change.
+        // Nobody still reads the old table: every thread's last read precedes the previous tile's proj_out stage barrier.
+        const int b_first = (tile * kTile) / a.HW;
+        {
+            const int last = tile * kTile + kTile - 1;
+            const int b_last = (last < a.npix ? last : a.npix - 1) / a.HW;
+            if (b_first != tab_b0 || b_last != tab_b1) {
+                tab_b0 = b_first; tab_b1 = b_last;
+                const int slot = r >> 6, j = r & 63;
+                const float cj = __ldg(a.cvec + static_cast<size_t>(slot ? b_last : b_first) * a.cvec_ld + j);
+                tail->ctab[wg][slot][0][j] = cj;
+                tail->ctab[wg][slot][1][j] = cj + f_b2[j];
+                named_bar_sync(1 + wg, 128);
+            }
+        }
+        const float* ct = &tail->ctab[wg][(pc / a.HW) != b_first ? 1 : 0][0][0];      // c at ct[j], b2 + c at ct[64 + j]
 
-        // staging blocks (X slot, A1 block 0) are read by the previous tile's TMA stores: wait before anyone rewrites them
+        // X (shot) and A1 are sources of the previous tile's TMA stores: they must have been read before anyone rewrites them
+        // (every thread's first write to either comes after the next named barrier, which thread 0 joins after this wait)
         if (r == 0) tma_store_wait_read();
 
         if constexpr (kShot) {
             // ---- shot_mlp1.fc1 on cat[clean, x_t] (ref Diffusion_arch.py:598; clean first) --------------------------
             float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f), x4 = c4;
-            if (p < a.npix) { c4 = __ldg(a.clean + p); x4 = a.x[p]; }
+            if (live) { c4 = __ldg(a.clean + p); x4 = a.x[p]; }
             uint4 u;
             u.x = pack_bf16(c4.x, c4.y); u.y = pack_bf16(c4.z, c4.w); u.z = pack_bf16(x4.x, x4.y); u.w = pack_bf16(x4.z, x4.w);
             sts128(swz(sA0, r, 0), u);
             sts128(swz(sA0, r, 1), make_uint4(0u, 0u, 0u, 0u));
             NDIFF_STAGE(issue_gemm<64>(tmem_d, sA0, sW, 1, 1));
-            {
-                uint32_t raw[2][32];
-                tmem_ld32(tmem_rd, raw[0]);
-                tmem_ld32(tmem_rd + 32, raw[1]);
-                tmem_ld_wait();
 #pragma unroll
-                for (int h = 0; h < 2; ++h) store_half_gelu_f16(sA0, r, h, raw[h], tail->fvec + h * 32);
+            for (int h = 0; h < 2; ++h) {
+                uint32_t raw[32];
+                tmem_ld32(tmem_rd + h * 32, raw);
+                tmem_ld_wait();
+                store_half_gelu_f16(sA0, r, h, raw, tail->fvec + h * 32);
             }
             // ---- shot_mlp1.fc2 -> s1 (stored: it is the branch's residual r_s, ref :599) ------------------------------
             NDIFF_STAGE((issue_gemm<64, true>(tmem_d, sA0, sW + 64 * 128, 1, 4)));
-            {
-                uint32_t raw[2][32];
-                tmem_ld32(tmem_rd, raw[0]);
-                tmem_ld32(tmem_rd + 32, raw[1]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t raw[32];
+                tmem_ld32(tmem_rd + h * 32, raw);
                 tmem_ld_wait();
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const float v0 = __uint_as_float(raw[h][j]) + tail->fvec[64 + h * 32 + j];
-                        const float v1 = __uint_as_float(raw[h][j + 1]) + tail->fvec[64 + h * 32 + j + 1];
-                        xr[h * 16 + j / 2] = pack_bf16(v0, v1);
-                    }
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj)
-                        sts128(swz(sX, r, h * 4 + jj), make_uint4(xr[h * 16 + jj * 4], xr[h * 16 + jj * 4 + 1],
-                                                                   xr[h * 16 + jj * 4 + 2], xr[h * 16 + jj * 4 + 3]));
+                for (int j = 0; j < 32; j += 2) {
+                    const float v0 = __uint_as_float(raw[j]) + tail->fvec[64 + h * 32 + j];
+                    const float v1 = __uint_as_float(raw[j + 1]) + tail->fvec[64 + h * 32 + j + 1];
+                    xr[h * 16 + j / 2] = pack_bf16(v0, v1);
                 }
             }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)      // s1 staged in the X slot; stored by TMA at the next barrier
+                sts128(swz(sX, r, j), make_uint4(xr[j * 4], xr[j * 4 + 1], xr[j * 4 + 2], xr[j * 4 + 3]));
         } else {
             mbar_wait(bar_x, xph);
             xph ^= 1;
@@ -195,30 +219,36 @@ __global__ void __launch_bounds__(256, 1) pixel_chain_kernel(const __grid_consta
             }
         }
 
-        // ---- y = x + c ; A0 = LayerNorm_C(y) * g + b   (AttnBlock.norm2 on the collapsed attention, ref :438-439) ------
+        // ---- y = x + c ; A0 = (y - mean) * rstd   (AttnBlock.norm2 on the collapsed attention, ref :438-439; the affine
+        //      g, b of the LayerNorm lives in W1 / b1).  One pass for the moments, one to normalise; y is re-derived from the
+        //      packed row instead of being held in 64 registers.
         {
-            float sum = 0.f;
+            float sum = 0.f, sq = 0.f;
 #pragma unroll
             for (int j = 0; j < 64; j += 4) {
-                const float4 c4 = __ldg(reinterpret_cast<const float4*>(cvp + j));
+                const float4 c4 = *reinterpret_cast<const float4*>(ct + j);
                 const float2 f0 = unpack_bf16(xr[j / 2]), f1 = unpack_bf16(xr[j / 2 + 1]);
-                y[j] = f0.x + c4.x; y[j + 1] = f0.y + c4.y; y[j + 2] = f1.x + c4.z; y[j + 3] = f1.y + c4.w;
-                sum += (y[j] + y[j + 1]) + (y[j + 2] + y[j + 3]);
+                const float y0 = f0.x + c4.x, y1 = f0.y + c4.y, y2 = f1.x + c4.z, y3 = f1.y + c4.w;
+                sum += (y0 + y1) + (y2 + y3);
+                sq = fmaf(y0, y0, sq); sq = fmaf(y1, y1, sq); sq = fmaf(y2, y2, sq); sq = fmaf(y3, y3, sq);
             }
             const float mean = sum * (1.0f / 64.0f);
-            float sq = 0.f;
-#pragma unroll
-            for (int j = 0; j < 64; ++j) { const float d = y[j] - mean; sq = fmaf(d, d, sq); }
-            const float rstd = rsqrtf(sq * (1.0f / 64.0f) + 1e-5f);
+            const float rstd = rsqrtf(fmaxf(sq * (1.0f / 64.0f) - mean * mean, 0.f) + 1e-5f);
+            const float nb = -mean * rstd;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaf((y[h * 32 + j] - mean) * rstd, f_lng[h * 32 + j], f_lnb[h * 32 + j]);
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 c4 = *reinterpret_cast<const float4*>(ct + h * 32 + j);
+                    const float2 f0 = unpack_bf16(xr[(h * 32 + j) / 2]), f1 = unpack_bf16(xr[(h * 32 + j) / 2 + 1]);
+                    v[j] = fmaf(f0.x + c4.x, rstd, nb); v[j + 1] = fmaf(f0.y + c4.y, rstd, nb);
+                    v[j + 2] = fmaf(f1.x + c4.z, rstd, nb); v[j + 3] = fmaf(f1.y + c4.w, rstd, nb);
+                }
                 store_half(sA0, r, h, v);
             }
         }
-        // ---- FeedForward.net.0: Linear(C, 2C) + GELU   (ref :405-422) -----------------------------------------------------
+        // ---- FeedForward.net.0: Linear(C, 2C) + GELU   (ref :405-422); hidden K block hh -> operand block A0 / A1 ------------
         fence_proxy_async();
         tc_fence_before();
         named_bar_sync(1 + wg, 128);
@@ -239,84 +269,75 @@ __global__ void __launch_bounds__(256, 1) pixel_chain_kernel(const __grid_consta
         mph ^= 1;
         tc_fence_after();
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {       // hidden K block hh = accumulator columns [64 hh, 64 hh + 64)
-            uint32_t raw[2][32];
-            tmem_ld32(tmem_rd + hh * 64, raw[0]);
-            tmem_ld32(tmem_rd + hh * 64 + 32, raw[1]);
-            tmem_ld_wait();
-#pragma unroll
-            for (int h = 0; h < 2; ++h) store_half_gelu_f16(sA1 + hh * kBlk, r, h, raw[h], f_b1 + hh * 64 + h * 32);
-        }
-        // ---- FeedForward.net.2: Linear(2C, C); z = ff + y --------------------------------------------------------------
-        NDIFF_STAGE((issue_gemm<64, true>(tmem_d, sA1, sW2, 2, 4)));
-        {
-            uint32_t raw[2][32];
-            tmem_ld32(tmem_rd, raw[0]);
-            tmem_ld32(tmem_rd + 32, raw[1]);
-            tmem_ld_wait();
+        for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 c4 = __ldg(reinterpret_cast<const float4*>(cvp + h * 32 + j));
-                    const float2 f0 = unpack_bf16(xr[(h * 32 + j) / 2]), f1 = unpack_bf16(xr[(h * 32 + j) / 2 + 1]);
-                    v[j] = __uint_as_float(raw[h][j]) + f_b2[h * 32 + j] + (f0.x + c4.x);
-                    v[j + 1] = __uint_as_float(raw[h][j + 1]) + f_b2[h * 32 + j + 1] + (f0.y + c4.y);
-                    v[j + 2] = __uint_as_float(raw[h][j + 2]) + f_b2[h * 32 + j + 2] + (f1.x + c4.z);
-                    v[j + 3] = __uint_as_float(raw[h][j + 3]) + f_b2[h * 32 + j + 3] + (f1.y + c4.w);
-                }
-                store_half(sA0, r, h, v);
+                uint32_t raw[32];
+                tmem_ld32(tmem_rd + hh * 64 + h * 32, raw);
+                tmem_ld_wait();
+                store_half_gelu_f16(sA0 + hh * kBlk, r, h, raw, f_b1 + hh * 64 + h * 32);
             }
+        }
+        // ---- FeedForward.net.2: Linear(2C, C); z = ff + y --------------------------------------------------------------
+        NDIFF_STAGE((issue_gemm<64, true>(tmem_d, sA0, sW2, 2, 4)));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint32_t raw[32];
+            tmem_ld32(tmem_rd + h * 32, raw);
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 c4 = *reinterpret_cast<const float4*>(ct + 64 + h * 32 + j);      // b2 + c
+                const float2 f0 = unpack_bf16(xr[(h * 32 + j) / 2]), f1 = unpack_bf16(xr[(h * 32 + j) / 2 + 1]);
+                v[j] = __uint_as_float(raw[j]) + (f0.x + c4.x);
+                v[j + 1] = __uint_as_float(raw[j + 1]) + (f0.y + c4.y);
+                v[j + 2] = __uint_as_float(raw[j + 2]) + (f1.x + c4.z);
+                v[j + 3] = __uint_as_float(raw[j + 3]) + (f1.y + c4.w);
+            }
+            store_half(sA0, r, h, v);
         }
         // ---- proj_out (1x1 conv) + x_in   (ref :441-443) -------------------------------------------------------------------
         NDIFF_STAGE(issue_gemm<64>(tmem_d, sA0, sWp, 1, 4));
-        {
-            uint32_t raw[2][32];
-            tmem_ld32(tmem_rd, raw[0]);
-            tmem_ld32(tmem_rd + 32, raw[1]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint32_t raw[32];
+            tmem_ld32(tmem_rd + h * 32, raw);
             tmem_ld_wait();
+            float v[32];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const float2 f = unpack_bf16(xr[(h * 32 + j) / 2]);
-                    v[j] = __uint_as_float(raw[h][j]) + f_bp[h * 32 + j] + f.x;
-                    v[j + 1] = __uint_as_float(raw[h][j + 1]) + f_bp[h * 32 + j + 1] + f.y;
-                }
-                store_half(kShot ? sA0 : sA1, r, h, v);      // attn: staging for the TMA store; shot: operand of shot_mlp2.fc1
+            for (int j = 0; j < 32; j += 2) {
+                const float2 f = unpack_bf16(xr[(h * 32 + j) / 2]);
+                v[j] = __uint_as_float(raw[j]) + f_bp[h * 32 + j] + f.x;
+                v[j + 1] = __uint_as_float(raw[j + 1]) + f_bp[h * 32 + j + 1] + f.y;
             }
+            store_half(kShot ? sA0 : sA1, r, h, v);      // attn: staging for the TMA store; shot: operand of shot_mlp2.fc1
         }
         if constexpr (kShot) {
             // ---- shot_mlp2: fc1 + GELU, fc2   (ref :601) ---------------------------------------------------------------------
             NDIFF_STAGE(issue_gemm<64>(tmem_d, sA0, sWm1, 1, 4));
-            {
-                uint32_t raw[2][32];
-                tmem_ld32(tmem_rd, raw[0]);
-                tmem_ld32(tmem_rd + 32, raw[1]);
-                tmem_ld_wait();
 #pragma unroll
-                for (int h = 0; h < 2; ++h) store_half_gelu_f16(sA0, r, h, raw[h], f_bm1 + h * 32);
+            for (int h = 0; h < 2; ++h) {
+                uint32_t raw[32];
+                tmem_ld32(tmem_rd + h * 32, raw);
+                tmem_ld_wait();
+                store_half_gelu_f16(sA0, r, h, raw, f_bm1 + h * 32);
             }
             NDIFF_STAGE((issue_gemm<64, true>(tmem_d, sA0, sWm2, 1, 4)));
-            {
-                uint32_t raw[2][32];
-                tmem_ld32(tmem_rd, raw[0]);
-                tmem_ld32(tmem_rd + 32, raw[1]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t raw[32];
+                tmem_ld32(tmem_rd + h * 32, raw);
                 tmem_ld_wait();
+                float v[32];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[h][j]) + f_bm2[h * 32 + j];
-                    store_half(sA1, r, h, v);
-                }
+                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) + f_bm2[h * 32 + j];
+                store_half(sA1, r, h, v);
             }
         }
-        // ---- output tile: staged in A1 block 0, stored by TMA (rows beyond npix are clipped by the tensor map) ------------
+        // ---- output tile: staged in A1, stored by TMA (rows beyond npix are clipped by the tensor map) ---------------------
         fence_proxy_async();
-        tc_fence_before();
+        tc_fence_before();        // the accumulator drains above must be ordered before the next tile's MMA overwrites TMEM
         named_bar_sync(1 + wg, 128);
         if (r == 0) {
             tma_store_2d(&a.tmOut, sA1, 0, tile * kTile);
@@ -329,7 +350,7 @@ __global__ void __launch_bounds__(256, 1) pixel_chain_kernel(const __grid_consta
     __syncthreads();
     if (tid < 32) {
         tc_fence_after();
-        tmem_dealloc<256>(tail->tmem_base);
+        tmem_dealloc<kTmemCols>(tail->tmem_base);
     }
 }
 
@@ -344,7 +365,36 @@ __global__ void pack_chain_weight_kernel(const float* __restrict__ src, uint16_t
     }
 }
 
+
+__global__ void fold_layernorm_kernel(const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ g,
+                                      const float* __restrict__ beta, float* __restrict__ w_out, float* __restrict__ b_out,
+                                      int K) {
+    __shared__ float red[32];
+    const int n = blockIdx.x;
+    float acc = 0.f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const float wv = w[static_cast<size_t>(n) * K + k];
+        w_out[static_cast<size_t>(n) * K + k] = wv * g[k];
+        acc = fmaf(wv, beta[k], acc);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = b[n];
+        for (int i = 0; i < (blockDim.x + 31) / 32; ++i) t += red[i];
+        b_out[n] = t;
+    }
+}
+
 }  // namespace
+
+int fold_layernorm_launch(const float* w, const float* b, const float* g, const float* beta, float* w_out, float* b_out, int N,
+                          int K, cudaStream_t s) {
+    fold_layernorm_kernel<<<N, 64, 0, s>>>(w, b, g, beta, w_out, b_out, K);
+    NDIFF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
 
 int pack_chain_weight_launch(const float* src, __nv_bfloat16* dst, int N, int K, bool f16, cudaStream_t s) {
     const int KB = (K + 63) / 64;
@@ -356,7 +406,7 @@ int pack_chain_weight_launch(const float* src, __nv_bfloat16* dst, int N, int K,
 
 static int chain_smem_bytes(int prog) {
     const int rows = prog == kProgShot ? kChainShotRows : kChainAttnRows;
-    return 1024 + rows * 128 + 2 * kWgBytes + static_cast<int>(sizeof(ChainTail));
+    return 1024 + rows * 128 + kNWG * kWgBytes + static_cast<int>(sizeof(ChainTail));
 }
 
 int pixel_chain_init() {
@@ -400,7 +450,7 @@ int pixel_chain_plan(const ChainDesc& d, int num_sms, ChainPlan* plan) {
     const uint64_t wdims[2] = {64, static_cast<uint64_t>(rows)};
     const uint32_t wbox[2] = {64, 64};
     if (encode_tensor_map(&a.tmW, d.weights, 2, wdims, astr, wbox, true)) return 1;
-    const int want = (a.n_tiles + 1) / 2;
+    const int want = (a.n_tiles + kNWG - 1) / kNWG;
     plan->grid = want < num_sms ? want : num_sms;
     plan->smem_bytes = chain_smem_bytes(d.prog);
     NDIFF_REQUIRE(plan->smem_bytes <= 227 * 1024, "pixel chain: shared-memory budget exceeded");
@@ -409,9 +459,9 @@ int pixel_chain_plan(const ChainDesc& d, int num_sms, ChainPlan* plan) {
 
 int pixel_chain_launch(const ChainPlan& plan, cudaStream_t stream) {
     if (plan.prog == kProgShot)
-        NDIFF_CUDA_OK(launch_pdl(pixel_chain_kernel<kProgShot>, dim3(plan.grid), dim3(256), plan.smem_bytes, stream, plan.args));
+        NDIFF_CUDA_OK(launch_pdl(pixel_chain_kernel<kProgShot>, dim3(plan.grid), dim3(kThreads), plan.smem_bytes, stream, plan.args));
     else
-        NDIFF_CUDA_OK(launch_pdl(pixel_chain_kernel<kProgAttn>, dim3(plan.grid), dim3(256), plan.smem_bytes, stream, plan.args));
+        NDIFF_CUDA_OK(launch_pdl(pixel_chain_kernel<kProgAttn>, dim3(plan.grid), dim3(kThreads), plan.smem_bytes, stream, plan.args));
     return 0;
 }
 

@@ -18,7 +18,8 @@ enum ChainProg : int {
 // rows of the bf16 weight blob ([rows][64], one 128-byte row per output channel per 64-wide K block) and floats of the
 // parameter block, in program order:
 //   attn : W1 (ff.net.0.0, 128 rows) | W2 kblock 0, 1 (ff.net.2, 64 + 64, fp16) | Wp (proj_out, 64)      = 320 rows
-//          [ln_g 64][ln_b 64][b1 128][b2 64][bp 64]                                                         = 384 floats
+//          [reserved 128][b1 128][b2 64][bp 64]                                                             = 384 floats
+//          (AttnBlock.norm2's affine is folded by the packer: W1 <- W1 diag(ln_g), b1 <- b1 + W1 ln_b)
 //   shot : W0 (shot_mlp1.fc1, K = 8 zero-padded, 64) | Wfc2 (shot_mlp1.fc2, 64, fp16) | attn 320 | Wm1 | Wm2 (fp16) = 576 rows
 //          [b0 64][bfc2 64] + attn 384 + [bm1 64][bm2 64]                                                  = 640 floats
 constexpr int kChainAttnRows = 320, kChainAttnFloats = 384;
@@ -63,5 +64,8 @@ int pixel_chain_init();
 // dst[(kb * N + n) * 64 + kk] = src[n * K + kb * 64 + kk] (zero beyond K): fp32 [N][K] -> 16-bit K-blocked rows.
 // f16 = true for the layers whose A operand is a GELU output (kept in fp16 on chip: ff.net.2, shot_mlp1.fc2, shot_mlp2.fc2).
 int pack_chain_weight_launch(const float* src, __nv_bfloat16* dst, int N, int K, bool f16, cudaStream_t s);
+// w_out[n][k] = w[n][k] * g[k];  b_out[n] = b[n] + sum_k w[n][k] * beta[k]   (LayerNorm affine folded into the next Linear)
+int fold_layernorm_launch(const float* w, const float* b, const float* g, const float* beta, float* w_out, float* b_out, int N,
+                          int K, cudaStream_t s);
 
 }  // namespace ndiff

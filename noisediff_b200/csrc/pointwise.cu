@@ -415,6 +415,164 @@ __global__ void __launch_bounds__(256) final_kernel(const FinalArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// dim = 64 fast path of the fused heads + posterior update.  A warp owns 32 consecutive pixels (never straddling a sample:
+// HW % 32 == 0).  Phase 1: 8 passes of 4 pixels x 8 lanes, all 16-byte loads of the 32 pixels issued up front, each lane
+// dots its channel octet against head weights held in registers; a reduce-scatter butterfly (28 shuffles) leaves lane
+// (grp, sub) with the four head outputs of pixel 4*sub + grp.  Phase 2: ALL 32 lanes run Philox / Box-Muller and the
+// posterior arithmetic for one pixel each (the generic kernel below does that with 1 lane in 8).
+// kGn: the xf operand is SiLU(GroupNorm(xf)) + gn_res evaluated on the fly — final_res_block.block2.norm never
+// materialises (ref Diffusion_arch.py:135-170,640-643).
+// ---------------------------------------------------------------------------------------------------------------
+template <bool kGn>
+__global__ void __launch_bounds__(256) final64_kernel(const FinalArgs a) {
+    const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+    pdl_trigger();
+    float wfr[4][8], wsr[4][8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { wfr[k][j] = __ldg(a.wf + k * 64 + sub * 8 + j); wsr[k][j] = __ldg(a.ws + k * 64 + sub * 8 + j); }
+    }
+    const float bsum[4] = {a.bs[0] + a.bfin[0], a.bs[1] + a.bfin[1], a.bs[2] + a.bfin[2], a.bs[3] + a.bfin[3]};
+    float gam[8], bet[8];
+    if (kGn) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { gam[j] = __ldg(a.gn_gamma + sub * 8 + j); bet[j] = __ldg(a.gn_beta + sub * 8 + j); }
+    }
+    pdl_wait();
+    StepParams sp{};
+    int step = 0, rel = 0;
+    const float* noise = nullptr;
+    float* snap = nullptr;
+    unsigned long long seed = 0ull;
+    if (a.chain) {
+        sp = a.chain->cur; step = a.chain->step; rel = step - a.chain->base_step;
+        noise = a.chain->noise; snap = a.chain->snap; seed = a.chain->seed;
+    }
+    const size_t HW = a.HW, npix = static_cast<size_t>(a.npix), nB = npix / HW;
+    const size_t n_chunks = npix >> 5;
+    const size_t n_warps = static_cast<size_t>(gridDim.x) * (blockDim.x >> 5);
+    const size_t gw = static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const size_t c_begin = n_chunks * gw / n_warps, c_end = n_chunks * (gw + 1) / n_warps;   // contiguous range per warp
+    float A[8], Bc[8];
+    long long cur_b = -1;
+    const uint4* xfv = reinterpret_cast<const uint4*>(a.xf);
+    const uint4* sfv = reinterpret_cast<const uint4*>(a.sf);
+    const uint4* rsv = reinterpret_cast<const uint4*>(a.gn_res);
+    for (size_t ch = c_begin; ch < c_end; ++ch) {
+        const size_t pix0 = ch << 5;
+        const size_t bimg = pix0 / HW;
+        if (kGn && static_cast<long long>(bimg) != cur_b) {
+            cur_b = static_cast<long long>(bimg);
+            const int gs = 64 / a.gn_G, g = (sub * 8) / gs;
+            const double inv_n = 1.0 / (static_cast<double>(a.HW) * gs);
+            const double s = static_cast<double>(static_cast<long long>(a.gn_stats[(bimg * a.gn_G + g) * 2])) * (1.0 / 16777216.0);
+            const double ss = static_cast<double>(static_cast<long long>(a.gn_stats[(bimg * a.gn_G + g) * 2 + 1])) * (1.0 / 16777216.0);
+            const double meand = s * inv_n;
+            const float mean = static_cast<float>(meand);
+            const float var = fmaxf(static_cast<float>(ss * inv_n - meand * meand), 0.f);
+            const float rstd = rsqrtf(var + a.gn_eps);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { A[j] = rstd * gam[j]; Bc[j] = bet[j] - mean * A[j]; }
+        }
+        // ---- phase 1: per-lane partial dot products of 8 x 4 pixels -------------------------------------------------
+        uint4 fv[8], gv[8], rv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const size_t idx = (pix0 + i * 4 + grp) * 8 + sub;
+            fv[i] = __ldg(xfv + idx);
+            gv[i] = __ldg(sfv + idx);
+            if (kGn && rsv) rv[i] = __ldg(rsv + idx);
+        }
+        float o[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float f[8], g[8];
+            unpack8(fv[i], f);
+            unpack8(gv[i], g);
+            if (kGn) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = silu(fmaf(f[j], A[j], Bc[j]));
+                if (rsv) {
+                    float r[8];
+                    unpack8(rv[i], r);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] += r[j];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float acc = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc = fmaf(f[j], wfr[k][j], fmaf(g[j], wsr[k][j], acc));
+                o[i][k] = acc;
+            }
+        }
+        // ---- reduce-scatter over the 8 lanes of a pixel group: lane `sub` ends with pass `sub` -------------------------
+        float t4[4][4], t2[2][4], v[4];
+        const bool hi = (sub & 4) != 0, mid = (sub & 2) != 0, lo = (sub & 1) != 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float keep = hi ? o[j + 4][k] : o[j][k], send = hi ? o[j][k] : o[j + 4][k];
+                t4[j][k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float keep = mid ? t4[j + 2][k] : t4[j][k], send = mid ? t4[j][k] : t4[j + 2][k];
+                t2[j][k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float keep = lo ? t2[1][k] : t2[0][k], send = lo ? t2[0][k] : t2[1][k];
+            // reference order: shot_noise (= fc2 out + bias) + read_noise (= final_conv out + bias)
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 1) + bsum[k];
+        }
+        // ---- phase 2: one pixel per lane -------------------------------------------------------------------------------
+        const size_t pix = pix0 + sub * 4 + grp;
+        if (a.v_out) reinterpret_cast<float4*>(a.v_out)[pix] = make_float4(v[0], v[1], v[2], v[3]);
+        if (!a.chain) continue;
+        const size_t hw = pix - bimg * HW;
+        const size_t plane0 = ((static_cast<size_t>(rel) * nB + bimg) * 4) * HW + hw;   // NCHW offset of channel 0
+        const float4 xi4 = reinterpret_cast<const float4*>(a.x)[pix];
+        const float xi[4] = {xi4.x, xi4.y, xi4.z, xi4.w};
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        if (sp.sigma != 0.f) {
+            if (noise) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) z[k] = __ldg(noise + plane0 + k * HW);
+            } else {
+                const float4 z4 = philox_normal4(seed, static_cast<unsigned long long>(step) + 1ull, pix);
+                z[0] = z4.x; z[1] = z4.y; z[2] = z4.z; z[3] = z4.w;
+            }
+        }
+        float xn[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            // separate roundings (no FMA contraction) to follow the reference's elementwise torch ops
+            float x0 = __fadd_rn(__fmul_rn(sp.p, xi[k]), __fmul_rn(sp.q, v[k]));
+            if (sp.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+            float m = __fadd_rn(__fmul_rn(sp.a, x0), __fmul_rn(sp.b, xi[k]));
+            if (sp.c != 0.f) {
+                const float eps = __fdiv_rn(__fadd_rn(__fmul_rn(sp.r1, xi[k]), -x0), sp.r2);
+                m = __fadd_rn(m, __fmul_rn(sp.c, eps));
+            }
+            xn[k] = sp.sigma != 0.f ? __fadd_rn(m, __fmul_rn(sp.sigma, z[k])) : m;
+        }
+        reinterpret_cast<float4*>(a.x)[pix] = make_float4(xn[0], xn[1], xn[2], xn[3]);
+        if (snap) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) snap[plane0 + k * HW] = xn[k];
+        }
+    }
+}
+
 __global__ void chain_advance_kernel(ChainState* chain) {
     pdl_wait();
     chain->step += 1;
@@ -585,7 +743,8 @@ inline int blocks_for(size_t n, int per_block, int cap = 1 << 20) {
 // ---------------------------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------------------------
-static int g_gn_occ[2][3] = {{0, 0, 0}, {0, 0, 0}};   // resident blocks per SM of each gn_apply variant (pointwise_init)
+static int g_gn_occ[2][3] = {{0, 0, 0}, {0, 0, 0}};
+static int g_final_occ[2] = {0, 0};                  // resident blocks per SM of final64_kernel<false / true>   // resident blocks per SM of each gn_apply variant (pointwise_init)
 
 int gn_apply_launch(const GnApplyArgs& a, cudaStream_t s) {
     NDIFF_REQUIRE(a.C % 64 == 0 && a.C <= 512 && a.C % a.G == 0 && (a.C / a.G) % 8 == 0,
@@ -647,6 +806,8 @@ int pointwise_init() {
         NDIFF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_gn_occ[1][0], gn_apply_kernel<true, 0>, kGnThreads, 0));
         NDIFF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_gn_occ[1][1], gn_apply_kernel<true, 1>, kGnThreads, 0));
         NDIFF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_gn_occ[1][2], gn_apply_kernel<true, 2>, kGnThreads, 0));
+        NDIFF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_final_occ[0], final64_kernel<false>, 256, 0));
+        NDIFF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_final_occ[1], final64_kernel<true>, 256, 0));
     }
     const int smem = (kIcHalo * kIcHalo + 49 * 4 * 16) * sizeof(float4);
     NDIFF_CUDA_OK(cudaFuncSetAttribute(init_conv7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -674,8 +835,22 @@ int upsample2x_launch(const bf16* in, bf16* out, int B, int H, int W, int C, cud
 
 int final_launch(const FinalArgs& a, cudaStream_t s) {
     NDIFF_REQUIRE(a.C == 64 || a.C == 128 || a.C == 256, "final heads: C/8 must be a power of two <= 32");
-    const size_t threads = static_cast<size_t>(a.npix) * (a.C / 8);
-    NDIFF_CUDA_OK(launch_pdl(final_kernel, dim3(blocks_for(threads, 256, g_num_sms * 4)), dim3(256), 8 * a.C * sizeof(float), s, a));
+    if (a.C == 64 && a.HW % 32 == 0) {
+        // one wave of 256-thread blocks, every warp walks a contiguous range of 32-pixel chunks
+        const int occ = g_final_occ[a.gn_stats ? 1 : 0] > 0 ? g_final_occ[a.gn_stats ? 1 : 0] : 1;
+        const int blocks = blocks_for(static_cast<size_t>(a.npix) / 32, 8, g_num_sms * occ);
+        if (a.gn_stats) {
+            NDIFF_REQUIRE(a.gn_gamma && a.gn_beta && a.gn_G > 0 && 64 % a.gn_G == 0 && (64 / a.gn_G) % 8 == 0,
+                          "final heads: bad fused GroupNorm arguments");
+            NDIFF_CUDA_OK(launch_pdl(final64_kernel<true>, dim3(blocks), dim3(256), 0, s, a));
+        } else {
+            NDIFF_CUDA_OK(launch_pdl(final64_kernel<false>, dim3(blocks), dim3(256), 0, s, a));
+        }
+    } else {
+        NDIFF_REQUIRE(!a.gn_stats, "final heads: the fused GroupNorm form needs dim = 64");
+        const size_t threads = static_cast<size_t>(a.npix) * (a.C / 8);
+        NDIFF_CUDA_OK(launch_pdl(final_kernel, dim3(blocks_for(threads, 256, g_num_sms * 4)), dim3(256), 8 * a.C * sizeof(float), s, a));
+    }
     NDIFF_CUDA_OK(cudaGetLastError());
     if (a.chain) {
         NDIFF_CUDA_OK(launch_pdl(chain_advance_kernel, dim3(1), dim3(1), 0, s, a.chain));

@@ -70,6 +70,10 @@ struct FinalArgs {
     // posterior update (null chain => skipped); noise / snapshot pointers live in the ChainState
     ChainState* chain;
     float* x;                                // fp32 NHWC4 state (= this step's network input), updated in place
+    // optional (dim = 64): xf is a raw conv output and the heads read SiLU(GroupNorm(xf)) + gn_res instead — the last
+    // GroupNorm-apply pass of final_res_block folded into this kernel.  gn_stats: that conv's fixed-point sums [B][G][2].
+    const unsigned long long* gn_stats; const float* gn_gamma; const float* gn_beta; const bf16* gn_res;
+    int gn_G; float gn_eps;
 };
 int final_launch(const FinalArgs& a, cudaStream_t s);
 

@@ -235,16 +235,22 @@ def _attn_params(seed):
     rn = lambda *s, sc=1.0: torch.randn(*s, generator=g, device="cuda") * sc
     p = dict(ln_g=1 + 0.3 * rn(64), ln_b=0.2 * rn(64), W1=_bf(rn(128, 64, sc=0.125)), b1=0.3 * rn(128),
              W2=_bf(rn(64, 128, sc=0.09)), b2=0.3 * rn(64), Wp=_bf(rn(64, 64, sc=0.125)), bp=0.3 * rn(64))
-    blob = torch.cat([_blob(p["W1"]), _blob(p["W2"], f16=True), _blob(p["Wp"])])
-    fvec = torch.cat([p["ln_g"], p["ln_b"], p["b1"], p["b2"], p["bp"]])
+    # packer convention (pixel_chain.cuh): LayerNorm's affine is folded into the first Linear
+    p["W1f"] = _bf(p["W1"] * p["ln_g"][None, :])
+    p["b1f"] = p["b1"] + p["W1"] @ p["ln_b"]
+    blob = torch.cat([_blob(p["W1f"]), _blob(p["W2"], f16=True), _blob(p["Wp"])])
+    fvec = torch.cat([torch.zeros(128, device="cuda"), p["b1f"], p["b2"], p["bp"]])
     return p, blob, fvec
 
 
 def _attn_ref(tok, cv, p):
     """tok: [npix, 64] fp32 (bf16-representable), cv: [npix, 64].  Rounds to bf16 where the kernel stores bf16."""
     y = tok + cv
-    u = _bf(F.layer_norm(y, (64,), p["ln_g"], p["ln_b"], eps=1e-5))
-    h = _hf(F.gelu(u @ p["W1"].T + p["b1"]))              # hidden activations stay on chip in fp16
+    u = _bf(F.layer_norm(y, (64,), None, None, eps=1e-5))
+    h = _hf(F.gelu(u @ p["W1f"].T + p["b1f"]))            # hidden activations stay on chip in fp16
+    # the folded form is the unfolded block up to the bf16 rounding of the weights
+    h_ref = F.gelu(F.layer_norm(y, (64,), p["ln_g"], p["ln_b"], eps=1e-5) @ p["W1"].T + p["b1"])
+    assert ((h - h_ref).norm() / h_ref.norm()).item() < 1e-2
     z = _bf(h @ p["W2"].T + p["b2"] + y)
     return z @ p["Wp"].T + p["bp"] + tok
 
