@@ -29,6 +29,7 @@ struct SmemTail {  // lives after the operand rings
     uint32_t tmem_base;
     uint32_t pad_;
     alignas(16) float bias[128];   // this CTA's N-tile slice of the bias (zeros when the layer has none)
+    alignas(16) float bias2[128];  // kHalo1R: bias slice of the fused 1x1 residual convolution
 };
 
 // Tap geometry of the single-copy halo mode (compile-time: TW = 8 so that one 8-row UMMA group == one output row).
@@ -41,6 +42,7 @@ constexpr int kHaloStage2 = (kHaloCopy2 + 1023) / 1024 * 1024;
 constexpr int kSubStep = (kHaloTH * kHaloPitch) >> 4;                    // descriptor offset of the second sub-tile
 // taps per streamed weight stage in halo mode
 __host__ __device__ constexpr int halo_btaps(int nt, int sub) { return (sub == 2 && nt == 128) ? 1 : 3; }
+constexpr int kResBTaps = 2;                                             // kHalo1R: 10 weight blocks per channel block, two per stage
 constexpr int kUpBTaps = 4;                                              // kHaloUp: one stage = the 4 taps of one phase
 
 template <int NT, int MODE, bool RES>
@@ -48,11 +50,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem is only guaranteed 16-B aligned by the ABI; SWIZZLE_128B wants 1024
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    constexpr bool kHalo = MODE == kHalo1 || MODE == kHalo2 || MODE == kHaloUp;
+    constexpr bool kHalo = MODE == kHalo1 || MODE == kHalo2 || MODE == kHaloUp || MODE == kHalo1R;
     constexpr bool kUp = MODE == kHaloUp;
+    constexpr bool kRes2 = MODE == kHalo1R;                      // second accumulator: 1x1 conv of the same input (centre tap)
     constexpr int kSub = MODE == kHalo2 ? 2 : 1;                 // 128-pixel sub-tiles (TMEM accumulators) per CTA tile
-    constexpr int kHTaps = kUp ? 4 : 9;                          // taps per (channel block[, phase]) in the halo modes
-    constexpr int kBG = kUp ? kUpBTaps : (kHalo ? halo_btaps(NT, kSub) : 1);   // taps per streamed weight stage
+    constexpr int kHTaps = kUp ? 4 : (kRes2 ? 10 : 9);           // weight blocks per (channel block[, phase]) in the halo modes
+    constexpr int kBG = kUp ? kUpBTaps : (kRes2 ? kResBTaps : (kHalo ? halo_btaps(NT, kSub) : 1));   // taps per streamed weight stage
+    constexpr int kAccCols = (kRes2 ? 4 : 2 * kSub) * NT;        // TMEM columns: double-buffered accumulators
     constexpr int kBTap = NT * 128;                              // one [NT x 64] weight block (one tap of one channel block)
     constexpr int kBStage = kBG * kBTap;
     constexpr int kAStage = MODE == kHalo2 ? kHaloStage2 : (kHalo ? kHaloStage : 128 * 128);
@@ -68,7 +72,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int CB = a.cb0 + a.cb1;
-    const int TAPS = kUp ? 16 : (kHalo ? 9 : a.taps_y * a.taps_x);    // weight blocks per channel block
+    const int TAPS = kUp ? 16 : (kHalo ? kHTaps : a.taps_y * a.taps_x);    // weight blocks per channel block
     const int nt = blockIdx.x % a.n_tiles;                       // this CTA's N tile for its whole life
     // contiguous range of M tiles per CTA: consecutive tiles share halo rows in L2 and (almost always) the sample index,
     // which lets the epilogue keep GroupNorm partial sums in registers across tiles
@@ -88,8 +92,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         for (int i = 0; i < 2; ++i) { mbar_init(&tail->tmem_full[i], 1); mbar_init(&tail->tmem_empty[i], kEpiWarps); }
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc<2 * kSub * NT>(&tail->tmem_base);
-    if (threadIdx.x < NT) tail->bias[threadIdx.x] = a.bias ? __ldg(a.bias + nt * NT + threadIdx.x) : 0.f;
+    if (warp == 2) tmem_alloc<kAccCols>(&tail->tmem_base);
+    if (threadIdx.x < NT) {
+        tail->bias[threadIdx.x] = a.bias ? __ldg(a.bias + nt * NT + threadIdx.x) : 0.f;
+        if (kRes2) tail->bias2[threadIdx.x] = a.bias2 ? __ldg(a.bias2 + nt * NT + threadIdx.x) : 0.f;
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -215,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                         }
                         __syncwarp();
                     } else if constexpr (RES) {
-                        const uint32_t b_base = umma_desc_lo(ringB + cb * 9 * kBTap);
+                        const uint32_t b_base = umma_desc_lo(ringB + cb * kHTaps * kBTap);
                         if (elect_one()) {
                             // rolled tap loops on purpose: unrolled, ptxas hoists all 72 descriptor updates ahead of the
                             // first MMA (spilling uniform registers) and the tensor pipe idles meanwhile
@@ -239,6 +246,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                                 }
                                 a_row += kHaloPitch >> 4;
                             }
+                            if constexpr (kRes2) {      // 1x1 residual conv: centre tap of the same halo box, weight block 9
+                                const uint32_t d2 = tmem_base + (2 + acc) * NT, ac = a_base + ((kHaloPitch + 128) >> 4);
+                                umma_bf16_lohi_pred(d2, ac, hiA, b_cur, hiB, idesc, cb > 0 ? 1u : 0u);
+                                umma_bf16_lohi<true>(d2, ac + 2, hiA, b_cur + 2, hiB, idesc);
+                                umma_bf16_lohi<true>(d2, ac + 4, hiA, b_cur + 4, hiB, idesc);
+                                umma_bf16_lohi<true>(d2, ac + 6, hiA, b_cur + 6, hiB, idesc);
+                            }
                             umma_commit(bar_emptyA + sa * 8);
                         }
                         __syncwarp();
@@ -253,11 +267,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll 1
                                 for (int t = 0; t < kBG; ++t) {
                                     const int tap = g * kBG + t;
-                                    const int ky = kUp ? py + (tap >> 1) : (tap * 11) >> 5, kx = kUp ? px + (tap & 1) : tap - 3 * ky;
+                                    const bool rtap = kRes2 && tap == 9;      // fused 1x1 residual conv: centre tap -> 2nd accumulator
+                                    const int ky = kUp ? py + (tap >> 1) : (rtap ? 1 : (tap * 11) >> 5);
+                                    const int kx = kUp ? px + (tap & 1) : (rtap ? 1 : tap - 3 * ky);
                                     const uint32_t a_cur = a_base + ((ky * kHaloPitch + kx * 128) >> 4);
+                                    if (rtap) accum = cb > 0 ? 1u : 0u;
 #pragma unroll
                                     for (int sub = 0; sub < kSub; ++sub) {
-                                        const uint32_t d = d_tmem + sub * NT, as = a_cur + sub * kSubStep;
+                                        const uint32_t d = rtap ? tmem_base + (2 + acc) * NT : d_tmem + sub * NT, as = a_cur + sub * kSubStep;
                                         umma_bf16_lohi_pred(d, as, hiA, b_cur, hiB, idesc, accum);
                                         umma_bf16_lohi<true>(d, as + 2, hiA, b_cur + 2, hiB, idesc);
                                         umma_bf16_lohi<true>(d, as + 4, hiA, b_cur + 4, hiB, idesc);
@@ -346,9 +363,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
             mbar_wait(bar_tfull + acc * 8, pacc);
             tc_fence_after();
+            constexpr int kPasses = kRes2 ? 2 : kSub;      // kHalo1R: pass 1 drains the residual-conv accumulator
 #pragma unroll 1
-            for (int sub = 0; sub < kSub; ++sub) {
-                const int y = ty * a.TH + sub * kHaloTH + (r >> a.lgTW), x = tx * a.TW + (r & (a.TW - 1));
+            for (int sub = 0; sub < kPasses; ++sub) {
+                const bool pass2 = kRes2 && sub == 1;
+                const int y = ty * a.TH + (kRes2 ? 0 : sub) * kHaloTH + (r >> a.lgTW), x = tx * a.TW + (r & (a.TW - 1));
                 const bool valid = (y < a.H) && (x < a.W);
                 // kHaloUp writes output pixel (2y + py, 2x + px) of the [B, 2H, 2W] grid
                 const size_t pix = kUp ? (static_cast<size_t>(b) * 2 * a.H + 2 * y + (phase >> 1)) * (2 * a.W) + 2 * x + (phase & 1)
@@ -356,10 +375,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 uint32_t raw[kSlots][32];
 #pragma unroll
                 for (int k = 0; k < kSlots; ++k)
-                    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (acc * kSub + sub) * NT + (cset + 2 * k) * 32,
+                    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (pass2 ? (2 + acc) : (acc * kSub + sub)) * NT +
+                                  (cset + 2 * k) * 32,
                               raw[k]);
                 tmem_ld_wait();
-                if (sub == kSub - 1) {
+                if (sub == kPasses - 1) {
                     // everything this warp needs from the accumulators is in registers: hand the TMEM stage back right away
                     tc_fence_before();
                     __syncwarp();
@@ -372,15 +392,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        const float4 bv = *reinterpret_cast<const float4*>(&tail->bias[ch * 32 + j]);
+                        const float4 bv = *reinterpret_cast<const float4*>(pass2 ? &tail->bias2[ch * 32 + j] : &tail->bias[ch * 32 + j]);
                         v[j] = __uint_as_float(raw[k][j]) + bv.x; v[j + 1] = __uint_as_float(raw[k][j + 1]) + bv.y;
                         v[j + 2] = __uint_as_float(raw[k][j + 2]) + bv.z; v[j + 3] = __uint_as_float(raw[k][j + 3]) + bv.w;
                     }
-                    if (a.act == kActGelu) {
+                    if (a.act == kActGelu && !pass2) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
                     }
-                    if (a.vec) {
+                    if (a.vec && !pass2) {
                         const float* vp = a.vec + static_cast<size_t>(b) * a.vec_ld + nbase;
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
@@ -388,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                             v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
                         }
                     }
-                    if (a.res && valid) {
+                    if (a.res && valid && !pass2) {
                         const uint4* rp = reinterpret_cast<const uint4*>(a.res + pix * a.res_ld + nbase);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -400,7 +420,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                             f = unpack_bf16(u.w); v[j * 8 + 6] += f.x; v[j * 8 + 7] += f.y;
                         }
                     }
-                    if (a.stats && valid) {
+                    if (a.stats && valid && !pass2) {
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             float t0 = 0.f, t1 = 0.f;
@@ -410,7 +430,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                         }
                     }
                     if (valid) {
-                        uint4* op = reinterpret_cast<uint4*>(a.out + pix * a.out_ld + nbase);
+                        uint4* op = reinterpret_cast<uint4*>(pass2 ? a.out2 + pix * a.out2_ld + nbase : a.out + pix * a.out_ld + nbase);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             uint4 u;
@@ -432,7 +452,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc<2 * kSub * NT>(tmem_base);
+        tmem_dealloc<kAccCols>(tmem_base);
     }
 }
 
@@ -505,7 +525,7 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     a.B = d.B; a.H = d.H; a.W = d.W;
     int TW = d.TW;
     if (TW == 0) {
-        if (d.mode == kHalo1 || d.mode == kHalo2 || d.mode == kHaloUp) TW = kHaloTW;
+        if (d.mode == kHalo1 || d.mode == kHalo2 || d.mode == kHaloUp || d.mode == kHalo1R) TW = kHaloTW;
         else TW = d.W >= 64 ? 64 : (d.W >= 32 ? 32 : (d.W >= 16 ? 16 : 8));
     }
     NDIFF_REQUIRE(TW >= 8 && TW <= 128 && (TW & (TW - 1)) == 0, "tile width must be a power of two in [8,128]");
@@ -514,8 +534,9 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     a.tiles_x = (d.W + a.TW - 1) / a.TW;
     a.tiles_y = (d.H + a.TH - 1) / a.TH;
     a.cb0 = d.C0 / 64; a.cb1 = d.C1 / 64;
-    const bool halo1 = d.mode == kHalo1 || d.mode == kHalo2 || d.mode == kHaloUp;
+    const bool halo1 = d.mode == kHalo1 || d.mode == kHalo2 || d.mode == kHaloUp || d.mode == kHalo1R;
     const bool up = d.mode == kHaloUp;
+    const bool res2 = d.mode == kHalo1R;
     NDIFF_REQUIRE(d.mode == kDirect || d.mode == kS2D || halo1, "unknown convolution mode");
     NDIFF_REQUIRE(!halo1 || TW == kHaloTW, "halo mode needs TW == 8 (one 8-row UMMA group per output row)");
     if (up) { a.taps_y = 4; a.taps_x = 4; a.pad_y = 1; a.pad_x = 1; }      // 16 weight blocks per channel block (4 phases x 4 taps)
@@ -525,7 +546,7 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     a.n_tiles = d.Cout / NT;
     a.total_tiles = d.B * a.tiles_y * a.tiles_x * a.n_tiles * (up ? 4 : 1);
     const int b_tap = NT * 128;                          // one [NT x 64] weight block
-    const int b_stage = (up ? kUpBTaps : (halo1 ? halo_btaps(NT, sub) : 1)) * b_tap;   // streamed weights: bytes per ring stage
+    const int b_stage = (up ? kUpBTaps : (res2 ? kResBTaps : (halo1 ? halo_btaps(NT, sub) : 1))) * b_tap;   // streamed weights: bytes per ring stage
     if (d.mode == kHalo2) {
         a.a_copy_bytes = kHaloCopy2;
         a.a_stage_bytes = kHaloStage2;
@@ -540,7 +561,7 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
         a.a_copy_bytes = kHaloCopy;
         a.a_stage_bytes = kHaloStage;
         a.a_stages = 3;
-        a.b_stages = NT == 128 ? 3 : 5;
+        a.b_stages = res2 ? (NT == 128 ? 4 : 6) : (NT == 128 ? 3 : 5);
     } else {
         a.a_copy_bytes = 128 * 128;
         a.a_stage_bytes = 128 * 128;
@@ -555,7 +576,7 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     plan->grid = grid;
     // weights resident in shared memory when this CTA's slice fits next to >= 2 activation stages and is reused
     const int budget = 227 * 1024 - 1024 - static_cast<int>(sizeof(SmemTail));
-    const int n_kb = (a.cb0 + a.cb1) * a.taps_y * a.taps_x;
+    const int n_kb = (a.cb0 + a.cb1) * (a.taps_y * a.taps_x + (res2 ? 1 : 0));      // kHalo1R: + the 1x1 residual-conv block
     const int slice = n_kb * b_tap;
     const int m_per_cta = (a.total_tiles / a.n_tiles + grid / a.n_tiles - 1) / (grid / a.n_tiles);
     a.b_resident = (slice + 2 * a.a_stage_bytes <= budget && m_per_cta >= 2 && slice < (1 << 20)) ? 1 : 0;
@@ -600,7 +621,7 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
         }
     }
     {
-        const uint64_t Ktot = static_cast<uint64_t>(a.cb0 + a.cb1) * a.taps_y * a.taps_x * 64;
+        const uint64_t Ktot = static_cast<uint64_t>(a.cb0 + a.cb1) * (a.taps_y * a.taps_x + (res2 ? 1 : 0)) * 64;
         uint64_t dims[2] = {Ktot, static_cast<uint64_t>(d.Cout)};
         uint64_t str[1] = {Ktot * 2};
         uint32_t box[2] = {64, static_cast<uint32_t>(NT)};
@@ -609,6 +630,8 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     }
     a.bias = d.bias; a.vec = d.vec; a.vec_ld = d.vec_ld; a.res = d.res; a.res_ld = d.res_ld;
     a.out = d.out; a.out_ld = d.out_ld; a.act = d.act;
+    a.bias2 = d.bias2; a.out2 = d.out2; a.out2_ld = d.out2_ld;
+    NDIFF_REQUIRE(!res2 || (d.out2 != nullptr && d.out2_ld % 8 == 0), "kHalo1R needs the residual-conv output");
     a.stats = d.stats; a.G = d.groups;
     if (d.stats) {
         const int gs = d.Cout / d.groups;
@@ -648,6 +671,8 @@ int conv_gemm_init() {
     NDIFF_CUDA_OK((opt_in<128, kHalo2>()));
     NDIFF_CUDA_OK((opt_in<64, kHaloUp>()));
     NDIFF_CUDA_OK((opt_in<128, kHaloUp>()));
+    NDIFF_CUDA_OK((opt_in<64, kHalo1R>()));
+    NDIFF_CUDA_OK((opt_in<128, kHalo1R>()));
     return 0;
 }
 
@@ -656,12 +681,14 @@ int conv_gemm_launch(const ConvGemmPlan& plan, cudaStream_t stream) {
     if (plan.NT == 64) {
         if (mode == kHaloUp) return launch_res<64, kHaloUp>(plan, stream);
         if (mode == kHalo2) return launch_res<64, kHalo2>(plan, stream);
+        if (mode == kHalo1R) return launch_res<64, kHalo1R>(plan, stream);
         if (mode == kHalo1) return launch_res<64, kHalo1>(plan, stream);
         if (mode == kS2D) return launch_res<64, kS2D>(plan, stream);
         return launch_res<64, kDirect>(plan, stream);
     }
     if (mode == kHaloUp) return launch_res<128, kHaloUp>(plan, stream);
     if (mode == kHalo2) return launch_res<128, kHalo2>(plan, stream);
+    if (mode == kHalo1R) return launch_res<128, kHalo1R>(plan, stream);
     if (mode == kHalo1) return launch_res<128, kHalo1>(plan, stream);
     if (mode == kS2D) return launch_res<128, kS2D>(plan, stream);
     return launch_res<128, kDirect>(plan, stream);

@@ -14,6 +14,10 @@ enum ConvMode : int {
                   // Weights: [Cout][cblk][phase(4)][tap(4)][64].  H, W in the descriptor are the LOW-resolution size.
     kHalo2 = 4,   // kHalo1 with TWO vertically stacked 16x8 sub-tiles per CTA tile (32x8 pixels, one 34x10 halo box, two TMEM
                   // accumulators): every weight block read from shared memory / streamed from L2 feeds 256 pixels
+    kHalo1R = 6,  // kHalo1 plus the ResnetBlock's 1x1 res_conv of the SAME (concatenated) input (Diffusion_arch.py:157,169): the
+                  // centre tap of the halo box is multiplied by a tenth weight block into a second TMEM accumulator, so the
+                  // residual path costs 1/9 more MMAs instead of a second pass over the activations.
+                  // Weights: [Cout][cblk][10][64] (taps 0..8 = 3x3, 9 = res_conv); second output / bias: out2 / bias2.
     kHalo1 = 3,   // 3x3 pad 1: ONE (TH+2)x(TW+2) = 18x10-pixel halo box per 64-channel block (TH x TW = 16 x 8); the nine
                   // taps are 128-byte row shifts of the UMMA start address with SBO = (TW+2)*128.  Works because the
                   // 128-B swizzle is a function of the absolute shared-memory address for both TMA and UMMA
@@ -46,6 +50,9 @@ struct ConvGemmArgs {
     __nv_bfloat16* out;          // [B,H,W,out_ld]
     int out_ld;
     int act;
+    const float* bias2;          // kHalo1R: bias and output of the fused 1x1 residual convolution
+    __nv_bfloat16* out2;
+    int out2_ld;
     unsigned long long* stats;   // GroupNorm sums [B][G][2] (sum, sum of squares) in 2^-24 fixed point, or null
                                  // (integer atomics are associative: the result does not depend on tile order)
     int lgs;                     // log2(channels per group)
@@ -77,6 +84,7 @@ struct ConvGemmDesc {
     const __nv_bfloat16* res = nullptr; int res_ld = 0;
     __nv_bfloat16* out = nullptr; int out_ld = 0;
     int act = kActNone;
+    const float* bias2 = nullptr; __nv_bfloat16* out2 = nullptr; int out2_ld = 0;   // kHalo1R
     unsigned long long* stats = nullptr; int groups = 0;
     int force_nt = 0;                    // 0 = auto
     int TW = 0;                          // 0 = auto

@@ -68,6 +68,24 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restri
     }
 }
 
+// ResnetBlock block1 conv + res_conv sharing one pass over the input (conv_gemm.cuh kHalo1R):
+// dst[co][cblk][10][64]: taps 0..8 = the 3x3 kernel, tap 9 = the 1x1 res_conv weight.
+__global__ void pack_weight_res_kernel(const float* __restrict__ w3, const float* __restrict__ w1, bf16* __restrict__ dst,
+                                       int Cout, int Cin) {
+    const size_t total = static_cast<size_t>(Cout) * Cin * 10;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int cl = static_cast<int>(i % 64);
+        size_t r = i / 64;
+        const int tap = static_cast<int>(r % 10); r /= 10;
+        const int cb = static_cast<int>(r % (Cin / 64));
+        const int co = static_cast<int>(r / (Cin / 64));
+        const int ci = cb * 64 + cl;
+        const size_t o = static_cast<size_t>(co) * Cin + ci;
+        dst[i] = __float2bfloat16_rn(tap < 9 ? w3[o * 9 + tap] : w1[o]);
+    }
+}
+
 // Upsample(nearest x2) + conv3x3 as four 2x2 phase convolutions (conv_gemm.cuh kHaloUp):
 // dst[co][cblk][phase = py*2+px][tap = dy*2+dx][64]; rows {w0 | w1+w2} for py = 0 and {w0+w1 | w2} for py = 1, same in x.
 __global__ void pack_upconv_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int Cout, int Cin) {
@@ -335,6 +353,15 @@ int finalize(ndiff_engine* e, cudaStream_t s) {
         if (pack_conv(e, rb.name + ".block1.proj", rb.cout, rb.cin, 3, false, s)) return 1;
         if (pack_conv(e, rb.name + ".block2.proj", rb.cout, rb.cout, 3, false, s)) return 1;
         if (rb.cin != rb.cout && pack_conv(e, rb.name + ".res_conv", rb.cout, rb.cin, 1, false, s)) return 1;
+        if (rb.cin != rb.cout) {   // the same two layers as ONE operand for the fused kHalo1R form
+            const std::string key = rb.name + ".block1.proj#res";
+            bf16* dst = e->packed.count(key) ? e->packed[key] : nullptr;
+            if (!dst && e->alloc(&dst, static_cast<size_t>(rb.cout) * rb.cin * 10)) return 1;
+            pack_weight_res_kernel<<<256, 256, 0, s>>>(e->pf(rb.name + ".block1.proj.weight"), e->pf(rb.name + ".res_conv.weight"),
+                                                       dst, rb.cout, rb.cin);
+            NDIFF_CUDA_OK(cudaGetLastError());
+            e->packed[key] = dst;
+        }
         for (const char* blk : {".block1.norm", ".block2.norm"}) {
             if (check_shape(e, rb.name + blk + ".weight", {rb.cout})) return 1;
             if (check_shape(e, rb.name + blk + ".bias", {rb.cout})) return 1;
@@ -486,7 +513,8 @@ struct Builder {
 
     // generic conv / GEMM launch -> new activation
     Act conv(const std::string& wname, int mode, const Act& s0, const Act* s1, int Cout, int act, const float* vec,
-             int vec_ld, const Act* res, unsigned long long* stats, int groups) {
+             int vec_ld, const Act* res, unsigned long long* stats, int groups, const Act* out2 = nullptr,
+             const std::string& res_name = "") {
         const int Ho = mode == kS2D ? s0.H / 2 : s0.H, Wo = mode == kS2D ? s0.W / 2 : s0.W;
         Act out = make(Cout, Ho, Wo);
         if (err) return out;
@@ -499,7 +527,8 @@ struct Builder {
         d.B = e->B; d.H = Ho; d.W = Wo;
         d.src0 = s0.p; d.C0 = s0.C;
         if (s1) { d.src1 = s1->p; d.C1 = s1->C; }
-        d.weight = e->packed.at(wname);
+        d.weight = e->packed.at(mode == kHalo1R ? wname + "#res" : wname);
+        if (mode == kHalo1R) { d.bias2 = e->pf(res_name + ".bias"); d.out2 = out2->p; d.out2_ld = Cout; }
         d.Cout = Cout;
         d.bias = e->pf(wname + ".bias");
         d.vec = vec; d.vec_ld = vec_ld;
@@ -509,7 +538,7 @@ struct Builder {
         d.stats = stats; d.groups = groups;
         auto plan = std::make_shared<ConvGemmPlan>();
         if (conv_gemm_plan(d, e->num_sms, plan.get())) { err = 1; return out; }
-        const int taps = mode == kHalo1 ? 9 : (mode == kS2D ? 4 : 1);
+        const int taps = mode == kHalo1 ? 9 : (mode == kHalo1R ? 10 : (mode == kS2D ? 4 : 1));
         Op op;
         op.name = wname;
         op.flops = 2.0 * e->B * Ho * Wo * Cout * static_cast<double>(taps) * (s0.C + (s1 ? s1->C : 0));
@@ -538,7 +567,15 @@ struct Builder {
                  const Act* extra_res, bool defer_norm2 = false) {
         const int Cin = s0.C + (s1 ? s1->C : 0);
         unsigned long long* st1 = next_stats();
-        Act h = conv(n + ".block1.proj", kHalo1, s0, s1, Cout, kActNone, nullptr, 0, nullptr, st1, groups);
+        // res_conv (1x1 on the same concatenated input) rides along with block1's 3x3 conv as a tenth weight block
+        // (measured: a win where the activations dominate the traffic — C_out <= 128, i.e. the 128^2 and 256^2 levels; the
+        // 32^2 / 64^2 levels stream their weights and lose more to the smaller weight stages than the 1x1 pass costs)
+        const bool fuse_res = Cin != Cout && Cout <= 128 && fused && !direct3;
+        Act rfused;
+        if (fuse_res) rfused = make(Cout, s0.H, s0.W);
+        Act h = fuse_res ? conv(n + ".block1.proj", kHalo1R, s0, s1, Cout, kActNone, nullptr, 0, nullptr, st1, groups, &rfused,
+                                n + ".res_conv")
+                         : conv(n + ".block1.proj", kHalo1, s0, s1, Cout, kActNone, nullptr, 0, nullptr, st1, groups);
         gn(n + ".block1.norm", h, st1, groups, maps ? -1 : e->ss_off.at(n), maps, nullptr, nullptr);
         unsigned long long* st2 = next_stats();
         Act h2 = conv(n + ".block2.proj", kHalo1, h, nullptr, Cout, kActNone, nullptr, 0, nullptr, st2, groups);
@@ -546,12 +583,13 @@ struct Builder {
         if (defer_norm2) {
             // the consumer (fused heads kernel) applies block2.norm + the residual itself; the 1x1 res_conv output stays live
             Act r = s0;
-            if (Cin != Cout) r = conv(n + ".res_conv", kDirect, s0, s1, Cout, kActNone, nullptr, 0, nullptr, nullptr, 0);
+            if (fuse_res) r = rfused;
+            else if (Cin != Cout) r = conv(n + ".res_conv", kDirect, s0, s1, Cout, kActNone, nullptr, 0, nullptr, nullptr, 0);
             e->xf_stats = st2; e->xf_res = r; e->xf_groups = groups; e->xf_norm = n + ".block2.norm";
             return h2;
         }
         if (Cin != Cout) {
-            Act r = conv(n + ".res_conv", kDirect, s0, s1, Cout, kActNone, nullptr, 0, nullptr, nullptr, 0);
+            Act r = fuse_res ? rfused : conv(n + ".res_conv", kDirect, s0, s1, Cout, kActNone, nullptr, 0, nullptr, nullptr, 0);
             gn(n + ".block2.norm", h2, st2, groups, -1, nullptr, &r, extra_res);
             drop(r);
         } else {
