@@ -51,6 +51,7 @@ typedef struct ndiff_config {
 #define NDIFF_FLAG_PDL         32  /* chain the kernels of a step with programmatic dependent launch (measured: no gain inside a
                                       CUDA graph on B200, so it is off by default) */
 #define NDIFF_FLAG_HALO1       64  /* debug: 3x3 convs always use 128-pixel CTA tiles (one accumulator) */
+#define NDIFF_FLAG_NO_XF       128 /* debug: keep block1's GroupNorm-apply as its own pass instead of evaluating it inside block2's conv */
 #define NDIFF_FLAG_UNFUSED     16  /* debug: run the per-pixel 1x1 chains layer by layer instead of as fused tensor-core chains */
 
 /* One reverse step's scalars; the caller derives them from GaussianDiffusion's fp32 buffers

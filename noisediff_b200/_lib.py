@@ -18,6 +18,7 @@ FLAG_INIT_SIMT = 8
 FLAG_UNFUSED = 16
 FLAG_PDL = 32
 FLAG_HALO1 = 64
+FLAG_NO_XF = 128
 
 
 class Config(C.Structure):

@@ -22,14 +22,19 @@ namespace {
 constexpr int kEpiWarp0 = 4;
 constexpr int kEpiWarps = 8;                    // two warps per TMEM lane quarter, each takes every other 32-column chunk
 constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;
+constexpr int kXfWarp0 = kEpiWarp0 + kEpiWarps;  // XF kernels: four more warps transform the activation stages in place
+constexpr int kXfExtra = 4;                      // warps added by the XF kernels
+constexpr int kXfWarps = kXfExtra + 2;           // ... plus warps 2 and 3, idle after the TMEM allocation
+constexpr int kThreadsXf = (kXfWarp0 + kXfExtra) * 32;
 
 struct SmemTail {  // lives after the operand rings
-    uint64_t fullA[8], emptyA[8], fullB[16], emptyB[16];
+    uint64_t fullA[8], emptyA[8], fullB[16], emptyB[16], xfA[8];
     uint64_t tmem_full[2], tmem_empty[2];
     uint32_t tmem_base;
     uint32_t pad_;
     alignas(16) float bias[128];   // this CTA's N-tile slice of the bias (zeros when the layer has none)
     alignas(16) float bias2[128];  // kHalo1R: bias slice of the fused 1x1 residual convolution
+    alignas(16) float2 coef[512];  // XF: folded GroupNorm affine (A, B) per input channel of the current sample
 };
 
 // Tap geometry of the single-copy halo mode (compile-time: TW = 8 so that one 8-row UMMA group == one output row).
@@ -45,8 +50,13 @@ __host__ __device__ constexpr int halo_btaps(int nt, int sub) { return (sub == 2
 constexpr int kResBTaps = 2;                                             // kHalo1R: 10 weight blocks per channel block, two per stage
 constexpr int kUpBTaps = 4;                                              // kHaloUp: one stage = the 4 taps of one phase
 
-template <int NT, int MODE, bool RES>
-__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
+// XF: the input is the RAW output of the previous conv and the GroupNorm-apply pass that used to sit between the two
+// (y = SiLU(x * A_c + B_c), A/B folding mean, rstd, gamma, beta and the time scale/shift; Block.forward, ref :135-144) runs
+// here, in place on each activation stage between the TMA landing and the MMA: warps 2, 3, 12..15 rewrite the halo box in shared
+// memory (out-of-image pixels stay the TMA's zero fill = the conv's zero padding of the NORMALISED tensor), then hand the
+// stage to the MMA warp through xfA.  Same fp32 formulas and bf16 rounding as gn_apply_kernel, so results are bit-identical.
+template <int NT, int MODE, bool RES, bool XF = false>
+__global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem is only guaranteed 16-B aligned by the ABI; SWIZZLE_128B wants 1024
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -68,6 +78,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const uint32_t bar_fullA = smem_u32(&tail->fullA[0]), bar_emptyA = smem_u32(&tail->emptyA[0]);
     const uint32_t bar_fullB = smem_u32(&tail->fullB[0]), bar_emptyB = smem_u32(&tail->emptyB[0]);
     const uint32_t bar_tfull = smem_u32(&tail->tmem_full[0]), bar_tempty = smem_u32(&tail->tmem_empty[0]);
+    const uint32_t bar_xfA = smem_u32(&tail->xfA[0]);
+    const uint32_t bar_readyA = XF ? bar_xfA : bar_fullA;      // what the MMA warp waits on before reading an A stage
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -87,7 +99,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         tma_prefetch_desc(&a.tmB);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < a_stages; ++i) { mbar_init(&tail->fullA[i], 1); mbar_init(&tail->emptyA[i], 1); }
+        for (int i = 0; i < a_stages; ++i) { mbar_init(&tail->fullA[i], 1); mbar_init(&tail->emptyA[i], 1); mbar_init(&tail->xfA[i], kXfWarps); }
         for (int i = 0; i < b_stages; ++i) { mbar_init(&tail->fullB[i], 1); mbar_init(&tail->emptyB[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tail->tmem_full[i], 1); mbar_init(&tail->tmem_empty[i], kEpiWarps); }
         fence_mbar_init();
@@ -201,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const uint32_t d_tmem = tmem_base + acc * kSub * NT;
             for (int cb = 0; cb < CB; ++cb) {
                 if constexpr (kHalo) {
-                    mbar_wait(bar_fullA + sa * 8, pa);
+                    mbar_wait(bar_readyA + sa * 8, pa);
                     tc_fence_after();
                     const uint32_t a_base = umma_desc_lo(ringA + sa * kAStage);
                     if constexpr (RES && kUp) {
@@ -316,7 +328,99 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             __syncwarp();
             if (++acc == 2) { acc = 0; pacc ^= 1; }
         }
-    } else if (warp >= kEpiWarp0) {
+    } else if (XF && (warp == 2 || warp == 3 || warp >= kXfWarp0)) {
+        // ================================ in-place GroupNorm-apply + SiLU on the landed activation stages ===============
+        if constexpr (XF && kHalo && !kUp) {
+            const int t = (warp >= kXfWarp0 ? warp - kXfWarp0 + 2 : warp - 2) * 32 + lane;           // 0..191
+            const int o = t & 7;                                 // this thread's channel octet inside a 64-channel block
+            constexpr int kBoxW = kHaloTW + 2;
+            constexpr int kPix = (kSub * kHaloTH + 2) * kBoxW;   // pixels of one halo box
+            const int Cin = CB * 64;
+            int sa = 0, pa = 0, cur_b = -1;
+            pdl_wait();                                          // statistics / scale-shift come from the previous kernels
+            for (int mt = m_begin; mt < m_end; ++mt) {
+                int m = mt;
+                const int tx = m % a.tiles_x; m /= a.tiles_x;
+                const int ty = m % a.tiles_y;
+                const int b = m / a.tiles_y;
+                if (b != cur_b) {
+                    cur_b = b;
+                    named_bar_sync(1, kXfWarps * 32);            // nobody still reads the previous sample's table
+                    for (int c = t; c < Cin; c += kXfWarps * 32) {
+                        const int g = c >> a.xf_lgs;
+                        const double inv_n = 1.0 / (static_cast<double>(a.H) * a.W * (1 << a.xf_lgs));
+                        const double s_ = static_cast<double>(static_cast<long long>(a.xf_stats[(b * a.xf_G + g) * 2])) * (1.0 / 16777216.0);
+                        const double q_ = static_cast<double>(static_cast<long long>(a.xf_stats[(b * a.xf_G + g) * 2 + 1])) * (1.0 / 16777216.0);
+                        const double meand = s_ * inv_n;
+                        const float mean = static_cast<float>(meand);
+                        const float var = fmaxf(static_cast<float>(q_ * inv_n - meand * meand), 0.f);
+                        const float rstd = rsqrtf(var + a.xf_eps);
+                        float Aj = rstd * __ldg(a.xf_gamma + c);
+                        float Bj = __ldg(a.xf_beta + c) - mean * Aj;
+                        if (a.xf_ss) {
+                            const float sc = a.xf_ss[static_cast<size_t>(b) * a.xf_ss_ld + c] + 1.0f;
+                            const float sh = a.xf_ss[static_cast<size_t>(b) * a.xf_ss_ld + Cin + c];
+                            Aj *= sc;
+                            Bj = Bj * sc + sh;
+                        }
+                        // stored halved: SiLU(y) = h + h tanh(h) with h = y / 2 = fma(x, A/2, B/2) — exact, powers of two
+                        tail->coef[c] = make_float2(0.5f * Aj, 0.5f * Bj);
+                    }
+                    named_bar_sync(1, kXfWarps * 32);
+                }
+                const int gx0 = tx * a.TW - 1, gy0 = ty * a.TH - 1;
+                for (int cb = 0; cb < CB; ++cb) {
+                    float A[8], Bc[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j += 2) {
+                        const float4 c2 = *reinterpret_cast<const float4*>(&tail->coef[cb * 64 + o * 8 + j]);
+                        A[j] = c2.x; Bc[j] = c2.y; A[j + 1] = c2.z; Bc[j + 1] = c2.w;
+                    }
+                    mbar_wait(bar_fullA + sa * 8, pa);
+                    const uint32_t base = ringA + sa * kAStage;
+                    // batches of kXfBatch chunks per thread: all 16-byte loads of a batch are issued before any arithmetic, and
+                    // the loop body is branch-free (loads are always inside the stage; only the store is predicated)
+                    constexpr int kXfBatch = kSub == 2 ? 5 : 4;      // 15 = 3 x 5 (34 x 10 box) / 8 = 2 x 4 (18 x 10 box) passes of 24 pixels
+                    constexpr int kIters = (kPix + kXfWarps * 4 - 1) / (kXfWarps * 4);
+#pragma unroll 1
+                    for (int i0 = 0; i0 < kIters; i0 += kXfBatch) {
+                        uint4 u[kXfBatch];
+                        uint32_t addr[kXfBatch];
+                        bool ok[kXfBatch];
+#pragma unroll
+                        for (int k = 0; k < kXfBatch; ++k) {
+                            const int pr = (t >> 3) + (i0 + k) * (kXfWarps * 4);
+                            const int p = pr < kPix ? pr : kPix - 1;
+                            const int hy = (p * 205) >> 11;          // p / 10 for p < 1024
+                            const int hx = p - hy * kBoxW;
+                            ok[k] = pr < kPix && static_cast<unsigned>(gy0 + hy) < static_cast<unsigned>(a.H) &&
+                                    static_cast<unsigned>(gx0 + hx) < static_cast<unsigned>(a.W);
+                            addr[k] = base + p * 128 + ((o ^ (p & 7)) << 4);
+                            u[k] = lds128(addr[k]);
+                        }
+#pragma unroll
+                        for (int k = 0; k < kXfBatch; ++k) {
+                            const float2 f0 = unpack_bf16(u[k].x), f1 = unpack_bf16(u[k].y), f2 = unpack_bf16(u[k].z), f3 = unpack_bf16(u[k].w);
+                            auto act = [](float x, float ah, float bh) {
+                                const float h = fmaf(x, ah, bh);
+                                return fmaf(h, tanh_approx(h), h);
+                            };
+                            uint4 w;
+                            w.x = pack_bf16(act(f0.x, A[0], Bc[0]), act(f0.y, A[1], Bc[1]));
+                            w.y = pack_bf16(act(f1.x, A[2], Bc[2]), act(f1.y, A[3], Bc[3]));
+                            w.z = pack_bf16(act(f2.x, A[4], Bc[4]), act(f2.y, A[5], Bc[5]));
+                            w.w = pack_bf16(act(f3.x, A[6], Bc[6]), act(f3.y, A[7], Bc[7]));
+                            if (ok[k]) sts128(addr[k], w);
+                        }
+                    }
+                    fence_proxy_async();                         // generic-proxy writes -> visible to the tensor core's reads
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_xfA + sa * 8);
+                    if (++sa == a_stages) { sa = 0; pa ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
         // ================================ epilogue =============================================================
         // Warp w may read TMEM lanes 32*(w%4)..+31 (= 32 pixels of the tile); the two warps of a lane quarter split the
         // tile's 32-column chunks.  GroupNorm partial sums (per 8 columns) stay in registers across tiles and are flushed
@@ -631,6 +735,15 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     a.bias = d.bias; a.vec = d.vec; a.vec_ld = d.vec_ld; a.res = d.res; a.res_ld = d.res_ld;
     a.out = d.out; a.out_ld = d.out_ld; a.act = d.act;
     a.bias2 = d.bias2; a.out2 = d.out2; a.out2_ld = d.out2_ld;
+    plan->xf = d.xf_stats != nullptr;
+    if (plan->xf) {
+        NDIFF_REQUIRE((d.mode == kHalo1 || d.mode == kHalo2) && d.C1 == 0 && d.C0 <= 512, "fused GroupNorm input: single-source 3x3 conv with C_in <= 512");
+        NDIFF_REQUIRE(d.xf_gamma && d.xf_beta && d.xf_groups > 0 && d.C0 % d.xf_groups == 0, "fused GroupNorm input: bad arguments");
+        const int gs = d.C0 / d.xf_groups;
+        NDIFF_REQUIRE(gs >= 8 && (gs & (gs - 1)) == 0, "fused GroupNorm input: group size must be a power of two >= 8");
+        a.xf_stats = d.xf_stats; a.xf_gamma = d.xf_gamma; a.xf_beta = d.xf_beta; a.xf_ss = d.xf_ss; a.xf_ss_ld = d.xf_ss_ld;
+        a.xf_G = d.xf_groups; a.xf_lgs = ilog2(gs); a.xf_eps = d.xf_eps;
+    }
     NDIFF_REQUIRE(!res2 || (d.out2 != nullptr && d.out2_ld % 8 == 0), "kHalo1R needs the residual-conv output");
     a.stats = d.stats; a.G = d.groups;
     if (d.stats) {
@@ -645,6 +758,13 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
 namespace {
 template <int NT, int MODE, bool RES>
 int launch_one(const ConvGemmPlan& plan, cudaStream_t stream) {
+    if constexpr (MODE == kHalo1 || MODE == kHalo2) {
+        if (plan.xf) {
+            NDIFF_CUDA_OK(launch_pdl(conv_gemm_kernel<NT, MODE, RES, true>, dim3(plan.grid), dim3(kThreadsXf), plan.smem_bytes, stream,
+                                     plan.args));
+            return 0;
+        }
+    }
     NDIFF_CUDA_OK(launch_pdl(conv_gemm_kernel<NT, MODE, RES>, dim3(plan.grid), dim3(kThreads), plan.smem_bytes, stream, plan.args));
     return 0;
 }
@@ -656,6 +776,12 @@ template <int NT, int MODE>
 cudaError_t opt_in() {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<NT, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
+    if constexpr (MODE == kHalo1 || MODE == kHalo2) {
+        e = cudaFuncSetAttribute(conv_gemm_kernel<NT, MODE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(conv_gemm_kernel<NT, MODE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+    }
     return cudaFuncSetAttribute(conv_gemm_kernel<NT, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 }  // namespace

@@ -53,6 +53,11 @@ struct ConvGemmArgs {
     const float* bias2;          // kHalo1R: bias and output of the fused 1x1 residual convolution
     __nv_bfloat16* out2;
     int out2_ld;
+    // XF kernels: GroupNorm-apply + scale/shift + SiLU of the INPUT, evaluated in shared memory (see conv_gemm.cu)
+    const unsigned long long* xf_stats;   // the producing conv's sums [B][xf_G][2]
+    const float* xf_gamma; const float* xf_beta;
+    const float* xf_ss; int xf_ss_ld;     // per-sample [scale C | shift C] at xf_ss[b * xf_ss_ld], or null
+    int xf_G, xf_lgs; float xf_eps;
     unsigned long long* stats;   // GroupNorm sums [B][G][2] (sum, sum of squares) in 2^-24 fixed point, or null
                                  // (integer atomics are associative: the result does not depend on tile order)
     int lgs;                     // log2(channels per group)
@@ -63,6 +68,7 @@ struct ConvGemmArgs {
 struct ConvGemmPlan {
     ConvGemmArgs args;
     int NT;          // 64 or 128
+    bool xf;         // input transform (fused GroupNorm-apply) variant
     int grid;
     int smem_bytes;
 };
@@ -86,6 +92,9 @@ struct ConvGemmDesc {
     int act = kActNone;
     const float* bias2 = nullptr; __nv_bfloat16* out2 = nullptr; int out2_ld = 0;   // kHalo1R
     unsigned long long* stats = nullptr; int groups = 0;
+    // fused GroupNorm-apply of the input (kHalo1 / kHalo2, single source): statistics of the producing conv etc.
+    const unsigned long long* xf_stats = nullptr; const float* xf_gamma = nullptr; const float* xf_beta = nullptr;
+    const float* xf_ss = nullptr; int xf_ss_ld = 0; int xf_groups = 0; float xf_eps = 1e-5f;
     int force_nt = 0;                    // 0 = auto
     int TW = 0;                          // 0 = auto
 };

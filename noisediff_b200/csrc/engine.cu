@@ -490,16 +490,25 @@ int finalize(ndiff_engine* e, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------------------
 // plan construction
 // ------------------------------------------------------------------------------------------------------------
+struct XfSpec {      // GroupNorm-apply of a conv's INPUT (ConvGemmDesc::xf_*)
+    const unsigned long long* stats = nullptr;
+    const float* gamma = nullptr; const float* beta = nullptr;
+    const float* ss = nullptr; int ss_ld = 0;
+    int groups = 0;
+};
+
 struct Builder {
     ndiff_engine* e;
     int err = 0;
     int stats_slot = 0;
     bool direct3;
     bool fused;       // per-pixel 1x1 chains run as one kernel (pixel_chain.cuh)
+    bool xf_ok;       // block1.norm folded into block2's conv (conv_gemm.cu XF kernels)
 
     explicit Builder(ndiff_engine* eng)
         : e(eng), direct3((eng->cfg.flags & NDIFF_FLAG_CONV_DIRECT) != 0),
-          fused((eng->cfg.flags & NDIFF_FLAG_UNFUSED) == 0 && eng->dim == 64) {}
+          fused((eng->cfg.flags & NDIFF_FLAG_UNFUSED) == 0 && eng->dim == 64),
+          xf_ok((eng->cfg.flags & (NDIFF_FLAG_UNFUSED | NDIFF_FLAG_NO_XF | NDIFF_FLAG_CONV_DIRECT)) == 0) {}
 
     Act make(int C, int H, int W) {
         Act a; a.C = C; a.H = H; a.W = W;
@@ -514,7 +523,7 @@ struct Builder {
     // generic conv / GEMM launch -> new activation
     Act conv(const std::string& wname, int mode, const Act& s0, const Act* s1, int Cout, int act, const float* vec,
              int vec_ld, const Act* res, unsigned long long* stats, int groups, const Act* out2 = nullptr,
-             const std::string& res_name = "") {
+             const std::string& res_name = "", const XfSpec* xf = nullptr) {
         const int Ho = mode == kS2D ? s0.H / 2 : s0.H, Wo = mode == kS2D ? s0.W / 2 : s0.W;
         Act out = make(Cout, Ho, Wo);
         if (err) return out;
@@ -536,6 +545,10 @@ struct Builder {
         d.out = out.p; d.out_ld = Cout;
         d.act = act;
         d.stats = stats; d.groups = groups;
+        if (xf) {
+            d.xf_stats = xf->stats; d.xf_gamma = xf->gamma; d.xf_beta = xf->beta; d.xf_ss = xf->ss; d.xf_ss_ld = xf->ss_ld;
+            d.xf_groups = xf->groups;
+        }
         auto plan = std::make_shared<ConvGemmPlan>();
         if (conv_gemm_plan(d, e->num_sms, plan.get())) { err = 1; return out; }
         const int taps = mode == kHalo1 ? 9 : (mode == kHalo1R ? 10 : (mode == kS2D ? 4 : 1));
@@ -576,9 +589,22 @@ struct Builder {
         Act h = fuse_res ? conv(n + ".block1.proj", kHalo1R, s0, s1, Cout, kActNone, nullptr, 0, nullptr, st1, groups, &rfused,
                                 n + ".res_conv")
                          : conv(n + ".block1.proj", kHalo1, s0, s1, Cout, kActNone, nullptr, 0, nullptr, st1, groups);
-        gn(n + ".block1.norm", h, st1, groups, maps ? -1 : e->ss_off.at(n), maps, nullptr, nullptr);
+        // block1.norm (GroupNorm + time scale/shift + SiLU) has ONE consumer, block2's conv: it is evaluated inside that conv,
+        // on the activation tiles in shared memory, instead of as a read-modify-write pass over HBM.  (ResnetBlock2's per-pixel
+        // scale/shift maps stay a separate pass.)
+        // (measured: a win at the 128^2 and 256^2 levels; below that the tensors are L2-sized, the separate pass costs 15-50 us
+        // and the in-kernel transform, which competes with the MMA for shared-memory bandwidth, costs more)
+        const bool fuse_norm1 = xf_ok && !maps && s0.H * s0.W >= (e->H * e->W) / 4;
+        XfSpec xs;
+        if (fuse_norm1) {
+            xs.stats = st1; xs.gamma = e->pf(n + ".block1.norm.weight"); xs.beta = e->pf(n + ".block1.norm.bias");
+            xs.ss = e->ss_cur + e->ss_off.at(n); xs.ss_ld = e->ss_total; xs.groups = groups;
+        } else {
+            gn(n + ".block1.norm", h, st1, groups, maps ? -1 : e->ss_off.at(n), maps, nullptr, nullptr);
+        }
         unsigned long long* st2 = next_stats();
-        Act h2 = conv(n + ".block2.proj", kHalo1, h, nullptr, Cout, kActNone, nullptr, 0, nullptr, st2, groups);
+        Act h2 = conv(n + ".block2.proj", kHalo1, h, nullptr, Cout, kActNone, nullptr, 0, nullptr, st2, groups, nullptr, "",
+                      fuse_norm1 ? &xs : nullptr);
         drop(h);
         if (defer_norm2) {
             // the consumer (fused heads kernel) applies block2.norm + the residual itself; the 1x1 res_conv output stays live

@@ -67,10 +67,19 @@ def test_forward_matches_reference_layer_by_layer():
     assert dict(rows)["pos_emb"] < 1e-5 and dict(rows)["out(v)"] < 2.5e-2
 
 
-@pytest.mark.parametrize("flags", [_lib.FLAG_CONV_DIRECT | _lib.FLAG_NO_GRAPH, _lib.FLAG_INIT_SIMT, _lib.FLAG_UNFUSED, _lib.FLAG_HALO1 | _lib.FLAG_PDL])
+@pytest.mark.parametrize("flags", [_lib.FLAG_CONV_DIRECT | _lib.FLAG_NO_GRAPH, _lib.FLAG_INIT_SIMT, _lib.FLAG_UNFUSED, _lib.FLAG_HALO1 | _lib.FLAG_PDL,
+                                   _lib.FLAG_NO_XF])
 def test_forward_other_conv_staging_modes_agree(flags):
     rows, _, _ = layer_report(flags=flags)
     assert all(e < 3e-2 for _, e in rows), rows
+
+
+def test_fused_groupnorm_input_is_bit_identical_to_the_separate_pass():
+    """block1.norm evaluated inside block2's conv (on the tiles in shared memory) uses the same fp32 formulas and bf16 rounding
+    as the stand-alone GroupNorm-apply kernel: the network output must not move."""
+    _, a, _ = layer_report(flags=0)
+    _, b, _ = layer_report(flags=_lib.FLAG_NO_XF)
+    assert rel_l2(a, b) < 1e-6, rel_l2(a, b)
 
 
 def test_forward_full_size_golden(net):
