@@ -168,6 +168,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner must not precede the JSON line on stdout
         dist.init_process_group("nccl", device_id=dev)
     W = max(args.warmup, 3)
     K = max(args.steps, 1)

@@ -24,7 +24,9 @@ constexpr int kEpiWarps = 8;                    // two warps per TMEM lane quart
 constexpr int kThreads = (kEpiWarp0 + kEpiWarps) * 32;
 constexpr int kXfWarp0 = kEpiWarp0 + kEpiWarps;  // XF kernels: four more warps transform the activation stages in place
 constexpr int kXfExtra = 4;                      // warps added by the XF kernels
-constexpr int kXfWarps = kXfExtra + 2;           // ... plus warps 2 and 3, idle after the TMEM allocation
+constexpr int kXfWarps = kXfExtra + 2;           // ... plus warps 2 and 3, idle after the TMEM allocation.  (Measured: ten transform
+                                                 // warps with four epilogue warps are SLOWER — the transform shares the shared-memory
+                                                 // pipe with the MMA's operand reads, which is what bounds the 64-channel layers.)
 constexpr int kThreadsXf = (kXfWarp0 + kXfExtra) * 32;
 
 struct SmemTail {  // lives after the operand rings
