@@ -238,6 +238,8 @@ struct ndiff_engine {
     Act xf{}, sf{};
     // final_res_block.block2.norm folded into the heads kernel (FinalArgs::gn_*): xf is then the raw block2 conv output
     const unsigned long long* xf_stats = nullptr; Act xf_res{}; int xf_groups = 0; std::string xf_norm;
+    float* sn = nullptr;           // fp32 [npix][4] shot-noise image written by the fused shot-branch tail (pixel_chain.cuh), or unused
+    bool tail_fused = false;
     cudaGraphExec_t step_exec = nullptr, fwd_exec = nullptr;
     cudaStream_t cap_stream = nullptr;
     double conv_flops = 0.0;
@@ -416,6 +418,19 @@ int finalize(ndiff_engine* e, cudaStream_t s) {
         NDIFF_CUDA_OK(cudaMemcpyAsync(f + 64, e->pf("shot_mlp1.fc2.bias"), sizeof(float) * 64, cudaMemcpyDeviceToDevice, s));
         NDIFF_CUDA_OK(cudaMemcpyAsync(f + 512, e->pf("shot_mlp2.fc1.bias"), sizeof(float) * 64, cudaMemcpyDeviceToDevice, s));
         NDIFF_CUDA_OK(cudaMemcpyAsync(f + 576, e->pf("shot_mlp2.fc2.bias"), sizeof(float) * 64, cudaMemcpyDeviceToDevice, s));
+        // shot-branch tail: fc1 (bf16 rows) | fc2 (fp16, 4 live rows of 16) | zero padding
+        if (!e->chain_w.count("tail")) {
+            if (e->alloc(&e->chain_w["tail"], static_cast<size_t>(kTailRows) * 64)) return 1;
+            if (e->alloc(&e->chain_f["tail"], kTailFloats)) return 1;
+        }
+        bf16* tw = e->chain_w["tail"];
+        float* tf = e->chain_f["tail"];
+        NDIFF_CUDA_OK(cudaMemsetAsync(tw, 0, sizeof(bf16) * kTailRows * 64, s));
+        NDIFF_CUDA_OK(cudaMemsetAsync(tf, 0, sizeof(float) * kTailFloats, s));
+        if (pack_chain_weight_launch(e->pf("shot_mlp3.fc1.weight"), tw, 64, 64, false, s)) return 1;
+        if (pack_chain_weight_launch(e->pf("shot_mlp3.fc2.weight"), tw + 64 * 64, 4, 64, true, s)) return 1;
+        NDIFF_CUDA_OK(cudaMemcpyAsync(tf, e->pf("shot_mlp3.fc1.bias"), sizeof(float) * 64, cudaMemcpyDeviceToDevice, s));
+        NDIFF_CUDA_OK(cudaMemcpyAsync(tf + 64, e->pf("shot_mlp3.fc2.bias"), sizeof(float) * 4, cudaMemcpyDeviceToDevice, s));
     }
     for (int i = 0; i < 3; ++i) {
         if (pack_conv(e, "downs." + std::to_string(i) + ".3.1", d[i + 1], d[i], 1, true, s)) return 1;
@@ -491,6 +506,13 @@ int finalize(ndiff_engine* e, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------------------
 // plan construction
 // ------------------------------------------------------------------------------------------------------------
+struct DeferredNorm {   // a ResnetBlock whose last GroupNorm-apply (+ residual) is left to the consuming kernel
+    const unsigned long long* stats = nullptr;
+    Act res{};
+    int groups = 0;
+    std::string norm;
+};
+
 struct XfSpec {      // GroupNorm-apply of a conv's INPUT (ConvGemmDesc::xf_*)
     const unsigned long long* stats = nullptr;
     const float* gamma = nullptr; const float* beta = nullptr;
@@ -579,7 +601,7 @@ struct Builder {
 
     // ResnetBlock / ResnetBlock2 (ref :146-196): returns block output; consumes nothing
     Act resblock(const std::string& n, const Act& s0, const Act* s1, int Cout, int groups, const bf16* maps,
-                 const Act* extra_res, bool defer_norm2 = false) {
+                 const Act* extra_res, DeferredNorm* defer = nullptr) {
         const int Cin = s0.C + (s1 ? s1->C : 0);
         unsigned long long* st1 = next_stats();
         // res_conv (1x1 on the same concatenated input) rides along with block1's 3x3 conv as a tenth weight block
@@ -608,12 +630,12 @@ struct Builder {
         Act h2 = conv(n + ".block2.proj", kHalo1, h, nullptr, Cout, kActNone, nullptr, 0, nullptr, st2, groups, nullptr, "",
                       fuse_norm1 ? &xs : nullptr);
         drop(h);
-        if (defer_norm2) {
-            // the consumer (fused heads kernel) applies block2.norm + the residual itself; the 1x1 res_conv output stays live
+        if (defer) {
+            // the consumer (heads kernel / shot-branch tail) applies block2.norm + the residual itself; the residual stays live
             Act r = s0;
             if (fuse_res) r = rfused;
             else if (Cin != Cout) r = conv(n + ".res_conv", kDirect, s0, s1, Cout, kActNone, nullptr, 0, nullptr, nullptr, 0);
-            e->xf_stats = st2; e->xf_res = r; e->xf_groups = groups; e->xf_norm = n + ".block2.norm";
+            defer->stats = st2; defer->res = r; defer->groups = groups; defer->norm = n + ".block2.norm";
             return h2;
         }
         if (Cin != Cout) {
@@ -726,11 +748,36 @@ int build_plan(ndiff_engine* e) {
         b.drop(s3);
         b.name("shot_mlp2", s4);
     }
-    Act s5 = b.resblock("shot_time", s4, nullptr, dim, 2, nullptr, &s1);   // + r (ref :603) folded into the apply pass
-    b.drop(s4); b.drop(s1);
-    Act s6 = b.gemm("shot_mlp3.fc1", s5, dim, kActGelu);
-    b.drop(s5);
-    e->sf = s6;
+    // fused tail: block2.norm + residuals + shot_mlp3 (fc1, GELU, fc2) in one per-pixel kernel that leaves the 4-channel
+    // shot-noise image (debug runs that keep every activation use the layer-by-layer form)
+    e->tail_fused = b.fused && !e->keep_all;
+    if (e->tail_fused) {
+        DeferredNorm dn;
+        Act h2 = b.resblock("shot_time", s4, nullptr, dim, 2, nullptr, &s1, &dn);
+        if (b.err) return 1;
+        if (!e->sn && e->alloc(&e->sn, static_cast<size_t>(npix) * 4)) return 1;
+        TailDesc td;
+        td.npix = npix; td.HW = H * W;
+        td.h2 = h2.p; td.r1 = dn.res.p; td.r2 = s1.p;
+        td.weights = e->chain_w.at("tail"); td.fvec = e->chain_f.at("tail");
+        td.stats = dn.stats; td.gamma = e->pf(dn.norm + ".weight"); td.beta = e->pf(dn.norm + ".bias"); td.groups = dn.groups;
+        td.out = e->sn;
+        auto plan = std::make_shared<TailPlan>();
+        if (tail_chain_plan(td, e->num_sms, plan.get())) return 1;
+        Op op; op.name = "shot_time.block2.norm+shot_mlp3(fused chain)";
+        op.flops = 2.0 * npix * (64.0 * 64 + 64.0 * 4);
+        op.chain = true;
+        op.fn = [plan](cudaStream_t st) { return tail_chain_launch(*plan, st); };
+        e->net_ops.push_back(op);
+        b.drop(h2); b.drop(s4); b.drop(s1);
+        e->sf = Act{};
+    } else {
+        Act s5 = b.resblock("shot_time", s4, nullptr, dim, 2, nullptr, &s1);   // + r (ref :603) folded into the apply pass
+        b.drop(s4); b.drop(s1);
+        Act s6 = b.gemm("shot_mlp3.fc1", s5, dim, kActGelu);
+        b.drop(s5);
+        e->sf = s6;
+    }
 
     // ---- main U-Net (ref :606-643)
     Act x0 = b.make(dim, H, W);
@@ -849,7 +896,9 @@ int build_plan(ndiff_engine* e) {
     // materialise it instead, so the layer-by-layer parity test still sees the block output)
     const bool fuse_tail = b.fused && !e->keep_all;
     e->xf_stats = nullptr;
-    Act fr = b.resblock("final_res_block", pb2, &x0, dim, 8, nullptr, nullptr, fuse_tail);
+    DeferredNorm fdn;
+    Act fr = b.resblock("final_res_block", pb2, &x0, dim, 8, nullptr, nullptr, fuse_tail ? &fdn : nullptr);
+    if (fuse_tail) { e->xf_stats = fdn.stats; e->xf_res = fdn.res; e->xf_groups = fdn.groups; e->xf_norm = fdn.norm; }
     b.drop(pb2); b.drop(x0);
     e->xf = fr;
     if (b.err) return 1;
@@ -873,6 +922,7 @@ int run_net(ndiff_engine* e, cudaStream_t s, bool zero_stats = true) {
 int final_args(ndiff_engine* e, bool chain, FinalArgs* f) {
     memset(f, 0, sizeof(*f));
     f->xf = e->xf.p; f->sf = e->sf.p;
+    if (e->tail_fused) { f->sf = nullptr; f->sn = reinterpret_cast<const float4*>(e->sn); }
     f->wf = e->pf("final_conv.weight"); f->bfin = e->pf("final_conv.bias");
     f->ws = e->pf("shot_mlp3.fc2.weight"); f->bs = e->pf("shot_mlp3.fc2.bias");
     f->npix = e->B * e->H * e->W; f->C = e->dim; f->HW = e->H * e->W;

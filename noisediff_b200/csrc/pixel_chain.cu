@@ -354,6 +354,160 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Shot-branch tail: GroupNorm-apply + residuals -> fc1 -> GELU -> fc2 (see pixel_chain.cuh).  Same skeleton as the chain
+// kernel: three warpgroups, thread r = pixel r of its warpgroup's tile; the three input tiles arrive by TMA into three
+// blocks, the operand block A0 feeds both GEMMs.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kTailWgBytes = 4 * kBlk;     // H | R1 | R2 | A0
+
+struct TailSmem {
+    uint64_t bar_w, bar_x[kNWG], bar_mma[kNWG];
+    uint32_t tmem_base;
+    uint32_t pad_;
+    float fvec[kTailFloats];
+    alignas(16) float ctab[kNWG][2][2][64];     // per warpgroup / sample slot: [0] A/2, [1] B/2 of the folded GroupNorm affine
+};
+
+__global__ void __launch_bounds__(kThreads, 1) tail_chain_kernel(const __grid_constant__ TailArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int kWBytes = kTailRows * 128;
+    TailSmem* tail = reinterpret_cast<TailSmem*>(smem + kWBytes + kNWG * kTailWgBytes);
+    const int tid = threadIdx.x, wg = tid >> 7, r = tid & 127, q = (tid >> 5) & 3;
+    const uint32_t sW = smem_u32(smem);
+    const uint32_t sH = sW + kWBytes + wg * kTailWgBytes, sR1 = sH + kBlk, sR2 = sR1 + kBlk, sA0 = sR2 + kBlk;
+    const uint32_t bar_w = smem_u32(&tail->bar_w), bar_x = smem_u32(&tail->bar_x[wg]), bar_mma = smem_u32(&tail->bar_mma[wg]);
+    if (tid == 0) {
+        tma_prefetch_desc(&a.tmW); tma_prefetch_desc(&a.tmH); tma_prefetch_desc(&a.tmR1); tma_prefetch_desc(&a.tmR2);
+        mbar_init(&tail->bar_w, 1);
+        for (int i = 0; i < kNWG; ++i) { mbar_init(&tail->bar_x[i], 1); mbar_init(&tail->bar_mma[i], 1); }
+        fence_mbar_init();
+    }
+    if (tid < 32) tmem_alloc<kTmemCols>(&tail->tmem_base);
+    for (int i = tid; i < kTailFloats; i += kThreads) tail->fvec[i] = __ldg(a.fvec + i);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tail->tmem_base + wg * 128;
+    const uint32_t tmem_rd = tmem_d + (static_cast<uint32_t>(q * 32) << 16);
+    if (tid == 0) {
+        mbar_expect_tx(bar_w, kWBytes);
+        for (int i = 0; i < kTailRows / 64; ++i) tma_load_2d(sW + i * 64 * 128, &a.tmW, bar_w, 0, i * 64);
+    }
+    pdl_trigger();
+    pdl_wait();
+    const int tile0 = blockIdx.x * kNWG + wg, tile_step = gridDim.x * kNWG;
+    auto load_tile = [&](int tile) {
+        mbar_expect_tx(bar_x, 3 * kBlk);
+        tma_load_2d(sH, &a.tmH, bar_x, 0, tile * kTile);
+        tma_load_2d(sR1, &a.tmR1, bar_x, 0, tile * kTile);
+        tma_load_2d(sR2, &a.tmR2, bar_x, 0, tile * kTile);
+    };
+    if (r == 0 && tile0 < a.n_tiles) load_tile(tile0);
+    uint32_t xph = 0, mph = 0;
+    bool w_ready = false;
+    int tab_b0 = -1, tab_b1 = -1;
+    for (int tile = tile0; tile < a.n_tiles; tile += tile_step) {
+        const int p = tile * kTile + r;
+        const bool live = p < a.npix;
+        const int pc = live ? p : a.npix - 1;
+        const int b_first = (tile * kTile) / a.HW;
+        {
+            const int last = tile * kTile + kTile - 1;
+            const int b_last = (last < a.npix ? last : a.npix - 1) / a.HW;
+            if (b_first != tab_b0 || b_last != tab_b1) {     // (the previous tile's readers are past its first stage barrier)
+                tab_b0 = b_first; tab_b1 = b_last;
+                const int slot = r >> 6, c = r & 63, b = slot ? b_last : b_first;
+                const int g = c >> a.lgs;
+                const double inv_n = 1.0 / (static_cast<double>(a.HW) * (1 << a.lgs));
+                const double s_ = static_cast<double>(static_cast<long long>(a.stats[(b * a.G + g) * 2])) * (1.0 / 16777216.0);
+                const double q_ = static_cast<double>(static_cast<long long>(a.stats[(b * a.G + g) * 2 + 1])) * (1.0 / 16777216.0);
+                const double meand = s_ * inv_n;
+                const float mean = static_cast<float>(meand);
+                const float var = fmaxf(static_cast<float>(q_ * inv_n - meand * meand), 0.f);
+                const float rstd = rsqrtf(var + a.eps);
+                const float Aj = rstd * __ldg(a.gamma + c);
+                const float Bj = __ldg(a.beta + c) - mean * Aj;
+                tail->ctab[wg][slot][0][c] = 0.5f * Aj;      // SiLU(y) = h + h tanh(h), h = y / 2 (exact halving)
+                tail->ctab[wg][slot][1][c] = 0.5f * Bj;
+                named_bar_sync(1 + wg, 128);
+            }
+        }
+        const float* ct = &tail->ctab[wg][(pc / a.HW) != b_first ? 1 : 0][0][0];
+        // ---- y = SiLU(GN(h2)) + s4 + s1 -> A0 ---------------------------------------------------------------------------
+        mbar_wait(bar_x, xph);
+        xph ^= 1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint4 h = lds128(swz(sH, r, j)), r1 = lds128(swz(sR1, r, j)), r2 = lds128(swz(sR2, r, j));
+            const float4 a0 = *reinterpret_cast<const float4*>(ct + j * 8), a1 = *reinterpret_cast<const float4*>(ct + j * 8 + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(ct + 64 + j * 8), b1 = *reinterpret_cast<const float4*>(ct + 64 + j * 8 + 4);
+            auto act = [](float x, float ah, float bh) {
+                const float hh = fmaf(x, ah, bh);
+                return fmaf(hh, tanh_approx(hh), hh);
+            };
+            const float2 h0 = unpack_bf16(h.x), h1 = unpack_bf16(h.y), h2 = unpack_bf16(h.z), h3 = unpack_bf16(h.w);
+            const float2 p0 = unpack_bf16(r1.x), p1 = unpack_bf16(r1.y), p2 = unpack_bf16(r1.z), p3 = unpack_bf16(r1.w);
+            const float2 q0 = unpack_bf16(r2.x), q1 = unpack_bf16(r2.y), q2 = unpack_bf16(r2.z), q3 = unpack_bf16(r2.w);
+            uint4 u;
+            // same association as gn_apply_kernel: (SiLU + res1) + res2
+            u.x = pack_bf16((act(h0.x, a0.x, b0.x) + p0.x) + q0.x, (act(h0.y, a0.y, b0.y) + p0.y) + q0.y);
+            u.y = pack_bf16((act(h1.x, a0.z, b0.z) + p1.x) + q1.x, (act(h1.y, a0.w, b0.w) + p1.y) + q1.y);
+            u.z = pack_bf16((act(h2.x, a1.x, b1.x) + p2.x) + q2.x, (act(h2.y, a1.y, b1.y) + p2.y) + q2.y);
+            u.w = pack_bf16((act(h3.x, a1.z, b1.z) + p3.x) + q3.x, (act(h3.y, a1.w, b1.w) + p3.y) + q3.y);
+            sts128(swz(sA0, r, j), u);
+        }
+        // ---- shot_mlp3.fc1 + GELU -----------------------------------------------------------------------------------------
+        fence_proxy_async();
+        tc_fence_before();
+        named_bar_sync(1 + wg, 128);
+        if (r == 0) {
+            if (tile + tile_step < a.n_tiles) load_tile(tile + tile_step);     // everybody has consumed the three input blocks
+            if (!w_ready) { mbar_wait(bar_w, 0); w_ready = true; }
+            tc_fence_after();
+            issue_gemm<64>(tmem_d, sA0, sW, 1, 4);
+            umma_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, mph);
+        mph ^= 1;
+        tc_fence_after();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint32_t raw[32];
+            tmem_ld32(tmem_rd + h * 32, raw);
+            tmem_ld_wait();
+            store_half_gelu_f16(sA0, r, h, raw, tail->fvec + h * 32);
+        }
+        // ---- shot_mlp3.fc2 (64 -> 4, N padded to 16) ------------------------------------------------------------------------
+        fence_proxy_async();
+        tc_fence_before();
+        named_bar_sync(1 + wg, 128);
+        if (r == 0) {
+            tc_fence_after();
+            issue_gemm<16, true>(tmem_d, sA0, sW + 64 * 128, 1, 4);
+            umma_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, mph);
+        mph ^= 1;
+        tc_fence_after();
+        {
+            uint32_t raw[4];
+            tmem_ld4(tmem_rd, raw);
+            tmem_ld_wait();
+            if (live)
+                a.out[p] = make_float4(__uint_as_float(raw[0]) + tail->fvec[64], __uint_as_float(raw[1]) + tail->fvec[65],
+                                       __uint_as_float(raw[2]) + tail->fvec[66], __uint_as_float(raw[3]) + tail->fvec[67]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) {
+        tc_fence_after();
+        tmem_dealloc<kTmemCols>(tail->tmem_base);
+    }
+}
+
 __global__ void pack_chain_weight_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int N, int K, int KB,
                                          int f16) {
     const int total = KB * N * 64;
@@ -454,6 +608,50 @@ int pixel_chain_plan(const ChainDesc& d, int num_sms, ChainPlan* plan) {
     plan->grid = want < num_sms ? want : num_sms;
     plan->smem_bytes = chain_smem_bytes(d.prog);
     NDIFF_REQUIRE(plan->smem_bytes <= 227 * 1024, "pixel chain: shared-memory budget exceeded");
+    return 0;
+}
+
+static int tail_smem_bytes() { return 1024 + kTailRows * 128 + kNWG * kTailWgBytes + static_cast<int>(sizeof(TailSmem)); }
+
+int tail_chain_plan(const TailDesc& d, int num_sms, TailPlan* plan) {
+    {
+        static std::once_flag once;
+        static int init_rc = 0;
+        std::call_once(once, [] {
+            init_rc = cudaFuncSetAttribute(tail_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tail_smem_bytes()) == cudaSuccess ? 0 : 1;
+        });
+        NDIFF_REQUIRE(init_rc == 0, "tail chain: cannot opt in to the shared-memory size");
+    }
+    TailArgs& a = plan->args;
+    memset(&a, 0, sizeof(a));
+    NDIFF_REQUIRE(d.npix > 0 && d.HW > 0 && d.h2 && d.r1 && d.r2 && d.weights && d.fvec && d.stats && d.gamma && d.beta && d.out,
+                  "tail chain: null argument");
+    NDIFF_REQUIRE(d.groups > 0 && 64 % d.groups == 0, "tail chain: bad group count");
+    const int gs = 64 / d.groups;
+    NDIFF_REQUIRE(gs >= 8 && (gs & (gs - 1)) == 0, "tail chain: group size must be a power of two >= 8");
+    a.npix = d.npix; a.HW = d.HW; a.n_tiles = (d.npix + kTile - 1) / kTile;
+    a.fvec = d.fvec; a.stats = d.stats; a.gamma = d.gamma; a.beta = d.beta; a.G = d.groups; a.eps = 1e-5f;
+    a.lgs = 0;
+    while ((1 << a.lgs) < gs) ++a.lgs;
+    a.out = reinterpret_cast<float4*>(d.out);
+    const uint64_t adims[2] = {64, static_cast<uint64_t>(d.npix)};
+    const uint64_t astr[1] = {128};
+    const uint32_t abox[2] = {64, kTile};
+    if (encode_tensor_map(&a.tmH, d.h2, 2, adims, astr, abox, true)) return 1;
+    if (encode_tensor_map(&a.tmR1, d.r1, 2, adims, astr, abox, true)) return 1;
+    if (encode_tensor_map(&a.tmR2, d.r2, 2, adims, astr, abox, true)) return 1;
+    const uint64_t wdims[2] = {64, static_cast<uint64_t>(kTailRows)};
+    const uint32_t wbox[2] = {64, 64};
+    if (encode_tensor_map(&a.tmW, d.weights, 2, wdims, astr, wbox, true)) return 1;
+    const int want = (a.n_tiles + kNWG - 1) / kNWG;
+    plan->grid = want < num_sms ? want : num_sms;
+    plan->smem_bytes = tail_smem_bytes();
+    NDIFF_REQUIRE(plan->smem_bytes <= 227 * 1024, "tail chain: shared-memory budget exceeded");
+    return 0;
+}
+
+int tail_chain_launch(const TailPlan& plan, cudaStream_t stream) {
+    NDIFF_CUDA_OK(launch_pdl(tail_chain_kernel, dim3(plan.grid), dim3(kThreads), plan.smem_bytes, stream, plan.args));
     return 0;
 }
 

@@ -57,6 +57,34 @@ struct ChainDesc {
     __nv_bfloat16* out2 = nullptr;
 };
 
+// ---- tail of the shot-noise branch (Diffusion_arch.py:602-604) as ONE per-pixel kernel ---------------------------------------
+//   y = SiLU(GroupNorm(h2)) + s4 + s1        shot_time.block2.norm + the ResnetBlock residual + r_s   (:135-170, :603)
+//   shot_noise = fc2(GELU(fc1(y)))           shot_mlp3                                                  (:604)
+// h2 is the RAW output of shot_time.block2.proj (its GroupNorm sums come from that conv's epilogue); the result is the
+// 4-channel fp32 shot-noise image the heads kernel adds to final_conv's output.
+// weight blob: [128][64] 16-bit rows = fc1 (64 rows, bf16) | fc2 (16 rows, fp16, rows 4..15 zero) | zero padding;
+// fvec: [b_fc1 64][b_fc2 4][pad 60].
+constexpr int kTailRows = 128, kTailFloats = 128;
+struct TailArgs {
+    CUtensorMap tmH, tmR1, tmR2, tmW;
+    int npix, HW, n_tiles;
+    const float* fvec;
+    const unsigned long long* stats;    // [B][G][2] fixed-point sums of h2
+    const float* gamma; const float* beta;
+    int G, lgs; float eps;
+    float4* out;                        // [npix] fp32 x 4
+};
+struct TailPlan { TailArgs args; int grid; int smem_bytes; };
+struct TailDesc {
+    int npix = 0, HW = 0;
+    const __nv_bfloat16* h2 = nullptr; const __nv_bfloat16* r1 = nullptr; const __nv_bfloat16* r2 = nullptr;
+    const __nv_bfloat16* weights = nullptr; const float* fvec = nullptr;
+    const unsigned long long* stats = nullptr; const float* gamma = nullptr; const float* beta = nullptr; int groups = 0;
+    float* out = nullptr;
+};
+int tail_chain_plan(const TailDesc& d, int num_sms, TailPlan* plan);
+int tail_chain_launch(const TailPlan& plan, cudaStream_t stream);
+
 int pixel_chain_plan(const ChainDesc& d, int num_sms, ChainPlan* plan);
 int pixel_chain_launch(const ChainPlan& plan, cudaStream_t stream);
 int pixel_chain_init();

@@ -424,22 +424,19 @@ __global__ void __launch_bounds__(256) final_kernel(const FinalArgs a) {
 // kGn: the xf operand is SiLU(GroupNorm(xf)) + gn_res evaluated on the fly — final_res_block.block2.norm never
 // materialises (ref Diffusion_arch.py:135-170,640-643).
 // ---------------------------------------------------------------------------------------------------------------
-template <bool kGn>
-__global__ void __launch_bounds__(256) final64_kernel(const FinalArgs a) {
+template <bool kGn, bool kSf>
+__global__ void __launch_bounds__(256, 2) final64_kernel(const FinalArgs a) {
+    __shared__ __align__(16) float sw[2][4][64];      // final_conv / shot_mlp3.fc2 head weights
     const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
     pdl_trigger();
-    float wfr[4][8], wsr[4][8];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { wfr[k][j] = __ldg(a.wf + k * 64 + sub * 8 + j); wsr[k][j] = __ldg(a.ws + k * 64 + sub * 8 + j); }
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        sw[0][i >> 6][i & 63] = __ldg(a.wf + i);
+        sw[1][i >> 6][i & 63] = kSf ? __ldg(a.ws + i) : 0.f;
     }
-    const float bsum[4] = {a.bs[0] + a.bfin[0], a.bs[1] + a.bfin[1], a.bs[2] + a.bfin[2], a.bs[3] + a.bfin[3]};
-    float gam[8], bet[8];
-    if (kGn) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { gam[j] = __ldg(a.gn_gamma + sub * 8 + j); bet[j] = __ldg(a.gn_beta + sub * 8 + j); }
-    }
+    __syncthreads();
+    // kSf == false: the shot head arrives precomputed in a.sn (bias included)
+    const float bsum[4] = {(kSf ? a.bs[0] : 0.f) + a.bfin[0], (kSf ? a.bs[1] : 0.f) + a.bfin[1],
+                           (kSf ? a.bs[2] : 0.f) + a.bfin[2], (kSf ? a.bs[3] : 0.f) + a.bfin[3]};
     pdl_wait();
     StepParams sp{};
     int step = 0, rel = 0;
@@ -455,7 +452,7 @@ __global__ void __launch_bounds__(256) final64_kernel(const FinalArgs a) {
     const size_t n_warps = static_cast<size_t>(gridDim.x) * (blockDim.x >> 5);
     const size_t gw = static_cast<size_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const size_t c_begin = n_chunks * gw / n_warps, c_end = n_chunks * (gw + 1) / n_warps;   // contiguous range per warp
-    float A[8], Bc[8];
+    float A[8], Bc[8];          // folded GroupNorm affine, halved: SiLU(y) = h + h tanh(h), h = y / 2 = fma(x, A, B)
     long long cur_b = -1;
     const uint4* xfv = reinterpret_cast<const uint4*>(a.xf);
     const uint4* sfv = reinterpret_cast<const uint4*>(a.sf);
@@ -474,39 +471,55 @@ __global__ void __launch_bounds__(256) final64_kernel(const FinalArgs a) {
             const float var = fmaxf(static_cast<float>(ss * inv_n - meand * meand), 0.f);
             const float rstd = rsqrtf(var + a.gn_eps);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { A[j] = rstd * gam[j]; Bc[j] = bet[j] - mean * A[j]; }
+            for (int j = 0; j < 8; ++j) {
+                const float Aj = rstd * __ldg(a.gn_gamma + sub * 8 + j);
+                const float Bj = __ldg(a.gn_beta + sub * 8 + j) - mean * Aj;
+                A[j] = 0.5f * Aj; Bc[j] = 0.5f * Bj;
+            }
         }
-        // ---- phase 1: per-lane partial dot products of 8 x 4 pixels -------------------------------------------------
-        uint4 fv[8], gv[8], rv[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const size_t idx = (pix0 + i * 4 + grp) * 8 + sub;
-            fv[i] = __ldg(xfv + idx);
-            gv[i] = __ldg(sfv + idx);
-            if (kGn && rsv) rv[i] = __ldg(rsv + idx);
-        }
+        // ---- phase 1: per-lane partial dot products of 8 x 4 pixels, in two batches of four passes ------------------------
         float o[8][4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float f[8], g[8];
-            unpack8(fv[i], f);
-            unpack8(gv[i], g);
-            if (kGn) {
+        for (int hb = 0; hb < 2; ++hb) {
+            uint4 fv[4], gv[4], rv[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = silu(fmaf(f[j], A[j], Bc[j]));
-                if (rsv) {
-                    float r[8];
-                    unpack8(rv[i], r);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) f[j] += r[j];
-                }
+            for (int ii = 0; ii < 4; ++ii) {
+                const size_t idx = (pix0 + (hb * 4 + ii) * 4 + grp) * 8 + sub;
+                fv[ii] = __ldg(xfv + idx);
+                if (kSf) gv[ii] = __ldg(sfv + idx);
+                if (kGn && rsv) rv[ii] = __ldg(rsv + idx);
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float acc = 0.f;
+            for (int ii = 0; ii < 4; ++ii) {
+                float f[8], g[8];
+                unpack8(fv[ii], f);
+                if (kSf) unpack8(gv[ii], g);
+                if (kGn) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc = fmaf(f[j], wfr[k][j], fmaf(g[j], wsr[k][j], acc));
-                o[i][k] = acc;
+                    for (int j = 0; j < 8; ++j) {
+                        const float h = fmaf(f[j], A[j], Bc[j]);
+                        f[j] = fmaf(h, tanh_approx(h), h);
+                    }
+                    if (rsv) {
+                        float r[8];
+                        unpack8(rv[ii], r);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] += r[j];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(&sw[0][k][sub * 8]), w1 = *reinterpret_cast<const float4*>(&sw[0][k][sub * 8 + 4]);
+                    float acc = f[0] * w0.x;
+                    acc = fmaf(f[1], w0.y, acc); acc = fmaf(f[2], w0.z, acc); acc = fmaf(f[3], w0.w, acc);
+                    acc = fmaf(f[4], w1.x, acc); acc = fmaf(f[5], w1.y, acc); acc = fmaf(f[6], w1.z, acc); acc = fmaf(f[7], w1.w, acc);
+                    if (kSf) {
+                        const float4 v0 = *reinterpret_cast<const float4*>(&sw[1][k][sub * 8]), v1 = *reinterpret_cast<const float4*>(&sw[1][k][sub * 8 + 4]);
+                        acc = fmaf(g[0], v0.x, acc); acc = fmaf(g[1], v0.y, acc); acc = fmaf(g[2], v0.z, acc); acc = fmaf(g[3], v0.w, acc);
+                        acc = fmaf(g[4], v1.x, acc); acc = fmaf(g[5], v1.y, acc); acc = fmaf(g[6], v1.z, acc); acc = fmaf(g[7], v1.w, acc);
+                    }
+                    o[hb * 4 + ii][k] = acc;
+                }
             }
         }
         // ---- reduce-scatter over the 8 lanes of a pixel group: lane `sub` ends with pass `sub` -------------------------
@@ -536,6 +549,10 @@ __global__ void __launch_bounds__(256) final64_kernel(const FinalArgs a) {
         }
         // ---- phase 2: one pixel per lane -------------------------------------------------------------------------------
         const size_t pix = pix0 + sub * 4 + grp;
+        if (!kSf) {         // reference order: shot_noise + read_noise
+            const float4 s4 = __ldg(a.sn + pix);
+            v[0] = s4.x + v[0]; v[1] = s4.y + v[1]; v[2] = s4.z + v[2]; v[3] = s4.w + v[3];
+        }
         if (a.v_out) reinterpret_cast<float4*>(a.v_out)[pix] = make_float4(v[0], v[1], v[2], v[3]);
         if (!a.chain) continue;
         const size_t hw = pix - bimg * HW;
@@ -744,7 +761,7 @@ inline int blocks_for(size_t n, int per_block, int cap = 1 << 20) {
 // launchers
 // ---------------------------------------------------------------------------------------------------------------
 static int g_gn_occ[2][3] = {{0, 0, 0}, {0, 0, 0}};
-static int g_final_occ[2] = {0, 0};                  // resident blocks per SM of final64_kernel<false / true>   // resident blocks per SM of each gn_apply variant (pointwise_init)
+static int g_final_occ[2][2] = {{0, 0}, {0, 0}};      // resident blocks per SM of final64_kernel<kGn, kSf>   // resident blocks per SM of each gn_apply variant (pointwise_init)
 
 int gn_apply_launch(const GnApplyArgs& a, cudaStream_t s) {
     NDIFF_REQUIRE(a.C % 64 == 0 && a.C <= 512 && a.C % a.G == 0 && (a.C / a.G) % 8 == 0,
@@ -806,8 +823,10 @@ int pointwise_init() {
         NDIFF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_gn_occ[1][0], gn_apply_kernel<true, 0>, kGnThreads, 0));
         NDIFF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_gn_occ[1][1], gn_apply_kernel<true, 1>, kGnThreads, 0));
         NDIFF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_gn_occ[1][2], gn_apply_kernel<true, 2>, kGnThreads, 0));
-        NDIFF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_final_occ[0], final64_kernel<false>, 256, 0));
-        NDIFF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_final_occ[1], final64_kernel<true>, 256, 0));
+        NDIFF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_final_occ[0][0], final64_kernel<false, false>, 256, 0));
+        NDIFF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_final_occ[0][1], final64_kernel<false, true>, 256, 0));
+        NDIFF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_final_occ[1][0], final64_kernel<true, false>, 256, 0));
+        NDIFF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&g_final_occ[1][1], final64_kernel<true, true>, 256, 0));
     }
     const int smem = (kIcHalo * kIcHalo + 49 * 4 * 16) * sizeof(float4);
     NDIFF_CUDA_OK(cudaFuncSetAttribute(init_conv7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -837,17 +856,21 @@ int final_launch(const FinalArgs& a, cudaStream_t s) {
     NDIFF_REQUIRE(a.C == 64 || a.C == 128 || a.C == 256, "final heads: C/8 must be a power of two <= 32");
     if (a.C == 64 && a.HW % 32 == 0) {
         // one wave of 256-thread blocks, every warp walks a contiguous range of 32-pixel chunks
-        const int occ = g_final_occ[a.gn_stats ? 1 : 0] > 0 ? g_final_occ[a.gn_stats ? 1 : 0] : 1;
+        const int occ_q = g_final_occ[a.gn_stats ? 1 : 0][a.sn ? 0 : 1];
+        const int occ = occ_q > 0 ? occ_q : 1;
         const int blocks = blocks_for(static_cast<size_t>(a.npix) / 32, 8, g_num_sms * occ);
+        NDIFF_REQUIRE(a.sn || (a.sf && a.ws && a.bs), "final heads: neither a shot feature map nor a precomputed shot head");
         if (a.gn_stats) {
             NDIFF_REQUIRE(a.gn_gamma && a.gn_beta && a.gn_G > 0 && 64 % a.gn_G == 0 && (64 / a.gn_G) % 8 == 0,
                           "final heads: bad fused GroupNorm arguments");
-            NDIFF_CUDA_OK(launch_pdl(final64_kernel<true>, dim3(blocks), dim3(256), 0, s, a));
+            if (a.sn) NDIFF_CUDA_OK(launch_pdl(final64_kernel<true, false>, dim3(blocks), dim3(256), 0, s, a));
+            else NDIFF_CUDA_OK(launch_pdl(final64_kernel<true, true>, dim3(blocks), dim3(256), 0, s, a));
         } else {
-            NDIFF_CUDA_OK(launch_pdl(final64_kernel<false>, dim3(blocks), dim3(256), 0, s, a));
+            if (a.sn) NDIFF_CUDA_OK(launch_pdl(final64_kernel<false, false>, dim3(blocks), dim3(256), 0, s, a));
+            else NDIFF_CUDA_OK(launch_pdl(final64_kernel<false, true>, dim3(blocks), dim3(256), 0, s, a));
         }
     } else {
-        NDIFF_REQUIRE(!a.gn_stats, "final heads: the fused GroupNorm form needs dim = 64");
+        NDIFF_REQUIRE(!a.gn_stats && !a.sn, "final heads: the fused forms need dim = 64");
         const size_t threads = static_cast<size_t>(a.npix) * (a.C / 8);
         NDIFF_CUDA_OK(launch_pdl(final_kernel, dim3(blocks_for(threads, 256, g_num_sms * 4)), dim3(256), 8 * a.C * sizeof(float), s, a));
     }

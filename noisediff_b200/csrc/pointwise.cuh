@@ -74,6 +74,9 @@ struct FinalArgs {
     // GroupNorm-apply pass of final_res_block folded into this kernel.  gn_stats: that conv's fixed-point sums [B][G][2].
     const unsigned long long* gn_stats; const float* gn_gamma; const float* gn_beta; const bf16* gn_res;
     int gn_G; float gn_eps;
+    // optional (dim = 64): the shot-noise head was already evaluated by the shot-branch tail kernel — sn[pix] = shot_mlp3 output
+    // INCLUDING its bias; sf / ws / bs are then unused.
+    const float4* sn;
 };
 int final_launch(const FinalArgs& a, cudaStream_t s);
 
