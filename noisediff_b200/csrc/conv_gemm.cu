@@ -503,8 +503,14 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
                         v[j + 2] = __uint_as_float(raw[k][j + 2]) + bv.z; v[j + 3] = __uint_as_float(raw[k][j + 3]) + bv.w;
                     }
                     if (a.act == kActGelu && !pass2) {
+                        // packed-fp16 tanh form: one MUFU per PAIR of elements (the ex2 + rcp form needs four); its error
+                        // (~5e-4 relative) is below the bf16 rounding of the store
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                        for (int j = 0; j < 32; j += 2) {
+                            const uint32_t hh = gelu_f16x2(v[j], v[j + 1]);
+                            const float2 ff = __half22float2(*reinterpret_cast<const __half2*>(&hh));
+                            v[j] = ff.x; v[j + 1] = ff.y;
+                        }
                     }
                     if (a.vec && !pass2) {
                         const float* vp = a.vec + static_cast<size_t>(b) * a.vec_ld + nbase;
