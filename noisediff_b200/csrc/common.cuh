@@ -199,6 +199,21 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 // all committed bulk stores of this thread have finished READING their shared-memory source
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// 256-bit global accesses (sm_100): one instruction moves a full 32-byte sector per lane — half the LSU / L1 tag work of two
+// 128-bit accesses for the row-per-thread epilogue pattern.  `p` must be 32-byte aligned.
+struct alignas(32) uint8x { uint4 lo, hi; };
+__device__ __forceinline__ uint8x ldg256(const void* p) {
+    uint8x v;
+    asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v.lo.x), "=r"(v.lo.y), "=r"(v.lo.z), "=r"(v.lo.w), "=r"(v.hi.x), "=r"(v.hi.y), "=r"(v.hi.z), "=r"(v.hi.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg256(void* p, const uint4& lo, const uint4& hi) {
+    asm volatile("st.global.v8.u32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w),
+                 "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+                 : "memory");
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));

@@ -521,10 +521,11 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
                         }
                     }
                     if (a.res && valid && !pass2) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(a.res + pix * a.res_ld + nbase);
+                        const __nv_bfloat16* rp = a.res + pix * a.res_ld + nbase;
+                        const uint8x r0 = ldg256(rp), r1 = ldg256(rp + 16);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const uint4 u = __ldg(rp + j);
+                            const uint4 u = j == 0 ? r0.lo : (j == 1 ? r0.hi : (j == 2 ? r1.lo : r1.hi));
                             float2 f;
                             f = unpack_bf16(u.x); v[j * 8 + 0] += f.x; v[j * 8 + 1] += f.y;
                             f = unpack_bf16(u.y); v[j * 8 + 2] += f.x; v[j * 8 + 3] += f.y;
@@ -542,16 +543,17 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
                         }
                     }
                     if (valid) {
-                        uint4* op = reinterpret_cast<uint4*>(pass2 ? a.out2 + pix * a.out2_ld + nbase : a.out + pix * a.out_ld + nbase);
+                        __nv_bfloat16* op = pass2 ? a.out2 + pix * a.out2_ld + nbase : a.out + pix * a.out_ld + nbase;
+                        uint4 u[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            uint4 u;
-                            u.x = pack_bf16(v[j * 8 + 0], v[j * 8 + 1]);
-                            u.y = pack_bf16(v[j * 8 + 2], v[j * 8 + 3]);
-                            u.z = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]);
-                            u.w = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
-                            op[j] = u;
+                            u[j].x = pack_bf16(v[j * 8 + 0], v[j * 8 + 1]);
+                            u[j].y = pack_bf16(v[j * 8 + 2], v[j * 8 + 3]);
+                            u[j].z = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]);
+                            u[j].w = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
                         }
+                        stg256(op, u[0], u[1]);          // two full 32-byte sectors per lane
+                        stg256(op + 16, u[2], u[3]);
                     }
                 }
             }
