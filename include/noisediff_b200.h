@@ -126,6 +126,24 @@ NDIFF_API int32_t ndiff_op_conv(int32_t mode, int32_t B, int32_t H, int32_t W, c
                       int32_t C1, int32_t taps_y, int32_t taps_x, int32_t pad_y, int32_t pad_x, const void* weight_packed,
                       int32_t Cout, const float* bias, const float* vec, int32_t vec_ld, const void* res, int32_t act,
                       void* stats, int32_t groups, void* out, int32_t force_nt, int32_t tile_w, void* stream);
+/* The fused forms of the ResnetBlock 3x3 convolutions (pad 1), as single operators:
+ *   mode 6 (kHalo1R): weight_packed = [Cout][Cin/64][10][64] — taps 0..8 the 3x3 kernel, tap 9 the block's 1x1 res_conv
+ *     (Diffusion_arch.py:157,169); ex->out2 / ex->bias2 receive res_conv(x).
+ *   ex->xf_stats != NULL (modes 3 / 4, one source): the input is the RAW output of the previous conv and
+ *     SiLU(GroupNorm(x) * (scale + 1) + shift) (Block.forward, :135-144) is applied to it inside the kernel;
+ *     xf_stats = that conv's fixed-point sums [B][xf_groups][2], xf_ss = per-sample [scale C | shift C] rows or NULL. */
+typedef struct ndiff_conv_ex {
+    void* out2; const float* bias2;
+    const void* xf_stats; const float* xf_gamma; const float* xf_beta; const float* xf_ss; int32_t xf_ss_ld; int32_t xf_groups;
+} ndiff_conv_ex;
+NDIFF_API int32_t ndiff_op_conv_ex(int32_t mode, int32_t B, int32_t H, int32_t W, const void* src0, int32_t C0, const void* src1,
+                         int32_t C1, const void* weight_packed, int32_t Cout, const float* bias, void* stats, int32_t groups,
+                         void* out, const ndiff_conv_ex* ex, void* stream);
+/* Tail of the shot-noise branch (Diffusion_arch.py:602-604): y = SiLU(GroupNorm(h2)) + r1 + r2; out = fc2(GELU(fc1(y))).
+ * h2 / r1 / r2: bf16 [npix][64]; weights_blob / fvec as documented in noisediff_b200/csrc/pixel_chain.cuh; out: fp32 [npix][4]. */
+NDIFF_API int32_t ndiff_op_tail_chain(int32_t npix, int32_t HW, const void* h2, const void* r1, const void* r2,
+                            const void* weights_blob, const float* fvec, const void* stats, const float* gamma, const float* beta,
+                            int32_t groups, float* out_npix4, void* stream);
 /* Same operator, launched `iters` times back to back after 3 warm-up launches and timed with CUDA events on `stream`
  * (kernel-variant selection experiments and the per-shape roofline table; blocks until done). */
 NDIFF_API int32_t ndiff_op_conv_time(int32_t mode, int32_t B, int32_t H, int32_t W, const void* src0, int32_t C0, const void* src1,

@@ -8,6 +8,7 @@ Both call the C-ABI CUDA library in ``noisediff_b200/csrc`` (see ``include/noise
 from .arch import NoiseDiffNet
 from .diffusion import GaussianDiffusion, ModelPrediction, make_betas
 from .engine import Engine
+from . import frames  # noqa: F401
 from . import _lib, tiles
 
 __all__ = ["NoiseDiffNet", "GaussianDiffusion", "ModelPrediction", "make_betas", "Engine"]

@@ -26,6 +26,11 @@ class Config(C.Structure):
                 ("device", C.c_int32), ("flags", C.c_int32)]
 
 
+class ConvEx(C.Structure):      # ndiff_conv_ex
+    _fields_ = [("out2", C.c_void_p), ("bias2", C.c_void_p), ("xf_stats", C.c_void_p), ("xf_gamma", C.c_void_p),
+                ("xf_beta", C.c_void_p), ("xf_ss", C.c_void_p), ("xf_ss_ld", C.c_int32), ("xf_groups", C.c_int32)]
+
+
 class Step(C.Structure):
     _fields_ = [("t", C.c_int32), ("p", C.c_float), ("q", C.c_float), ("a", C.c_float), ("b", C.c_float),
                 ("c", C.c_float), ("r1", C.c_float), ("r2", C.c_float), ("sigma", C.c_float), ("clip", C.c_int32),
@@ -60,6 +65,8 @@ _SIGS = {
     "ndiff_op_layernorm": (C.c_int32, [_P, _P, C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "ndiff_op_pixel_chain": (C.c_int32, [C.c_int32] * 3 + [_P] * 6 + [C.c_int32, _P, _P, _P]),
     "ndiff_op_philox_normal": (C.c_int32, [_P, C.c_int64, C.c_uint64, C.c_uint64, _P]),
+    "ndiff_op_conv_ex": (C.c_int32, [C.c_int32] * 4 + [_P, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P, _P, C.c_int32, _P, _P, _P]),
+    "ndiff_op_tail_chain": (C.c_int32, [C.c_int32, C.c_int32] + [_P] * 8 + [C.c_int32, _P, _P]),
 }
 
 _lib = None

@@ -1318,7 +1318,8 @@ int32_t ndiff_time_layers(ndiff_engine* e, int32_t iters, float* ms_out, char* n
 static int op_conv_plan(int32_t mode, int32_t B, int32_t H, int32_t W, const void* src0, int32_t C0, const void* src1,
                         int32_t C1, int32_t taps_y, int32_t taps_x, int32_t pad_y, int32_t pad_x, const void* weight_packed,
                         int32_t Cout, const float* bias, const float* vec, int32_t vec_ld, const void* res, int32_t act,
-                        void* stats, int32_t groups, void* out, int32_t force_nt, int32_t tile_w, ConvGemmPlan* plan) {
+                        void* stats, int32_t groups, void* out, int32_t force_nt, int32_t tile_w, ConvGemmPlan* plan,
+                        const ndiff_conv_ex* ex = nullptr) {
     int dev = 0;
     NDIFF_CUDA_OK(cudaGetDevice(&dev));
     cudaDeviceProp prop;
@@ -1335,7 +1336,40 @@ static int op_conv_plan(int32_t mode, int32_t B, int32_t H, int32_t W, const voi
     d.out = static_cast<bf16*>(out); d.out_ld = Cout;
     d.act = act; d.stats = static_cast<unsigned long long*>(stats); d.groups = groups;
     d.force_nt = force_nt; d.TW = tile_w;
+    if (ex) {
+        d.out2 = static_cast<bf16*>(ex->out2); d.out2_ld = Cout; d.bias2 = ex->bias2;
+        d.xf_stats = static_cast<const unsigned long long*>(ex->xf_stats); d.xf_gamma = ex->xf_gamma; d.xf_beta = ex->xf_beta;
+        d.xf_ss = ex->xf_ss; d.xf_ss_ld = ex->xf_ss_ld; d.xf_groups = ex->xf_groups;
+    }
     return conv_gemm_plan(d, prop.multiProcessorCount, plan);
+}
+
+int32_t ndiff_op_conv_ex(int32_t mode, int32_t B, int32_t H, int32_t W, const void* src0, int32_t C0, const void* src1,
+                         int32_t C1, const void* weight_packed, int32_t Cout, const float* bias, void* stats, int32_t groups,
+                         void* out, const ndiff_conv_ex* ex, void* stream) {
+    NDIFF_REQUIRE(ex != nullptr, "null extension block");
+    ConvGemmPlan plan;
+    if (op_conv_plan(mode, B, H, W, src0, C0, src1, C1, 3, 3, 1, 1, weight_packed, Cout, bias, nullptr, 0, nullptr, 0, stats,
+                     groups, out, 0, 0, &plan, ex)) return 1;
+    return conv_gemm_launch(plan, as_stream(stream));
+}
+
+int32_t ndiff_op_tail_chain(int32_t npix, int32_t HW, const void* h2, const void* r1, const void* r2, const void* weights_blob,
+                            const float* fvec, const void* stats, const float* gamma, const float* beta, int32_t groups,
+                            float* out_npix4, void* stream) {
+    int dev = 0;
+    NDIFF_CUDA_OK(cudaGetDevice(&dev));
+    int sms = 0;
+    NDIFF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    TailDesc d;
+    d.npix = npix; d.HW = HW;
+    d.h2 = static_cast<const bf16*>(h2); d.r1 = static_cast<const bf16*>(r1); d.r2 = static_cast<const bf16*>(r2);
+    d.weights = static_cast<const bf16*>(weights_blob); d.fvec = fvec;
+    d.stats = static_cast<const unsigned long long*>(stats); d.gamma = gamma; d.beta = beta; d.groups = groups;
+    d.out = out_npix4;
+    TailPlan plan;
+    if (tail_chain_plan(d, sms, &plan)) return 1;
+    return tail_chain_launch(plan, as_stream(stream));
 }
 
 int32_t ndiff_op_conv(int32_t mode, int32_t B, int32_t H, int32_t W, const void* src0, int32_t C0, const void* src1,

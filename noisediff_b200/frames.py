@@ -1,0 +1,121 @@
+"""Full-frame noise synthesis: tile-grid producer + asynchronous ``.npy`` writer (BASELINE config 4).
+
+What the reference does for one long-exposure frame (``dataloader/dataset.py:203-281`` + ``Trainer.test``,
+``models/trainer_diffusion.py:240-325``): cut the packed 4x1424x2128 frame into overlapping ``ps x ps`` crops (88 at
+ps = 256, 24 at ps = 512), attach each crop's position map and the ISO/ratio index, run ``diffusion.sample`` batch by batch
+and ``np.save`` every generated crop as ``<clean>+<noisy|clean>+<x>_<y>.npy`` (float32, (4, ps, ps)) under
+``<save_folder>/npy/generated``.  The crops are independent outputs — the reference does no stitching.
+
+Here the crops and position maps are built on the device from the resident frame (no DataLoader round trip), ranks take
+contiguous slices of the crop list (``tiles.shard``; no collective), and the files are written by a background thread from
+pinned host buffers so that disk I/O never stalls the next batch's chain.
+"""
+from __future__ import annotations
+
+import os
+import queue
+import threading
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import tiles
+
+
+def crop_batch(clean_frame: torch.Tensor, origins: Sequence[Tuple[int, int]], ps: int, iso_ratio_idx: int) -> Dict[str, torch.Tensor]:
+    """Condition dict for the crops at `origins` ((x, y) pairs) of one packed frame (4, H, W): what
+    ``NoiseImageGenerationDataset.__getitem__`` yields per item (``dataset.py:242-281``), batched, on the frame's device."""
+    if clean_frame.dim() != 3 or clean_frame.shape[0] != 4:
+        raise ValueError(f"expected a packed (4, H, W) frame, got {tuple(clean_frame.shape)}")
+    _, fh, fw = clean_frame.shape
+    dev = clean_frame.device
+    clean = torch.stack([clean_frame[:, y:y + ps, x:x + ps] for x, y in origins]).float().contiguous()
+    if clean.shape[-2:] != (ps, ps):
+        raise ValueError("crop origin outside the frame")
+    pos = torch.stack([tiles.position_map(ps, ps, x, y, fh, fw, device=dev) for x, y in origins])
+    idx = torch.full((len(origins),), int(iso_ratio_idx), dtype=torch.long, device=dev)
+    return {"clean_img": clean, "position": pos, "iso_ratio_idx": idx}
+
+
+def npy_name(clean_name: str, x: int, y: int, noisy_name: Optional[str] = None) -> str:
+    """``Trainer.test`` file name (``models/trainer_diffusion.py:305-312``): both names lose their '.ARW' suffix."""
+    c = clean_name.split(".ARW")[0]
+    s = (noisy_name if noisy_name is not None else clean_name).split(".ARW")[0]
+    return f"{c}+{s}+{int(x)}_{int(y)}.npy"
+
+
+class NpyWriter:
+    """Background ``np.save`` of generated crops.  ``submit`` copies a finished batch to pinned host memory with a
+    non-blocking D2H copy and returns; the worker waits for the copy's event and writes the files."""
+
+    def __init__(self, folder: str, depth: int = 4):
+        self.folder = folder
+        os.makedirs(folder, exist_ok=True)
+        self._q: "queue.Queue" = queue.Queue(maxsize=depth)
+        self._err: Optional[BaseException] = None
+        self.paths: List[str] = []
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def _run(self):
+        while True:
+            item = self._q.get()
+            if item is None:
+                return
+            host, event, names = item
+            try:
+                if event is not None:
+                    event.synchronize()
+                arr = host.numpy()
+                for i, n in enumerate(names):
+                    path = os.path.join(self.folder, n)
+                    np.save(path, arr[i])
+                    self.paths.append(path)
+            except BaseException as e:          # surfaced by close()
+                self._err = e
+
+    def submit(self, batch: torch.Tensor, names: Sequence[str]):
+        if len(names) != batch.shape[0]:
+            raise ValueError("one file name per item")
+        if batch.is_cuda:
+            host = torch.empty(batch.shape, dtype=torch.float32, pin_memory=True)
+            host.copy_(batch.detach().float(), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(batch.device))
+        else:
+            host, ev = batch.detach().float().contiguous().clone(), None
+        self._q.put((host, ev, list(names)))
+
+    def close(self) -> List[str]:
+        self._q.put(None)
+        self._t.join()
+        if self._err is not None:
+            raise self._err
+        return self.paths
+
+
+@torch.inference_mode()
+def synthesize_frame(diffusion, clean_frame: torch.Tensor, *, iso_ratio_idx: int, clean_name: str, save_folder: str,
+                     noisy_name: Optional[str] = None, batch_size: int = 64, rank: int = 0, world_size: int = 1,
+                     dark_frame: bool = False) -> List[str]:
+    """Generates this rank's share of the noise crops of one frame and writes them the way ``Trainer.test`` does.
+    `diffusion` is a ``GaussianDiffusion`` (its ``image_size`` is the crop size).  Returns the written paths."""
+    ps = int(diffusion.image_size)
+    dev = diffusion.device
+    frame = clean_frame.to(dev)
+    _, fh, fw = frame.shape
+    origins = tiles.tile_origins(ps, fh, fw)
+    mine = [origins[i] for i in tiles.shard(len(origins), world_size, rank)]
+    writer = NpyWriter(os.path.join(save_folder, "npy", "generated"))
+    try:
+        for lo in range(0, len(mine), batch_size):
+            part = mine[lo:lo + batch_size]
+            cond = crop_batch(frame, part, ps, iso_ratio_idx)
+            if dark_frame:                                   # ref :287-290: a zero clean image
+                cond["clean_img"] = torch.zeros_like(cond["clean_img"])
+            out = diffusion.sample(batch_size=len(part), condition=cond)
+            writer.submit(out, [npy_name(clean_name, x, y, noisy_name) for x, y in part])
+    finally:
+        paths = writer.close()
+    return paths

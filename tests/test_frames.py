@@ -1,0 +1,92 @@
+"""Tile-grid producer and .npy writer of full-frame synthesis: host logic on CPU, the end-to-end path on a
+GPU.  Reference behaviour: dataloader/dataset.py:203-281 (grid, crops, position maps), models/trainer_diffusion.py:296-317
+(file names, float32 (4, ps, ps) arrays)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from noisediff_b200 import frames, tiles
+
+
+def _ref_grid(h, w, ps):
+    """dataset.py:203-219 restated with numpy, verbatim logic."""
+    step = ps - ps // 4
+    hs = np.arange(0, h - ps + 1, step)
+    if h - (hs[-1] + ps) < ps:
+        hs = np.append(hs, h - ps)
+    ws = np.arange(0, w - ps + 1, step)
+    if w - (ws[-1] + ps) < ps:
+        ws = np.append(ws, w - ps)
+    return [(int(x), int(y)) for y in hs for x in ws]
+
+
+@pytest.mark.parametrize("ps,count", [(256, 88), (512, 24)])
+def test_tile_grid_matches_reference(ps, count):
+    got = tiles.tile_origins(ps)
+    assert got == _ref_grid(tiles.FULL_H, tiles.FULL_W, ps) and len(got) == count
+
+
+def test_crop_batch_and_names():
+    g = torch.Generator().manual_seed(0)
+    frame = torch.rand((4, 96, 160), generator=g)
+    origins = tiles.tile_origins(32, 96, 160)
+    assert origins == _ref_grid(96, 160, 32)
+    cond = frames.crop_batch(frame, origins[:5], 32, 24)
+    assert cond["clean_img"].shape == (5, 4, 32, 32) and cond["position"].shape == (5, 2, 32, 32)
+    x, y = origins[3]
+    assert torch.equal(cond["clean_img"][3], frame[:, y:y + 32, x:x + 32])
+    # utils/util.py:138-147 make_coord(H, W, rescale=True): row / (H - 1), col / (W - 1)
+    assert torch.allclose(cond["position"][3, 0, :, 0], torch.arange(y, y + 32).float() / 95)
+    assert torch.allclose(cond["position"][3, 1, 0, :], torch.arange(x, x + 32).float() / 159)
+    assert cond["iso_ratio_idx"].tolist() == [24] * 5
+    assert frames.npy_name("00001_00_10s.ARW", 192, 1168) == "00001_00_10s+00001_00_10s+192_1168.npy"
+    assert frames.npy_name("a.ARW", 0, 0, noisy_name="b.ARW") == "a+b+0_0.npy"
+
+
+class _FakeDiffusion:
+    """Stands in for GaussianDiffusion on CPU: 'noise' = clean + position-dependent pattern, so files are checkable."""
+    image_size = 32
+    device = torch.device("cpu")
+
+    def sample(self, batch_size, condition):
+        assert batch_size == condition["clean_img"].shape[0]
+        return condition["clean_img"] + condition["position"].sum(1, keepdim=True)
+
+
+def test_two_ranks_cover_the_frame_once(tmp_path):
+    frame = torch.rand((4, 96, 160), generator=torch.Generator().manual_seed(1))
+    origins = tiles.tile_origins(32, 96, 160)
+    all_paths = []
+    for rank in range(2):
+        all_paths += frames.synthesize_frame(_FakeDiffusion(), frame, iso_ratio_idx=3, clean_name="f.ARW", save_folder=str(tmp_path),
+                                             batch_size=4, rank=rank, world_size=2)
+    names = sorted(os.path.basename(p) for p in all_paths)
+    assert names == sorted(frames.npy_name("f.ARW", x, y) for x, y in origins) and len(set(names)) == len(origins)
+    x, y = origins[-1]
+    arr = np.load(os.path.join(str(tmp_path), "npy", "generated", frames.npy_name("f.ARW", x, y)))
+    assert arr.dtype == np.float32 and arr.shape == (4, 32, 32)
+    want = frames.crop_batch(frame, [(x, y)], 32, 3)
+    assert np.allclose(arr, (want["clean_img"] + want["position"].sum(1, keepdim=True))[0].numpy())
+
+
+@pytest.mark.gpu
+def test_frame_synthesis_equals_direct_sampling(tmp_path):
+    import copy
+    import noisediff_b200 as nd
+    from tests.util import seeded_net
+    net = copy.deepcopy(seeded_net()).cuda()
+    gd = nd.GaussianDiffusion(net, image_size=32, timesteps=6, beta_schedule="sigmoid2", objective="pred_v").cuda()
+    gd.noise_source = "philox"
+    frame = torch.rand((4, 64, 96), generator=torch.Generator().manual_seed(2)) * 0.3
+    origins = tiles.tile_origins(32, 64, 96)
+    torch.manual_seed(11)
+    paths = frames.synthesize_frame(gd, frame, iso_ratio_idx=24, clean_name="g.ARW", save_folder=str(tmp_path), batch_size=len(origins))
+    assert len(paths) == len(origins)
+    torch.manual_seed(11)
+    direct = gd.sample(batch_size=len(origins), condition=frames.crop_batch(frame.cuda(), origins, 32, 24)).cpu().numpy()
+    for i, (x, y) in enumerate(origins):
+        arr = np.load(os.path.join(str(tmp_path), "npy", "generated", frames.npy_name("g.ARW", x, y)))
+        assert arr.shape == (4, 32, 32) and np.isfinite(arr).all()
+        assert np.array_equal(arr, direct[i])

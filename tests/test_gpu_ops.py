@@ -305,3 +305,105 @@ def test_shot_chain(case):
     ref = h5 @ Wm2.T + bm2
     assert _rel(out2.float(), s1) < 4e-3, _rel(out2.float(), s1)
     assert _rel(out.float(), ref) < 8e-3, _rel(out.float(), ref)
+
+
+# ---- fused forms of the ResnetBlock convolutions (conv_gemm.cu kHalo1R / XF) and the shot-branch tail ------------------------
+def _stats_buf(B, G_):
+    return torch.zeros((B, G_, 2), dtype=torch.int64, device="cuda")
+
+
+@pytest.mark.parametrize("case", [(2, 32, 32, 64, 64, 64), (1, 64, 64, 128, 64, 128), (2, 16, 24, 256, 128, 256), (2, 128, 128, 64, 64, 64),
+                                  (8, 32, 32, 512, 256, 512)])
+def test_conv3x3_with_fused_res_conv(case):
+    """block1.proj (3x3) and res_conv (1x1) of a ResnetBlock on the same concatenated input in one launch (ref
+    Diffusion_arch.py:157,163-169)."""
+    B, H, W, c0, c1, co = case
+    x0, x1 = _rand((B, c0, H, W), 50), _rand((B, c1, H, W), 51)
+    w3 = _rand((co, c0 + c1, 3, 3), 52, 1.0 / math.sqrt(9 * (c0 + c1)))
+    w1 = _rand((co, c0 + c1, 1, 1), 53, 1.0 / math.sqrt(c0 + c1))
+    b3, b1 = torch.randn(co, device="cuda"), torch.randn(co, device="cuda")
+    xin = torch.cat([x0, x1], 1)
+    wp = torch.cat([w3.reshape(co, (c0 + c1) // 64, 64, 9), w1.reshape(co, (c0 + c1) // 64, 64, 1)], dim=3)
+    wp = wp.permute(0, 1, 3, 2).contiguous().to(torch.bfloat16)               # [Cout][cblk][10][64]
+    out = torch.empty((B, H, W, co), dtype=torch.bfloat16, device="cuda")
+    out2 = torch.empty_like(out)
+    stats = _stats_buf(B, 8)
+    ex = _lib.ConvEx(out2.data_ptr(), b1.data_ptr(), None, None, None, None, 0, 0)
+    import ctypes as C
+    _lib.check(_lib.lib().ndiff_op_conv_ex(6, B, H, W, G.P(G.to_nhwc_bf16(x0)), c0, G.P(G.to_nhwc_bf16(x1)), c1, G.P(wp), co,
+                                           G.P(b3), G.P(stats), 8, G.P(out), C.byref(ex), G.stream()))
+    torch.cuda.synchronize()
+    ref3 = F.conv2d(xin, w3, b3, padding=1)
+    _check(out, ref3)
+    _check(out2, F.conv2d(xin, w1, b1))
+    # the GroupNorm sums of the 3x3 output ride along as usual
+    got = stats.double() / 2 ** 24
+    o = G.from_nhwc(out).double().reshape(B, 8, -1)
+    assert torch.allclose(got[:, :, 0], o.sum(-1), rtol=2e-3, atol=2.0)
+
+
+@pytest.mark.parametrize("mode", [G.MODE_HALO1, G.MODE_HALO2])
+@pytest.mark.parametrize("case", [(2, 32, 32, 64, 2, True), (3, 64, 64, 64, 8, True), (1, 32, 48, 128, 8, True), (2, 16, 16, 256, 8, False),
+                                  (1, 128, 128, 64, 8, True)])
+def test_conv3x3_with_groupnorm_apply_on_the_input(case, mode):
+    """block1.norm (GroupNorm + scale/shift + SiLU) evaluated inside block2's conv must equal the stand-alone
+    GroupNorm-apply kernel followed by the plain conv — bit for bit (same formulas, same bf16 rounding)."""
+    B, H, W, c, groups, with_ss = case
+    if mode == G.MODE_HALO2 and c != 64:
+        pytest.skip("256-pixel tiles are planned for the 64-channel layers only")
+    h = G.to_nhwc_bf16(_rand((B, c, H, W), 60, 1.7) + 0.4)
+    gamma, beta = 1 + 0.2 * torch.randn(c, device="cuda"), 0.3 * torch.randn(c, device="cuda")
+    ss = 0.3 * torch.randn(B, 2 * c + 32, device="cuda") if with_ss else None       # row pitch larger than 2C on purpose
+    hf = h.float()
+    stats = torch.stack([(hf.reshape(B, H * W, groups, c // groups).sum((1, 3)) * 2 ** 24).round(),
+                         ((hf * hf).reshape(B, H * W, groups, c // groups).sum((1, 3)) * 2 ** 24).round()], dim=2).to(torch.int64)
+    w = _rand((c, c, 3, 3), 61, 1.0 / math.sqrt(9 * c))
+    bias = torch.randn(c, device="cuda")
+    # separate pass, then plain conv
+    hn = torch.empty_like(h)
+    _lib.check(_lib.lib().ndiff_op_gn_apply(G.P(h), G.P(hn), G.P(stats), G.P(gamma), G.P(beta), G.P(ss), ss.shape[1] if with_ss else 0,
+                                            0, None, None, None, B, H * W, c, groups, G.stream()))
+    ref = G.conv(mode, hn, G.pack_weight(w), c, bias=bias)
+    # fused
+    import ctypes as C
+    out = torch.empty((B, H, W, c), dtype=torch.bfloat16, device="cuda")
+    ex = _lib.ConvEx(None, None, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), ss.data_ptr() if with_ss else None,
+                     ss.shape[1] if with_ss else 0, groups)
+    _lib.check(_lib.lib().ndiff_op_conv_ex(mode, B, H, W, G.P(h), c, None, 0, G.P(G.pack_weight(w)), c, G.P(bias), None, 0,
+                                           G.P(out), C.byref(ex), G.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref), (out.float() - ref.float()).abs().max().item()
+    # ... and both follow the fp32 definition
+    y = F.group_norm(G.from_nhwc(h), groups, gamma, beta, eps=1e-5)
+    if with_ss:
+        y = y * (ss[:, :c, None, None] + 1) + ss[:, c:2 * c, None, None]
+    _check(out, F.conv2d(_bf(F.silu(y)), w, bias, padding=1), tol=2.5e-2)
+
+
+@pytest.mark.parametrize("case", [(2, 16, 16), (3, 8, 8), (1, 8, 24), (2, 256, 256)])
+def test_shot_tail_chain(case):
+    B, H, W = case
+    npix, HW = B * H * W, H * W
+    g = torch.Generator(device="cuda").manual_seed(71)
+    rn = lambda *s, sc=1.0: torch.randn(*s, generator=g, device="cuda") * sc
+    h2 = _bf(rn(npix, 64, sc=1.5) + 0.3)
+    r1, r2 = _bf(rn(npix, 64)), _bf(rn(npix, 64))
+    gamma, beta = 1 + 0.2 * rn(64), 0.3 * rn(64)
+    W1, b1 = _bf(rn(64, 64, sc=0.125)), 0.3 * rn(64)
+    W2, b2 = _bf(rn(4, 64, sc=0.125)), 0.3 * rn(4)
+    groups = 2
+    hb = h2.reshape(B, HW, groups, 32)
+    stats = torch.stack([(hb.sum((1, 3)) * 2 ** 24).round(), ((hb * hb).sum((1, 3)) * 2 ** 24).round()], dim=2).to(torch.int64)
+    blob = torch.zeros(128, 64, dtype=torch.bfloat16, device="cuda")
+    blob[:64] = _blob(W1)
+    blob[64:68] = _blob(W2, f16=True)
+    fvec = torch.zeros(128, device="cuda")
+    fvec[:64], fvec[64:68] = b1, b2
+    out = torch.zeros((npix, 4), device="cuda")
+    _lib.check(_lib.lib().ndiff_op_tail_chain(npix, HW, G.P(h2.to(torch.bfloat16)), G.P(r1.to(torch.bfloat16)), G.P(r2.to(torch.bfloat16)),
+                                              G.P(blob), G.P(fvec), G.P(stats), G.P(gamma), G.P(beta), groups, G.P(out), G.stream()))
+    torch.cuda.synchronize()
+    y = F.group_norm(h2.reshape(B, HW, 64).permute(0, 2, 1), groups, gamma, beta, eps=1e-5).permute(0, 2, 1).reshape(npix, 64)
+    y = _bf(F.silu(y) + r1 + r2)
+    ref = _hf(F.gelu(y @ W1.T + b1)) @ _hf(W2).T + b2
+    assert _rel(out, ref) < 6e-3, _rel(out, ref)
