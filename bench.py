@@ -238,7 +238,7 @@ def main():
     achieved = conv_fl / (conv_ms * 1e-3) / 1e12
     traffic = None
     try:     # dram__bytes_read.sum + dram__bytes_write.sum per conv_gemm launch from the committed ncu pass (profiles/)
-        with open(os.path.join(ROOT, "profiles", "ncu_r1_step_summary.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "ncu_r1_step_summary_mb64.json")) as f:
             traffic = json.load(f)["conv_gemm"]["dram_bytes_per_launch"]
     except Exception:
         pass

@@ -141,40 +141,53 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
         for (int k = 0; k < 8; ++k) { gg[j][k] = g[c + k]; bb[j][k] = beta[c + k]; }
     }
     const float inv_c = 1.0f / static_cast<float>(C);
-    for (size_t p0 = warp * ppw; p0 < npix; p0 += nwarps * ppw) {
-        const size_t pix = p0 + slot;
-        const bool live = pix < npix;
-        const size_t pp = live ? pix : npix - 1;
-        const float* vp = vec + (pp / HW) * static_cast<size_t>(vec_ld);
-        float f[VPL][8];
-        float sum = 0.f;
+    // kLnU pixels per lane group and iteration: all 16-byte loads are issued before the first reduction, so the shuffles and
+    // the dependent arithmetic of one pixel overlap the memory latency of the others
+    constexpr int kLnU = VPL == 1 ? 4 : 2;
+    for (size_t p0 = warp * ppw * kLnU; p0 < npix; p0 += nwarps * ppw * kLnU) {
+        float f[kLnU][VPL][8];
+        size_t pixs[kLnU];
+        uint4 raw[kLnU][VPL];
 #pragma unroll
-        for (int j = 0; j < VPL; ++j) {
-            const int cvi = sub + j * L;
-            unpack8(__ldg(reinterpret_cast<const uint4*>(x) + pp * cv + cvi), f[j]);
-            const float4 v0 = __ldg(reinterpret_cast<const float4*>(vp + cvi * 8));
-            const float4 v1 = __ldg(reinterpret_cast<const float4*>(vp + cvi * 8 + 4));
-            f[j][0] += v0.x; f[j][1] += v0.y; f[j][2] += v0.z; f[j][3] += v0.w;
-            f[j][4] += v1.x; f[j][5] += v1.y; f[j][6] += v1.z; f[j][7] += v1.w;
+        for (int u = 0; u < kLnU; ++u) {
+            pixs[u] = p0 + u * ppw + slot;
+            const size_t pp = pixs[u] < npix ? pixs[u] : npix - 1;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) sum += f[j][k];
+            for (int j = 0; j < VPL; ++j) raw[u][j] = __ldg(reinterpret_cast<const uint4*>(x) + pp * cv + sub + j * L);
         }
-        for (int o = L >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        const float mean = sum * inv_c;
-        float sq = 0.f;
 #pragma unroll
-        for (int j = 0; j < VPL; ++j)
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { const float d = f[j][k] - mean; sq += d * d; }
-        for (int o = L >> 1; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        const float rstd = rsqrtf(sq * inv_c + 1e-5f);
-        if (live) {
+        for (int u = 0; u < kLnU; ++u) {
+            const size_t pp = pixs[u] < npix ? pixs[u] : npix - 1;
+            const float* vp = vec + (pp / HW) * static_cast<size_t>(vec_ld);
+            float sum = 0.f;
 #pragma unroll
             for (int j = 0; j < VPL; ++j) {
-                float o8[8];
+                const int cvi = sub + j * L;
+                unpack8(raw[u][j], f[u][j]);
+                const float4 v0 = __ldg(reinterpret_cast<const float4*>(vp + cvi * 8));
+                const float4 v1 = __ldg(reinterpret_cast<const float4*>(vp + cvi * 8 + 4));
+                f[u][j][0] += v0.x; f[u][j][1] += v0.y; f[u][j][2] += v0.z; f[u][j][3] += v0.w;
+                f[u][j][4] += v1.x; f[u][j][5] += v1.y; f[u][j][6] += v1.z; f[u][j][7] += v1.w;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) o8[k] = (f[j][k] - mean) * rstd * gg[j][k] + bb[j][k];
-                reinterpret_cast<uint4*>(out)[pix * cv + sub + j * L] = pack8(o8);
+                for (int k = 0; k < 8; ++k) sum += f[u][j][k];
+            }
+            for (int o = L >> 1; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const float mean = sum * inv_c;
+            float sq = 0.f;
+#pragma unroll
+            for (int j = 0; j < VPL; ++j)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { const float d = f[u][j][k] - mean; sq += d * d; }
+            for (int o = L >> 1; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            const float rstd = rsqrtf(sq * inv_c + 1e-5f);
+            if (pixs[u] < npix) {
+#pragma unroll
+                for (int j = 0; j < VPL; ++j) {
+                    float o8[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) o8[k] = (f[u][j][k] - mean) * rstd * gg[j][k] + bb[j][k];
+                    reinterpret_cast<uint4*>(out)[pixs[u] * cv + sub + j * L] = pack8(o8);
+                }
             }
         }
     }
@@ -794,7 +807,7 @@ int layernorm_launch(const bf16* x, const float* vec, int vec_ld, const float* g
     const size_t npix = static_cast<size_t>(B) * HW;
     const int L = C / 8 > 32 ? 32 : C / 8;
     const int ppw = 32 / L;
-    const int grid = blocks_for(npix, 8 * ppw * 4, 148 * 8);
+    const int grid = blocks_for(npix, 8 * ppw * 4, 148 * 8);      // (a grid-stride loop: any grid covers the tensor)
     if (C == 512)
         NDIFF_CUDA_OK(launch_pdl(layernorm_kernel<2>, dim3(grid), dim3(256), 0, s, x, vec, vec_ld, g, beta, out, HW, C, L, npix));
     else

@@ -69,9 +69,12 @@ class Engine:
         if tuple(clean_img.shape) != (B, 4, H, W) or tuple(position.shape) != (B, 2, H, W) or iso_ratio_idx.numel() != B:
             raise ValueError(f"condition shapes do not match the engine geometry (B={B}, H={H}, W={W}): "
                              f"{tuple(clean_img.shape)}, {tuple(position.shape)}, {tuple(iso_ratio_idx.shape)}")
-        key = (clean_img.data_ptr(), clean_img._version, position.data_ptr(), position._version,
-               iso_ratio_idx.data_ptr(), iso_ratio_idx._version, self.weights_version)
-        if key == self._cond_key:
+        try:
+            key = (clean_img.data_ptr(), clean_img._version, position.data_ptr(), position._version,
+                   iso_ratio_idx.data_ptr(), iso_ratio_idx._version, self.weights_version)
+        except RuntimeError:          # inference tensors carry no version counter: no safe identity, never cached
+            key = None
+        if key is not None and key == self._cond_key:
             return
         c = _f32c(clean_img, self.device)
         p = _f32c(position, self.device)

@@ -330,7 +330,8 @@ def test_conv3x3_with_fused_res_conv(case):
     stats = _stats_buf(B, 8)
     ex = _lib.ConvEx(out2.data_ptr(), b1.data_ptr(), None, None, None, None, 0, 0)
     import ctypes as C
-    _lib.check(_lib.lib().ndiff_op_conv_ex(6, B, H, W, G.P(G.to_nhwc_bf16(x0)), c0, G.P(G.to_nhwc_bf16(x1)), c1, G.P(wp), co,
+    s0, s1 = G.to_nhwc_bf16(x0), G.to_nhwc_bf16(x1)          # (named: the raw pointers must outlive the call)
+    _lib.check(_lib.lib().ndiff_op_conv_ex(6, B, H, W, G.P(s0), c0, G.P(s1), c1, G.P(wp), co,
                                            G.P(b3), G.P(stats), 8, G.P(out), C.byref(ex), G.stream()))
     torch.cuda.synchronize()
     ref3 = F.conv2d(xin, w3, b3, padding=1)
@@ -369,7 +370,8 @@ def test_conv3x3_with_groupnorm_apply_on_the_input(case, mode):
     out = torch.empty((B, H, W, c), dtype=torch.bfloat16, device="cuda")
     ex = _lib.ConvEx(None, None, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), ss.data_ptr() if with_ss else None,
                      ss.shape[1] if with_ss else 0, groups)
-    _lib.check(_lib.lib().ndiff_op_conv_ex(mode, B, H, W, G.P(h), c, None, 0, G.P(G.pack_weight(w)), c, G.P(bias), None, 0,
+    wpk = G.pack_weight(w)
+    _lib.check(_lib.lib().ndiff_op_conv_ex(mode, B, H, W, G.P(h), c, None, 0, G.P(wpk), c, G.P(bias), None, 0,
                                            G.P(out), C.byref(ex), G.stream()))
     torch.cuda.synchronize()
     assert torch.equal(out, ref), (out.float() - ref.float()).abs().max().item()
@@ -400,7 +402,8 @@ def test_shot_tail_chain(case):
     fvec = torch.zeros(128, device="cuda")
     fvec[:64], fvec[64:68] = b1, b2
     out = torch.zeros((npix, 4), device="cuda")
-    _lib.check(_lib.lib().ndiff_op_tail_chain(npix, HW, G.P(h2.to(torch.bfloat16)), G.P(r1.to(torch.bfloat16)), G.P(r2.to(torch.bfloat16)),
+    hb16, r1b, r2b = h2.to(torch.bfloat16), r1.to(torch.bfloat16), r2.to(torch.bfloat16)     # (named: pointers must outlive the call)
+    _lib.check(_lib.lib().ndiff_op_tail_chain(npix, HW, G.P(hb16), G.P(r1b), G.P(r2b),
                                               G.P(blob), G.P(fvec), G.P(stats), G.P(gamma), G.P(beta), groups, G.P(out), G.stream()))
     torch.cuda.synchronize()
     y = F.group_norm(h2.reshape(B, HW, 64).permute(0, 2, 1), groups, gamma, beta, eps=1e-5).permute(0, 2, 1).reshape(npix, 64)
