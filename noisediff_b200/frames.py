@@ -45,6 +45,26 @@ def npy_name(clean_name: str, x: int, y: int, noisy_name: Optional[str] = None) 
     return f"{c}+{s}+{int(x)}_{int(y)}.npy"
 
 
+def parse_npy_name(name: str) -> Tuple[str, str, int, int]:
+    """Inverse of :func:`npy_name`, the way the downstream consumer reads it (``dataloader/dataset_denoising.py:56-59,136-138``):
+    ``clean+noisy+x_y.npy`` -> (clean, noisy, x, y)."""
+    clean, noisy, coord = os.path.basename(name).split(".npy")[0].split("+")
+    x, y = coord.split("_")
+    return clean, noisy, int(x), int(y)
+
+
+def consumer_subfolder(iso: int, ratio: int) -> str:
+    """Folder the denoiser's synthetic-pair dataset expects per camera setting (``dataset_denoising.py:47-52``)."""
+    return f"ISO{int(iso)}_Ratio{int(ratio)}"
+
+
+def compose_noisy(clean_crop: torch.Tensor, noise: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """What the consumer does with a generated crop (``dataset_denoising.py:140-153``, without dark shading):
+    noise clipped to [-1, 1], added to the clean crop, both clipped to [0, 1].  Returns (clean, noisy)."""
+    noisy = (noise.clamp(-1.0, 1.0).float() + clean_crop.float()).clamp(0.0, 1.0)
+    return clean_crop.float().clamp(0.0, 1.0), noisy
+
+
 class NpyWriter:
     """Background ``np.save`` of generated crops.  ``submit`` copies a finished batch to pinned host memory with a
     non-blocking D2H copy and returns; the worker waits for the copy's event and writes the files."""
@@ -98,7 +118,7 @@ class NpyWriter:
 @torch.inference_mode()
 def synthesize_frame(diffusion, clean_frame: torch.Tensor, *, iso_ratio_idx: int, clean_name: str, save_folder: str,
                      noisy_name: Optional[str] = None, batch_size: int = 64, rank: int = 0, world_size: int = 1,
-                     dark_frame: bool = False) -> List[str]:
+                     dark_frame: bool = False, iso: Optional[int] = None, ratio: Optional[int] = None) -> List[str]:
     """Generates this rank's share of the noise crops of one frame and writes them the way ``Trainer.test`` does.
     `diffusion` is a ``GaussianDiffusion`` (its ``image_size`` is the crop size).  Returns the written paths."""
     ps = int(diffusion.image_size)
@@ -107,7 +127,10 @@ def synthesize_frame(diffusion, clean_frame: torch.Tensor, *, iso_ratio_idx: int
     _, fh, fw = frame.shape
     origins = tiles.tile_origins(ps, fh, fw)
     mine = [origins[i] for i in tiles.shard(len(origins), world_size, rank)]
-    writer = NpyWriter(os.path.join(save_folder, "npy", "generated"))
+    # Trainer.test() layout by default; with (iso, ratio) the files go straight into the folder the denoiser's dataset globs
+    folder = os.path.join(save_folder, consumer_subfolder(iso, ratio)) if iso is not None and ratio is not None \
+        else os.path.join(save_folder, "npy", "generated")
+    writer = NpyWriter(folder)
     try:
         for lo in range(0, len(mine), batch_size):
             part = mine[lo:lo + batch_size]

@@ -45,6 +45,19 @@ def test_crop_batch_and_names():
     assert frames.npy_name("a.ARW", 0, 0, noisy_name="b.ARW") == "a+b+0_0.npy"
 
 
+def test_consumer_contract():
+    """dataset_denoising.py:47-59,136-153: folder / file-name parsing and the noise + clean composition."""
+    assert frames.consumer_subfolder(800, 250) == "ISO800_Ratio250"
+    n = frames.npy_name("00001_00_10s.ARW", 192, 1168, noisy_name="00001_00_0.04s.ARW")
+    assert frames.parse_npy_name("/x/" + n) == ("00001_00_10s", "00001_00_0.04s", 192, 1168)
+    g = torch.Generator().manual_seed(3)
+    clean = torch.rand((4, 8, 8), generator=g) * 1.2 - 0.1
+    noise = torch.randn((4, 8, 8), generator=g) * 0.8
+    c, nz = frames.compose_noisy(clean, noise)
+    want = np.clip(np.clip(noise.numpy(), -1.0, 1.0).astype(np.float32) + clean.numpy(), 0.0, 1.0)
+    assert np.array_equal(nz.numpy(), want) and np.array_equal(c.numpy(), np.clip(clean.numpy(), 0.0, 1.0))
+
+
 class _FakeDiffusion:
     """Stands in for GaussianDiffusion on CPU: 'noise' = clean + position-dependent pattern, so files are checkable."""
     image_size = 32
@@ -69,6 +82,10 @@ def test_two_ranks_cover_the_frame_once(tmp_path):
     assert arr.dtype == np.float32 and arr.shape == (4, 32, 32)
     want = frames.crop_batch(frame, [(x, y)], 32, 3)
     assert np.allclose(arr, (want["clean_img"] + want["position"].sum(1, keepdim=True))[0].numpy())
+    # consumer layout: <save_folder>/ISO{iso}_Ratio{ratio}/
+    p2 = frames.synthesize_frame(_FakeDiffusion(), frame, iso_ratio_idx=3, clean_name="f.ARW", save_folder=str(tmp_path), batch_size=64,
+                                 iso=800, ratio=250)
+    assert len(p2) == len(origins) and all(os.path.dirname(p).endswith("ISO800_Ratio250") for p in p2)
 
 
 @pytest.mark.gpu
