@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
                                 tma_load_5d(ringA + sa * kAStage, tm, bar_fullA + sa * 8, c0, kx, x0, ky, b * a.H + y0);
                             else
                                 tma_load_4d(ringA + sa * kAStage, tm, bar_fullA + sa * 8, c0, x0 + kx - a.pad_x,
-                                            y0 + ky - a.pad_y, b);
+                                            y0 + ky * a.tap_sy - a.pad_y, b);
                         }
                         __syncwarp();
                         if (++sa == a_stages) { sa = 0; pa ^= 1; }
@@ -657,6 +657,7 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     else if (halo1) { a.taps_y = 3; a.taps_x = 3; a.pad_y = 1; a.pad_x = 1; }
     else if (d.mode == kS2D) { a.taps_y = 2; a.taps_x = 2; a.pad_y = 0; a.pad_x = 0; }
     else { a.taps_y = d.taps_y; a.taps_x = d.taps_x; a.pad_y = d.pad_y; a.pad_x = d.pad_x; }
+    a.tap_sy = d.tap_sy > 0 ? d.tap_sy : 1;
     a.n_tiles = d.Cout / NT;
     a.total_tiles = d.B * a.tiles_y * a.tiles_x * a.n_tiles * (up ? 4 : 1);
     const int b_tap = NT * 128;                          // one [NT x 64] weight block

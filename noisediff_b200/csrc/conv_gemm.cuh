@@ -35,6 +35,7 @@ struct ConvGemmArgs {
     int tiles_x, tiles_y;  // tiles per image
     int cb0, cb1;          // 64-channel blocks taken from source 0 / source 1 (concat order: 0 then 1)
     int taps_y, taps_x, pad_y, pad_x;  // tap grid of kDirect (kHalo3: 3,3,1,1; kS2D: 2,2,0,0)
+    int tap_sy;            // kDirect: input-row step between consecutive ky taps (1; 2 for the row-paired 7x7 init_conv)
     int n_tiles;           // Cout / NT
     int total_tiles;
     int a_stages, b_stages;
@@ -79,6 +80,7 @@ struct ConvGemmDesc {
     const __nv_bfloat16* src0 = nullptr; int C0 = 0;   // NHWC bf16, C0 % 64 == 0
     const __nv_bfloat16* src1 = nullptr; int C1 = 0;   // optional second concat source
     int taps_y = 1, taps_x = 1, pad_y = 0, pad_x = 0;
+    int tap_sy = 1;                      // kDirect: input-row step per ky tap
     // kDirect special: source 0 described by an explicit (possibly overlapping-window) 4-D map
     bool custom_src0 = false;
     uint64_t cdim[4] = {0, 0, 0, 0};     // dims innermost first

@@ -120,9 +120,11 @@ __global__ void init_conv_pack_kernel(const float* __restrict__ src, float* __re
     }
 }
 
-// init_conv on tensor cores: x_t is re-laid as bf16 [B][H+6][W+8][8] (3-pixel zero border, channels 4..7 zero) so that the
-// 7 taps of one kernel row are ONE contiguous 128-byte window (8 pixels x 8 channels) -> one SWIZZLE_128B operand row.
-__global__ void xpad_pack_kernel(const float4* __restrict__ x, uint4* __restrict__ xpad, int H, int W, size_t npix) {
+// init_conv on tensor cores: x_t is re-laid as bf16 [B][H+6][W+8][8] with a 3-pixel zero border, where element (r, c) holds
+// the 4 channels of padded pixel (r, c) AND, in channels 4..7, those of the pixel one row below (r + 1, c).  One contiguous
+// 128-byte window (8 pixels x 8 values) is then the 7 taps of TWO kernel rows -> one SWIZZLE_128B operand row, and the 7x7 conv
+// is 4 row-pair GEMM taps (input rows y, y+2, y+4, y+6) instead of 7 single-row taps whose K blocks were half zeros.
+__global__ void xpad_pack_kernel(const float4* __restrict__ x, uint2* __restrict__ xpad, int H, int W, size_t npix) {
     pdl_trigger();
     pdl_wait();
     const size_t pix = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -132,17 +134,20 @@ __global__ void xpad_pack_kernel(const float4* __restrict__ x, uint4* __restrict
     const int yy = static_cast<int>(r % H);
     const size_t b = r / H;
     const float4 v = x[pix];
-    uint4 o;
-    o.x = pack_bf16(v.x, v.y); o.y = pack_bf16(v.z, v.w); o.z = 0u; o.w = 0u;
-    xpad[(b * (H + 6) + yy + 3) * (W + 8) + xx + 3] = o;
+    const uint2 o = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    const size_t at = (b * (H + 6) + yy + 3) * (W + 8) + xx + 3;      // element index of padded pixel (yy + 3, xx + 3)
+    xpad[at * 2] = o;                                                  // its own row: channels 0..3
+    xpad[(at - (W + 8)) * 2 + 1] = o;                                  // the row above sees it as "one row below": channels 4..7
 }
 
 __global__ void init_conv_pack_tc_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int Cout) {
-    // dst[co][ky(7)][kxw(8)][ci(8)]  <-  src[co][ci(4)][7][7]; zero where ci >= 4 or kxw == 7
-    const int total = Cout * 7 * 64;
+    // dst[co][kp(4)][kxw(8)][8]  <-  src[co][ci(4)][7][7]: values 0..3 = kernel row 2 kp, values 4..7 = kernel row 2 kp + 1;
+    // zero where the row is 7 or kxw == 7
+    const int total = Cout * 4 * 64;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int ci = i & 7, kxw = (i >> 3) & 7, ky = (i >> 6) % 7, co = i / (7 * 64);
-        const float v = (ci < 4 && kxw < 7) ? src[((co * 4 + ci) * 7 + ky) * 7 + kxw] : 0.f;
+        const int v8 = i & 7, kxw = (i >> 3) & 7, kp = (i >> 6) & 3, co = i >> 8;
+        const int ci = v8 & 3, ky = 2 * kp + (v8 >> 2);
+        const float v = (ky < 7 && kxw < 7) ? src[((co * 4 + ci) * 7 + ky) * 7 + kxw] : 0.f;
         dst[i] = __float2bfloat16_rn(v);
     }
 }
@@ -788,7 +793,7 @@ int build_plan(ndiff_engine* e) {
         ConvGemmDesc d;
         d.mode = kDirect; d.B = B; d.H = H; d.W = W;
         d.src0 = e->xpad; d.C0 = 64;
-        d.taps_y = 7; d.taps_x = 1; d.pad_y = 0; d.pad_x = 0;
+        d.taps_y = 4; d.taps_x = 1; d.pad_y = 0; d.pad_x = 0; d.tap_sy = 2;      // four row-pair taps: input rows y, y+2, y+4, y+6
         d.custom_src0 = true;
         d.cdim[0] = 64; d.cdim[1] = static_cast<uint64_t>(W); d.cdim[2] = static_cast<uint64_t>(H + 6); d.cdim[3] = static_cast<uint64_t>(B);
         d.cstride[0] = 16; d.cstride[1] = static_cast<uint64_t>(W + 8) * 16; d.cstride[2] = static_cast<uint64_t>(H + 6) * (W + 8) * 16;
@@ -798,7 +803,7 @@ int build_plan(ndiff_engine* e) {
         const bool tc_ok = (e->cfg.flags & NDIFF_FLAG_INIT_SIMT) == 0 && conv_gemm_plan(d, e->num_sms, plan.get()) == 0;
         if (tc_ok) {
             Op pk; pk.name = "init_conv.pack";
-            const float4* xs = reinterpret_cast<const float4*>(e->x); uint4* xp = reinterpret_cast<uint4*>(e->xpad);
+            const float4* xs = reinterpret_cast<const float4*>(e->x); uint2* xp = reinterpret_cast<uint2*>(e->xpad);
             pk.fn = [=](cudaStream_t st) {
                 NDIFF_CUDA_OK(launch_pdl(xpad_pack_kernel, dim3((npix + 255) / 256), dim3(256), 0, st, xs, xp, H, W,
                                          static_cast<size_t>(npix)));
