@@ -417,11 +417,16 @@ int finalize(ndiff_engine* e, cudaStream_t s) {
         if (pack_chain_weight_launch(e->pf("shot_mlp1.fc1.weight"), w, 64, 8, false, s)) return 1;
         if (pack_chain_weight_launch(e->pf("shot_mlp1.fc2.weight"), w + 64 * 64, 64, 64, true, s)) return 1;
         if (pack_attn_chain("shot_attn", w + 128 * 64, f + 128)) return 1;
-        if (pack_chain_weight_launch(e->pf("shot_mlp2.fc1.weight"), w + 448 * 64, 64, 64, false, s)) return 1;
+        // shot_attn.proj_out folded into shot_mlp2.fc1: rows 384..447 (the attention block's Wp slot) = Wm1, applied to s1;
+        // rows 448..511 = Wm1 Wp, applied to z; bias slot of fc1 = bm1 + Wm1 bp  (pixel_chain.cuh)
+        if (pack_chain_weight_launch(e->pf("shot_mlp2.fc1.weight"), w + 384 * 64, 64, 64, false, s)) return 1;
+        if (!e->fold_tmp && e->alloc(&e->fold_tmp, 128 * 64)) return 1;
+        if (fold_linear_launch(e->pf("shot_mlp2.fc1.weight"), e->pf("shot_attn.proj_out.weight"), e->pf("shot_attn.proj_out.bias"),
+                               e->pf("shot_mlp2.fc1.bias"), e->fold_tmp, f + 512, 64, s)) return 1;
+        if (pack_chain_weight_launch(e->fold_tmp, w + 448 * 64, 64, 64, false, s)) return 1;
         if (pack_chain_weight_launch(e->pf("shot_mlp2.fc2.weight"), w + 512 * 64, 64, 64, true, s)) return 1;
         NDIFF_CUDA_OK(cudaMemcpyAsync(f, e->pf("shot_mlp1.fc1.bias"), sizeof(float) * 64, cudaMemcpyDeviceToDevice, s));
         NDIFF_CUDA_OK(cudaMemcpyAsync(f + 64, e->pf("shot_mlp1.fc2.bias"), sizeof(float) * 64, cudaMemcpyDeviceToDevice, s));
-        NDIFF_CUDA_OK(cudaMemcpyAsync(f + 512, e->pf("shot_mlp2.fc1.bias"), sizeof(float) * 64, cudaMemcpyDeviceToDevice, s));
         NDIFF_CUDA_OK(cudaMemcpyAsync(f + 576, e->pf("shot_mlp2.fc2.bias"), sizeof(float) * 64, cudaMemcpyDeviceToDevice, s));
         // shot-branch tail: fc1 (bf16 rows) | fc2 (fp16, 4 live rows of 16) | zero padding
         if (!e->chain_w.count("tail")) {

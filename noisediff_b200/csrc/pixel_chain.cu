@@ -297,25 +297,30 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
             }
             store_half(sA0, r, h, v);
         }
-        // ---- proj_out (1x1 conv) + x_in   (ref :441-443) -------------------------------------------------------------------
-        NDIFF_STAGE(issue_gemm<64>(tmem_d, sA0, sWp, 1, 4));
+        if constexpr (!kShot) {
+            // ---- proj_out (1x1 conv) + x_in   (ref :441-443) ---------------------------------------------------------------
+            NDIFF_STAGE(issue_gemm<64>(tmem_d, sA0, sWp, 1, 4));
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            uint32_t raw[32];
-            tmem_ld32(tmem_rd + h * 32, raw);
-            tmem_ld_wait();
-            float v[32];
+            for (int h = 0; h < 2; ++h) {
+                uint32_t raw[32];
+                tmem_ld32(tmem_rd + h * 32, raw);
+                tmem_ld_wait();
+                float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-                const float2 f = unpack_bf16(xr[(h * 32 + j) / 2]);
-                v[j] = __uint_as_float(raw[j]) + f_bp[h * 32 + j] + f.x;
-                v[j + 1] = __uint_as_float(raw[j + 1]) + f_bp[h * 32 + j + 1] + f.y;
+                for (int j = 0; j < 32; j += 2) {
+                    const float2 f = unpack_bf16(xr[(h * 32 + j) / 2]);
+                    v[j] = __uint_as_float(raw[j]) + f_bp[h * 32 + j] + f.x;
+                    v[j + 1] = __uint_as_float(raw[j + 1]) + f_bp[h * 32 + j + 1] + f.y;
+                }
+                store_half(sA1, r, h, v);               // staging for the TMA store
             }
-            store_half(kShot ? sA0 : sA1, r, h, v);      // attn: staging for the TMA store; shot: operand of shot_mlp2.fc1
         }
         if constexpr (kShot) {
-            // ---- shot_mlp2: fc1 + GELU, fc2   (ref :601) ---------------------------------------------------------------------
-            NDIFF_STAGE(issue_gemm<64>(tmem_d, sA0, sWm1, 1, 4));
+            // ---- proj_out + x_in folded into shot_mlp2.fc1 (both linear, nothing else reads the attention block's output):
+            //      fc1(Wp z + bp + s1) = (Wm1 Wp) z + Wm1 s1 + (Wm1 bp + bm1) — ONE K = 128 GEMM over [s1 | z], whose operand
+            //      blocks are the X slot (s1, staged for its TMA store) and A0 (z); the packer supplies [Wm1 | Wm1 Wp] and the
+            //      folded bias.  Then GELU, fc2   (ref :441-443, :601).
+            NDIFF_STAGE(issue_gemm<64>(tmem_d, sX, sWp, 2, 4));
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 uint32_t raw[32];
@@ -542,6 +547,28 @@ __global__ void fold_layernorm_kernel(const float* __restrict__ w, const float* 
 }
 
 }  // namespace
+
+namespace {
+__global__ void fold_linear_kernel(const float* __restrict__ a, const float* __restrict__ w, const float* __restrict__ b1,
+                                   const float* __restrict__ b2, float* __restrict__ w_out, float* __restrict__ b_out, int N) {
+    const int n = blockIdx.x, k = threadIdx.x;          // one output row per block, one column per thread
+    float acc = 0.f;
+    for (int j = 0; j < N; ++j) acc = fmaf(a[n * N + j], w[j * N + k], acc);
+    w_out[n * N + k] = acc;
+    if (k == 0) {
+        float t = b2[n];
+        for (int j = 0; j < N; ++j) t = fmaf(a[n * N + j], b1[j], t);
+        b_out[n] = t;
+    }
+}
+}  // namespace
+
+int fold_linear_launch(const float* a, const float* w, const float* b1, const float* b2, float* w_out, float* b_out, int N,
+                       cudaStream_t s) {
+    fold_linear_kernel<<<N, N, 0, s>>>(a, w, b1, b2, w_out, b_out, N);
+    NDIFF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
 
 int fold_layernorm_launch(const float* w, const float* b, const float* g, const float* beta, float* w_out, float* b_out, int N,
                           int K, cudaStream_t s) {

@@ -20,8 +20,10 @@ enum ChainProg : int {
 //   attn : W1 (ff.net.0.0, 128 rows) | W2 kblock 0, 1 (ff.net.2, 64 + 64, fp16) | Wp (proj_out, 64)      = 320 rows
 //          [reserved 128][b1 128][b2 64][bp 64]                                                             = 384 floats
 //          (AttnBlock.norm2's affine is folded by the packer: W1 <- W1 diag(ln_g), b1 <- b1 + W1 ln_b)
-//   shot : W0 (shot_mlp1.fc1, K = 8 zero-padded, 64) | Wfc2 (shot_mlp1.fc2, 64, fp16) | attn 320 | Wm1 | Wm2 (fp16) = 576 rows
-//          [b0 64][bfc2 64] + attn 384 + [bm1 64][bm2 64]                                                  = 640 floats
+//   shot : W0 (shot_mlp1.fc1, K = 8 zero-padded, 64) | Wfc2 (shot_mlp1.fc2, 64, fp16) | W1 128 | W2 128 (as attn) |
+//          Wm1 (64, applied to s1) | Wm1 Wp (64, applied to z) | Wm2 (fp16)                                 = 576 rows
+//          (shot_attn.proj_out and shot_mlp2.fc1 are both linear and are folded into one K = 128 GEMM by the packer)
+//          [b0 64][bfc2 64] + attn 384 (bp slot unused) + [bm1 + Wm1 bp 64][bm2 64]                          = 640 floats
 constexpr int kChainAttnRows = 320, kChainAttnFloats = 384;
 constexpr int kChainShotRows = 576, kChainShotFloats = 640;
 
@@ -92,6 +94,9 @@ int pixel_chain_init();
 // dst[(kb * N + n) * 64 + kk] = src[n * K + kb * 64 + kk] (zero beyond K): fp32 [N][K] -> 16-bit K-blocked rows.
 // f16 = true for the layers whose A operand is a GELU output (kept in fp16 on chip: ff.net.2, shot_mlp1.fc2, shot_mlp2.fc2).
 int pack_chain_weight_launch(const float* src, __nv_bfloat16* dst, int N, int K, bool f16, cudaStream_t s);
+// w_out = a @ w (fp32 [N][N] row-major each);  b_out[n] = b2[n] + sum_k a[n][k] b1[k]   (two stacked Linears folded into one)
+int fold_linear_launch(const float* a, const float* w, const float* b1, const float* b2, float* w_out, float* b_out, int N,
+                       cudaStream_t s);
 // w_out[n][k] = w[n][k] * g[k];  b_out[n] = b[n] + sum_k w[n][k] * beta[k]   (LayerNorm affine folded into the next Linear)
 int fold_layernorm_launch(const float* w, const float* b, const float* g, const float* beta, float* w_out, float* b_out, int N,
                           int K, cudaStream_t s);

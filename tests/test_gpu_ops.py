@@ -289,8 +289,10 @@ def test_shot_chain(case):
     W0, b0 = _bf(rn(64, 8, sc=0.35)), 0.3 * rn(64)
     Wf, bf_ = _bf(rn(64, 64, sc=0.125)), 0.3 * rn(64)
     Wm1, bm1, Wm2, bm2 = _bf(rn(64, 64, sc=0.125)), 0.3 * rn(64), _bf(rn(64, 64, sc=0.125)), 0.3 * rn(64)
-    blob = torch.cat([_blob(W0), _blob(Wf, f16=True), ablob, _blob(Wm1), _blob(Wm2, f16=True)])
-    fvec = torch.cat([b0, bf_, afvec, bm1, bm2])
+    # packer convention (pixel_chain.cuh): shot_attn.proj_out is folded into shot_mlp2.fc1 — the attention block's Wp rows hold
+    # Wm1 (applied to s1), the next 64 rows Wm1 Wp (applied to z), and fc1's bias slot holds bm1 + Wm1 bp
+    blob = torch.cat([_blob(W0), _blob(Wf, f16=True), ablob[:256], _blob(Wm1), _blob(_bf(Wm1 @ p["Wp"])), _blob(Wm2, f16=True)])
+    fvec = torch.cat([b0, bf_, afvec, bm1 + Wm1 @ p["bp"], bm2])
     assert blob.shape == (576, 64) and fvec.numel() == 640
     out = torch.zeros((npix, 64), dtype=torch.bfloat16, device="cuda")
     out2 = torch.zeros_like(out)
