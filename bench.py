@@ -168,8 +168,19 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner must not precede the JSON line on stdout
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to the C-level stdout when the communicator comes up; stdout must carry exactly one
+        # JSON line, so file descriptor 1 points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
     B, mb = args.batch, min(args.micro_batch, args.batch)
