@@ -366,17 +366,23 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
                             Bj = Bj * sc + sh;
                         }
                         // stored halved: SiLU(y) = h + h tanh(h) with h = y / 2 = fma(x, A/2, B/2) — exact, powers of two
-                        tail->coef[c] = make_float2(0.5f * Aj, 0.5f * Bj);
+                        reinterpret_cast<float*>(tail->coef)[c] = 0.5f * Aj;            // A / 2 for channels 0..511,
+                        reinterpret_cast<float*>(tail->coef)[512 + c] = 0.5f * Bj;      // then B / 2
                     }
                     named_bar_sync(1, kXfWarps * 32);
                 }
                 const int gx0 = tx * a.TW - 1, gy0 = ty * a.TH - 1;
                 for (int cb = 0; cb < CB; ++cb) {
+                    // explicit ld.shared (a generic load of this table showed 16 wavefronts per instruction in ncu); the table is
+                    // stored as two float arrays so that the eight channel octets of a warp read 8 x 32 contiguous bytes each
                     float A[8], Bc[8];
-#pragma unroll
-                    for (int j = 0; j < 8; j += 2) {
-                        const float4 c2 = *reinterpret_cast<const float4*>(&tail->coef[cb * 64 + o * 8 + j]);
-                        A[j] = c2.x; Bc[j] = c2.y; A[j + 1] = c2.z; Bc[j + 1] = c2.w;
+                    {
+                        const uint32_t ca = smem_u32(&tail->coef[0]) + (cb * 64 + o * 8) * 4;
+                        const uint4 a0 = lds128(ca), a1 = lds128(ca + 16), b0 = lds128(ca + 2048), b1 = lds128(ca + 2048 + 16);
+                        A[0] = __uint_as_float(a0.x); A[1] = __uint_as_float(a0.y); A[2] = __uint_as_float(a0.z); A[3] = __uint_as_float(a0.w);
+                        A[4] = __uint_as_float(a1.x); A[5] = __uint_as_float(a1.y); A[6] = __uint_as_float(a1.z); A[7] = __uint_as_float(a1.w);
+                        Bc[0] = __uint_as_float(b0.x); Bc[1] = __uint_as_float(b0.y); Bc[2] = __uint_as_float(b0.z); Bc[3] = __uint_as_float(b0.w);
+                        Bc[4] = __uint_as_float(b1.x); Bc[5] = __uint_as_float(b1.y); Bc[6] = __uint_as_float(b1.z); Bc[7] = __uint_as_float(b1.w);
                     }
                     mbar_wait(bar_fullA + sa * 8, pa);
                     const uint32_t base = ringA + sa * kAStage;
