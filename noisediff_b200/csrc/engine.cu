@@ -9,7 +9,6 @@
 //     positional branch and the time MLP are hoisted out of the per-pixel work;
 //   * final_conv + shot_mlp3.fc2 + the DDPM/DDIM posterior update are one kernel; a whole step replays as one graph.
 #include <cstddef>
-#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -565,8 +564,7 @@ struct Builder {
         if (mode == kHalo1 && direct3) { d.mode = kDirect; d.taps_y = 3; d.taps_x = 3; d.pad_y = 1; d.pad_x = 1; }
         // 256-pixel CTA tiles where the whole weight slice stays resident next to the larger halo stages (measured: +4 %
         // on the 64 -> 64 layers; streamed-weight shapes are faster with 128-pixel tiles and deeper rings)
-        else if (mode == kHalo1 && Ho >= 32 && Cout == 64 && s0.C == 64 && !s1 && !(e->cfg.flags & NDIFF_FLAG_HALO1) &&
-                 !(xf && getenv("NDIFF_XF_HALO1"))) d.mode = kHalo2;
+        else if (mode == kHalo1 && Ho >= 32 && Cout == 64 && s0.C == 64 && !s1 && !(e->cfg.flags & NDIFF_FLAG_HALO1)) d.mode = kHalo2;
         d.B = e->B; d.H = Ho; d.W = Wo;
         d.src0 = s0.p; d.C0 = s0.C;
         if (s1) { d.src1 = s1->p; d.C1 = s1->C; }
