@@ -139,3 +139,21 @@ def test_fast_gelu_coefficients_track_exact_erf_gelu():
     approx = x / (1 + torch.exp(x * p))               # the kernel's ex2(x * p * log2 e) == exp(x * p)
     exact = 0.5 * x * (1 + torch.erf(x / 2 ** 0.5))
     assert float((approx - exact).abs().max()) < 4e-5
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the driver's reference arm): one JSON line on stdout with the contract's keys, no GPU needed."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "patches/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
