@@ -150,7 +150,7 @@ def main():
     ap.add_argument("--dump-layers", default=None, help="write the per-layer CUDA-event table (name, ms, flops) to this JSON file")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--cpu-steps", type=int, default=40, help="timed CPU reverse steps of the cpu_baseline leg (~0.28 s each on 16 cores)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -244,7 +244,7 @@ class GaussianDiffusion(nn.Module):
         state = [x_T[lo:hi].contiguous() if x_T is not None else None for lo, hi in groups]
         conds = [(condition["clean_img"][lo:hi], condition["position"][lo:hi], condition["iso_ratio_idx"][lo:hi])
                  for lo, hi in groups]
-        all_imgs = [x_T] if return_all and x_T is not None else []
+        snaps, xT_parts = [], [None] * len(groups)
         done = 0
         started = [False] * len(groups)
         while done < n_steps:
@@ -274,6 +274,8 @@ class GaussianDiffusion(nn.Module):
                 if not started[gi]:
                     eng.chain_begin(steps, fit(state[gi]) if state[gi] is not None else None, base_seed + gi)
                     started[gi] = True
+                    if return_all and x_T is None:        # x_T was drawn in the library (Philox): read it back for slot 0
+                        xT_parts[gi] = eng.chain_read()[: hi - lo]
                 elif len(groups) > 1:
                     eng.chain_seek(done, fit(state[gi]), base_seed + gi)
                 nz = fit(chunk_noise[:, lo:hi], 1) if chunk_noise is not None else None
@@ -285,14 +287,12 @@ class GaussianDiffusion(nn.Module):
                 if return_all:
                     snaps_full[:, lo:hi] = sn[:, : hi - lo]
             if return_all:
-                all_imgs.extend(snaps_full[i] for i in range(n))
+                snaps.extend(snaps_full[i] for i in range(n))
             done += n
-        img = torch.cat(state, dim=0)
-        if return_all:
-            if x_T is None:
-                raise ValueError("return_all_timesteps needs noise_source='torch' (x_T must exist on the host side)")
-            return torch.stack(all_imgs, dim=1)
-        return img
+        if return_all:                                    # (B, n_steps + 1, C, H, W), slot 0 = x_T (ref :389-399)
+            first = x_T if x_T is not None else torch.cat(xT_parts, dim=0)
+            return torch.stack([first] + snaps, dim=1)
+        return torch.cat(state, dim=0)
 
     @torch.inference_mode()
     def p_sample_loop(self, shape, condition=None, return_all_timesteps=False, preset_mean=None):
@@ -320,15 +320,36 @@ class GaussianDiffusion(nn.Module):
         raise NotImplementedError("interpolate() passes self_cond as the condition in the reference (ref :468-469), "
                                   "which NoiseDiffNet cannot consume; it is unreachable there too")
 
-    # ---- training-side API kept for signature compatibility (SURVEY.md §8f N1 is out of this round's scope) ------
+    # ---- training-side API: signatures kept; the loss is evaluated forward-only (backward is not built) ----
     def q_sample(self, x_start, t, noise=None):
         noise = torch.randn_like(x_start) if noise is None else noise
         return _gather(self.sqrt_alphas_cumprod, t, x_start.dim()) * x_start + \
             _gather(self.sqrt_one_minus_alphas_cumprod, t, x_start.dim()) * noise
 
     def p_losses(self, x_start, t, condition=None, noise=None, offset_noise_strength=None):
-        raise NotImplementedError("diffusion training (forward+backward) is the next scope row (SURVEY.md §8f N1); "
-                                  "the B200 library is inference-only in this round")
+        """Loss VALUE of the training objective (ref :481-531): q_sample -> network (per-sample t) -> weighted MSE against the
+        objective's target.  Forward half of SURVEY.md §8f N1 only — validation / loss curves under ``torch.no_grad()``; the
+        library has no backward kernels yet, so asking for gradients raises instead of silently returning a detached loss."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.model.parameters()):
+            raise NotImplementedError("diffusion training (forward+backward) is the next scope row (SURVEY.md §8f N1); "
+                                      "the B200 library evaluates the loss only under torch.no_grad()")
+        noise = torch.randn_like(x_start) if noise is None else noise
+        ons = self.offset_noise_strength if offset_noise_strength is None else offset_noise_strength
+        if ons > 0.:                                                                   # ref :490-492
+            noise = noise + ons * torch.randn(x_start.shape[:2], device=self.device)[:, :, None, None]
+        x = self.q_sample(x_start=x_start, t=t, noise=noise)
+        out = self.model(x, t, condition)
+        if self.objective == "pred_noise":
+            target = noise
+        elif self.objective == "pred_x0":
+            target = x_start
+        else:
+            target = self.predict_v(x_start, t, noise)
+        loss = F.mse_loss(out, target, reduction="none").flatten(1).mean(dim=1)        # ref :518-519
+        loss = loss * self.loss_weight.gather(-1, t)
+        if self.objective == "pred_x0":                                                # ref :522-526 (its prints are dropped)
+            return loss.mean() + (out.mean(dim=(2, 3)) - target.mean(dim=(2, 3))).abs().mean()
+        return loss.mean()
 
     def forward(self, img, condition, *args, **kwargs):
         b, c, h, w = img.shape

@@ -277,6 +277,27 @@ def ddpm_step(tab, objective: str, x: Tensor, t: int, out: Tensor, z: Optional[T
     return mean + 0.0, x0
 
 
+def p_losses(sd: SD, tab, objective: str, x_start: Tensor, t: Tensor, condition, noise: Tensor) -> Tensor:
+    """Training loss value, denoising_diffusion_pytorch.py:481-531 (q_sample :473-479, predict_v :310-314); per-sample ``t``.
+    The reference's offset noise is off by default (strength 0) and its pred_x0 prints are not restated."""
+    def ex(name):
+        return tab[name][t].reshape(-1, 1, 1, 1)
+    x = ex("sqrt_alphas_cumprod") * x_start + ex("sqrt_one_minus_alphas_cumprod") * noise
+    out = net_forward(sd, x, t, condition)
+    if objective == "pred_noise":
+        target = noise
+    elif objective == "pred_x0":
+        target = x_start
+    elif objective == "pred_v":
+        target = ex("sqrt_alphas_cumprod") * noise - ex("sqrt_one_minus_alphas_cumprod") * x_start
+    else:
+        raise ValueError(objective)
+    loss = ((out - target) ** 2).flatten(1).mean(dim=1) * tab["loss_weight"][t]
+    if objective == "pred_x0":
+        return loss.mean() + (out.mean(dim=(2, 3)) - target.mean(dim=(2, 3))).abs().mean()
+    return loss.mean()
+
+
 def ddim_pairs(T: int, S: int) -> List[Tuple[int, int]]:
     """denoising_diffusion_pytorch.py:409-411."""
     times = torch.linspace(-1, T - 1, steps=S + 1)

@@ -18,7 +18,7 @@ import torch
 
 import noisediff_b200 as nd
 from oracle import noisediff_oracle as O
-from tests.util import seeded_net, seeded_sd
+from tests.util import load, noise_stats, sd_hash, seeded_net, seeded_sd
 
 pytestmark = pytest.mark.gpu
 
@@ -71,3 +71,43 @@ def test_noise_statistics_match_oracle():
     assert rel <= 0.15
     # and the two sample sets are genuinely different draws
     assert float((got - ref).abs().mean()) > 0.1 * float(ref.std())
+
+
+def test_1k_noise_statistics_match_reference_fixture():
+    """BASELINE.json: per-channel mean/variance and the 2-D noise power spectrum of 1k samples must match the reference.
+    Reference side: tests/golden/stats_1k.npz — 1024 samples of the UNMODIFIED reference (oracle/make_golden_stats.py; 32x32,
+    T = 24, one shared condition), plus the difference between two independent reference sets (``self_*``) as the sampling-noise
+    yardstick.  CUDA side: 1024 chains through the public sample() API with in-kernel Philox noise.  Stated tolerances
+    (two-sided sampling error of 1024 patches + the bf16 path's systematic error):
+      per-channel mean  |dm| <= 0.03 * std        per-channel variance  |dv| / v <= 4 %
+      radial PSD (8 annuli, per channel)  |dP| / P <= 6 %
+      2-D PSD (4 x 32 x 32 bins, DC excluded)  rms |dP| / P <= 8 %,  max <= 30 %
+    """
+    import copy
+    import numpy as np
+    z = load("stats_1k.npz")
+    n, S, T = int(z["n"]), int(z["size"]), int(z["timesteps"])
+    assert str(z["weights_sha256"]) == sd_hash(seeded_sd())
+    net = copy.deepcopy(seeded_net()).cuda()
+    one = O.synthetic_condition(1, S, S, seed=int(z["cond_seed"]))
+    cond = {k: v.expand(n, *v.shape[1:]).contiguous().cuda() for k, v in one.items()}
+    gd = nd.GaussianDiffusion(net, image_size=S, timesteps=T, beta_schedule="sigmoid2", objective="pred_v").cuda()
+    gd.noise_source, gd.micro_batch = "philox", 64
+    torch.manual_seed(7)
+    got = gd.sample(batch_size=n, condition=cond).cpu()
+    assert got.shape == (n, 4, S, S) and torch.isfinite(got).all()
+    st = noise_stats(got)
+    dm = np.abs(st["mean"] - z["mean"]) / np.sqrt(z["var"])
+    dv = np.abs(st["var"] - z["var"]) / z["var"]
+    dr = np.abs(st["radial"] - z["radial"]) / z["radial"]
+    nzb = z["psd2d"] > 0
+    dp = np.abs(st["psd2d"] - z["psd2d"])[nzb] / z["psd2d"][nzb]
+    print("mean ref", z["mean"].tolist(), "got", st["mean"].tolist(), "|dm|/std", dm.tolist(), "(ref self", z["self_mean"].tolist(), ")")
+    print("var  ref", z["var"].tolist(), "got", st["var"].tolist(), "|dv|/v", dv.tolist(), "(ref self", z["self_var"].tolist(), ")")
+    print("radial PSD max rel", float(dr.max()), "(ref self", float(z["self_radial_max"]), ")")
+    print("2-D PSD rel: rms", float(np.sqrt((dp ** 2).mean())), "max", float(dp.max()),
+          "(ref self rms", float(z["self_psd2d_rms"]), "max", float(z["self_psd2d_max"]), ")")
+    assert (dm <= 0.03).all()
+    assert (dv <= 0.04).all()
+    assert float(dr.max()) <= 0.06
+    assert float(np.sqrt((dp ** 2).mean())) <= 0.08 and float(dp.max()) <= 0.30

@@ -120,8 +120,13 @@ def test_elementwise_helpers_match_oracle():
     mean, _, logvar = gd.q_posterior(x0.clamp(-1, 1), x, t)
     assert torch.allclose(mean + (0.5 * logvar).exp() * z, ref, atol=0, rtol=0)
     assert torch.equal(gd.q_sample(x, t, z), tab["sqrt_alphas_cumprod"][7] * x + tab["sqrt_one_minus_alphas_cumprod"][7] * z)
+    # training: gradients are not built — asking for them raises; the loss value is a no_grad/CUDA-only call
+    trainable = nd.GaussianDiffusion(nd.NoiseDiffNet(net_args()), image_size=8, timesteps=20, beta_schedule="sigmoid2")
     with pytest.raises(NotImplementedError):
-        gd(torch.zeros(1, 4, 8, 8), {})
+        trainable(torch.zeros(1, 4, 8, 8), {})
+    with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA"):
+        gd(torch.zeros(1, 4, 8, 8), {"clean_img": torch.zeros(1, 4, 8, 8), "position": torch.zeros(1, 2, 8, 8),
+                                     "iso_ratio_idx": torch.zeros(1, dtype=torch.long)})
 
 
 def test_fast_gelu_coefficients_track_exact_erf_gelu():

@@ -59,6 +59,16 @@ def test_other_objectives_match_reference(objective):
     assert rel_l2(torch.stack(xs, dim=1), torch.from_numpy(z[objective])) < 1e-6
 
 
+@pytest.mark.parametrize("objective", ["pred_v", "pred_noise", "pred_x0"])
+def test_training_loss_value_matches_reference(objective):
+    z = load("losses.npz")
+    assert str(z["weights_sha256"]) == sd_hash(seeded_sd())
+    tab = O.schedule_tables(str(z[objective + "/schedule"]), int(z[objective + "/T"]), objective)
+    loss = O.p_losses(seeded_sd(), tab, objective, torch.from_numpy(z["x_start"]), torch.from_numpy(z[objective + "/t"]),
+                      _cond(z), torch.from_numpy(z["noise"]))
+    assert abs(float(loss) - float(z[objective + "/loss"])) <= 1e-6 * float(z[objective + "/loss"])
+
+
 def test_schedule_tables_bit_exact():
     z = load("schedules.npz")
     for name in ("linear", "cosine", "sigmoid1", "sigmoid2", "sigmoid3"):

@@ -55,3 +55,19 @@ def load(name):
 def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
     a, b = a.double().cpu(), b.double().cpu()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def noise_stats(x: torch.Tensor, nbins: int = 8):
+    """x: [n, C, S, S] -> dict of float64 arrays: per-channel mean / variance over (n, S, S); psd2d [C, S, S] = mean
+    periodogram |FFT2(x - patch mean)|^2 / S^2 (a noise-spectrum estimate removes each patch's DC); radial [C, nbins] = psd2d
+    averaged over annuli of |f|, normalised to sum 1 per channel."""
+    x = x.double().cpu()
+    mean, var = x.mean(dim=(0, 2, 3)), x.var(dim=(0, 2, 3))
+    xc = x - x.mean(dim=(-1, -2), keepdim=True)
+    psd = torch.fft.fft2(xc).abs().pow(2).mean(dim=0) / (x.shape[-1] * x.shape[-2])
+    f = torch.fft.fftfreq(x.shape[-1]).abs()
+    rad = torch.sqrt(f[:, None] ** 2 + f[None, :] ** 2)
+    edges = torch.linspace(0, float(rad.max()) + 1e-9, nbins + 1)
+    radial = torch.stack([psd[:, (rad >= edges[i]) & (rad < edges[i + 1])].mean(dim=1) for i in range(nbins)], dim=1)
+    radial = radial / radial.sum(dim=1, keepdim=True)
+    return {"mean": mean.numpy(), "var": var.numpy(), "psd2d": psd.numpy(), "radial": radial.numpy()}
