@@ -79,9 +79,11 @@ def test_1k_noise_statistics_match_reference_fixture():
     T = 24, one shared condition), plus the difference between two independent reference sets (``self_*``) as the sampling-noise
     yardstick.  CUDA side: 1024 chains through the public sample() API with in-kernel Philox noise.  Stated tolerances
     (two-sided sampling error of 1024 patches + the bf16 path's systematic error):
-      per-channel mean  |dm| <= 0.03 * std        per-channel variance  |dv| / v <= 4 %
+      per-channel mean  |dm| <= 0.015 * std       per-channel variance  |dv| / v <= 2.5 %
       radial PSD (8 annuli, per channel)  |dP| / P <= 6 %
-      2-D PSD (4 x 32 x 32 bins, DC excluded)  rms |dP| / P <= 8 %,  max <= 30 %
+      2-D PSD (4 x 32 x 32 bins, DC excluded)  rms |dP| / P <= 6.5 %,  max <= 35 %
+    For scale, two independent 1024-sample sets of the reference itself differ by 0.0017 std / 0.28 % / 1.7 % / rms 4.5 %, max 23 %
+    (a periodogram bin averaged over 1024 patches has a relative standard error of 1/32; the difference of two, 4.4 %).
     """
     import copy
     import numpy as np
@@ -107,7 +109,7 @@ def test_1k_noise_statistics_match_reference_fixture():
     print("radial PSD max rel", float(dr.max()), "(ref self", float(z["self_radial_max"]), ")")
     print("2-D PSD rel: rms", float(np.sqrt((dp ** 2).mean())), "max", float(dp.max()),
           "(ref self rms", float(z["self_psd2d_rms"]), "max", float(z["self_psd2d_max"]), ")")
-    assert (dm <= 0.03).all()
-    assert (dv <= 0.04).all()
+    assert (dm <= 0.015).all()
+    assert (dv <= 0.025).all()
     assert float(dr.max()) <= 0.06
-    assert float(np.sqrt((dp ** 2).mean())) <= 0.08 and float(dp.max()) <= 0.30
+    assert float(np.sqrt((dp ** 2).mean())) <= 0.065 and float(dp.max()) <= 0.35
