@@ -1129,6 +1129,13 @@ int32_t ndiff_chain_begin(ndiff_engine* e, const ndiff_step* steps_host, int32_t
     NDIFF_CUDA_OK(cudaSetDevice(e->cfg.device));
     cudaStream_t s = as_stream(stream);
     if (n_steps > e->ss_table_rows) {
+        // The captured step graph holds the two table pointers by value (chain_step_begin_kernel's arguments): a longer chain
+        // after a shorter one on the same engine must re-capture, or every replay would index the old, shorter tables.
+        if (e->step_exec) {
+            NDIFF_CUDA_OK(cudaDeviceSynchronize());
+            NDIFF_CUDA_OK(cudaGraphExecDestroy(e->step_exec));
+            e->step_exec = nullptr;
+        }
         if (e->alloc(&e->step_table, n_steps)) return 1;
         if (e->alloc(&e->ss_table, static_cast<size_t>(n_steps) * e->ss_total)) return 1;
         e->ss_table_rows = n_steps;

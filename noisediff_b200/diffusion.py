@@ -270,7 +270,8 @@ class GaussianDiffusion(nn.Module):
                     return torch.cat([t, t[tuple(idx)].repeat(*rep)], dim=dim).contiguous()
                 eng = net.engine_for(mb, H, W, dev)
                 c, p, i = conds[gi]
-                eng.set_condition(fit(c.to(dev)), fit(p.to(dev)), fit(i.to(dev)))
+                if len(groups) > 1 or not started[gi]:     # one micro-batch owns its engine for the whole chain: set once
+                    eng.set_condition(fit(c.to(dev)), fit(p.to(dev)), fit(i.to(dev)))
                 if not started[gi]:
                     eng.chain_begin(steps, fit(state[gi]) if state[gi] is not None else None, base_seed + gi)
                     started[gi] = True

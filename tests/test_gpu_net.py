@@ -291,3 +291,25 @@ def test_training_loss_value_golden(net, objective):
     ref = float(z[objective + "/loss"])
     print(objective, float(loss), ref)
     assert loss.dim() == 0 and abs(float(loss) - ref) <= 2e-2 * ref      # bf16 network output vs the fp32 reference
+
+
+def test_longer_chain_after_shorter_on_the_same_engine(net):
+    """The step graph is captured once per engine; a later chain with MORE steps grows the per-step tables and must re-capture
+    (regression: the replayed graph kept indexing the first chain's shorter tables)."""
+    cond = {k: v.cuda() for k, v in O.synthetic_condition(2, 32, 32, seed=13).items()}
+    short = nd.GaussianDiffusion(net, image_size=32, timesteps=3, beta_schedule="sigmoid2").cuda()
+    long_ = nd.GaussianDiffusion(net, image_size=32, timesteps=60, beta_schedule="sigmoid2").cuda()
+    short.chunk_steps = long_.chunk_steps = 25
+    net.release_engines()                               # fresh engine: its first chain is the short one
+    torch.manual_seed(1)
+    short.sample(batch_size=2, condition=cond)
+    torch.manual_seed(2)
+    a = long_.sample(batch_size=2, condition=cond)
+    net.release_engines()                               # fresh engine again: the long chain comes first
+    torch.manual_seed(2)
+    b = long_.sample(batch_size=2, condition=cond)
+    torch.manual_seed(1)
+    short.sample(batch_size=2, condition=cond)          # shorter after longer keeps the tables and the graph
+    torch.manual_seed(2)
+    c = long_.sample(batch_size=2, condition=cond)
+    assert torch.isfinite(a).all() and torch.equal(a, b) and torch.equal(c, b)
