@@ -15,7 +15,7 @@ from __future__ import annotations
 import os
 import queue
 import threading
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, NamedTuple, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -90,6 +90,8 @@ class NpyWriter:
                 arr = host.numpy()
                 for i, n in enumerate(names):
                     path = os.path.join(self.folder, n)
+                    if os.path.dirname(n):                   # names may carry a sub-folder (one per camera setting)
+                        os.makedirs(os.path.dirname(path), exist_ok=True)
                     np.save(path, arr[i])
                     self.paths.append(path)
             except BaseException as e:          # surfaced by close()
@@ -139,6 +141,73 @@ def synthesize_frame(diffusion, clean_frame: torch.Tensor, *, iso_ratio_idx: int
                 cond["clean_img"] = torch.zeros_like(cond["clean_img"])
             out = diffusion.sample(batch_size=len(part), condition=cond)
             writer.submit(out, [npy_name(clean_name, x, y, noisy_name) for x, y in part])
+    finally:
+        paths = writer.close()
+    return paths
+
+
+class FrameJob(NamedTuple):
+    """One long-exposure frame to synthesise noise for: what one ``NoiseImageGenerationDataset`` file contributes
+    (``dataloader/dataset.py:222-281``) plus where ``Trainer.test`` puts its crops (``models/trainer_diffusion.py:296-317``)."""
+    clean_frame: torch.Tensor                 # packed (4, H, W), host (ideally pinned) or device
+    iso_ratio_idx: int
+    clean_name: str
+    noisy_name: Optional[str] = None
+    dark_frame: bool = False                  # ref :287-290: a zero clean image
+    iso: Optional[int] = None                 # with (iso, ratio): files go to the consumer's ISO{iso}_Ratio{ratio}/ folder
+    ratio: Optional[int] = None
+
+
+def plan_crops(jobs: Sequence[FrameJob], ps: int) -> List[Tuple[int, int, int]]:
+    """(job index, x, y) of every crop of every frame: frames in the given order, crops in the reference's grid order."""
+    out = []
+    for j, job in enumerate(jobs):
+        _, fh, fw = job.clean_frame.shape
+        out.extend((j, x, y) for x, y in tiles.tile_origins(ps, fh, fw))
+    return out
+
+
+def _job_folder(job: FrameJob) -> str:
+    return consumer_subfolder(job.iso, job.ratio) if job.iso is not None and job.ratio is not None else os.path.join("npy", "generated")
+
+
+@torch.inference_mode()
+def synthesize_frames(diffusion, jobs: Sequence[FrameJob], *, save_folder: str, batch_size: int = 64, rank: int = 0,
+                      world_size: int = 1) -> List[str]:
+    """Several frames at once: the crops of ALL frames form one list, ranks take contiguous slices of it and sample it in FULL
+    batches that may span frames.  One frame gives a rank of an 8-GPU box only 11 crops (88 / 8) — a batch size at which the 3x3
+    convolutions at the 32x32 / 64x64 levels run far below their rate — whereas a list of frames keeps every
+    engine at `batch_size` crops until the very last batch.  Crops stay independent outputs, written exactly as
+    :func:`synthesize_frame` writes them; no collective."""
+    ps = int(diffusion.image_size)
+    dev = diffusion.device
+    plan = plan_crops(jobs, ps)
+    mine = [plan[i] for i in tiles.shard(len(plan), world_size, rank)]
+    writer = NpyWriter(save_folder)
+    resident: Dict[int, torch.Tensor] = {}       # frames of the current batch on the device
+    try:
+        for lo in range(0, len(mine), batch_size):
+            part = mine[lo:lo + batch_size]
+            for j in [j for j in resident if j < part[0][0]]:
+                del resident[j]                   # the slice is ordered by frame: earlier frames are finished
+            conds, names = [], []
+            k = 0
+            while k < len(part):                  # runs of crops from the same frame
+                j = part[k][0]
+                n = next((i for i, c in enumerate(part[k:]) if c[0] != j), len(part) - k)
+                run = [(x, y) for _, x, y in part[k:k + n]]
+                job = jobs[j]
+                if j not in resident:
+                    resident[j] = job.clean_frame.to(dev, non_blocking=True)
+                cond = crop_batch(resident[j], run, ps, job.iso_ratio_idx)
+                if job.dark_frame:
+                    cond["clean_img"] = torch.zeros_like(cond["clean_img"])
+                conds.append(cond)
+                names += [os.path.join(_job_folder(job), npy_name(job.clean_name, x, y, job.noisy_name)) for x, y in run]
+                k += len(run)
+            cond = {key: torch.cat([c[key] for c in conds]) for key in conds[0]}
+            out = diffusion.sample(batch_size=len(part), condition=cond)
+            writer.submit(out, names)
     finally:
         paths = writer.close()
     return paths

@@ -88,6 +88,67 @@ def test_two_ranks_cover_the_frame_once(tmp_path):
     assert len(p2) == len(origins) and all(os.path.dirname(p).endswith("ISO800_Ratio250") for p in p2)
 
 
+def _jobs():
+    g = torch.Generator().manual_seed(5)
+    return [frames.FrameJob(torch.rand((4, 96, 160), generator=g), 3, "a_10s.ARW", "a_0.1s.ARW"),
+            frames.FrameJob(torch.rand((4, 64, 64), generator=g), 24, "b_10s.ARW", iso=800, ratio=250),
+            frames.FrameJob(torch.rand((4, 96, 96), generator=g), 7, "c_10s.ARW", dark_frame=True)]
+
+
+def test_packed_multi_frame_synthesis_covers_every_crop_once(tmp_path):
+    """Several frames as ONE crop list: batches span frames, ranks take contiguous slices, every crop is written once with the
+    name / folder / content a per-frame run gives it."""
+    jobs = _jobs()
+    plan = frames.plan_crops(jobs, 32)
+    per_frame = [len(tiles.tile_origins(32, *j.clean_frame.shape[1:])) for j in jobs]
+    assert len(plan) == sum(per_frame) and [p[0] for p in plan] == sum(([i] * n for i, n in enumerate(per_frame)), [])
+    for world in (1, 2, 3):
+        root = tmp_path / f"w{world}"
+        paths = []
+        for rank in range(world):
+            paths += frames.synthesize_frames(_FakeDiffusion(), jobs, save_folder=str(root), batch_size=7, rank=rank, world_size=world)
+        assert len(paths) == len(plan) == len(set(paths))
+        for j, x, y in plan:
+            job = jobs[j]
+            sub = "ISO800_Ratio250" if job.iso else os.path.join("npy", "generated")
+            arr = np.load(os.path.join(str(root), sub, frames.npy_name(job.clean_name, x, y, job.noisy_name)))
+            want = frames.crop_batch(job.clean_frame, [(x, y)], 32, job.iso_ratio_idx)
+            clean = torch.zeros_like(want["clean_img"]) if job.dark_frame else want["clean_img"]
+            assert arr.dtype == np.float32 and np.allclose(arr, (clean + want["position"].sum(1, keepdim=True))[0].numpy())
+    # a single job through the packed path writes what synthesize_frame writes
+    one = frames.synthesize_frames(_FakeDiffusion(), jobs[:1], save_folder=str(tmp_path / "p"), batch_size=5)
+    ref = frames.synthesize_frame(_FakeDiffusion(), jobs[0].clean_frame, iso_ratio_idx=3, clean_name="a_10s.ARW", noisy_name="a_0.1s.ARW",
+                                  save_folder=str(tmp_path / "q"), batch_size=64)
+    assert [os.path.basename(p) for p in one] == [os.path.basename(p) for p in ref]
+    assert all(np.array_equal(np.load(a), np.load(b)) for a, b in zip(one, ref))
+
+
+@pytest.mark.gpu
+def test_packed_multi_frame_synthesis_on_gpu(tmp_path):
+    """Two frames in one batch on the CUDA path: identical to sampling the concatenated condition directly."""
+    import copy
+    import noisediff_b200 as nd
+    from tests.util import seeded_net
+    net = copy.deepcopy(seeded_net()).cuda()
+    gd = nd.GaussianDiffusion(net, image_size=32, timesteps=5, beta_schedule="sigmoid2", objective="pred_v").cuda()
+    gd.noise_source = "philox"
+    g = torch.Generator().manual_seed(6)
+    jobs = [frames.FrameJob(torch.rand((4, 64, 64), generator=g) * 0.3, 24, "u.ARW"),
+            frames.FrameJob(torch.rand((4, 64, 96), generator=g) * 0.3, 3, "v.ARW", iso=800, ratio=250)]
+    plan = frames.plan_crops(jobs, 32)
+    torch.manual_seed(21)
+    paths = frames.synthesize_frames(gd, jobs, save_folder=str(tmp_path), batch_size=len(plan))
+    assert len(paths) == len(plan)
+    conds = [frames.crop_batch(jobs[j].clean_frame.cuda(), [(x, y)], 32, jobs[j].iso_ratio_idx) for j, x, y in plan]
+    cond = {k: torch.cat([c[k] for c in conds]) for k in conds[0]}
+    torch.manual_seed(21)
+    direct = gd.sample(batch_size=len(plan), condition=cond).cpu().numpy()
+    for i, p in enumerate(paths):
+        arr = np.load(p)
+        assert arr.shape == (4, 32, 32) and np.isfinite(arr).all() and np.array_equal(arr, direct[i])
+    assert os.path.dirname(paths[-1]).endswith("ISO800_Ratio250") and os.path.dirname(paths[0]).endswith(os.path.join("npy", "generated"))
+
+
 @pytest.mark.gpu
 def test_frame_synthesis_equals_direct_sampling(tmp_path):
     import copy
