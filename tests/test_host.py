@@ -64,6 +64,42 @@ def test_net_attributes_and_state_dict_names():
         net(torch.zeros(1, 4, 12, 12), torch.zeros(1, dtype=torch.long), {})
 
 
+def test_drop_in_through_the_references_own_plugin_registry():
+    """a new `models/archs/B200_arch.py` exporting the class is all the reference's registry needs
+    (models/modules.py:20-41,86-92).  Drives the LIVE reference's define_G / init_net with `--net_name NoiseDiffNetB200`, then
+    the strict checkpoint exchange of Trainer.load_networks (models/trainer_diffusion.py:333-349) in both directions."""
+    import importlib
+    import types
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not mounted")
+    RefNet, RefGD = ref_shim.load()
+    M = importlib.import_module("models.modules")
+    plug = types.ModuleType("models.archs.B200_arch")          # what importing the new arch file yields
+    plug.NoiseDiffNetB200 = nd.NoiseDiffNet
+    M._arch_modules.append(plug)
+    try:
+        args = SimpleNamespace(net_name="NoiseDiffNetB200", gpu_ids=[], device=torch.device("cpu"), dist=False, **vars(net_args()))
+        net = M.define_G(args)
+        assert isinstance(net, nd.NoiseDiffNet)
+        with pytest.raises(ValueError):
+            M.define_G(SimpleNamespace(**{**vars(args), "net_name": "NoSuchNet"}))
+    finally:
+        M._arch_modules.remove(plug)
+    torch.manual_seed(0)
+    ref = RefNet(net_args())
+    ckpt = {"module." + k: v for k, v in ref.state_dict().items()}           # a DataParallel-saved reference checkpoint
+    net.load_state_dict({k[7:]: v for k, v in ckpt.items()}, strict=True)
+    assert all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), ref.state_dict().values()))
+    ref.load_state_dict(net.state_dict(), strict=True)                       # and back: same 416 keys and shapes
+    # the reference's GaussianDiffusion reads the same attributes off either network class (denoising_diffusion_pytorch.py:184-198)
+    mine = nd.GaussianDiffusion(nn.DataParallel(net), image_size=64, timesteps=10, beta_schedule="sigmoid2")
+    theirs = RefGD(nn.DataParallel(ref), image_size=64, timesteps=10, beta_schedule="sigmoid2", objective="pred_v")
+    assert (mine.channels, mine.self_condition, mine.num_timesteps, mine.objective, mine.is_ddim_sampling) == \
+        (theirs.channels, theirs.self_condition, theirs.num_timesteps, theirs.objective, theirs.is_ddim_sampling)
+    assert sorted(k for k, _ in mine.named_buffers(recurse=False)) == sorted(k for k, _ in theirs.named_buffers(recurse=False))
+
+
 @pytest.mark.parametrize("name", ["linear", "cosine", "sigmoid1", "sigmoid2", "sigmoid3"])
 def test_schedule_buffers_match_reference(name):
     z = load("schedules.npz")
