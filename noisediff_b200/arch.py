@@ -95,6 +95,10 @@ class _PosEnc(nn.Module):                      # ref LearnedSinusoidalPosEmb :32
 
 
 class NoiseDiffNet(nn.Module):
+    #: engines kept alive per network (one per (device, batch, H, W) seen); each owns GiBs of activation buffers at the bench
+    #: geometry, so a loop over ragged batch sizes must not accumulate them
+    max_engines = 4
+
     def __init__(self, args):
         super().__init__()
         dim = int(args.dim)
@@ -144,7 +148,7 @@ class NoiseDiffNet(nn.Module):
         self.shot_time = _ResnetBlock(dim, dim, time_emb_dim=time_dim, groups=2)
         self.shot_mlp3 = _Mlp(dim, dim, 4)
 
-        self._engines = {}          # (device index, B, H, W) -> engine.Engine
+        self._engines = {}          # (device index, B, H, W) -> engine.Engine, least recently used first
         self._weights_version = None
 
     @property
@@ -161,10 +165,12 @@ class NoiseDiffNet(nn.Module):
             raise RuntimeError("noisediff_b200.NoiseDiffNet runs only on CUDA (sm_100a); there is no CPU path")
         key = (device.index if device.index is not None else torch.cuda.current_device(), batch, height, width)
         ver = self._param_version()
-        eng = self._engines.get(key)
+        eng = self._engines.pop(key, None)
         if eng is None:
+            while len(self._engines) >= max(int(self.max_engines), 1):
+                self._engines.pop(next(iter(self._engines))).close()      # least recently used: frees its activation pool
             eng = _engine.Engine(dim=self.dim, batch=batch, height=height, width=width, device=key[0])
-            self._engines[key] = eng
+        self._engines[key] = eng                                          # (re)inserted last = most recently used
         if eng.weights_version != ver:
             eng.load_state_dict({k: v.detach() for k, v in self.state_dict().items()})
             eng.weights_version = ver

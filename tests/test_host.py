@@ -64,6 +64,36 @@ def test_net_attributes_and_state_dict_names():
         net(torch.zeros(1, 4, 12, 12), torch.zeros(1, dtype=torch.long), {})
 
 
+def test_engine_cache_is_bounded_lru(monkeypatch):
+    """A generation loop with ragged batch sizes must not pile up engines (each owns its activation pool)."""
+    from noisediff_b200 import arch
+    made, closed = [], []
+
+    class FakeEngine:
+        def __init__(self, *, dim, batch, height, width, device):
+            self.key, self.weights_version = (batch, height, width), None
+            made.append(self.key)
+
+        def load_state_dict(self, sd):
+            assert len(sd) == 416
+
+        def close(self):
+            closed.append(self.key)
+
+    monkeypatch.setattr(arch._engine, "Engine", FakeEngine)
+    net = nd.NoiseDiffNet(net_args())
+    dev = torch.device("cuda", 0)
+    for b in (1, 2, 3, 4):
+        net.engine_for(b, 32, 32, dev)
+    assert made == [(b, 32, 32) for b in (1, 2, 3, 4)] and closed == []
+    net.engine_for(1, 32, 32, dev)                         # touch: batch 1 becomes the most recently used
+    net.engine_for(5, 32, 32, dev)                         # fifth geometry evicts the least recently used (batch 2)
+    assert closed == [(2, 32, 32)] and len(net._engines) == 4
+    assert net.engine_for(1, 32, 32, dev).key == (1, 32, 32) and made.count((1, 32, 32)) == 1
+    net.release_engines()
+    assert len(net._engines) == 0 and len(closed) == 5
+
+
 def test_drop_in_through_the_references_own_plugin_registry():
     """a new `models/archs/B200_arch.py` exporting the class is all the reference's registry needs
     (models/modules.py:20-41,86-92).  Drives the LIVE reference's define_G / init_net with `--net_name NoiseDiffNetB200`, then
