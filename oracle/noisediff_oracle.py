@@ -298,6 +298,36 @@ def p_losses(sd: SD, tab, objective: str, x_start: Tensor, t: Tensor, condition,
     return loss.mean()
 
 
+def loss_gradients(sd: SD, tab, objective: str, x_start: Tensor, t: Tensor, condition, noise: Tensor) -> Tuple[Tensor, SD]:
+    """``loss.backward()`` of the training step (models/trainer_diffusion.py:179-188): autograd through this restatement of
+    p_losses.  Returns (loss, {name: dloss/dparam}); parameters the loss does not reach (the dead ``attn.to_q / to_k / norm1``
+    of every AttnBlock — 1-token softmax, Diffusion_arch.py:361-402) get zeros, where the reference leaves ``.grad = None``."""
+    leaf = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    with torch.enable_grad():
+        loss = p_losses(leaf, tab, objective, x_start, t, condition, noise)
+        loss.backward()
+    return loss.detach(), {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaf.items()}
+
+
+def adam_step(params: SD, grads: SD, state: Dict[str, Dict[str, Tensor]], lr: float = 1e-4, beta1: float = 0.9, beta2: float = 0.999,
+              eps: float = 1e-8, weight_decay: float = 0.0) -> SD:
+    """One ``torch.optim.Adam.step()`` as Trainer.train runs it (models/trainer_diffusion.py:92,189; lr / weight_decay from
+    train_diffusion.py:85-87), written out: m <- b1 m + (1-b1) g; v <- b2 v + (1-b2) g^2;
+    p <- p - lr/(1-b1^k) * m / (sqrt(v)/sqrt(1-b2^k) + eps).  ``state`` carries (step, m, v) per parameter between calls."""
+    out = {}
+    for k, p in params.items():
+        g = grads[k]
+        if weight_decay:
+            g = g + weight_decay * p
+        st = state.setdefault(k, {"step": 0, "m": torch.zeros_like(p), "v": torch.zeros_like(p)})
+        st["step"] += 1
+        st["m"] = beta1 * st["m"] + (1 - beta1) * g
+        st["v"] = beta2 * st["v"] + (1 - beta2) * g * g
+        denom = st["v"].sqrt() / math.sqrt(1 - beta2 ** st["step"]) + eps
+        out[k] = p - (lr / (1 - beta1 ** st["step"])) * st["m"] / denom
+    return out
+
+
 def ddim_pairs(T: int, S: int) -> List[Tuple[int, int]]:
     """denoising_diffusion_pytorch.py:409-411."""
     times = torch.linspace(-1, T - 1, steps=S + 1)

@@ -69,6 +69,45 @@ def test_training_loss_value_matches_reference(objective):
     assert abs(float(loss) - float(z[objective + "/loss"])) <= 1e-6 * float(z[objective + "/loss"])
 
 
+def test_next_row_dim48_forward_matches_reference():
+    """SURVEY §8f N3 (the shipped --dim 48): the oracle and the host module tree are already generic in dim; the CUDA library is
+    not (ndiff_engine_create rejects dim != 64) — this fixture is what its 48-channel kernels will be built against."""
+    import noisediff_b200 as nd
+    from tests.util import net_args
+    z = load("next_rows.npz")
+    torch.manual_seed(0)
+    net = nd.NoiseDiffNet(net_args(48))
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    assert sd_hash(sd) == str(z["dim48/weights_sha256"]) and sum(v.numel() for v in sd.values()) == int(z["dim48/n_params"])
+    out = O.net_forward(sd, torch.from_numpy(z["dim48/x"]), torch.from_numpy(z["dim48/t"]), O.synthetic_condition(1, 64, 64, seed=5))
+    assert rel_l2(out, torch.from_numpy(z["dim48/out"])) < 1e-6
+
+
+def test_next_row_training_step_matches_reference():
+    """loss, every parameter's gradient norm, a few gradients in full, and the parameters after one Adam step."""
+    z, zl = load("next_rows.npz"), load("losses.npz")
+    sd = seeded_sd()
+    tab = O.schedule_tables("sigmoid2", 1000, "pred_v")
+    loss, grads = O.loss_gradients(sd, tab, "pred_v", torch.from_numpy(zl["x_start"]), torch.from_numpy(zl["pred_v/t"]), _cond(zl),
+                                   torch.from_numpy(zl["noise"]))
+    assert abs(float(loss) - float(z["train/loss"])) <= 1e-6 * float(z["train/loss"])
+    names, norms = [str(n) for n in z["train/names"]], z["train/grad_norms"]
+    assert len(names) == 416
+    dead = [n for n, g in zip(names, norms) if g == 0.0]
+    assert dead and all(("attn.to_q" in n or "attn.to_k" in n or ".norm1." in n) for n in dead)      # and nothing else is dead
+    for n, g in zip(names, norms):
+        mine = float(grads[n].double().norm())
+        assert abs(mine - g) <= 2e-4 * g + 1e-9, (n, mine, g)
+    small = [k[len("train/grad/"):] for k in z if k.startswith("train/grad/")]
+    for k in small:
+        assert rel_l2(grads[k], torch.from_numpy(z["train/grad/" + k])) < 1e-4, k
+    params = {k: sd[k] for k in small}
+    after = O.adam_step(params, {k: grads[k] for k in small}, {}, lr=float(z["train/lr"]))
+    for k in small:
+        ref = torch.from_numpy(z["train/after/" + k])
+        assert not torch.equal(ref, sd[k]) and torch.allclose(after[k], ref, rtol=0, atol=2e-7), k
+
+
 def test_schedule_tables_bit_exact():
     z = load("schedules.npz")
     for name in ("linear", "cosine", "sigmoid1", "sigmoid2", "sigmoid3"):
