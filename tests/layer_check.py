@@ -1,4 +1,4 @@
-"""Per-layer rel-L2 of the engine's activations vs the CPU oracle at an arbitrary geometry (development aid)."""
+"""Per-layer rel-L2 of the engine's activations vs the CPU oracle at an arbitrary geometry (development aid; a checker, so it lives under tests/: only tests, smoke() and the bench CPU leg touch oracle/)."""
 import copy
 import os
 import sys

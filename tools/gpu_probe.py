@@ -86,14 +86,14 @@ def main():
             guarded(f"conv3_halo3_tw{tw}", lambda: conv_case(1, 4, 256, 256, 64, 64, tile_w=tw, check=False))
     if "net" in which:
         from tests.util import seeded_net
-        from oracle import noisediff_oracle as O
+        from noisediff_b200 import tiles
         import copy
         net = copy.deepcopy(seeded_net()).cuda()
         for B in (2, 4, 8):
             def run(B=B):
                 gd = nd.GaussianDiffusion(net, image_size=256, timesteps=1000, beta_schedule="sigmoid2").cuda()
                 eng = net.engine_for(B, 256, 256, torch.device("cuda", 0))
-                cond = {k: v.cuda() for k, v in O.synthetic_condition(B, 256, 256).items()}
+                cond = {k: v.cuda() for k, v in tiles.synthetic_condition(B, 256).items()}
                 eng.set_condition(cond["clean_img"], cond["position"], cond["iso_ratio_idx"])
                 steps = gd.ddpm_steps()
                 eng.chain_begin(steps, None, 1)
