@@ -229,10 +229,9 @@ class GaussianDiffusion(nn.Module):
         net = self._net()
         B, Cc, H, W = shape
         dev = self.device
-        if dev.type != "cuda":
-            raise RuntimeError("noisediff_b200 samples only on CUDA (sm_100a); there is no CPU path")
         n_steps = len(steps)
         mb = min(B, int(self.micro_batch))
+        net.engine_for(mb, H, W, dev)       # raises off-GPU / without the library before any RNG is consumed: there is no CPU path
         groups = [(lo, min(lo + mb, B)) for lo in range(0, B, mb)]
         use_torch_rng = self.noise_source == "torch" and noises is None
         if self.noise_source not in ("torch", "philox"):
