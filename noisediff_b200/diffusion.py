@@ -230,6 +230,8 @@ class GaussianDiffusion(nn.Module):
         B, Cc, H, W = shape
         dev = self.device
         n_steps = len(steps)
+        if B == 0:                      # the reference runs an empty batch through and returns an empty result
+            return torch.empty((0, n_steps + 1, Cc, H, W) if return_all else (0, Cc, H, W), device=dev)
         mb = min(B, int(self.micro_batch))
         net.engine_for(mb, H, W, dev)       # raises off-GPU / without the library before any RNG is consumed: there is no CPU path
         groups = [(lo, min(lo + mb, B)) for lo in range(0, B, mb)]

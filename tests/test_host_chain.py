@@ -192,3 +192,12 @@ def test_philox_mode_hands_seeds_to_the_library_and_reads_x_T_back(rig):
     gd.noise_source = "nonsense"
     with pytest.raises(ValueError):
         gd.sample(batch_size=4, condition=cond)
+
+
+def test_empty_batch_returns_empty_like_the_reference(rig):
+    make, engines = rig
+    gd = make(T=4)
+    cond = {k: v[:0] for k, v in _cond(1).items()}
+    assert gd.sample(batch_size=0, condition=cond).shape == (0, 4, 8, 8)
+    assert gd.sample(batch_size=0, condition=cond, return_all_timesteps=True).shape == (0, 5, 4, 8, 8)
+    assert not engines                                    # no engine is planned for nothing
