@@ -23,6 +23,22 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert _lib.lib().ndiff_abi_version() == 1
 
 
+def test_c_abi_from_plain_c(tmp_path):
+    """The header is valid C99 (-pedantic) and a C program can link the library and read its errors."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "abi_client")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "abi_client.c"), "-o", exe, "-L", libdir, "-lnoisediff_b200",
+                    "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "dim = 64" in r.stdout and "multiples of 8" in r.stdout
+
+
 def test_abi_struct_layouts():
     assert ctypes.sizeof(_lib.Step) == 48 and ctypes.sizeof(_lib.Config) == 24
 
