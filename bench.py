@@ -30,8 +30,11 @@ PATCH = 256
 BATCH = 64
 METRIC = "noise patches/s (4x256x256, full 1000-step reverse chain)"
 UNIT = "patches/s"
-# reference-executed 3x3-conv FLOPs per patch per step (direct form)
-CONV3_FLOPS_PER_PATCH_STEP = 234.34e9
+# 3x3-conv FLOPs per patch per step.  The reference executes 234.34 GFLOP (direct form); the three
+# Upsample convs run here as four 2x2 phase convolutions (12.89 instead of 28.99 GFLOP), and §8(d)'s rule is to count the
+# FLOPs actually needed, never more than the reference executes: 234.34 - 28.99 + 12.89.
+CONV3_FLOPS_DIRECT = 234.34e9
+CONV3_FLOPS_PER_PATCH_STEP = 218.24e9
 
 
 def _peaks():
@@ -258,6 +261,7 @@ def main():
                 "launches_per_step": n_conv, "avg_launch_us": conv_ms * 1e3 / max(n_conv, 1),
                 "flops_per_launch_avg": conv_fl / max(n_conv, 1), "peak_source": peaks["source"],
                 "conv3x3_frac_of_burst_peak": CONV3_FLOPS_PER_PATCH_STEP * mb / (c3_ms * 1e-3) / 1e12 / peaks["burst"],
+                "conv3x3_frac_of_burst_peak_direct_form_flops": CONV3_FLOPS_DIRECT * mb / (c3_ms * 1e-3) / 1e12 / peaks["burst"],
                 "conv_share_of_step": conv_ms * n_mb / ms_step if world == 1 else None}
 
     # ---- end to end through the public API with host buffers: the WHOLE chain --------------------------------------------
