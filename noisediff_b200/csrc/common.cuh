@@ -283,6 +283,44 @@ __device__ __forceinline__ void umma_bf16_lohi_pred(uint32_t d_tmem, uint32_t a_
         ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Weight-stationary form (EXPERIMENT, conv_gemm.cu kWs): the B operand goes through collector buffer kBuf (b0..b3).  kReuse ==
+// false reads B from shared memory and keeps it in the collector (SASS: UTCHMMA.WS ... B_KEEP); kReuse == true multiplies by the
+// kept copy without touching shared memory again (B_REUSE).  Two M = 128 sub-tiles that share one weight block then read it once.
+template <int kBuf, bool kReuse>
+__device__ __forceinline__ void umma_bf16_ws_pred(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                  uint32_t idesc, uint32_t accumulate) {
+    static_assert(kBuf >= 0 && kBuf < 4, "four collector buffers");
+#define NDIFF_WS_MMA(BUF, OP)                                                                                              \
+    asm volatile(                                                                                                          \
+        "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\t"                                                                    \
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"                                                              \
+        "setp.ne.u32 p, %6, 0;\n\t"                                                                                        \
+        "tcgen05.mma.ws.cta_group::1.kind::f16.collector::" BUF "::" OP " [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),       \
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)                                            \
+        : "memory")
+    if constexpr (kBuf == 0 && !kReuse) NDIFF_WS_MMA("b0", "fill");
+    if constexpr (kBuf == 1 && !kReuse) NDIFF_WS_MMA("b1", "fill");
+    if constexpr (kBuf == 2 && !kReuse) NDIFF_WS_MMA("b2", "fill");
+    if constexpr (kBuf == 3 && !kReuse) NDIFF_WS_MMA("b3", "fill");
+    if constexpr (kBuf == 0 && kReuse) NDIFF_WS_MMA("b0", "lastuse");
+    if constexpr (kBuf == 1 && kReuse) NDIFF_WS_MMA("b1", "lastuse");
+    if constexpr (kBuf == 2 && kReuse) NDIFF_WS_MMA("b2", "lastuse");
+    if constexpr (kBuf == 3 && kReuse) NDIFF_WS_MMA("b3", "lastuse");
+#undef NDIFF_WS_MMA
+}
+// One weight block (K = 64 = four K16 steps) against the two stacked 128-pixel sub-tiles of a kHalo2 tile: sub-tile 0 fills the
+// four collector buffers, sub-tile 1 reuses them.  Same issue order as the plain form (sub-tile outer, K step inner).
+__device__ __forceinline__ void umma_bf16_ws_pair(uint32_t d0, uint32_t d1, uint32_t a0, uint32_t a1, uint32_t a_hi, uint32_t b_lo,
+                                                  uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    umma_bf16_ws_pred<0, false>(d0, a0, a_hi, b_lo, b_hi, idesc, accumulate);
+    umma_bf16_ws_pred<1, false>(d0, a0 + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+    umma_bf16_ws_pred<2, false>(d0, a0 + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
+    umma_bf16_ws_pred<3, false>(d0, a0 + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
+    umma_bf16_ws_pred<0, true>(d1, a1, a_hi, b_lo, b_hi, idesc, accumulate);
+    umma_bf16_ws_pred<1, true>(d1, a1 + 2, a_hi, b_lo + 2, b_hi, idesc, 1u);
+    umma_bf16_ws_pred<2, true>(d1, a1 + 4, a_hi, b_lo + 4, b_hi, idesc, 1u);
+    umma_bf16_ws_pred<3, true>(d1, a1 + 6, a_hi, b_lo + 6, b_hi, idesc, 1u);
+}
 // Running-descriptor form: bumps both descriptor address words by compile-time increments and issues an accumulating
 // MMA.  The in-place "+r" operands chain consecutive calls, so ptxas emits add / add / UTCHMMA per MMA instead of
 // materialising (and spilling) a long list of independent descriptors.

@@ -12,6 +12,7 @@
 // Block.proj, res_conv, Downsample, AttnBlock.{ff,proj_out} and Mlp.fc* (models/archs/Diffusion_arch.py:128-443).
 #include "conv_gemm.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -57,8 +58,15 @@ constexpr int kUpBTaps = 4;                                              // kHal
 // here, in place on each activation stage between the TMA landing and the MMA: warps 2, 3, 12..15 rewrite the halo box in shared
 // memory (out-of-image pixels stay the TMA's zero fill = the conv's zero padding of the NORMALISED tensor), then hand the
 // stage to the MMA warp through xfA.  Same fp32 formulas and bf16 rounding as gn_apply_kernel, so results are bit-identical.
-template <int NT, int MODE, bool RES, bool XF = false>
+// WS (EXPERIMENT, off unless NDIFF_EXPERIMENT_WS=1; N = 64 kHalo2 only): the two 128-pixel sub-tiles of a tile multiply the SAME
+// weight block, and the 64-output-channel layers are bound by the shared-memory reads of their operands (4 KB of A + 2 KB of B per
+// 32-cycle MMA).  tcgen05.mma.ws keeps B in a collector buffer, so sub-tile 1 reuses what sub-tile 0 loaded: 6 -> 5 KB per MMA,
+// the same saving as a cta_group::2 pair without the cluster.  Unmeasured: whether .ws issues at the full M = 128 rate and writes
+// the accumulator in the same lane = row layout is what the first run must show (tests/test_gpu_ops.py, halo2 cases, with the
+// environment variable set).
+template <int NT, int MODE, bool RES, bool XF = false, bool WS = false>
 __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
+    static_assert(!WS || (MODE == kHalo2 && NT == 64), "the weight-stationary form exists for the N = 64 kHalo2 kernels only");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem is only guaranteed 16-B aligned by the ABI; SWIZZLE_128B wants 1024
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -246,6 +254,9 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
                                 uint32_t a_cur = a_row;
 #pragma unroll 1
                                 for (int kx = 0; kx < 3; ++kx) {
+                                    if constexpr (WS) {
+                                        umma_bf16_ws_pair(d_tmem, d_tmem + NT, a_cur, a_cur + kSubStep, hiA, b_cur, hiB, idesc, accum);
+                                    } else {
 #pragma unroll
                                     for (int sub = 0; sub < kSub; ++sub) {
                                         const uint32_t d = d_tmem + sub * NT, as = a_cur + sub * kSubStep;
@@ -253,6 +264,7 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
                                         umma_bf16_lohi<true>(d, as + 2, hiA, b_cur + 2, hiB, idesc);
                                         umma_bf16_lohi<true>(d, as + 4, hiA, b_cur + 4, hiB, idesc);
                                         umma_bf16_lohi<true>(d, as + 6, hiA, b_cur + 6, hiB, idesc);
+                                    }
                                     }
                                     accum = 1u;
                                     a_cur += 128 >> 4;
@@ -286,6 +298,9 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
                                     const int kx = kUp ? px + (tap & 1) : (rtap ? 1 : tap - 3 * ky);
                                     const uint32_t a_cur = a_base + ((ky * kHaloPitch + kx * 128) >> 4);
                                     if (rtap) accum = cb > 0 ? 1u : 0u;
+                                    if constexpr (WS) {
+                                        umma_bf16_ws_pair(d_tmem, d_tmem + NT, a_cur, a_cur + kSubStep, hiA, b_cur, hiB, idesc, accum);
+                                    } else {
 #pragma unroll
                                     for (int sub = 0; sub < kSub; ++sub) {
                                         const uint32_t d = rtap ? tmem_base + (2 + acc) * NT : d_tmem + sub * NT, as = a_cur + sub * kSubStep;
@@ -293,6 +308,7 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
                                         umma_bf16_lohi<true>(d, as + 2, hiA, b_cur + 2, hiB, idesc);
                                         umma_bf16_lohi<true>(d, as + 4, hiA, b_cur + 4, hiB, idesc);
                                         umma_bf16_lohi<true>(d, as + 6, hiA, b_cur + 6, hiB, idesc);
+                                    }
                                     }
                                     accum = 1u;
                                     b_cur += kBTap >> 4;
@@ -753,6 +769,10 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     a.out = d.out; a.out_ld = d.out_ld; a.act = d.act;
     a.bias2 = d.bias2; a.out2 = d.out2; a.out2_ld = d.out2_ld;
     plan->xf = d.xf_stats != nullptr;
+    {   // EXPERIMENT switch, read once per process (see the comment above conv_gemm_kernel)
+        static const bool ws_env = [] { const char* v = getenv("NDIFF_EXPERIMENT_WS"); return v != nullptr && v[0] == '1'; }();
+        plan->ws = ws_env && NT == 64 && d.mode == kHalo2;
+    }
     if (plan->xf) {
         NDIFF_REQUIRE((d.mode == kHalo1 || d.mode == kHalo2) && d.C1 == 0 && d.C0 <= 512, "fused GroupNorm input: single-source 3x3 conv with C_in <= 512");
         NDIFF_REQUIRE(d.xf_gamma && d.xf_beta && d.xf_groups > 0 && d.C0 % d.xf_groups == 0, "fused GroupNorm input: bad arguments");
@@ -775,6 +795,17 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
 namespace {
 template <int NT, int MODE, bool RES>
 int launch_one(const ConvGemmPlan& plan, cudaStream_t stream) {
+    if constexpr (MODE == kHalo2 && NT == 64) {
+        if (plan.ws) {
+            if (plan.xf)
+                NDIFF_CUDA_OK(launch_pdl(conv_gemm_kernel<NT, MODE, RES, true, true>, dim3(plan.grid), dim3(kThreadsXf), plan.smem_bytes,
+                                         stream, plan.args));
+            else
+                NDIFF_CUDA_OK(launch_pdl(conv_gemm_kernel<NT, MODE, RES, false, true>, dim3(plan.grid), dim3(kThreads), plan.smem_bytes,
+                                         stream, plan.args));
+            return 0;
+        }
+    }
     if constexpr (MODE == kHalo1 || MODE == kHalo2) {
         if (plan.xf) {
             NDIFF_CUDA_OK(launch_pdl(conv_gemm_kernel<NT, MODE, RES, true>, dim3(plan.grid), dim3(kThreadsXf), plan.smem_bytes, stream,
@@ -797,6 +828,16 @@ cudaError_t opt_in() {
         e = cudaFuncSetAttribute(conv_gemm_kernel<NT, MODE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(conv_gemm_kernel<NT, MODE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+    }
+    if constexpr (MODE == kHalo2 && NT == 64) {
+        e = cudaFuncSetAttribute(conv_gemm_kernel<NT, MODE, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(conv_gemm_kernel<NT, MODE, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(conv_gemm_kernel<NT, MODE, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(conv_gemm_kernel<NT, MODE, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
     }
     return cudaFuncSetAttribute(conv_gemm_kernel<NT, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -1,6 +1,7 @@
 """GPU parity of the individual sm_100a kernels against plain fp32 torch ops on the same (bf16-rounded) inputs.
 All calls go through the C ABI (include/noisediff_b200.h)."""
 import math
+import os
 
 import pytest
 import torch
@@ -412,3 +413,17 @@ def test_shot_tail_chain(case):
     y = _bf(F.silu(y) + r1 + r2)
     ref = _hf(F.gelu(y @ W1.T + b1)) @ _hf(W2).T + b2
     assert _rel(out, ref) < 6e-3, _rel(out, ref)
+
+
+@pytest.mark.skipif(os.environ.get("NDIFF_TEST_EXPERIMENTAL") != "1", reason="experimental kernel variant: set NDIFF_TEST_EXPERIMENTAL=1")
+def test_experimental_weight_stationary_conv_variant():
+    """The N = 64 kHalo2 kernels with tcgen05.mma.ws (collector-buffer reuse of the weight block across the two sub-tiles;
+    conv_gemm.cu, `WS`).  Never measured or verified on hardware yet, so it is off unless NDIFF_EXPERIMENT_WS=1 and this test is
+    opt-in: it re-runs the halo2 parity cases (plain, fused GroupNorm input) in a child process with the variant enabled."""
+    import subprocess
+    import sys
+    env = dict(os.environ, NDIFF_EXPERIMENT_WS="1")
+    env.pop("NDIFF_TEST_EXPERIMENTAL")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", os.path.abspath(__file__), "-m", "gpu", "-k",
+                        "(test_conv3x3 and halo2) or groupnorm_apply_on_the_input"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
