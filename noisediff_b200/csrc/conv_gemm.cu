@@ -609,6 +609,12 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+// EXPERIMENT switch (NDIFF_EXPERIMENT_WS=1), read once per process.
+bool ws_experiment_enabled() {
+    static const bool on = [] { const char* v = getenv("NDIFF_EXPERIMENT_WS"); return v != nullptr && v[0] == '1'; }();
+    return on;
+}
+
 int ilog2(int v) {
     int l = 0;
     while ((1 << l) < v) ++l;
@@ -769,10 +775,7 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     a.out = d.out; a.out_ld = d.out_ld; a.act = d.act;
     a.bias2 = d.bias2; a.out2 = d.out2; a.out2_ld = d.out2_ld;
     plan->xf = d.xf_stats != nullptr;
-    {   // EXPERIMENT switch, read once per process (see the comment above conv_gemm_kernel)
-        static const bool ws_env = [] { const char* v = getenv("NDIFF_EXPERIMENT_WS"); return v != nullptr && v[0] == '1'; }();
-        plan->ws = ws_env && NT == 64 && d.mode == kHalo2;
-    }
+    plan->ws = ws_experiment_enabled() && NT == 64 && d.mode == kHalo2;      // see the comment above conv_gemm_kernel
     if (plan->xf) {
         NDIFF_REQUIRE((d.mode == kHalo1 || d.mode == kHalo2) && d.C1 == 0 && d.C0 <= 512, "fused GroupNorm input: single-source 3x3 conv with C_in <= 512");
         NDIFF_REQUIRE(d.xf_gamma && d.xf_beta && d.xf_groups > 0 && d.C0 % d.xf_groups == 0, "fused GroupNorm input: bad arguments");
@@ -830,7 +833,9 @@ cudaError_t opt_in() {
         e = cudaFuncSetAttribute(conv_gemm_kernel<NT, MODE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
     }
+    // the experimental kernels are touched only when the experiment is switched on: a default run never references them
     if constexpr (MODE == kHalo2 && NT == 64) {
+      if (ws_experiment_enabled()) {
         e = cudaFuncSetAttribute(conv_gemm_kernel<NT, MODE, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(conv_gemm_kernel<NT, MODE, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -839,6 +844,7 @@ cudaError_t opt_in() {
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(conv_gemm_kernel<NT, MODE, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
+      }
     }
     return cudaFuncSetAttribute(conv_gemm_kernel<NT, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
