@@ -88,6 +88,23 @@ def test_two_ranks_cover_the_frame_once(tmp_path):
     assert len(p2) == len(origins) and all(os.path.dirname(p).endswith("ISO800_Ratio250") for p in p2)
 
 
+def test_writer_surfaces_io_errors_and_rejects_mismatched_names(tmp_path):
+    """A failed np.save in the background thread must not be lost: close() re-raises it."""
+    blocker = tmp_path / "not_a_dir"
+    blocker.write_text("x")
+    w = frames.NpyWriter(str(tmp_path))
+    with pytest.raises(ValueError):
+        w.submit(torch.zeros(2, 4, 8, 8), ["only_one.npy"])
+    w.submit(torch.zeros(1, 4, 8, 8), [os.path.join("not_a_dir", "a.npy")])          # parent "directory" is a file
+    with pytest.raises(OSError):
+        w.close()
+    ok = frames.NpyWriter(str(tmp_path / "fine"))
+    ok.submit(torch.ones(2, 4, 8, 8), ["a.npy", os.path.join("sub", "b.npy")])
+    paths = ok.close()
+    assert [os.path.relpath(p, str(tmp_path / "fine")) for p in paths] == ["a.npy", os.path.join("sub", "b.npy")]
+    assert np.load(paths[1]).dtype == np.float32 and float(np.load(paths[1]).mean()) == 1.0
+
+
 def _jobs():
     g = torch.Generator().manual_seed(5)
     return [frames.FrameJob(torch.rand((4, 96, 160), generator=g), 3, "a_10s.ARW", "a_0.1s.ARW"),
