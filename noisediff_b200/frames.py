@@ -45,6 +45,12 @@ def npy_name(clean_name: str, x: int, y: int, noisy_name: Optional[str] = None) 
     return f"{c}+{s}+{int(x)}_{int(y)}.npy"
 
 
+def dark_npy_name(index: int, iso: int, ratio: int, x: int, y: int) -> str:
+    """``Trainer.test`` file name in ``--dark_frame`` mode (``models/trainer_diffusion.py:318-322``): a running item counter
+    over the whole run instead of the frame names, ``%05d_<iso>_<ratio>+<x>_<y>.npy``."""
+    return f"{int(index):05d}_{int(iso)}_{int(ratio)}+{int(x)}_{int(y)}.npy"
+
+
 def parse_npy_name(name: str) -> Tuple[str, str, int, int]:
     """Inverse of :func:`npy_name`, the way the downstream consumer reads it (``dataloader/dataset_denoising.py:56-59,136-138``):
     ``clean+noisy+x_y.npy`` -> (clean, noisy, x, y)."""
@@ -120,15 +126,21 @@ class NpyWriter:
 @torch.inference_mode()
 def synthesize_frame(diffusion, clean_frame: torch.Tensor, *, iso_ratio_idx: int, clean_name: str, save_folder: str,
                      noisy_name: Optional[str] = None, batch_size: int = 64, rank: int = 0, world_size: int = 1,
-                     dark_frame: bool = False, iso: Optional[int] = None, ratio: Optional[int] = None) -> List[str]:
+                     dark_frame: bool = False, iso: Optional[int] = None, ratio: Optional[int] = None,
+                     index_base: int = 0) -> List[str]:
     """Generates this rank's share of the noise crops of one frame and writes them the way ``Trainer.test`` does.
-    `diffusion` is a ``GaussianDiffusion`` (its ``image_size`` is the crop size).  Returns the written paths."""
+    `diffusion` is a ``GaussianDiffusion`` (its ``image_size`` is the crop size).  Returns the written paths.
+    ``dark_frame`` (ref :287-290,318-322): zero clean image, files named by a running counter (``index_base`` + the crop's position
+    in the frame's grid, so ranks never collide) and the ISO / ratio, which must then be given."""
     ps = int(diffusion.image_size)
     dev = diffusion.device
     frame = clean_frame.to(dev)
     _, fh, fw = frame.shape
     origins = tiles.tile_origins(ps, fh, fw)
-    mine = [origins[i] for i in tiles.shard(len(origins), world_size, rank)]
+    my_range = tiles.shard(len(origins), world_size, rank)
+    mine = [origins[i] for i in my_range]
+    if dark_frame and (iso is None or ratio is None):
+        raise ValueError("dark_frame file names carry the ISO and the ratio (trainer_diffusion.py:320-321): pass iso= and ratio=")
     # Trainer.test() layout by default; with (iso, ratio) the files go straight into the folder the denoiser's dataset globs
     folder = os.path.join(save_folder, consumer_subfolder(iso, ratio)) if iso is not None and ratio is not None \
         else os.path.join(save_folder, "npy", "generated")
@@ -140,7 +152,11 @@ def synthesize_frame(diffusion, clean_frame: torch.Tensor, *, iso_ratio_idx: int
             if dark_frame:                                   # ref :287-290: a zero clean image
                 cond["clean_img"] = torch.zeros_like(cond["clean_img"])
             out = diffusion.sample(batch_size=len(part), condition=cond)
-            writer.submit(out, [npy_name(clean_name, x, y, noisy_name) for x, y in part])
+            if dark_frame:
+                names = [dark_npy_name(index_base + my_range[lo + i], iso, ratio, x, y) for i, (x, y) in enumerate(part)]
+            else:
+                names = [npy_name(clean_name, x, y, noisy_name) for x, y in part]
+            writer.submit(out, names)
     finally:
         paths = writer.close()
     return paths
@@ -182,7 +198,10 @@ def synthesize_frames(diffusion, jobs: Sequence[FrameJob], *, save_folder: str, 
     ps = int(diffusion.image_size)
     dev = diffusion.device
     plan = plan_crops(jobs, ps)
-    mine = [plan[i] for i in tiles.shard(len(plan), world_size, rank)]
+    my_range = tiles.shard(len(plan), world_size, rank)
+    mine = [plan[i] for i in my_range]
+    if any(j.dark_frame and (j.iso is None or j.ratio is None) for j in jobs):
+        raise ValueError("dark_frame file names carry the ISO and the ratio (trainer_diffusion.py:320-321): set FrameJob.iso / .ratio")
     writer = NpyWriter(save_folder)
     resident: Dict[int, torch.Tensor] = {}       # frames of the current batch on the device
     try:
@@ -203,7 +222,11 @@ def synthesize_frames(diffusion, jobs: Sequence[FrameJob], *, save_folder: str, 
                 if job.dark_frame:
                     cond["clean_img"] = torch.zeros_like(cond["clean_img"])
                 conds.append(cond)
-                names += [os.path.join(_job_folder(job), npy_name(job.clean_name, x, y, job.noisy_name)) for x, y in run]
+                if job.dark_frame:                # running counter over the whole job list = the crop's index in the plan
+                    names += [os.path.join(_job_folder(job), dark_npy_name(my_range[lo + k + i], job.iso, job.ratio, x, y))
+                              for i, (x, y) in enumerate(run)]
+                else:
+                    names += [os.path.join(_job_folder(job), npy_name(job.clean_name, x, y, job.noisy_name)) for x, y in run]
                 k += len(run)
             cond = {key: torch.cat([c[key] for c in conds]) for key in conds[0]}
             out = diffusion.sample(batch_size=len(part), condition=cond)

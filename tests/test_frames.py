@@ -109,7 +109,7 @@ def _jobs():
     g = torch.Generator().manual_seed(5)
     return [frames.FrameJob(torch.rand((4, 96, 160), generator=g), 3, "a_10s.ARW", "a_0.1s.ARW"),
             frames.FrameJob(torch.rand((4, 64, 64), generator=g), 24, "b_10s.ARW", iso=800, ratio=250),
-            frames.FrameJob(torch.rand((4, 96, 96), generator=g), 7, "c_10s.ARW", dark_frame=True)]
+            frames.FrameJob(torch.rand((4, 96, 96), generator=g), 7, "c_10s.ARW", dark_frame=True, iso=1600, ratio=100)]
 
 
 def test_packed_multi_frame_synthesis_covers_every_crop_once(tmp_path):
@@ -125,10 +125,12 @@ def test_packed_multi_frame_synthesis_covers_every_crop_once(tmp_path):
         for rank in range(world):
             paths += frames.synthesize_frames(_FakeDiffusion(), jobs, save_folder=str(root), batch_size=7, rank=rank, world_size=world)
         assert len(paths) == len(plan) == len(set(paths))
-        for j, x, y in plan:
+        for idx, (j, x, y) in enumerate(plan):
             job = jobs[j]
-            sub = "ISO800_Ratio250" if job.iso else os.path.join("npy", "generated")
-            arr = np.load(os.path.join(str(root), sub, frames.npy_name(job.clean_name, x, y, job.noisy_name)))
+            sub = frames.consumer_subfolder(job.iso, job.ratio) if job.iso else os.path.join("npy", "generated")
+            # dark frames: Trainer.test's running item counter (here: the crop's index in the whole plan) + ISO + ratio
+            name = frames.dark_npy_name(idx, job.iso, job.ratio, x, y) if job.dark_frame else frames.npy_name(job.clean_name, x, y, job.noisy_name)
+            arr = np.load(os.path.join(str(root), sub, name))
             want = frames.crop_batch(job.clean_frame, [(x, y)], 32, job.iso_ratio_idx)
             clean = torch.zeros_like(want["clean_img"]) if job.dark_frame else want["clean_img"]
             assert arr.dtype == np.float32 and np.allclose(arr, (clean + want["position"].sum(1, keepdim=True))[0].numpy())
@@ -185,3 +187,20 @@ def test_frame_synthesis_equals_direct_sampling(tmp_path):
         arr = np.load(os.path.join(str(tmp_path), "npy", "generated", frames.npy_name("g.ARW", x, y)))
         assert arr.shape == (4, 32, 32) and np.isfinite(arr).all()
         assert np.array_equal(arr, direct[i])
+
+
+def test_dark_frame_names_follow_trainer_test(tmp_path):
+    """models/trainer_diffusion.py:318-322: '%05d' % npy_num + '_' + iso + '_' + ratio + '+' + 'x_y' + '.npy', zero clean image."""
+    assert frames.dark_npy_name(7, 800.0, 250.0, 192, 1168) == "00007_800_250+192_1168.npy"
+    frame = torch.rand((4, 64, 96), generator=torch.Generator().manual_seed(4))
+    origins = tiles.tile_origins(32, 64, 96)
+    with pytest.raises(ValueError):
+        frames.synthesize_frame(_FakeDiffusion(), frame, iso_ratio_idx=3, clean_name="f.ARW", save_folder=str(tmp_path), dark_frame=True)
+    paths = []
+    for rank in range(2):
+        paths += frames.synthesize_frame(_FakeDiffusion(), frame, iso_ratio_idx=3, clean_name="f.ARW", save_folder=str(tmp_path), batch_size=5,
+                                         rank=rank, world_size=2, dark_frame=True, iso=800, ratio=250, index_base=100)
+    assert [os.path.basename(p) for p in paths] == [frames.dark_npy_name(100 + i, 800, 250, x, y) for i, (x, y) in enumerate(origins)]
+    x, y = origins[4]
+    want = frames.crop_batch(frame, [(x, y)], 32, 3)["position"].sum(1, keepdim=True)[0].expand(4, 32, 32)      # clean image is zero
+    assert np.allclose(np.load(paths[4]), want.numpy())
