@@ -422,7 +422,7 @@ def test_experimental_weight_stationary_conv_variant():
     opt-in: it re-runs the halo2 parity cases (plain, fused GroupNorm input) in a child process with the variant enabled."""
     import subprocess
     import sys
-    env = dict(os.environ, NDIFF_EXPERIMENT_WS="1")
+    env = dict(os.environ, NDIFF_EXPERIMENT_WS="2")          # 1: the N = 64 kHalo2 kernels, 2: also the N = 128 ones
     env.pop("NDIFF_TEST_EXPERIMENTAL")
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", os.path.abspath(__file__), "-m", "gpu", "-k",
                         "(test_conv3x3 and halo2) or groupnorm_apply_on_the_input"], env=env, capture_output=True, text=True, timeout=600)
