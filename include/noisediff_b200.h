@@ -79,6 +79,12 @@ NDIFF_API void    ndiff_engine_destroy(ndiff_engine* e);
  * which fails if any of the live keys is missing or mis-shaped.  Dead keys (attn.to_q/to_k, norm1) are accepted
  * and ignored. */
 NDIFF_API int32_t ndiff_load_param(ndiff_engine* e, const char* name, const float* data, int32_t ndim, const int64_t* shape);
+/* Same, ordered on `stream` (cudaMemcpyAsync): behind the work that produced `data` on that stream and ahead of the repack that
+ * ndiff_finalize_params enqueues on it — the form to use when reloading weights while other streams are busy (the stream-less
+ * form above fences the whole device instead).  Loading any parameter invalidates the condition: call ndiff_set_condition
+ * again before the next forward / chain. */
+NDIFF_API int32_t ndiff_load_param_async(ndiff_engine* e, const char* name, const float* data, int32_t ndim,
+                                         const int64_t* shape, void* stream);
 NDIFF_API int32_t ndiff_finalize_params(ndiff_engine* e, void* stream);
 
 /* Condition.  Replaces the step-invariant head of NoiseDiffNet.forward (Diffusion_arch.py:580-591): position
@@ -117,6 +123,10 @@ NDIFF_API int32_t ndiff_sample_host(ndiff_engine* e, const float* clean_host, co
 NDIFF_API int32_t ndiff_debug_tensor(ndiff_engine* e, const char* name, float* out_dev_nchw, int64_t* shape4, void* stream);
 NDIFF_API int64_t ndiff_launches_per_step(const ndiff_engine* e);
 NDIFF_API double  ndiff_conv_flops_per_step(const ndiff_engine* e);    /* executed tensor-core FLOPs per network evaluation */
+/* Per-op durations measured INSIDE the step: `iters` whole steps are enqueued back to back with a CUDA event between consecutive
+ * ops; ms_out[i] is the median over the iterations.  Row 0 is the step prologue, the last row the fused heads + posterior update.
+ * names_out: one line "name;flops;bytes" per row (executed FLOPs and algorithmic HBM bytes of that op).  After ndiff_chain_begin
+ * the iterations are real chain steps (iters + 1 steps must be left), otherwise forward evaluations.  ms_out == NULL: only *n_out. */
 NDIFF_API int32_t ndiff_time_layers(ndiff_engine* e, int32_t iters, float* ms_out, char* names_out, int32_t names_cap,
                           int32_t* n_out, void* stream);
 

@@ -44,6 +44,7 @@ _SIGS = {
     "ndiff_engine_create": (C.c_int32, [C.POINTER(Config), C.POINTER(_P)]),
     "ndiff_engine_destroy": (None, [_P]),
     "ndiff_load_param": (C.c_int32, [_P, C.c_char_p, _P, C.c_int32, C.POINTER(C.c_int64)]),
+    "ndiff_load_param_async": (C.c_int32, [_P, C.c_char_p, _P, C.c_int32, C.POINTER(C.c_int64), _P]),
     "ndiff_finalize_params": (C.c_int32, [_P, _P]),
     "ndiff_set_condition": (C.c_int32, [_P, _P, _P, _P, _P]),
     "ndiff_forward": (C.c_int32, [_P, _P, _P, _P, _P]),

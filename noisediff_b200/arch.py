@@ -157,7 +157,18 @@ class NoiseDiffNet(nn.Module):
 
     # ---- engine management -----------------------------------------------------------------------------------
     def _param_version(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        """Identity of the current weights: storage address + in-place version counter of every parameter.  The parameter LIST is
+        cached (the module-tree walk is what costs on the per-step ``p_sample`` API) and dropped whenever the module's tensors are
+        replaced (``.to()/.cuda()/.half()`` go through ``_apply``; ``load_state_dict`` copies in place and bumps the versions)."""
+        ps = self.__dict__.get("_param_list")
+        if ps is None:
+            ps = list(self.parameters())
+            self.__dict__["_param_list"] = ps
+        return tuple((p.data_ptr(), p._version) for p in ps)
+
+    def _apply(self, fn, *a, **kw):
+        self.__dict__.pop("_param_list", None)
+        return super()._apply(fn, *a, **kw)
 
     def engine_for(self, batch: int, height: int, width: int, device: torch.device) -> "_engine.Engine":
         """Returns the (cached) CUDA engine for this geometry with the current parameters uploaded."""
@@ -188,8 +199,10 @@ class NoiseDiffNet(nn.Module):
             f"your input dimensions {tuple(x.shape[-2:])} need to be divisible by {f}, given the unet"
         if condition is None:
             raise TypeError("NoiseDiffNet.forward needs condition={'clean_img','position','iso_ratio_idx'}")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and x.requires_grad:
-            raise NotImplementedError("the CUDA path is inference-only (training step is SURVEY §8f N1)")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            # a training call (autograd on, trainable weights) must not get a silently detached tensor back
+            raise NotImplementedError("NoiseDiffNet.forward on the CUDA library is inference-only: call it under torch.no_grad() / "
+                                      "inference_mode (the training step is SURVEY §8f N1)")
         B, C, H, W = x.shape
         eng = self.engine_for(B, H, W, x.device)
         eng.set_condition(condition["clean_img"], condition["position"], condition["iso_ratio_idx"])

@@ -8,6 +8,7 @@
 //   * the 1-token cross attention collapses to a per-sample vector (softmax over one key == 1), the
 //     positional branch and the time MLP are hoisted out of the per-pixel work;
 //   * final_conv + shot_mlp3.fc2 + the DDPM/DDIM posterior update are one kernel; a whole step replays as one graph.
+#include <algorithm>
 #include <cstddef>
 #include <cstring>
 #include <functional>
@@ -45,6 +46,7 @@ struct Op {
     std::string name;
     std::function<int(cudaStream_t)> fn;
     double flops = 0.0;
+    double bytes = 0.0;   // algorithmic HBM bytes: every input read once + every output written once (bf16 activations)
     int launches = 1;
     bool chain = false;   // fused per-pixel chain (its FLOPs are not convolution FLOPs)
 };
@@ -262,6 +264,12 @@ struct ndiff_engine {
         owned.push_back(p);
         *out = static_cast<T*>(p);
         return 0;
+    }
+    // frees a buffer obtained from alloc() (regrown tables / resized parameters must not pile up until engine destroy)
+    void release(void* p) {
+        if (!p) return;
+        auto it = std::find(owned.begin(), owned.end(), p);
+        if (it != owned.end()) { owned.erase(it); cudaFree(p); }
     }
     bf16* pool_get(size_t elems) {
         const size_t bytes = elems * sizeof(bf16);
@@ -587,6 +595,10 @@ struct Builder {
         Op op;
         op.name = wname;
         op.flops = 2.0 * e->B * Ho * Wo * Cout * static_cast<double>(taps) * (s0.C + (s1 ? s1->C : 0));
+        {
+            const double opix = static_cast<double>(e->B) * Ho * Wo, ipix = mode == kS2D ? 4.0 * opix : opix;
+            op.bytes = 2.0 * (ipix * (s0.C + (s1 ? s1->C : 0)) + opix * Cout * (1 + (res ? 1 : 0) + (mode == kHalo1R ? 1 : 0)));
+        }
         op.fn = [plan](cudaStream_t st) { return conv_gemm_launch(*plan, st); };
         e->net_ops.push_back(op);
         e->conv_flops += op.flops;
@@ -603,6 +615,7 @@ struct Builder {
         g.res1 = r1 ? r1->p : nullptr; g.res2 = r2 ? r2->p : nullptr;
         g.B = e->B; g.HW = xio.H * xio.W; g.C = xio.C; g.G = groups; g.eps = 1e-5f;
         Op op; op.name = nname;
+        op.bytes = 2.0 * e->B * g.HW * xio.C * (2 + (maps ? 2 : 0) + (r1 ? 1 : 0) + (r2 ? 1 : 0));
         op.fn = [g](cudaStream_t st) { return gn_apply_launch(g, st); };
         e->net_ops.push_back(op);
     }
@@ -674,6 +687,7 @@ struct Builder {
             if (pixel_chain_plan(d, e->num_sms, plan.get())) { err = 1; return o; }
             Op op; op.name = n + "(fused chain)";
             op.flops = 2.0 * d.npix * (64.0 * 128 + 128.0 * 64 + 64.0 * 64);
+            op.bytes = 2.0 * d.npix * 64 * 2;
             op.chain = true;
             op.fn = [plan](cudaStream_t st) { return pixel_chain_launch(*plan, st); };
             e->net_ops.push_back(op);
@@ -687,6 +701,7 @@ struct Builder {
             const float* g = e->pf(n + ".norm2.weight"); const float* bt = e->pf(n + ".norm2.bias");
             const int B = e->B, HW = xin.H * xin.W, ld = e->cv_total;
             Op op; op.name = n + ".norm2";
+            op.bytes = 2.0 * B * HW * C * 2;
             op.fn = [=](cudaStream_t st) { return layernorm_launch(xp, cv, ld, g, bt, up, B, HW, C, st); };
             e->net_ops.push_back(op);
         }
@@ -731,6 +746,7 @@ int build_plan(ndiff_engine* e) {
         if (pixel_chain_plan(d, e->num_sms, plan.get())) return 1;
         Op op; op.name = "shot_mlp1+shot_attn+shot_mlp2(fused chain)";
         op.flops = 2.0 * npix * (8.0 * 64 + 64.0 * 64 * 4 + 64.0 * 128 * 2);
+        op.bytes = static_cast<double>(npix) * (2 * 16 + 2 * 64 * 2);      // clean + x_t (fp32 x 4 each) in, s1 and s4 out
         op.chain = true;
         op.fn = [plan](cudaStream_t st) { return pixel_chain_launch(*plan, st); };
         e->net_ops.push_back(op);
@@ -774,6 +790,7 @@ int build_plan(ndiff_engine* e) {
         if (tail_chain_plan(td, e->num_sms, plan.get())) return 1;
         Op op; op.name = "shot_time.block2.norm+shot_mlp3(fused chain)";
         op.flops = 2.0 * npix * (64.0 * 64 + 64.0 * 4);
+        op.bytes = static_cast<double>(npix) * (3 * 64 * 2 + 16);
         op.chain = true;
         op.fn = [plan](cudaStream_t st) { return tail_chain_launch(*plan, st); };
         e->net_ops.push_back(op);
@@ -806,6 +823,7 @@ int build_plan(ndiff_engine* e) {
         const bool tc_ok = (e->cfg.flags & NDIFF_FLAG_INIT_SIMT) == 0 && conv_gemm_plan(d, e->num_sms, plan.get()) == 0;
         if (tc_ok) {
             Op pk; pk.name = "init_conv.pack";
+            pk.bytes = static_cast<double>(npix) * (16 + 16);
             const float4* xs = reinterpret_cast<const float4*>(e->x); uint2* xp = reinterpret_cast<uint2*>(e->xpad);
             pk.fn = [=](cudaStream_t st) {
                 NDIFF_CUDA_OK(launch_pdl(xpad_pack_kernel, dim3((npix + 255) / 256), dim3(256), 0, st, xs, xp, H, W,
@@ -815,6 +833,7 @@ int build_plan(ndiff_engine* e) {
             e->net_ops.push_back(pk);
             Op op; op.name = "init_conv";
             op.flops = 2.0 * npix * dim * 196.0;
+            op.bytes = static_cast<double>(npix) * (16 + 2.0 * dim);
             op.fn = [plan](cudaStream_t st) { return conv_gemm_launch(*plan, st); };
             e->net_ops.push_back(op);
             e->conv_flops += op.flops;
@@ -875,6 +894,7 @@ int build_plan(ndiff_engine* e) {
             if (conv_gemm_plan(d, e->num_sms, plan.get())) return 1;
             Op op; op.name = p + ".3.1";
             op.flops = 2.0 * B * (4.0 * a3.H * a3.W) * ci * 4.0 * a3.C;      // executed: 4 taps per output pixel
+            op.bytes = 2.0 * B * a3.H * a3.W * (a3.C + 4.0 * ci);
             op.fn = [plan](cudaStream_t st) { return conv_gemm_launch(*plan, st); };
             e->net_ops.push_back(op);
             e->conv_flops += op.flops;
@@ -916,6 +936,7 @@ int build_plan(ndiff_engine* e) {
 }
 
 int run_net(ndiff_engine* e, cudaStream_t s, bool zero_stats = true) {
+    g_use_pdl = (e->cfg.flags & NDIFF_FLAG_PDL) != 0;      // per engine: every launch of this engine's plan goes through here
     // GroupNorm sums are accumulated with atomics: clear the arena first (a kernel, not a memset node, so that the first
     // layer can hang off it with a programmatic edge)
     if (zero_stats) {
@@ -975,8 +996,23 @@ int capture(ndiff_engine* e, bool step, cudaGraphExec_t* exec, cudaStream_t user
 
 cudaStream_t as_stream(void* p) { return static_cast<cudaStream_t>(p); }
 
+// Entry points run on the engine's device and put the caller's current device back on return: a model on cuda:1 must not
+// silently switch the process (PyTorch's notion of the current device included) away from cuda:0.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 int ensure_time_bufs(ndiff_engine* e, int n) {
     if (n > e->t_buf_n) {
+        e->release(e->t_buf); e->release(e->st_buf);
+        e->t_buf = nullptr; e->st_buf = nullptr;
         if (e->alloc(&e->t_buf, n)) return 1;
         if (e->alloc(&e->st_buf, static_cast<size_t>(n) * e->dim * 4)) return 1;
         e->t_buf_n = n;
@@ -1003,7 +1039,7 @@ int32_t ndiff_engine_create(const ndiff_config* cfg, ndiff_engine** out) {
     int ndev = 0;
     NDIFF_CUDA_OK(cudaGetDeviceCount(&ndev));
     NDIFF_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "no such CUDA device");
-    NDIFF_CUDA_OK(cudaSetDevice(cfg->device));
+    DeviceGuard dev_guard(cfg->device);
     cudaDeviceProp prop;
     NDIFF_CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
     NDIFF_REQUIRE(prop.major == 10, "noisediff_b200 needs an sm_100a GPU (B200); found sm_" + std::to_string(prop.major) +
@@ -1015,7 +1051,6 @@ int32_t ndiff_engine_create(const ndiff_config* cfg, ndiff_engine** out) {
     e->num_sms = prop.multiProcessorCount;
     e->B = cfg->batch; e->H = cfg->height; e->W = cfg->width; e->dim = cfg->dim;
     e->keep_all = (cfg->flags & NDIFF_FLAG_KEEP_ACTS) != 0;
-    g_use_pdl = (cfg->flags & NDIFF_FLAG_PDL) != 0;
     const size_t npix = static_cast<size_t>(e->B) * e->H * e->W;
     if (e->alloc(&e->clean, npix * 4) || e->alloc(&e->x, npix * 4) || e->alloc(&e->v_out, npix * 4)) return 1;
     if (e->alloc(&e->map1, npix * 2 * e->dim) || e->alloc(&e->map2, npix * 2 * e->dim)) return 1;
@@ -1036,31 +1071,48 @@ int32_t ndiff_engine_create(const ndiff_config* cfg, ndiff_engine** out) {
 
 void ndiff_engine_destroy(ndiff_engine* e) {
     if (!e) return;
-    cudaSetDevice(e->cfg.device);
+    DeviceGuard dev_guard(e->cfg.device);
     cudaDeviceSynchronize();
     delete e;
 }
 
-int32_t ndiff_load_param(ndiff_engine* e, const char* name, const float* data, int32_t ndim, const int64_t* shape) {
+int32_t ndiff_load_param_async(ndiff_engine* e, const char* name, const float* data, int32_t ndim, const int64_t* shape,
+                               void* stream) {
     NDIFF_REQUIRE(e && name && data && ndim >= 0 && ndim <= 4, "bad argument");
-    NDIFF_CUDA_OK(cudaSetDevice(e->cfg.device));
+    DeviceGuard dev_guard(e->cfg.device);
     Param& p = e->params[name];
     size_t n = 1;
     std::vector<int64_t> shp(shape, shape + ndim);
     for (int64_t v : shp) n *= static_cast<size_t>(v);
     if (p.dev == nullptr || p.n != n) {
+        NDIFF_REQUIRE(!e->plan_built, std::string("parameter '") + name + "' changed size after the layer plan was built");
+        e->release(p.dev);
+        p.dev = nullptr;
         if (e->alloc(&p.dev, n)) return 1;
         p.n = n;
     }
     p.shape = shp;
-    NDIFF_CUDA_OK(cudaMemcpy(p.dev, data, n * sizeof(float), cudaMemcpyDefault));
+    // ordered on the caller's stream: behind whatever produced `data` there (an optimizer step), ahead of the repack that
+    // ndiff_finalize_params enqueues on the same stream, and behind earlier graph replays on it
+    NDIFF_CUDA_OK(cudaMemcpyAsync(p.dev, data, n * sizeof(float), cudaMemcpyDefault, as_stream(stream)));
     e->finalized = false;
+    e->cond_set = false;      // map1 / map2 / cvec were derived from the old weights: the condition must be set again
+    return 0;
+}
+
+int32_t ndiff_load_param(ndiff_engine* e, const char* name, const float* data, int32_t ndim, const int64_t* shape) {
+    // stream-less form: fence against everything in flight on the device, copy, and return with the copy complete
+    NDIFF_REQUIRE(e, "null engine");
+    DeviceGuard dev_guard(e->cfg.device);
+    NDIFF_CUDA_OK(cudaDeviceSynchronize());
+    if (ndiff_load_param_async(e, name, data, ndim, shape, nullptr)) return 1;
+    NDIFF_CUDA_OK(cudaStreamSynchronize(nullptr));
     return 0;
 }
 
 int32_t ndiff_finalize_params(ndiff_engine* e, void* stream) {
     NDIFF_REQUIRE(e, "null engine");
-    NDIFF_CUDA_OK(cudaSetDevice(e->cfg.device));
+    DeviceGuard dev_guard(e->cfg.device);
     // Packed buffers and fp32 parameter storage keep their addresses across reloads, so the layer plan and the
     // captured graphs stay valid; only the first call builds them.
     if (finalize(e, as_stream(stream))) return 1;
@@ -1073,7 +1125,7 @@ int32_t ndiff_set_condition(ndiff_engine* e, const float* clean_dev, const float
                             const int64_t* iso_idx_dev, void* stream) {
     NDIFF_REQUIRE(e && e->finalized, "engine has no finalized weights");
     NDIFF_REQUIRE(clean_dev && position_dev && iso_idx_dev, "null condition tensor");
-    NDIFF_CUDA_OK(cudaSetDevice(e->cfg.device));
+    DeviceGuard dev_guard(e->cfg.device);
     cudaStream_t s = as_stream(stream);
     const int HW = e->H * e->W;
     if (nchw_to_nhwc4_launch(clean_dev, e->clean, e->B, HW, s)) return 1;
@@ -1100,7 +1152,7 @@ int32_t ndiff_set_condition(ndiff_engine* e, const float* clean_dev, const float
 
 int32_t ndiff_forward(ndiff_engine* e, const float* x_dev, const int64_t* time_dev, float* out_dev, void* stream) {
     NDIFF_REQUIRE(e && e->finalized && e->cond_set, "engine needs weights and a condition before forward");
-    NDIFF_CUDA_OK(cudaSetDevice(e->cfg.device));
+    DeviceGuard dev_guard(e->cfg.device);
     cudaStream_t s = as_stream(stream);
     const int HW = e->H * e->W;
     if (ensure_time_bufs(e, e->B)) return 1;
@@ -1126,7 +1178,7 @@ int32_t ndiff_chain_begin(ndiff_engine* e, const ndiff_step* steps_host, int32_t
     NDIFF_REQUIRE(e && e->finalized && e->cond_set, "engine needs weights and a condition before sampling");
     NDIFF_REQUIRE(steps_host && n_steps > 0, "empty step table");
     static_assert(sizeof(ndiff_step) == sizeof(StepParams), "ABI step layout");
-    NDIFF_CUDA_OK(cudaSetDevice(e->cfg.device));
+    DeviceGuard dev_guard(e->cfg.device);
     cudaStream_t s = as_stream(stream);
     if (n_steps > e->ss_table_rows) {
         // The captured step graph holds the two table pointers by value (chain_step_begin_kernel's arguments): a longer chain
@@ -1136,6 +1188,8 @@ int32_t ndiff_chain_begin(ndiff_engine* e, const ndiff_step* steps_host, int32_t
             NDIFF_CUDA_OK(cudaGraphExecDestroy(e->step_exec));
             e->step_exec = nullptr;
         }
+        e->release(e->step_table); e->release(e->ss_table);
+        e->step_table = nullptr; e->ss_table = nullptr;
         if (e->alloc(&e->step_table, n_steps)) return 1;
         if (e->alloc(&e->ss_table, static_cast<size_t>(n_steps) * e->ss_total)) return 1;
         e->ss_table_rows = n_steps;
@@ -1166,7 +1220,7 @@ int32_t ndiff_chain_run(ndiff_engine* e, int32_t n, const float* noise_dev, cons
                         float* snapshots_dev, void* stream) {
     NDIFF_REQUIRE(e && e->n_steps > 0, "ndiff_chain_begin has not been called");
     NDIFF_REQUIRE(n > 0 && e->steps_done + n <= e->n_steps, "step count exceeds the chain length");
-    NDIFF_CUDA_OK(cudaSetDevice(e->cfg.device));
+    DeviceGuard dev_guard(e->cfg.device);
     cudaStream_t s = as_stream(stream);
     struct { int base; int pad; const float* noise; const float* teacher; float* snap; } io = {e->steps_done, 0, noise_dev,
                                                                                                teacher_dev, snapshots_dev};
@@ -1187,14 +1241,14 @@ int32_t ndiff_chain_run(ndiff_engine* e, int32_t n, const float* noise_dev, cons
 
 int32_t ndiff_chain_read(ndiff_engine* e, float* out_dev, void* stream) {
     NDIFF_REQUIRE(e && out_dev, "null argument");
-    NDIFF_CUDA_OK(cudaSetDevice(e->cfg.device));
+    DeviceGuard dev_guard(e->cfg.device);
     return nhwc4_to_nchw_launch(e->x, out_dev, e->B, e->H * e->W, as_stream(stream));
 }
 
 int32_t ndiff_chain_seek(ndiff_engine* e, int32_t step, const float* x_dev, uint64_t seed, void* stream) {
     NDIFF_REQUIRE(e && e->n_steps > 0 && x_dev, "ndiff_chain_begin has not been called / null state");
     NDIFF_REQUIRE(step >= 0 && step <= e->n_steps, "step out of range");
-    NDIFF_CUDA_OK(cudaSetDevice(e->cfg.device));
+    DeviceGuard dev_guard(e->cfg.device);
     cudaStream_t s = as_stream(stream);
     const unsigned long long sd = seed;
     NDIFF_CUDA_OK(cudaMemcpyAsync(&e->chain->step, &step, sizeof(int), cudaMemcpyHostToDevice, s));
@@ -1208,7 +1262,7 @@ int32_t ndiff_sample_host(ndiff_engine* e, const float* clean_host, const float*
                           const int64_t* iso_idx_host, const ndiff_step* steps_host, int32_t n_steps, uint64_t seed,
                           float* out_host) {
     NDIFF_REQUIRE(e && clean_host && position_host && iso_idx_host && out_host, "null argument");
-    NDIFF_CUDA_OK(cudaSetDevice(e->cfg.device));
+    DeviceGuard dev_guard(e->cfg.device);
     const size_t npix = static_cast<size_t>(e->B) * e->H * e->W;
     float* d_clean = nullptr; float* d_pos = nullptr; float* d_out = nullptr; long long* d_iso = nullptr;
     NDIFF_CUDA_OK(cudaMalloc(&d_clean, npix * 4 * sizeof(float)));
@@ -1241,7 +1295,7 @@ int32_t ndiff_sample_host(ndiff_engine* e, const float* clean_host, const float*
 
 int32_t ndiff_debug_tensor(ndiff_engine* e, const char* name, float* out_dev_nchw, int64_t* shape4, void* stream) {
     NDIFF_REQUIRE(e && name && shape4, "null argument");
-    NDIFF_CUDA_OK(cudaSetDevice(e->cfg.device));
+    DeviceGuard dev_guard(e->cfg.device);
     const std::string n(name);
     if (n == "pos_emb") {
         shape4[0] = e->B; shape4[1] = e->H; shape4[2] = e->W; shape4[3] = 8;   // NHWC fp32, copied verbatim
@@ -1287,41 +1341,72 @@ double ndiff_conv_flops_per_step(const ndiff_engine* e) { return e ? e->conv_flo
 
 int32_t ndiff_time_layers(ndiff_engine* e, int32_t iters, float* ms_out, char* names_out, int32_t names_cap,
                           int32_t* n_out, void* stream) {
+    // Per-launch durations measured INSIDE the step: the whole step (prologue, every layer in plan order, fused heads + update)
+    // is enqueued back to back on `stream` with a CUDA event between consecutive ops, `iters` times; the figure reported per op
+    // is the MEDIAN over the iterations.  Every kernel therefore runs behind its real predecessor, with the cache state and the
+    // clocks of a long-running chain — not in isolation.  Once a chain has begun the iterations are real chain steps (they
+    // advance the chain), otherwise they are forward evaluations.
     NDIFF_REQUIRE(e && e->plan_built && e->cond_set, "engine not ready");
-    NDIFF_CUDA_OK(cudaSetDevice(e->cfg.device));
+    DeviceGuard dev_guard(e->cfg.device);
     cudaStream_t s = as_stream(stream);
+    g_use_pdl = false;
     const int n_net = static_cast<int>(e->net_ops.size());
-    const int n = n_net + 1;     // + the fused heads / posterior-update kernel
+    const int n = n_net + 2;     // step prologue + layers + the fused heads / posterior-update kernel
     if (n_out) *n_out = n;
     if (!ms_out) return 0;
-    cudaEvent_t e0, e1;
-    NDIFF_CUDA_OK(cudaEventCreate(&e0));
-    NDIFF_CUDA_OK(cudaEventCreate(&e1));
+    const bool chain = e->n_steps > 0;
+    NDIFF_REQUIRE(iters >= 1, "iters must be positive");
+    NDIFF_REQUIRE(!chain || e->steps_done + iters + 1 <= e->n_steps, "not enough chain steps left to time (need iters + 1)");
+    if (chain) {      // library-drawn noise, no teacher forcing, no snapshots for the timed steps (same io block as ndiff_chain_run)
+        struct { int base; int pad; const float* noise; const float* teacher; float* snap; } io = {e->steps_done, 0, nullptr, nullptr, nullptr};
+        NDIFF_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<char*>(e->chain) + offsetof(ChainState, base_step), &io, sizeof(io),
+                                      cudaMemcpyHostToDevice, s));
+        NDIFF_CUDA_OK(cudaStreamSynchronize(s));
+    }
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& x : ev) NDIFF_CUDA_OK(cudaEventCreate(&x));
+    FinalArgs f;
+    final_args(e, chain, &f);
+    std::vector<std::vector<float>> samples(n);
+    for (int it = -1; it < iters; ++it) {      // iteration -1 is an untimed warm-up
+        NDIFF_CUDA_OK(cudaEventRecord(ev[0], s));
+        if (chain) {
+            chain_step_begin_kernel<<<32, 256, 0, s>>>(e->chain, e->step_table, e->ss_table, e->ss_total, e->ss_cur, e->B,
+                                                       e->H * e->W, reinterpret_cast<float4*>(e->x), e->stats,
+                                                       static_cast<int>(e->stats_bytes / sizeof(unsigned long long)));
+        } else {
+            zero_u64_kernel<<<32, 256, 0, s>>>(e->stats, static_cast<int>(e->stats_bytes / sizeof(unsigned long long)));
+        }
+        NDIFF_CUDA_OK(cudaGetLastError());
+        NDIFF_CUDA_OK(cudaEventRecord(ev[1], s));
+        for (int i = 0; i < n_net; ++i) {
+            if (e->net_ops[i].fn(s)) return 1;
+            NDIFF_CUDA_OK(cudaEventRecord(ev[i + 2], s));
+        }
+        if (final_launch(f, s)) return 1;
+        NDIFF_CUDA_OK(cudaEventRecord(ev[n], s));
+        NDIFF_CUDA_OK(cudaEventSynchronize(ev[n]));
+        if (chain) e->steps_done += 1;
+        if (it < 0) continue;
+        for (int i = 0; i < n; ++i) {
+            float ms = 0.f;
+            NDIFF_CUDA_OK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+            samples[i].push_back(ms);
+        }
+    }
+    for (auto& x : ev) cudaEventDestroy(x);
     std::string names;
-    NDIFF_CUDA_OK(cudaMemsetAsync(e->stats, 0, e->stats_bytes, s));
-    Op fin;
-    {
-        // chain form (Philox noise + posterior update on the engine's state) once a chain has begun, else the forward form
-        FinalArgs f;
-        final_args(e, e->n_steps > 0, &f);
-        fin.name = "final(heads+update)";
-        fin.fn = [f](cudaStream_t st) { return final_launch(f, st); };
-    }
     for (int i = 0; i < n; ++i) {
-        Op& op = i < n_net ? e->net_ops[i] : fin;
-        if (op.fn(s)) return 1;   // warm
-        NDIFF_CUDA_OK(cudaEventRecord(e0, s));
-        for (int k = 0; k < iters; ++k)
-            if (op.fn(s)) return 1;
-        NDIFF_CUDA_OK(cudaEventRecord(e1, s));
-        NDIFF_CUDA_OK(cudaEventSynchronize(e1));
-        float ms = 0.f;
-        NDIFF_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
-        ms_out[i] = ms / iters;
-        names += op.name + ";" + std::to_string(op.flops) + "\n";
+        std::sort(samples[i].begin(), samples[i].end());
+        ms_out[i] = samples[i][samples[i].size() / 2];
+        const Op* op = (i >= 1 && i <= n_net) ? &e->net_ops[i - 1] : nullptr;
+        const double npix = static_cast<double>(e->B) * e->H * e->W;
+        const std::string nm = i == 0 ? "step prologue" : (op ? op->name : "final(heads+update)");
+        const double fl = op ? op->flops : (i == n - 1 ? 2.0 * npix * e->dim * 4 : 0.0);
+        // heads + update: raw block2 output + residual (bf16 x dim each) in, shot image in, state read + written (+ v / noise)
+        const double by = op ? op->bytes : (i == n - 1 ? npix * (2.0 * 2 * e->dim + 16 + 32) : 0.0);
+        names += nm + ";" + std::to_string(fl) + ";" + std::to_string(by) + "\n";
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     if (names_out && names_cap > 0) {
         strncpy(names_out, names.c_str(), names_cap - 1);
         names_out[names_cap - 1] = 0;

@@ -14,6 +14,8 @@ import math
 from collections import namedtuple
 from typing import List, Optional, Tuple
 
+import ctypes as C
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -24,6 +26,12 @@ from .arch import NoiseDiffNet
 __all__ = ["GaussianDiffusion", "ModelPrediction"]
 
 ModelPrediction = namedtuple("ModelPrediction", ["pred_noise", "pred_x_start"])
+
+
+def _draws(flag: bool):
+    """ndiff_step.reserved[0] on the HOST side: this step consumes one (B, C, H, W) draw from the caller's generator in
+    noise_source='torch' mode.  The library ignores the field (it multiplies whatever noise it is handed by sigma)."""
+    return (C.c_int32 * 2)(1 if flag else 0, 0)
 
 
 def _gather(a: torch.Tensor, t: torch.Tensor, ndim: int) -> torch.Tensor:     # ref extract :91-94
@@ -196,7 +204,8 @@ class GaussianDiffusion(nn.Module):
             out.append(_lib.Step(t=t, p=p, q=q, a=float(tab["posterior_mean_coef1"][t]),
                                  b=float(tab["posterior_mean_coef2"][t]), c=0.0,
                                  r1=float(tab["sqrt_recip_alphas_cumprod"][t]),
-                                 r2=float(tab["sqrt_recipm1_alphas_cumprod"][t]), sigma=sigma, clip=1))
+                                 r2=float(tab["sqrt_recipm1_alphas_cumprod"][t]), sigma=sigma, clip=1,
+                                 reserved=_draws(t > 0)))                 # ref :371: randn_like iff t > 0
         return out
 
     def ddim_time_pairs(self) -> List[Tuple[int, int]]:
@@ -212,13 +221,13 @@ class GaussianDiffusion(nn.Module):
             p, q = self._xstart_coefs(t, tab)
             r1, r2 = float(tab["sqrt_recip_alphas_cumprod"][t]), float(tab["sqrt_recipm1_alphas_cumprod"][t])
             if tn < 0:                                                    # ref :422-425: img = x_start
-                out.append(_lib.Step(t=t, p=p, q=q, a=1.0, b=0.0, c=0.0, r1=r1, r2=r2, sigma=0.0, clip=1))
+                out.append(_lib.Step(t=t, p=p, q=q, a=1.0, b=0.0, c=0.0, r1=r1, r2=r2, sigma=0.0, clip=1, reserved=_draws(False)))
                 continue
             alpha, alpha_next = tab["alphas_cumprod"][t], tab["alphas_cumprod"][tn]
             sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()      # ref :430-431
             c = (1 - alpha_next - sigma ** 2).sqrt()
             out.append(_lib.Step(t=t, p=p, q=q, a=float(alpha_next.sqrt()), b=0.0, c=float(c), r1=r1, r2=r2,
-                                 sigma=float(sigma), clip=1))
+                                 sigma=float(sigma), clip=1, reserved=_draws(True)))   # ref :433: every non-final pair draws, even at eta = 0
         return out
 
     # ---- the fast path -------------------------------------------------------------------------------------------
@@ -252,9 +261,11 @@ class GaussianDiffusion(nn.Module):
             n = min(int(self.chunk_steps), n_steps - done)
             chunk_noise = None
             if use_torch_rng:
-                chunk_noise = torch.empty((n, B, Cc, H, W), device=dev)
+                # the global generator must end up where the reference leaves it: DDPM draws randn_like for every t > 0
+                # (ref :371), DDIM for every non-final pair whatever sigma is (ref :433, also at the default eta = 0)
+                chunk_noise = torch.zeros((n, B, Cc, H, W), device=dev)
                 for i in range(n):
-                    if steps[done + i].sigma != 0.0:      # the reference draws only when it adds noise (ref :371,:433)
+                    if steps[done + i].reserved[0]:
                         torch.randn((B, Cc, H, W), device=dev, out=chunk_noise[i])
             elif noises is not None:
                 chunk_noise = noises[done:done + n]

@@ -31,7 +31,8 @@ class Engine:
         self.device = torch.device("cuda", self.device_index)
         cfg = _lib.Config(dim, batch, height, width, self.device_index, flags)
         h = C.c_void_p()
-        _lib.check(self._lib.ndiff_engine_create(C.byref(cfg), C.byref(h)))
+        with torch.cuda.device(self.device_index):
+            _lib.check(self._lib.ndiff_engine_create(C.byref(cfg), C.byref(h)))
         self._h = h
         self.weights_version = None
         self._cond_key = None
@@ -40,7 +41,8 @@ class Engine:
     # ---- lifetime ---------------------------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None):
-            self._lib.ndiff_engine_destroy(self._h)
+            with torch.cuda.device(self.device_index):
+                self._lib.ndiff_engine_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -53,14 +55,17 @@ class Engine:
     def load_state_dict(self, sd: Dict[str, torch.Tensor]):
         """Mirror of ``Trainer.load_networks`` (ref models/trainer_diffusion.py:333-349): strips 'module.' and is
         strict about the live keys."""
-        for k, v in sd.items():
-            if k.startswith("module."):
-                k = k[7:]
-            t = v.detach().to(dtype=torch.float32).contiguous()
-            shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
-            _lib.check(self._lib.ndiff_load_param(self._h, k.encode(), _ptr(t), t.dim(), shape))
         with torch.cuda.device(self.device_index):
-            _lib.check(self._lib.ndiff_finalize_params(self._h, _stream(self.device_index)))
+            st = _stream(self.device_index)
+            keep = []
+            for k, v in sd.items():
+                if k.startswith("module."):
+                    k = k[7:]
+                t = v.detach().to(dtype=torch.float32).contiguous()
+                keep.append(t)                      # the copies are asynchronous on `st`: sources stay alive until finalize returns
+                shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
+                _lib.check(self._lib.ndiff_load_param_async(self._h, k.encode(), _ptr(t), t.dim(), shape, st))
+            _lib.check(self._lib.ndiff_finalize_params(self._h, st))    # synchronises `st` before returning
         self._cond_key = None
 
     # ---- condition --------------------------------------------------------------------------------------------
@@ -170,6 +175,6 @@ class Engine:
                                                    _stream(self.device_index)))
         rows = []
         for line, t in zip(names.value.decode().strip().split("\n"), list(ms)):
-            nm, fl = line.rsplit(";", 1)
-            rows.append((nm, float(t), float(fl)))
+            nm, fl, by = line.rsplit(";", 2)
+            rows.append((nm, float(t), float(fl), float(by)))      # (name, median ms inside the step, executed FLOPs, algorithmic bytes)
         return rows

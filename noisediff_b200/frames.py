@@ -12,6 +12,7 @@ pinned host buffers so that disk I/O never stalls the next batch's chain.
 """
 from __future__ import annotations
 
+import contextlib
 import os
 import queue
 import threading
@@ -21,6 +22,26 @@ import numpy as np
 import torch
 
 from . import tiles
+
+
+@contextlib.contextmanager
+def rank_noise_stream(diffusion, rank: int, world_size: int):
+    """Independent noise per rank, derived INSIDE the library.  Ranks of a sharded run are usually seeded identically (DDP
+    practice), which would give every rank the same x_T / z_t stream for its own crops — correlated synthetic noise across
+    shards.  One draw from the caller's CPU generator (identical on identically seeded ranks; it also makes successive calls
+    differ) is combined with the rank by ``tiles.rank_seed``, and the sampling inside the context runs on forked CPU + CUDA
+    generators seeded with the result — both ``noise_source='torch'`` (x_T, z_t from the CUDA generator) and ``'philox'`` (base
+    seed from the CPU generator) become rank-distinct, and the caller's generators continue as if only that one draw happened.
+    A single-rank run is left untouched (bit-identical to calling ``diffusion.sample`` directly)."""
+    if world_size <= 1:
+        yield
+        return
+    base = int(torch.randint(0, 2 ** 40, (1,)).item())
+    dev = diffusion.device
+    devices = [dev] if dev.type == "cuda" else []
+    with torch.random.fork_rng(devices=devices):
+        torch.manual_seed(tiles.rank_seed(base, rank))       # seeds the CPU and every CUDA generator of this process
+        yield
 
 
 def crop_batch(clean_frame: torch.Tensor, origins: Sequence[Tuple[int, int]], ps: int, iso_ratio_idx: int) -> Dict[str, torch.Tensor]:
@@ -146,17 +167,18 @@ def synthesize_frame(diffusion, clean_frame: torch.Tensor, *, iso_ratio_idx: int
         else os.path.join(save_folder, "npy", "generated")
     writer = NpyWriter(folder)
     try:
-        for lo in range(0, len(mine), batch_size):
-            part = mine[lo:lo + batch_size]
-            cond = crop_batch(frame, part, ps, iso_ratio_idx)
-            if dark_frame:                                   # ref :287-290: a zero clean image
-                cond["clean_img"] = torch.zeros_like(cond["clean_img"])
-            out = diffusion.sample(batch_size=len(part), condition=cond)
-            if dark_frame:
-                names = [dark_npy_name(index_base + my_range[lo + i], iso, ratio, x, y) for i, (x, y) in enumerate(part)]
-            else:
-                names = [npy_name(clean_name, x, y, noisy_name) for x, y in part]
-            writer.submit(out, names)
+        with rank_noise_stream(diffusion, rank, world_size):
+            for lo in range(0, len(mine), batch_size):
+                part = mine[lo:lo + batch_size]
+                cond = crop_batch(frame, part, ps, iso_ratio_idx)
+                if dark_frame:                                   # ref :287-290: a zero clean image
+                    cond["clean_img"] = torch.zeros_like(cond["clean_img"])
+                out = diffusion.sample(batch_size=len(part), condition=cond)
+                if dark_frame:
+                    names = [dark_npy_name(index_base + my_range[lo + i], iso, ratio, x, y) for i, (x, y) in enumerate(part)]
+                else:
+                    names = [npy_name(clean_name, x, y, noisy_name) for x, y in part]
+                writer.submit(out, names)
     finally:
         paths = writer.close()
     return paths
@@ -205,32 +227,33 @@ def synthesize_frames(diffusion, jobs: Sequence[FrameJob], *, save_folder: str, 
     writer = NpyWriter(save_folder)
     resident: Dict[int, torch.Tensor] = {}       # frames of the current batch on the device
     try:
-        for lo in range(0, len(mine), batch_size):
-            part = mine[lo:lo + batch_size]
-            for j in [j for j in resident if j < part[0][0]]:
-                del resident[j]                   # the slice is ordered by frame: earlier frames are finished
-            conds, names = [], []
-            k = 0
-            while k < len(part):                  # runs of crops from the same frame
-                j = part[k][0]
-                n = next((i for i, c in enumerate(part[k:]) if c[0] != j), len(part) - k)
-                run = [(x, y) for _, x, y in part[k:k + n]]
-                job = jobs[j]
-                if j not in resident:
-                    resident[j] = job.clean_frame.to(dev, non_blocking=True)
-                cond = crop_batch(resident[j], run, ps, job.iso_ratio_idx)
-                if job.dark_frame:
-                    cond["clean_img"] = torch.zeros_like(cond["clean_img"])
-                conds.append(cond)
-                if job.dark_frame:                # running counter over the whole job list = the crop's index in the plan
-                    names += [os.path.join(_job_folder(job), dark_npy_name(my_range[lo + k + i], job.iso, job.ratio, x, y))
-                              for i, (x, y) in enumerate(run)]
-                else:
-                    names += [os.path.join(_job_folder(job), npy_name(job.clean_name, x, y, job.noisy_name)) for x, y in run]
-                k += len(run)
-            cond = {key: torch.cat([c[key] for c in conds]) for key in conds[0]}
-            out = diffusion.sample(batch_size=len(part), condition=cond)
-            writer.submit(out, names)
+        with rank_noise_stream(diffusion, rank, world_size):
+            for lo in range(0, len(mine), batch_size):
+                part = mine[lo:lo + batch_size]
+                for j in [j for j in resident if j < part[0][0]]:
+                    del resident[j]                   # the slice is ordered by frame: earlier frames are finished
+                conds, names = [], []
+                k = 0
+                while k < len(part):                  # runs of crops from the same frame
+                    j = part[k][0]
+                    n = next((i for i, c in enumerate(part[k:]) if c[0] != j), len(part) - k)
+                    run = [(x, y) for _, x, y in part[k:k + n]]
+                    job = jobs[j]
+                    if j not in resident:
+                        resident[j] = job.clean_frame.to(dev, non_blocking=True)
+                    cond = crop_batch(resident[j], run, ps, job.iso_ratio_idx)
+                    if job.dark_frame:
+                        cond["clean_img"] = torch.zeros_like(cond["clean_img"])
+                    conds.append(cond)
+                    if job.dark_frame:                # running counter over the whole job list = the crop's index in the plan
+                        names += [os.path.join(_job_folder(job), dark_npy_name(my_range[lo + k + i], job.iso, job.ratio, x, y))
+                                  for i, (x, y) in enumerate(run)]
+                    else:
+                        names += [os.path.join(_job_folder(job), npy_name(job.clean_name, x, y, job.noisy_name)) for x, y in run]
+                    k += len(run)
+                cond = {key: torch.cat([c[key] for c in conds]) for key in conds[0]}
+                out = diffusion.sample(batch_size=len(part), condition=cond)
+                writer.submit(out, names)
     finally:
         paths = writer.close()
     return paths

@@ -102,7 +102,7 @@ def mlp1x1(sd: SD, pfx: str, x: Tensor) -> Tensor:
 def time_embedding(sd: SD, time: Tensor, dim: int) -> Tensor:
     """Diffusion_arch.py:94-107 + :502-507 — sinusoidal(dim, theta 1e4) -> Linear -> GELU -> Linear."""
     half = dim // 2
-    freq = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000.0) / (half - 1)))
+    freq = torch.exp(torch.arange(half, dtype=torch.float32, device=time.device) * -(math.log(10000.0) / (half - 1)))
     ang = time.to(torch.float32)[:, None] * freq[None, :]
     emb = torch.cat((ang.sin(), ang.cos()), dim=-1)
     return _linear(sd, "time_mlp.3", F.gelu(_linear(sd, "time_mlp.1", emb)))
@@ -361,13 +361,13 @@ def sample_chain(sd: SD, condition, x_T: Tensor, noises: Sequence[Tensor], *, T:
     if sampling_steps is None or sampling_steps >= T:
         for i, t in enumerate(reversed(range(T))):
             xin = teacher[i] if teacher is not None else x
-            out = net_forward(sd, xin, torch.full((b,), t, dtype=torch.long), condition)
+            out = net_forward(sd, xin, torch.full((b,), t, dtype=torch.long, device=x_T.device), condition)
             x, _ = ddpm_step(tab, objective, xin, t, out, noises[i] if t > 0 else None)
             xs.append(x)
     else:
         for i, (t, tn) in enumerate(ddim_pairs(T, sampling_steps)):
             xin = teacher[i] if teacher is not None else x
-            out = net_forward(sd, xin, torch.full((b,), t, dtype=torch.long), condition)
+            out = net_forward(sd, xin, torch.full((b,), t, dtype=torch.long, device=x_T.device), condition)
             x, _ = ddim_step(tab, objective, xin, t, tn, out, noises[i] if tn >= 0 else None, eta)
             xs.append(x)
     return xs

@@ -204,3 +204,43 @@ def test_dark_frame_names_follow_trainer_test(tmp_path):
     x, y = origins[4]
     want = frames.crop_batch(frame, [(x, y)], 32, 3)["position"].sum(1, keepdim=True)[0].expand(4, 32, 32)      # clean image is zero
     assert np.allclose(np.load(paths[4]), want.numpy())
+
+
+class _NoisyFakeDiffusion(_FakeDiffusion):
+    """'noise' really drawn from the generators a GaussianDiffusion would use (CPU here): torch.randn for the torch mode and a
+    torch.randint base seed for the Philox mode."""
+    def sample(self, batch_size, condition):
+        base = int(torch.randint(0, 2 ** 62, (1,)).item())
+        return torch.randn((batch_size, 4, 32, 32)) + (base % 1000) * 1e-6
+
+
+def test_identically_seeded_ranks_draw_independent_noise(tmp_path):
+    """ranks seeded identically (usual DDP practice) must not synthesise the same noise for their crops.  The rank is
+    folded into the stream inside synthesize_frame(s) (frames.rank_noise_stream); a single-rank run is untouched; the caller's
+    generator advances identically on every rank."""
+    frame = torch.zeros((4, 32, 64))                     # overlapping grid (x = 0, 24, 32; the reference repeats the border row): each rank gets a few crops
+    outs, states = [], []
+    for rank in range(2):
+        torch.manual_seed(1234)                          # every rank seeds the same way
+        p = frames.synthesize_frame(_NoisyFakeDiffusion(), frame, iso_ratio_idx=3, clean_name=f"r{rank}.ARW", save_folder=str(tmp_path),
+                                    batch_size=4, rank=rank, world_size=2)
+        states.append(torch.rand(1))
+        assert len(p) >= 1
+        outs.append(np.load(p[0]))
+    assert not np.allclose(outs[0], outs[1])             # different noise on the two shards
+    assert np.corrcoef(outs[0].ravel(), outs[1].ravel())[0, 1] < 0.1
+    assert torch.equal(states[0], states[1])             # the callers' generators stay in lock-step
+    # packed multi-frame path: same property
+    outs = []
+    for rank in range(2):
+        torch.manual_seed(1234)
+        p = frames.synthesize_frames(_NoisyFakeDiffusion(), [frames.FrameJob(frame, 3, "m.ARW")], save_folder=str(tmp_path / "m"),
+                                     batch_size=4, rank=rank, world_size=2)
+        outs.append(np.load(p[0]))
+    assert np.corrcoef(outs[0].ravel(), outs[1].ravel())[0, 1] < 0.1
+    # world_size == 1: exactly what a direct sample() call draws
+    torch.manual_seed(77)
+    p = frames.synthesize_frame(_NoisyFakeDiffusion(), frame[:, :, :32], iso_ratio_idx=3, clean_name="s.ARW", save_folder=str(tmp_path / "s"))
+    torch.manual_seed(77)
+    want = _NoisyFakeDiffusion().sample(4, None)        # a 32 x 32 frame is the same crop four times in the reference's grid
+    assert len(p) == 4 and np.array_equal(np.load(p[0]), want[3].numpy())      # (the repeats overwrite one file: the last one stays)

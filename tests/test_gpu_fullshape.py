@@ -1,0 +1,200 @@
+"""Parity at the shape the metric is quoted on (BASELINE configs[1]: 4 x 256 x 256 patches, T = 1000, sigmoid2, pred_v, batch 64).
+
+The CPU oracle needs ~17 min for one 256^2 chain, so here the SAME oracle code (oracle/noisediff_oracle.py, pure functional
+torch) runs on the B200 in fp32 with TF32 switched off (cuDNN/cuBLAS default to TF32 on this GPU) — it is the
+checker, the engine under test is reached through the C ABI as everywhere else.  Gates are north_star's: teacher-forced
+per-step ||x_{t-1} - ref|| / ||ref|| <= 2e-3, free-running final sample <= 1e-2."""
+import contextlib
+import ctypes as C
+
+import pytest
+import torch
+
+import noisediff_b200 as nd
+from noisediff_b200 import _lib
+from oracle import noisediff_oracle as O
+from tests.util import rel_l2, seeded_net, seeded_sd
+
+pytestmark = pytest.mark.gpu
+
+
+@contextlib.contextmanager
+def fp32_oracle_on_gpu():
+    """fp32 means fp32: no TF32 in cuDNN convolutions or cuBLAS matmuls while the oracle runs."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = False
+    try:
+        with torch.no_grad():
+            yield
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+
+
+@pytest.fixture(scope="module")
+def net():
+    import copy
+    return copy.deepcopy(seeded_net()).cuda()
+
+
+@pytest.fixture(scope="module")
+def sd_gpu():
+    return {k: v.cuda() for k, v in seeded_sd().items()}
+
+
+def distinct_condition(B, H, W, seed):
+    """Per-sample distinct clean images, tile origins and camera settings."""
+    cond = O.synthetic_condition(B, H, W, seed=seed)
+    cond["iso_ratio_idx"] = torch.tensor([(13 * i + 24) % 75 for i in range(B)])
+    scale = torch.linspace(0.4, 1.6, B).reshape(B, 1, 1, 1)
+    cond["clean_img"] = (cond["clean_img"] * scale).clamp(0, 1)
+    return {k: v.cuda() for k, v in cond.items()}
+
+
+def test_gpu_fp32_oracle_equals_cpu_oracle(sd_gpu):
+    """The checker itself: the oracle on the GPU (TF32 off) reproduces the CPU oracle to fp32 rounding."""
+    cond = O.synthetic_condition(2, 64, 64, seed=41)
+    x = torch.randn(2, 4, 64, 64, generator=torch.Generator().manual_seed(42))
+    t = torch.tensor([700, 30])
+    ref = O.net_forward(seeded_sd(), x, t, cond)
+    with fp32_oracle_on_gpu():
+        got = O.net_forward(sd_gpu, x.cuda(), t.cuda(), {k: v.cuda() for k, v in cond.items()})
+    assert rel_l2(got, ref) < 2e-5, rel_l2(got, ref)
+
+
+def test_teacher_forced_T1000_at_256_batch4(net, sd_gpu):
+    """Per-step gate at the metric's crop size, B = 4 with per-sample distinct conditions, t in {999, 500, 100, 10, 1, 0}."""
+    B, S = 4, 256
+    gd = nd.GaussianDiffusion(net, image_size=S, timesteps=1000, beta_schedule="sigmoid2", objective="pred_v").cuda()
+    tab = O.schedule_tables("sigmoid2", 1000)
+    ts = [999, 500, 100, 10, 1, 0]
+    all_steps = {s.t: s for s in gd.ddpm_steps()}
+    steps = [all_steps[t] for t in ts]
+    g = torch.Generator(device="cuda").manual_seed(3)
+    cond = distinct_condition(B, S, S, seed=61)
+    x0 = torch.randn(B, 4, S, S, generator=g, device="cuda") * 0.05
+    x_in = [float(tab["sqrt_alphas_cumprod"][t]) * x0 +
+            float(tab["sqrt_one_minus_alphas_cumprod"][t]) * torch.randn(B, 4, S, S, generator=g, device="cuda") for t in ts]
+    noises = torch.randn(len(ts), B, 4, S, S, generator=g, device="cuda")
+    eng = net.engine_for(B, S, S, torch.device("cuda", 0))
+    eng.set_condition(cond["clean_img"], cond["position"], cond["iso_ratio_idx"])
+    eng.chain_begin(steps, x_in[0], 0)
+    snaps = torch.empty((len(ts), B, 4, S, S), device="cuda")
+    eng.chain_run(len(ts), noises.contiguous(), torch.stack(x_in).contiguous(), snaps)
+    torch.cuda.synchronize()
+    worst = 0.0
+    with fp32_oracle_on_gpu():
+        for i, t in enumerate(ts):
+            out = O.net_forward(sd_gpu, x_in[i], torch.full((B,), t, dtype=torch.long, device="cuda"), cond)
+            ref, _ = O.ddpm_step(tab, "pred_v", x_in[i], t, out, noises[i])
+            per_sample = [rel_l2(snaps[i, b], ref[b]) for b in range(B)]
+            print(f"t={t:4d}  x_(t-1) rel-L2 per sample {['%.2e' % e for e in per_sample]}")
+            worst = max(worst, max(per_sample))
+    net.release_engines()
+    assert worst <= 2e-3, worst
+
+
+def _free_running(net, sd_gpu, B, S, T, seed, snap_every):
+    """Both sides run the whole T-step DDPM chain from the same x_T with the same injected z_t; returns
+    [(step index, rel-L2 of the state after that step)] and the final rel-L2."""
+    gd = nd.GaussianDiffusion(net, image_size=S, timesteps=T, beta_schedule="sigmoid2", objective="pred_v").cuda()
+    tab = O.schedule_tables("sigmoid2", T)
+    steps = gd.ddpm_steps()
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    cond = distinct_condition(B, S, S, seed=seed + 1)
+    x_T = torch.randn(B, 4, S, S, generator=g, device="cuda")
+    noises = torch.randn(T, B, 4, S, S, generator=g, device="cuda")
+    eng = net.engine_for(B, S, S, torch.device("cuda", 0))
+    eng.set_condition(cond["clean_img"], cond["position"], cond["iso_ratio_idx"])
+    eng.chain_begin(steps, x_T, 0)
+    mine = {}
+    done = 0
+    while done < T:
+        n = min(snap_every, T - done)
+        eng.chain_run(n, noises[done:done + n].contiguous())
+        done += n
+        mine[done] = eng.chain_read().clone()
+    torch.cuda.synchronize()
+    rows = []
+    with fp32_oracle_on_gpu():
+        x = x_T
+        for i, t in enumerate(reversed(range(T))):
+            out = O.net_forward(sd_gpu, x, torch.full((B,), t, dtype=torch.long, device="cuda"), cond)
+            x, _ = O.ddpm_step(tab, "pred_v", x, t, out, noises[i] if t > 0 else None)
+            if (i + 1) in mine:
+                rows.append((i + 1, rel_l2(mine[i + 1], x)))
+    net.release_engines()
+    return rows
+
+
+def test_free_running_T1000_chain_64(net, sd_gpu):
+    """The whole 1000-step reverse chain, free-running on both sides (error accumulation over 1000 bf16 network evaluations
+    is observed, not extrapolated): final sample <= 1e-2, every 100th state printed."""
+    rows = _free_running(net, sd_gpu, B=2, S=64, T=1000, seed=70, snap_every=100)
+    for n, e in rows:
+        print(f"after {n:4d} steps: state rel-L2 {e:.3e}")
+    assert rows[-1][0] == 1000 and rows[-1][1] <= 1e-2, rows[-1]
+
+
+def test_free_running_T1000_chain_256(net, sd_gpu):
+    """Same at the metric's crop size (one 4 x 256 x 256 patch; the fp32 oracle chain takes about a minute on the B200)."""
+    rows = _free_running(net, sd_gpu, B=1, S=256, T=1000, seed=80, snap_every=100)
+    for n, e in rows:
+        print(f"after {n:4d} steps: state rel-L2 {e:.3e}")
+    assert rows[-1][0] == 1000 and rows[-1][1] <= 1e-2, rows[-1]
+
+
+def test_batch64_at_256_replicas_are_bit_identical_to_batch1(net):
+    """The bench geometry (one engine, 64 patches of 256^2): 64 copies of one condition / x_t must each reproduce the B = 1
+    engine bit for bit — per-sample math only, and GroupNorm sums are fixed-point integer atomics (order-free).  Together with
+    the B <= 4 oracle gates above this pins the B = 64 engine to the oracle."""
+    S = 256
+    gd = nd.GaussianDiffusion(net, image_size=S, timesteps=1000, beta_schedule="sigmoid2", objective="pred_v").cuda()
+    steps = [s for s in gd.ddpm_steps() if s.t in (600, 599, 598)]
+    g = torch.Generator(device="cuda").manual_seed(90)
+    cond1 = distinct_condition(1, S, S, seed=91)
+    x = torch.randn(1, 4, S, S, generator=g, device="cuda")
+    z = torch.randn(3, 1, 4, S, S, generator=g, device="cuda")
+    outs = {}
+    for B in (1, 64):
+        eng = net.engine_for(B, S, S, torch.device("cuda", 0))
+        eng.set_condition(cond1["clean_img"].repeat(B, 1, 1, 1).contiguous(), cond1["position"].repeat(B, 1, 1, 1).contiguous(),
+                          cond1["iso_ratio_idx"].repeat(B).contiguous())
+        eng.chain_begin(steps, x.repeat(B, 1, 1, 1).contiguous(), 0)
+        eng.chain_run(3, z.repeat(1, B, 1, 1, 1).contiguous())
+        outs[B] = eng.chain_read().clone()
+        torch.cuda.synchronize()
+        net.release_engines()
+    assert torch.isfinite(outs[64]).all()
+    for b in range(64):
+        assert torch.equal(outs[64][b], outs[1][0]), f"sample {b} of the 64-patch engine differs from the single-patch engine"
+
+
+def philox_normal(n_pix, seed, stream_id):
+    """The library's own N(0,1) stream, NHWC4 -> returned as [n_pix, 4] (ndiff_op_philox_normal, include/noisediff_b200.h)."""
+    out = torch.empty((n_pix, 4), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.lib().ndiff_op_philox_normal(C.c_void_p(out.data_ptr()), n_pix, C.c_uint64(seed), C.c_uint64(stream_id),
+                                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    return out
+
+
+def test_sample_host_matches_oracle_on_its_own_philox_stream(net, sd_gpu):
+    """ndiff_sample_host (host buffers in, host buffer out, noise drawn inside the library) against the oracle fed with the SAME
+    Philox draws: x_T = stream 0, z of the i-th step = stream i + 1 (pointwise.cu), each a float4 per NHWC pixel."""
+    B, S, T, seed = 2, 64, 40, 1234
+    gd = nd.GaussianDiffusion(net, image_size=S, timesteps=T, beta_schedule="sigmoid2", objective="pred_v").cuda()
+    cond = {k: v.cpu() for k, v in distinct_condition(B, S, S, seed=95).items()}
+    eng = net.engine_for(B, S, S, torch.device("cuda", 0))
+    got = eng.sample_host(cond["clean_img"], cond["position"], cond["iso_ratio_idx"], gd.ddpm_steps(), seed=seed)
+    def draw(stream_id):
+        return philox_normal(B * S * S, seed, stream_id).reshape(B, S, S, 4).permute(0, 3, 1, 2).contiguous()
+    x_T = draw(0)
+    noises = [draw(i + 1) for i in range(T)]
+    with fp32_oracle_on_gpu():
+        xs = O.sample_chain(sd_gpu, {k: v.cuda() for k, v in cond.items()}, x_T, noises, T=T)
+    err = rel_l2(got, xs[-1])
+    print(f"ndiff_sample_host vs oracle on the same Philox stream (T={T}, {S}^2): final rel-L2 {err:.3e}")
+    net.release_engines()
+    assert err <= 1e-2, err

@@ -156,7 +156,10 @@ def test_preset_mean_replaces_x_T_but_still_consumes_the_draw(rig):
 
 
 @pytest.mark.parametrize("eta", [0.0, 0.7])
-def test_ddim_draws_noise_only_when_sigma_is_nonzero(rig, eta):
+def test_ddim_draws_noise_for_every_non_final_pair(rig, eta):
+    """ref :418-439: ``noise = torch.randn_like(img)`` sits outside any eta / sigma test, so every pair except the final
+    (t, -1) consumes one draw — also at the default eta = 0, where sigma * noise adds nothing.  What must match the reference
+    is the sample AND the state of the global generator afterwards (the x_T of the next sample() in a seeded loop)."""
     make, _ = rig
     gd = make(T=20, sampling_timesteps=5, ddim_sampling_eta=eta)
     assert gd.is_ddim_sampling and len(gd.ddim_steps()) == 5 and gd.ddim_time_pairs()[-1][1] == -1
@@ -170,10 +173,11 @@ def test_ddim_draws_noise_only_when_sigma_is_nonzero(rig, eta):
     eng.set_condition(cond["clean_img"], cond["position"], cond["iso_ratio_idx"])
     steps = gd.ddim_steps()
     eng.chain_begin(steps, x, 0)
-    for s in steps:
-        eng.chain_run(1, (torch.randn(2, 4, 8, 8) if s.sigma != 0.0 else torch.zeros(2, 4, 8, 8))[None])
+    for (t, tn), s in zip(gd.ddim_time_pairs(), steps):
+        eng.chain_run(1, (torch.randn(2, 4, 8, 8) if tn >= 0 else torch.zeros(2, 4, 8, 8))[None])
     assert torch.equal(got, eng.chain_read()) and torch.equal(after, torch.rand(1))
     assert sum(1 for s in steps if s.sigma != 0.0) == (0 if eta == 0.0 else 4)
+    assert [s.reserved[0] for s in steps] == [1, 1, 1, 1, 0]
 
 
 def test_philox_mode_hands_seeds_to_the_library_and_reads_x_T_back(rig):

@@ -111,8 +111,8 @@ def main():
                      "conv_tflops": eng.conv_flops_per_step / ms / 1e9}
                 if B in (4, 8):
                     rows = eng.time_layers(5)
-                    r["layers"] = [(n, round(t * 1e3, 1), round(f / max(t, 1e-9) / 1e9, 1)) for n, t, f in rows]
-                    r["sum_layers_ms"] = sum(t for _, t, _ in rows)
+                    r["layers"] = [(n, round(t * 1e3, 1), round(f / max(t, 1e-9) / 1e9, 1)) for n, t, f, _b in rows]
+                    r["sum_layers_ms"] = sum(r[1] for r in rows)
                 return r
             guarded(f"net_B{B}", run)
 

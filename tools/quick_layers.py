@@ -27,8 +27,8 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(); eng.chain_run(10); e1.record(); torch.cuda.synchronize()
 print(f"step {e0.elapsed_time(e1) / 10:.3f} ms  (B={B})")
 rows = eng.time_layers(5)
-tot = sum(t for _, t, _ in rows)
+tot = sum(r[1] for r in rows)
 print(f"sum of layers {tot:.3f} ms")
-for n, t, f in rows:
+for n, t, f, _b in rows:
     if flt in n:
         print(f"{n:48s} {t * 1e3:9.1f} us {f / t / 1e9 if t > 0 else 0:9.1f} TF/s")
