@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
                     named_bar_sync(1, kXfWarps * 32);            // nobody still reads the previous sample's table
                     for (int c = t; c < Cin; c += kXfWarps * 32) {
                         const int g = c >> a.xf_lgs;
-                        const double inv_n = 1.0 / (static_cast<double>(a.H) * a.W * (1 << a.xf_lgs));
+                        const double inv_n = 1.0 / (static_cast<double>(a.H) * a.W * (1 << a.xf_lgs) * a.xf_real_frac);
                         const double s_ = static_cast<double>(static_cast<long long>(a.xf_stats[(b * a.xf_G + g) * 2])) * (1.0 / 16777216.0);
                         const double q_ = static_cast<double>(static_cast<long long>(a.xf_stats[(b * a.xf_G + g) * 2 + 1])) * (1.0 / 16777216.0);
                         const double meand = s_ * inv_n;
@@ -783,6 +783,8 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
         NDIFF_REQUIRE(gs >= 8 && (gs & (gs - 1)) == 0, "fused GroupNorm input: group size must be a power of two >= 8");
         a.xf_stats = d.xf_stats; a.xf_gamma = d.xf_gamma; a.xf_beta = d.xf_beta; a.xf_ss = d.xf_ss; a.xf_ss_ld = d.xf_ss_ld;
         a.xf_G = d.xf_groups; a.xf_lgs = ilog2(gs); a.xf_eps = d.xf_eps;
+        NDIFF_REQUIRE(d.xf_real_frac > 0.f && d.xf_real_frac <= 1.f, "fused GroupNorm input: live channel fraction must be in (0, 1]");
+        a.xf_real_frac = d.xf_real_frac;
     }
     NDIFF_REQUIRE(!res2 || (d.out2 != nullptr && d.out2_ld % 8 == 0), "kHalo1R needs the residual-conv output");
     a.stats = d.stats; a.G = d.groups;

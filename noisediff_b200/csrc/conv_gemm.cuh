@@ -59,6 +59,7 @@ struct ConvGemmArgs {
     const float* xf_gamma; const float* xf_beta;
     const float* xf_ss; int xf_ss_ld;     // per-sample [scale C | shift C] at xf_ss[b * xf_ss_ld], or null
     int xf_G, xf_lgs; float xf_eps;
+    float xf_real_frac;                   // live fraction of every input group's channels (statistics count)
     unsigned long long* stats;   // GroupNorm sums [B][G][2] (sum, sum of squares) in 2^-24 fixed point, or null
                                  // (integer atomics are associative: the result does not depend on tile order)
     int lgs;                     // log2(channels per group)
@@ -98,6 +99,7 @@ struct ConvGemmDesc {
     // fused GroupNorm-apply of the input (kHalo1 / kHalo2, single source): statistics of the producing conv etc.
     const unsigned long long* xf_stats = nullptr; const float* xf_gamma = nullptr; const float* xf_beta = nullptr;
     const float* xf_ss = nullptr; int xf_ss_ld = 0; int xf_groups = 0; float xf_eps = 1e-5f;
+    float xf_real_frac = 1.0f;           // zero-padded channel layouts: live fraction of every group (element count of the statistics)
     int force_nt = 0;                    // 0 = auto
     int TW = 0;                          // 0 = auto
 };

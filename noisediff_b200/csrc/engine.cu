@@ -153,6 +153,18 @@ __global__ void init_conv_pack_tc_kernel(const float* __restrict__ src, bf16* __
     }
 }
 
+__global__ void embed_param_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, int Cc, int inner,
+                                   const int* __restrict__ rmap, const int* __restrict__ cmap, int pC) {
+    const size_t total = static_cast<size_t>(R) * Cc * inner;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int k = static_cast<int>(i % inner);
+        const int c = static_cast<int>((i / inner) % Cc);
+        const int r = static_cast<int>(i / (static_cast<size_t>(inner) * Cc));
+        dst[(static_cast<size_t>(rmap[r]) * pC + cmap[c]) * inner + k] = src[i];
+    }
+}
+
 __global__ void i64_to_i32_kernel(const long long* in, int* out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = static_cast<int>(in[i]);
@@ -205,9 +217,14 @@ using namespace ndiff;
 struct ndiff_engine {
     ndiff_config cfg{};
     int num_sms = 148;
-    int B = 0, H = 0, W = 0, dim = 0;
+    int B = 0, H = 0, W = 0;
+    int dim = 0;        // PHYSICAL base width the kernels run at (64); every channel count below is a multiple of it
+    int dim_real = 0;   // the model's `dim` (args.dim): 64, or smaller (the shipped checkpoint: 48) embedded with zero padding
+    float real_frac = 1.0f;   // dim_real / dim: live fraction of every GroupNorm group / LayerNorm row
     bool finalized = false, cond_set = false, plan_built = false;
-    std::map<std::string, Param> params;
+    std::map<std::string, Param> params;          // as loaded: the reference's state_dict, logical shapes
+    std::map<std::string, Param> phys;            // dim_real != dim: zero-padded, channel-permuted copies the kernels read
+    int* emb_maps = nullptr; size_t emb_maps_n = 0;   // device index tables of embed_params()
     std::vector<void*> owned;                       // every cudaMalloc'd pointer
     std::map<size_t, std::vector<void*>> pool_free;  // size -> free buffers
     std::map<void*, size_t> pool_size;
@@ -289,10 +306,12 @@ struct ndiff_engine {
         if (it != pool_size.end()) pool_free[it->second].push_back(it->first);
     }
     const Param* param(const std::string& name) const {
+        auto ip = phys.find(name);
+        if (ip != phys.end()) return &ip->second;
         auto it = params.find(name);
         return it == params.end() ? nullptr : &it->second;
     }
-    const float* pf(const std::string& name) const { return params.at(name).dev; }
+    const float* pf(const std::string& name) const { return param(name)->dev; }
 };
 
 namespace {
@@ -330,23 +349,23 @@ int pack_linear(ndiff_engine* e, const std::string& name, int N, int K, cudaStre
     return 0;
 }
 
-struct RbSpec { std::string name; int cin, cout, groups; bool pos; };
+struct RbSpec { std::string name; int cin, cout, groups; bool pos; int c0, c1; };   // cin = c0 + c1 (x, then the concatenated skip)
 
 std::vector<RbSpec> resblocks(int dim) {
     std::vector<RbSpec> v;
     const int d[5] = {dim, dim, dim * 2, dim * 4, dim * 8};
-    v.push_back({"shot_time", dim, dim, 2, false});
-    v.push_back({"pos_block1", dim, dim, 2, true});
+    v.push_back({"shot_time", dim, dim, 2, false, dim, 0});
+    v.push_back({"pos_block1", dim, dim, 2, true, dim, 0});
     for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 2; ++j) v.push_back({"downs." + std::to_string(i) + "." + std::to_string(j), d[i], d[i], 8, false});
-    v.push_back({"mid_block1", d[4], d[4], 8, false});
-    v.push_back({"mid_block2", d[4], d[4], 8, false});
+        for (int j = 0; j < 2; ++j) v.push_back({"downs." + std::to_string(i) + "." + std::to_string(j), d[i], d[i], 8, false, d[i], 0});
+    v.push_back({"mid_block1", d[4], d[4], 8, false, d[4], 0});
+    v.push_back({"mid_block2", d[4], d[4], 8, false, d[4], 0});
     for (int i = 0; i < 4; ++i) {
         const int co = d[4 - i], ci = d[3 - i];
-        for (int j = 0; j < 2; ++j) v.push_back({"ups." + std::to_string(i) + "." + std::to_string(j), co + ci, co, 8, false});
+        for (int j = 0; j < 2; ++j) v.push_back({"ups." + std::to_string(i) + "." + std::to_string(j), co + ci, co, 8, false, co, ci});
     }
-    v.push_back({"pos_block2", dim, dim, 2, true});
-    v.push_back({"final_res_block", dim * 2, dim, 8, false});
+    v.push_back({"pos_block2", dim, dim, 2, true, dim, 0});
+    v.push_back({"final_res_block", dim * 2, dim, 8, false, dim, dim});
     return v;
 }
 
@@ -360,8 +379,75 @@ std::vector<AttnSpec> attnblocks(int dim) {
     return v;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Models narrower than the kernels' 64-channel base (the shipped checkpoint: --dim 48, script.sh:10; channels 48/96/192/384,
+// GroupNorm groups of 6/12/24/48): every tensor with C live channels is laid out in C' = C * 64 / dim PHYSICAL channels as eight
+// slots of (C/8 live + zero padding) — slot = GroupNorm group of the 8-group blocks, and four consecutive slots = one group of
+// the 2-group blocks, so group boundaries stay powers of two in physical channels.  Weights are embedded once per load into
+// zero-initialised physical tensors (rows = permuted output channels, columns = permuted input channels of each concatenated
+// source); padding rows / biases / gammas are 0, so padded channels are exactly 0 everywhere and the network is, physically, the
+// dim = 64 network.  Only the element COUNT of the normalisations changes (real_frac).  Cost: the padded MACs are executed.
+// ------------------------------------------------------------------------------------------------------------
+struct EmbedSpec {
+    std::string name;
+    std::vector<int64_t> lshape, pshape;      // logical (state_dict) and physical shapes
+    std::vector<int> rmap, cmap;              // logical row / column -> physical row / column
+};
+
+struct EmbedBuilder {
+    int dim, base;                             // live and physical base width
+    std::vector<EmbedSpec> specs;
+    int P(int C) const { return C / dim * base; }                       // physical width of a C-channel tensor
+    std::vector<int> ident(int n) const { std::vector<int> m(n); for (int i = 0; i < n; ++i) m[i] = i; return m; }
+    std::vector<int> perm(int C) const {      // eight slots of C/8 live channels inside P(C)/8 physical ones
+        std::vector<int> m(C);
+        const int rs = C / 8, ps = P(C) / 8;
+        for (int c = 0; c < C; ++c) m[c] = (c / rs) * ps + c % rs;
+        return m;
+    }
+    std::vector<int> cat(int c0, int c1) const {   // [x | skip]: each source in its own layout, skip after ALL of x's physical channels
+        std::vector<int> m = perm(c0);
+        if (c1 > 0) for (int v : perm(c1)) m.push_back(P(c0) + v);
+        return m;
+    }
+    std::vector<int> scale_shift(int C) const {    // [scale C | shift C]
+        std::vector<int> m = perm(C);
+        for (int v : perm(C)) m.push_back(P(C) + v);
+        return m;
+    }
+    std::vector<int> s2d(int C) const {            // input channel c * 4 + p1 * 2 + p2 (Diffusion_arch.py:78-82)
+        std::vector<int> m(4 * C), pm = perm(C);
+        for (int c = 0; c < C; ++c) for (int t = 0; t < 4; ++t) m[c * 4 + t] = pm[c] * 4 + t;
+        return m;
+    }
+    void mat(const std::string& name, std::vector<int> rm, int pR, std::vector<int> cm, int pC, int kh = 0, int kw = 0) {
+        EmbedSpec sp;
+        sp.name = name;
+        sp.lshape = {static_cast<int64_t>(rm.size()), static_cast<int64_t>(cm.size())};
+        sp.pshape = {pR, pC};
+        if (kh > 0) { sp.lshape.push_back(kh); sp.lshape.push_back(kw); sp.pshape.push_back(kh); sp.pshape.push_back(kw); }
+        sp.rmap = std::move(rm); sp.cmap = std::move(cm);
+        specs.push_back(std::move(sp));
+    }
+    void vec(const std::string& name, std::vector<int> rm, int pR) {
+        EmbedSpec sp;
+        sp.name = name;
+        sp.lshape = {static_cast<int64_t>(rm.size())};
+        sp.pshape = {pR};
+        sp.rmap = std::move(rm); sp.cmap = {0};
+        specs.push_back(std::move(sp));
+    }
+    void conv(const std::string& n, int co, std::vector<int> cm, int pCin, int k) {
+        mat(n + ".weight", perm(co), P(co), std::move(cm), pCin, k, k);
+        vec(n + ".bias", perm(co), P(co));
+    }
+};
+
+int embed_params(ndiff_engine* e, cudaStream_t s);
+
 int finalize(ndiff_engine* e, cudaStream_t s) {
-    const int dim = e->dim, td = dim * 4;
+    if (e->dim_real != e->dim && embed_params(e, s)) return 1;
+    const int dim = e->dim, td = e->dim_real * 4;      // channel counts are physical; the time vector keeps its logical width
     const int d[5] = {dim, dim, dim * 2, dim * 4, dim * 8};
     // --- convolution / GEMM weights -> bf16 [Cout][cblk][tap][64]
     for (const RbSpec& rb : resblocks(dim)) {
@@ -474,7 +560,7 @@ int finalize(ndiff_engine* e, cudaStream_t s) {
     if (check_shape(e, "final_conv.weight", {4, dim, 1, 1}) || check_shape(e, "final_conv.bias", {4})) return 1;
     if (check_shape(e, "init_conv.weight", {dim, 4, 7, 7}) || check_shape(e, "init_conv.bias", {dim})) return 1;
     if (check_shape(e, "iso_embed.weight", {100, 16})) return 1;
-    if (check_shape(e, "time_mlp.1.weight", {td, dim}) || check_shape(e, "time_mlp.1.bias", {td})) return 1;
+    if (check_shape(e, "time_mlp.1.weight", {td, e->dim_real}) || check_shape(e, "time_mlp.1.bias", {td})) return 1;
     if (check_shape(e, "time_mlp.3.weight", {td, td}) || check_shape(e, "time_mlp.3.bias", {td})) return 1;
     if (check_shape(e, "pos_enc.weights.weight", {8, 2, 1, 1}) || check_shape(e, "pos_enc.weights.bias", {8})) return 1;
     if (check_shape(e, "pos_mlp.fc1.weight", {16, 24, 1, 1}) || check_shape(e, "pos_mlp.fc1.bias", {16})) return 1;
@@ -517,6 +603,92 @@ int finalize(ndiff_engine* e, cudaStream_t s) {
     for (const AttnSpec& ab : attnblocks(dim)) { e->cv_off[ab.name] = e->cv_total; e->cv_total += ab.C; }
     if (!e->cvec && e->alloc(&e->cvec, static_cast<size_t>(e->B) * e->cv_total)) return 1;
     e->finalized = true;
+    return 0;
+}
+
+int embed_params(ndiff_engine* e, cudaStream_t s) {
+    EmbedBuilder b{e->dim_real, e->dim, {}};
+    const int dim = e->dim_real, td = dim * 4;
+    const int d[5] = {dim, dim, dim * 2, dim * 4, dim * 8};
+    b.mat("init_conv.weight", b.perm(dim), b.P(dim), b.ident(4), 4, 7, 7);
+    b.vec("init_conv.bias", b.perm(dim), b.P(dim));
+    for (const RbSpec& rb : resblocks(dim)) {
+        b.conv(rb.name + ".block1.proj", rb.cout, b.cat(rb.c0, rb.c1), b.P(rb.c0) + (rb.c1 ? b.P(rb.c1) : 0), 3);
+        b.conv(rb.name + ".block2.proj", rb.cout, b.perm(rb.cout), b.P(rb.cout), 3);
+        if (rb.cin != rb.cout) b.conv(rb.name + ".res_conv", rb.cout, b.cat(rb.c0, rb.c1), b.P(rb.c0) + (rb.c1 ? b.P(rb.c1) : 0), 1);
+        for (const char* blk : {".block1.norm", ".block2.norm"}) {
+            b.vec(rb.name + blk + ".weight", b.perm(rb.cout), b.P(rb.cout));
+            b.vec(rb.name + blk + ".bias", b.perm(rb.cout), b.P(rb.cout));
+        }
+        // (scale, shift) head: Linear(time_dim, 2C) on the LOGICAL time vector, or conv1x1(8 -> 2C) of pos_emb
+        if (rb.pos) b.mat(rb.name + ".mlp.1.weight", b.scale_shift(rb.cout), 2 * b.P(rb.cout), b.ident(8), 8, 1, 1);
+        else b.mat(rb.name + ".mlp.1.weight", b.scale_shift(rb.cout), 2 * b.P(rb.cout), b.ident(td), td);
+        b.vec(rb.name + ".mlp.1.bias", b.scale_shift(rb.cout), 2 * b.P(rb.cout));
+    }
+    for (const AttnSpec& ab : attnblocks(dim)) {
+        const int C = ab.C, pC = b.P(C);
+        b.mat(ab.name + ".ff.net.0.0.weight", b.ident(2 * C), 2 * pC, b.perm(C), pC);      // hidden units: first 2C of 2C'
+        b.vec(ab.name + ".ff.net.0.0.bias", b.ident(2 * C), 2 * pC);
+        b.mat(ab.name + ".ff.net.2.weight", b.perm(C), pC, b.ident(2 * C), 2 * pC);
+        b.vec(ab.name + ".ff.net.2.bias", b.perm(C), pC);
+        b.conv(ab.name + ".proj_out", C, b.perm(C), pC, 1);
+        b.mat(ab.name + ".attn.to_out.0.weight", b.perm(C), pC, b.ident(128), 128);
+        b.vec(ab.name + ".attn.to_out.0.bias", b.perm(C), pC);
+        b.vec(ab.name + ".norm2.weight", b.perm(C), pC);
+        b.vec(ab.name + ".norm2.bias", b.perm(C), pC);
+    }
+    for (int i = 0; i < 3; ++i) {
+        b.conv("downs." + std::to_string(i) + ".3.1", d[i + 1], b.s2d(d[i]), 4 * b.P(d[i]), 1);
+        b.conv("ups." + std::to_string(i) + ".3.1", d[3 - i], b.perm(d[4 - i]), b.P(d[4 - i]), 3);
+    }
+    b.conv("downs.3.3", d[4], b.perm(d[3]), b.P(d[3]), 3);
+    b.conv("ups.3.3", d[0], b.perm(d[1]), b.P(d[1]), 3);
+    b.conv("shot_mlp1.fc1", dim, b.ident(8), 8, 1);
+    for (const char* n : {"shot_mlp1.fc2", "shot_mlp2.fc1", "shot_mlp2.fc2", "shot_mlp3.fc1"}) b.conv(n, dim, b.perm(dim), b.P(dim), 1);
+    b.mat("shot_mlp3.fc2.weight", b.ident(4), 4, b.perm(dim), b.P(dim), 1, 1);
+    b.mat("final_conv.weight", b.ident(4), 4, b.perm(dim), b.P(dim), 1, 1);
+
+    // validate the logical shapes, allocate (once, zero-filled: the padding is never written) and scatter
+    size_t n_maps = 0;
+    for (const EmbedSpec& sp : b.specs) n_maps += sp.rmap.size() + sp.cmap.size();
+    std::vector<int> host(n_maps);
+    if (e->emb_maps_n != n_maps) {
+        e->release(e->emb_maps);
+        e->emb_maps = nullptr;
+        if (e->alloc(&e->emb_maps, n_maps)) return 1;
+        e->emb_maps_n = n_maps;
+    }
+    size_t at = 0;
+    std::vector<std::pair<size_t, size_t>> offs;
+    for (const EmbedSpec& sp : b.specs) {
+        offs.push_back({at, at + sp.rmap.size()});
+        std::copy(sp.rmap.begin(), sp.rmap.end(), host.begin() + at); at += sp.rmap.size();
+        std::copy(sp.cmap.begin(), sp.cmap.end(), host.begin() + at); at += sp.cmap.size();
+    }
+    NDIFF_CUDA_OK(cudaMemcpyAsync(e->emb_maps, host.data(), n_maps * sizeof(int), cudaMemcpyHostToDevice, s));
+    NDIFF_CUDA_OK(cudaStreamSynchronize(s));      // `host` is a local
+    for (size_t i = 0; i < b.specs.size(); ++i) {
+        const EmbedSpec& sp = b.specs[i];
+        auto it = e->params.find(sp.name);
+        NDIFF_REQUIRE(it != e->params.end(), "missing state_dict entry '" + sp.name + "'");
+        NDIFF_REQUIRE(it->second.shape == sp.lshape, "state_dict entry '" + sp.name + "' has an unexpected shape for dim = " +
+                                                         std::to_string(e->dim_real));
+        Param& pp = e->phys[sp.name];
+        size_t n = 1;
+        for (int64_t v : sp.pshape) n *= static_cast<size_t>(v);
+        if (!pp.dev) {
+            if (e->alloc(&pp.dev, n)) return 1;
+            NDIFF_CUDA_OK(cudaMemsetAsync(pp.dev, 0, n * sizeof(float), s));
+            pp.n = n;
+            pp.shape = sp.pshape;
+        }
+        const int R = static_cast<int>(sp.rmap.size()), Cc = static_cast<int>(sp.cmap.size());
+        const int inner = sp.lshape.size() == 4 ? static_cast<int>(sp.lshape[2] * sp.lshape[3]) : 1;
+        const int pC = sp.pshape.size() >= 2 ? static_cast<int>(sp.pshape[1]) : 1;
+        embed_param_kernel<<<64, 256, 0, s>>>(it->second.dev, pp.dev, R, Cc, inner, e->emb_maps + offs[i].first,
+                                              e->emb_maps + offs[i].second, pC);
+        NDIFF_CUDA_OK(cudaGetLastError());
+    }
     return 0;
 }
 
@@ -587,7 +759,7 @@ struct Builder {
         d.stats = stats; d.groups = groups;
         if (xf) {
             d.xf_stats = xf->stats; d.xf_gamma = xf->gamma; d.xf_beta = xf->beta; d.xf_ss = xf->ss; d.xf_ss_ld = xf->ss_ld;
-            d.xf_groups = xf->groups;
+            d.xf_groups = xf->groups; d.xf_real_frac = e->real_frac;
         }
         auto plan = std::make_shared<ConvGemmPlan>();
         if (conv_gemm_plan(d, e->num_sms, plan.get())) { err = 1; return out; }
@@ -613,7 +785,7 @@ struct Builder {
         if (ss_off >= 0) { g.ss = e->ss_cur; g.ss_ld = e->ss_total; g.ss_off = ss_off; }
         g.maps = maps;
         g.res1 = r1 ? r1->p : nullptr; g.res2 = r2 ? r2->p : nullptr;
-        g.B = e->B; g.HW = xio.H * xio.W; g.C = xio.C; g.G = groups; g.eps = 1e-5f;
+        g.B = e->B; g.HW = xio.H * xio.W; g.C = xio.C; g.G = groups; g.eps = 1e-5f; g.real_frac = e->real_frac;
         Op op; op.name = nname;
         op.bytes = 2.0 * e->B * g.HW * xio.C * (2 + (maps ? 2 : 0) + (r1 ? 1 : 0) + (r2 ? 1 : 0));
         op.fn = [g](cudaStream_t st) { return gn_apply_launch(g, st); };
@@ -681,7 +853,7 @@ struct Builder {
             d.prog = kProgAttn;
             d.npix = e->B * xin.H * xin.W; d.HW = xin.H * xin.W;
             d.x = xin.p; d.weights = e->chain_w.at(n); d.fvec = e->chain_f.at(n);
-            d.cvec = cv; d.cvec_ld = e->cv_total;
+            d.cvec = cv; d.cvec_ld = e->cv_total; d.real_frac = e->real_frac;
             d.out = o.p;
             auto plan = std::make_shared<ChainPlan>();
             if (pixel_chain_plan(d, e->num_sms, plan.get())) { err = 1; return o; }
@@ -702,7 +874,8 @@ struct Builder {
             const int B = e->B, HW = xin.H * xin.W, ld = e->cv_total;
             Op op; op.name = n + ".norm2";
             op.bytes = 2.0 * B * HW * C * 2;
-            op.fn = [=](cudaStream_t st) { return layernorm_launch(xp, cv, ld, g, bt, up, B, HW, C, st); };
+            const float rf = e->real_frac;
+            op.fn = [=](cudaStream_t st) { return layernorm_launch(xp, cv, ld, g, bt, up, B, HW, C, st, rf); };
             e->net_ops.push_back(op);
         }
         Act hh = conv(n + ".ff.net.0.0", kDirect, u, nullptr, 2 * C, kActGelu, nullptr, 0, nullptr, nullptr, 0);
@@ -739,7 +912,7 @@ int build_plan(ndiff_engine* e) {
         d.prog = kProgShot;
         d.npix = npix; d.HW = H * W;
         d.weights = e->chain_w.at("shot"); d.fvec = e->chain_f.at("shot");
-        d.cvec = e->cvec + e->cv_off.at("shot_attn"); d.cvec_ld = e->cv_total;
+        d.cvec = e->cvec + e->cv_off.at("shot_attn"); d.cvec_ld = e->cv_total; d.real_frac = e->real_frac;
         d.clean = e->clean; d.xt = e->x;
         d.out = s4.p; d.out2 = s1.p;
         auto plan = std::make_shared<ChainPlan>();
@@ -784,7 +957,7 @@ int build_plan(ndiff_engine* e) {
         td.npix = npix; td.HW = H * W;
         td.h2 = h2.p; td.r1 = dn.res.p; td.r2 = s1.p;
         td.weights = e->chain_w.at("tail"); td.fvec = e->chain_f.at("tail");
-        td.stats = dn.stats; td.gamma = e->pf(dn.norm + ".weight"); td.beta = e->pf(dn.norm + ".bias"); td.groups = dn.groups;
+        td.stats = dn.stats; td.gamma = e->pf(dn.norm + ".weight"); td.beta = e->pf(dn.norm + ".bias"); td.groups = dn.groups; td.real_frac = e->real_frac;
         td.out = e->sn;
         auto plan = std::make_shared<TailPlan>();
         if (tail_chain_plan(td, e->num_sms, plan.get())) return 1;
@@ -957,7 +1130,7 @@ int final_args(ndiff_engine* e, bool chain, FinalArgs* f) {
     f->npix = e->B * e->H * e->W; f->C = e->dim; f->HW = e->H * e->W;
     if (chain) { f->chain = e->chain; f->x = e->x; } else { f->v_out = e->v_out; }
     if (e->xf_stats) {
-        f->gn_stats = e->xf_stats; f->gn_res = e->xf_res.p; f->gn_G = e->xf_groups; f->gn_eps = 1e-5f;
+        f->gn_stats = e->xf_stats; f->gn_res = e->xf_res.p; f->gn_G = e->xf_groups; f->gn_eps = 1e-5f; f->gn_real_frac = e->real_frac;
         f->gn_gamma = e->pf(e->xf_norm + ".weight"); f->gn_beta = e->pf(e->xf_norm + ".bias");
     }
     return 0;
@@ -1014,7 +1187,7 @@ int ensure_time_bufs(ndiff_engine* e, int n) {
         e->release(e->t_buf); e->release(e->st_buf);
         e->t_buf = nullptr; e->st_buf = nullptr;
         if (e->alloc(&e->t_buf, n)) return 1;
-        if (e->alloc(&e->st_buf, static_cast<size_t>(n) * e->dim * 4)) return 1;
+        if (e->alloc(&e->st_buf, static_cast<size_t>(n) * e->dim_real * 4)) return 1;
         e->t_buf_n = n;
     }
     return 0;
@@ -1032,7 +1205,9 @@ const char* ndiff_last_error(void) { return get_error(); }
 
 int32_t ndiff_engine_create(const ndiff_config* cfg, ndiff_engine** out) {
     NDIFF_REQUIRE(cfg && out, "null argument");
-    NDIFF_REQUIRE(cfg->dim == 64, "this build implements dim = 64 (channel counts must be multiples of 64)");
+    NDIFF_REQUIRE(cfg->dim >= 8 && cfg->dim <= 64 && cfg->dim % 8 == 0,
+                  "dim must be a multiple of 8 up to 64 (64 runs natively; smaller widths such as the shipped checkpoint's 48 are "
+                  "embedded in the 64-channel kernels with zero padding)");
     NDIFF_REQUIRE(cfg->batch >= 1 && cfg->batch <= 256, "batch must be in [1, 256]");
     NDIFF_REQUIRE(cfg->height % 8 == 0 && cfg->width % 8 == 0 && cfg->height >= 8 && cfg->width >= 8,
                   "height/width must be multiples of 8 (Diffusion_arch.py:578)");
@@ -1049,7 +1224,8 @@ int32_t ndiff_engine_create(const ndiff_config* cfg, ndiff_engine** out) {
     NDIFF_CUDA_OK(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
     e->cfg = *cfg;
     e->num_sms = prop.multiProcessorCount;
-    e->B = cfg->batch; e->H = cfg->height; e->W = cfg->width; e->dim = cfg->dim;
+    e->B = cfg->batch; e->H = cfg->height; e->W = cfg->width;
+    e->dim_real = cfg->dim; e->dim = 64; e->real_frac = static_cast<float>(cfg->dim) / 64.0f;
     e->keep_all = (cfg->flags & NDIFF_FLAG_KEEP_ACTS) != 0;
     const size_t npix = static_cast<size_t>(e->B) * e->H * e->W;
     if (e->alloc(&e->clean, npix * 4) || e->alloc(&e->x, npix * 4) || e->alloc(&e->v_out, npix * 4)) return 1;
@@ -1159,9 +1335,9 @@ int32_t ndiff_forward(ndiff_engine* e, const float* x_dev, const int64_t* time_d
     if (nchw_to_nhwc4_launch(x_dev, e->x, e->B, HW, s)) return 1;
     i64_to_i32_kernel<<<1, 256, 0, s>>>(reinterpret_cast<const long long*>(time_dev), e->t_buf, e->B);
     NDIFF_CUDA_OK(cudaGetLastError());
-    if (time_mlp_launch(e->t_buf, 1, e->B, e->dim, e->pf("time_mlp.1.weight"), e->pf("time_mlp.1.bias"),
+    if (time_mlp_launch(e->t_buf, 1, e->B, e->dim_real, e->pf("time_mlp.1.weight"), e->pf("time_mlp.1.bias"),
                         e->pf("time_mlp.3.weight"), e->pf("time_mlp.3.bias"), e->st_buf, s)) return 1;
-    if (rows_gemv_launch(e->ss_w, e->ss_b, e->st_buf, e->ss_cur, e->B, e->ss_total, e->dim * 4, s)) return 1;
+    if (rows_gemv_launch(e->ss_w, e->ss_b, e->st_buf, e->ss_cur, e->B, e->ss_total, e->dim_real * 4, s)) return 1;
     if (e->cfg.flags & NDIFF_FLAG_NO_GRAPH) {
         if (run_net(e, s)) return 1;
         FinalArgs f; final_args(e, false, &f);
@@ -1200,9 +1376,9 @@ int32_t ndiff_chain_begin(ndiff_engine* e, const ndiff_step* steps_host, int32_t
     NDIFF_CUDA_OK(cudaMemcpyAsync(e->step_table, steps_host, sizeof(StepParams) * n_steps, cudaMemcpyHostToDevice, s));
     NDIFF_CUDA_OK(cudaMemcpyAsync(e->t_buf, ts.data(), sizeof(int) * n_steps, cudaMemcpyHostToDevice, s));
     NDIFF_CUDA_OK(cudaStreamSynchronize(s));   // ts / steps_host may be pageable stack memory
-    if (time_mlp_launch(e->t_buf, 1, n_steps, e->dim, e->pf("time_mlp.1.weight"), e->pf("time_mlp.1.bias"),
+    if (time_mlp_launch(e->t_buf, 1, n_steps, e->dim_real, e->pf("time_mlp.1.weight"), e->pf("time_mlp.1.bias"),
                         e->pf("time_mlp.3.weight"), e->pf("time_mlp.3.bias"), e->st_buf, s)) return 1;
-    if (rows_gemv_launch(e->ss_w, e->ss_b, e->st_buf, e->ss_table, n_steps, e->ss_total, e->dim * 4, s)) return 1;
+    if (rows_gemv_launch(e->ss_w, e->ss_b, e->st_buf, e->ss_table, n_steps, e->ss_total, e->dim_real * 4, s)) return 1;
     ChainState cs;
     memset(&cs, 0, sizeof(cs));
     cs.step = 0; cs.n_steps = n_steps; cs.seed = seed;

@@ -232,8 +232,9 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
                 sum += (y0 + y1) + (y2 + y3);
                 sq = fmaf(y0, y0, sq); sq = fmaf(y1, y1, sq); sq = fmaf(y2, y2, sq); sq = fmaf(y3, y3, sq);
             }
-            const float mean = sum * (1.0f / 64.0f);
-            const float rstd = rsqrtf(fmaxf(sq * (1.0f / 64.0f) - mean * mean, 0.f) + 1e-5f);
+            // (zero-padded layouts: y is exactly 0 on the padding, so both moments are sums over the live channels)
+            const float mean = sum * a.inv_c;
+            const float rstd = rsqrtf(fmaxf(sq * a.inv_c - mean * mean, 0.f) + 1e-5f);
             const float nb = -mean * rstd;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -425,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, 1) tail_chain_kernel(const __grid_co
                 tab_b0 = b_first; tab_b1 = b_last;
                 const int slot = r >> 6, c = r & 63, b = slot ? b_last : b_first;
                 const int g = c >> a.lgs;
-                const double inv_n = 1.0 / (static_cast<double>(a.HW) * (1 << a.lgs));
+                const double inv_n = 1.0 / (static_cast<double>(a.HW) * (1 << a.lgs) * a.real_frac);
                 const double s_ = static_cast<double>(static_cast<long long>(a.stats[(b * a.G + g) * 2])) * (1.0 / 16777216.0);
                 const double q_ = static_cast<double>(static_cast<long long>(a.stats[(b * a.G + g) * 2 + 1])) * (1.0 / 16777216.0);
                 const double meand = s_ * inv_n;
@@ -614,6 +615,8 @@ int pixel_chain_plan(const ChainDesc& d, int num_sms, ChainPlan* plan) {
     plan->prog = d.prog;
     a.npix = d.npix; a.HW = d.HW; a.n_tiles = (d.npix + kTile - 1) / kTile;
     a.fvec = d.fvec; a.cvec = d.cvec; a.cvec_ld = d.cvec_ld;
+    NDIFF_REQUIRE(d.real_frac > 0.f && d.real_frac <= 1.f, "pixel chain: live channel fraction must be in (0, 1]");
+    a.inv_c = 1.0f / (64.0f * d.real_frac);
     const uint64_t adims[2] = {64, static_cast<uint64_t>(d.npix)};
     const uint64_t astr[1] = {128};
     const uint32_t abox[2] = {64, kTile};
@@ -658,6 +661,8 @@ int tail_chain_plan(const TailDesc& d, int num_sms, TailPlan* plan) {
     NDIFF_REQUIRE(gs >= 8 && (gs & (gs - 1)) == 0, "tail chain: group size must be a power of two >= 8");
     a.npix = d.npix; a.HW = d.HW; a.n_tiles = (d.npix + kTile - 1) / kTile;
     a.fvec = d.fvec; a.stats = d.stats; a.gamma = d.gamma; a.beta = d.beta; a.G = d.groups; a.eps = 1e-5f;
+    NDIFF_REQUIRE(d.real_frac > 0.f && d.real_frac <= 1.f, "tail chain: live channel fraction must be in (0, 1]");
+    a.real_frac = d.real_frac;
     a.lgs = 0;
     while ((1 << a.lgs) < gs) ++a.lgs;
     a.out = reinterpret_cast<float4*>(d.out);

@@ -36,6 +36,7 @@ struct ChainArgs {
     const float* fvec;    // parameter block (see above)
     const float* cvec;    // collapsed cross-attention vector of this block, per sample: cvec[b * cvec_ld + c]
     int cvec_ld;
+    float inv_c;          // 1 / (live channels of the 64): LayerNorm's element count under zero-padded channel layouts
     const float4* clean;  // shot: fp32 NHWC4 clean image and chain state
     const float4* x;
 };
@@ -54,6 +55,7 @@ struct ChainDesc {
     const __nv_bfloat16* weights = nullptr; // blob
     const float* fvec = nullptr;
     const float* cvec = nullptr; int cvec_ld = 0;
+    float real_frac = 1.0f;                 // live fraction of the 64 channels (engine.cu "physical channels")
     const float* clean = nullptr; const float* xt = nullptr;   // shot inputs (fp32 NHWC4)
     __nv_bfloat16* out = nullptr;
     __nv_bfloat16* out2 = nullptr;
@@ -74,6 +76,7 @@ struct TailArgs {
     const unsigned long long* stats;    // [B][G][2] fixed-point sums of h2
     const float* gamma; const float* beta;
     int G, lgs; float eps;
+    float real_frac;                    // live fraction of every group's channels (statistics count)
     float4* out;                        // [npix] fp32 x 4
 };
 struct TailPlan { TailArgs args; int grid; int smem_bytes; };
@@ -82,6 +85,7 @@ struct TailDesc {
     const __nv_bfloat16* h2 = nullptr; const __nv_bfloat16* r1 = nullptr; const __nv_bfloat16* r2 = nullptr;
     const __nv_bfloat16* weights = nullptr; const float* fvec = nullptr;
     const unsigned long long* stats = nullptr; const float* gamma = nullptr; const float* beta = nullptr; int groups = 0;
+    float real_frac = 1.0f;
     float* out = nullptr;
 };
 int tail_chain_plan(const TailDesc& d, int num_sms, TailPlan* plan);

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(const GnApplyArgs 
     float A[8], Bc[8];
     {
         const int g = c0 / gs;
-        const double inv_n = 1.0 / (static_cast<double>(a.HW) * gs);
+        const double inv_n = 1.0 / (static_cast<double>(a.HW) * gs * (a.real_frac > 0.f ? a.real_frac : 1.0f));
         const double s = static_cast<double>(static_cast<long long>(a.stats[(b * a.G + g) * 2])) * (1.0 / 16777216.0);
         const double ss = static_cast<double>(static_cast<long long>(a.stats[(b * a.G + g) * 2 + 1])) * (1.0 / 16777216.0);
         const double meand = s * inv_n;
@@ -125,7 +125,7 @@ template <int VPL>
 __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ vec,
                                                         int vec_ld, const float* __restrict__ g,
                                                         const float* __restrict__ beta, bf16* __restrict__ out,
-                                                        int HW, int C, int L, size_t npix) {
+                                                        int HW, int C, int L, size_t npix, float real_frac) {
     pdl_trigger();
     pdl_wait();
     const int lane = threadIdx.x & 31;
@@ -140,7 +140,10 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
 #pragma unroll
         for (int k = 0; k < 8; ++k) { gg[j][k] = g[c + k]; bb[j][k] = beta[c + k]; }
     }
-    const float inv_c = 1.0f / static_cast<float>(C);
+    // zero-padded channel layouts: x + vec is exactly 0 on the padding, so the sum is that of the live channels; the centred
+    // squares pick up n_pad * mean^2 from the padding, which is taken out again
+    const float inv_c = 1.0f / (static_cast<float>(C) * real_frac);
+    const float n_pad = static_cast<float>(C) * (1.0f - real_frac);
     // kLnU pixels per lane group and iteration: all 16-byte loads are issued before the first reduction, so the shuffles and
     // the dependent arithmetic of one pixel overlap the memory latency of the others
     constexpr int kLnU = VPL == 1 ? 4 : 2;
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
 #pragma unroll
                 for (int k = 0; k < 8; ++k) { const float d = f[u][j][k] - mean; sq += d * d; }
             for (int o = L >> 1; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-            const float rstd = rsqrtf(sq * inv_c + 1e-5f);
+            const float rstd = rsqrtf(fmaxf(sq - n_pad * mean * mean, 0.f) * inv_c + 1e-5f);
             if (pixs[u] < npix) {
 #pragma unroll
                 for (int j = 0; j < VPL; ++j) {
@@ -476,7 +479,7 @@ __global__ void __launch_bounds__(256, 2) final64_kernel(const FinalArgs a) {
         if (kGn && static_cast<long long>(bimg) != cur_b) {
             cur_b = static_cast<long long>(bimg);
             const int gs = 64 / a.gn_G, g = (sub * 8) / gs;
-            const double inv_n = 1.0 / (static_cast<double>(a.HW) * gs);
+            const double inv_n = 1.0 / (static_cast<double>(a.HW) * gs * (a.gn_real_frac > 0.f ? a.gn_real_frac : 1.0f));
             const double s = static_cast<double>(static_cast<long long>(a.gn_stats[(bimg * a.gn_G + g) * 2])) * (1.0 / 16777216.0);
             const double ss = static_cast<double>(static_cast<long long>(a.gn_stats[(bimg * a.gn_G + g) * 2 + 1])) * (1.0 / 16777216.0);
             const double meand = s * inv_n;
@@ -801,7 +804,8 @@ int gn_apply_launch(const GnApplyArgs& a, cudaStream_t s) {
 }
 
 int layernorm_launch(const bf16* x, const float* vec, int vec_ld, const float* g, const float* beta, bf16* out, int B,
-                     int HW, int C, cudaStream_t s) {
+                     int HW, int C, cudaStream_t s, float real_frac) {
+    NDIFF_REQUIRE(real_frac > 0.f && real_frac <= 1.f, "LayerNorm: live channel fraction must be in (0, 1]");
     NDIFF_REQUIRE(C == 64 || C == 128 || C == 256 || C == 512, "LayerNorm: C must be 64, 128, 256 or 512");
     NDIFF_REQUIRE(vec_ld % 4 == 0, "LayerNorm: per-sample vector stride must keep 16-byte alignment");
     const size_t npix = static_cast<size_t>(B) * HW;
@@ -809,9 +813,9 @@ int layernorm_launch(const bf16* x, const float* vec, int vec_ld, const float* g
     const int ppw = 32 / L;
     const int grid = blocks_for(npix, 8 * ppw * 4, 148 * 8);      // (a grid-stride loop: any grid covers the tensor)
     if (C == 512)
-        NDIFF_CUDA_OK(launch_pdl(layernorm_kernel<2>, dim3(grid), dim3(256), 0, s, x, vec, vec_ld, g, beta, out, HW, C, L, npix));
+        NDIFF_CUDA_OK(launch_pdl(layernorm_kernel<2>, dim3(grid), dim3(256), 0, s, x, vec, vec_ld, g, beta, out, HW, C, L, npix, real_frac));
     else
-        NDIFF_CUDA_OK(launch_pdl(layernorm_kernel<1>, dim3(grid), dim3(256), 0, s, x, vec, vec_ld, g, beta, out, HW, C, L, npix));
+        NDIFF_CUDA_OK(launch_pdl(layernorm_kernel<1>, dim3(grid), dim3(256), 0, s, x, vec, vec_ld, g, beta, out, HW, C, L, npix, real_frac));
     NDIFF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -905,7 +909,7 @@ int time_mlp_launch(const int* t, int t_stride, int n, int dim, const float* w1,
 
 int rows_gemv_launch(const float* W, const float* bias, const float* in, float* out, int n, int rows, int K,
                      cudaStream_t s) {
-    NDIFF_REQUIRE(K % 128 == 0, "gemv: K must be a multiple of 128");
+    NDIFF_REQUIRE(K % 4 == 0, "gemv: K must be a multiple of 4 (float4 rows)");
     dim3 grid((rows + 7) / 8, n);
     rows_gemv_kernel<<<grid, 256, 0, s>>>(W, bias, in, out, rows, K);
     NDIFF_CUDA_OK(cudaGetLastError());

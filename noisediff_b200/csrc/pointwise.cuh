@@ -42,12 +42,16 @@ struct GnApplyArgs {
     const bf16* res1; const bf16* res2;            // optional residuals added after SiLU
     int B, HW, C, G;
     float eps;
+    float real_frac;                               // live fraction of every group's channels (zero-padded layouts, engine.cu
+                                                   // "physical channels"); 0 is read as 1.  Sums over the padding are 0, so
+                                                   // only the element COUNT of the statistics changes.
 };
 int gn_apply_launch(const GnApplyArgs& a, cudaStream_t s);
 
 // u = LayerNorm_C(x + vec[b]) * g + beta   (AttnBlock.norm2 on the collapsed attention; Diffusion_arch.py:438-439)
+// real_frac: live fraction of the C channels (the rest is zero padding that must not enter mean / variance); 1 = all.
 int layernorm_launch(const bf16* x, const float* vec, int vec_ld, const float* g, const float* beta, bf16* out, int B,
-                     int HW, int C, cudaStream_t s);
+                     int HW, int C, cudaStream_t s, float real_frac = 1.0f);
 
 // shot_mlp1.fc1 on cat[clean, x_t] (8 -> C) + GELU  (Diffusion_arch.py:598, Mlp :340-356)
 int shot_in_launch(const float* clean, const float* x, const float* w, const float* bias, bf16* out, int npix, int C,
@@ -74,6 +78,7 @@ struct FinalArgs {
     // GroupNorm-apply pass of final_res_block folded into this kernel.  gn_stats: that conv's fixed-point sums [B][G][2].
     const unsigned long long* gn_stats; const float* gn_gamma; const float* gn_beta; const bf16* gn_res;
     int gn_G; float gn_eps;
+    float gn_real_frac;                      // as GnApplyArgs::real_frac
     // optional (dim = 64): the shot-noise head was already evaluated by the shot-branch tail kernel — sn[pix] = shot_mlp3 output
     // INCLUDING its bias; sf / ws / bs are then unused.
     const float4* sn;

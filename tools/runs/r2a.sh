@@ -9,3 +9,5 @@ tail -3 $O/ws_test.log
 cat $O/base.json $O/ws1.json $O/ws2.json | cut -c1-300
 timeout 900 python -m pytest tests/test_gpu_fullshape.py -m gpu -x -q -s > $O/fullshape.log 2>&1; echo "fullshape rc=$?"
 tail -40 $O/fullshape.log
+timeout 600 python -m pytest tests/test_gpu_dim48.py -m gpu -q -s > $O/dim48.log 2>&1; echo "dim48 rc=$?"
+tail -60 $O/dim48.log
