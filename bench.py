@@ -197,6 +197,96 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_split(args, rank, local_rank, world):
+    """BASELINE configs[2]: a fixed list of --total-patches patches, split statically (contiguous slices, sizes differ by at most
+    one) over the ranks; every rank runs the FULL 1000-step chain of its slice in batches of --batch through the public
+    GaussianDiffusion.sample() with per-rank Philox seeds and no collective on the data path.  value = total patches / the slowest
+    rank's wall time (strong scaling: total work fixed as N grows)."""
+    import torch
+    import torch.distributed as dist
+    from types import SimpleNamespace
+    import noisediff_b200 as nd
+    from noisediff_b200 import tiles
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
+    torch.manual_seed(0)
+    net = nd.NoiseDiffNet(SimpleNamespace(dim=args.dim, cond_dim=4, inp_dim=4, self_condition=False, normalize_condition=False))
+    net = net.eval().requires_grad_(False).to(dev)
+    gd = nd.GaussianDiffusion(net, image_size=args.patch, timesteps=T_CHAIN, beta_schedule="sigmoid2", objective="pred_v").to(dev)
+    gd.micro_batch, gd.noise_source = args.batch, "philox"
+    mine = tiles.shard(args.total_patches, world, rank)
+    batches = [list(mine)[lo:lo + args.batch] for lo in range(0, len(mine), args.batch)]
+    # warm-up: engine creation, weight packing, graph capture (a short chain on the first batch's geometry)
+    warm = nd.GaussianDiffusion(net, image_size=args.patch, timesteps=8, beta_schedule="sigmoid2", objective="pred_v").to(dev)
+    warm.micro_batch, warm.noise_source = args.batch, "philox"
+    n0 = len(batches[0]) if batches else 0
+    if n0:
+        c = {k: v.to(dev) for k, v in tiles.synthetic_condition(n0, args.patch, seed=1, first_tile=mine[0]).items()}
+        warm.sample(batch_size=n0, condition=c)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    torch.manual_seed(4242 + rank)            # Philox base seeds come from the CPU generator: distinct per rank
+    out_std, finite = [], True
+    # synthetic inputs of the whole slice, generated ahead of the timed region into pinned host memory (the H2D copies are timed)
+    pinned = [{k: v.pin_memory() for k, v in tiles.synthetic_condition(len(part), args.patch, seed=1000 + part[0], first_tile=part[0]).items()}
+              for part in batches]
+    if world > 1:
+        dist.barrier()
+    with ClockSampler(local_rank) as clk:
+        t0 = time.perf_counter()
+        for part, cond_host in zip(batches, pinned):
+            cond = {k: v.to(dev, non_blocking=True) for k, v in cond_host.items()}
+            out = gd.sample(batch_size=len(part), condition=cond)
+            host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+            host.copy_(out, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            finite = finite and bool(torch.isfinite(host).all())
+            out_std.append(float(host.std()))
+        wall = time.perf_counter() - t0
+    tt = torch.tensor([wall], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    wall_max = float(tt.item())
+    fin = torch.tensor([1.0 if finite else 0.0], device=dev)
+    if world > 1:
+        dist.all_reduce(fin, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        eng = net.engine_for(min(args.batch, max(n0, 1)), args.patch, args.patch, dev)
+        n_steps_total = sum(1 for _ in batches) * T_CHAIN
+        line = {
+            "metric": METRIC, "value": args.total_patches / wall_max, "unit": UNIT, "n_gpus": world, "steps": n_steps_total,
+            "warmup": 8, "ms_per_step": wall_max * 1e3 / max(n_steps_total, 1), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[2]: {args.total_patches} patches of 4x{args.patch}x{args.patch} (dim={args.dim}), full "
+                                   f"1000-step DDPM chains, static split over {world} rank(s) in batches of {args.batch}, per-rank Philox "
+                                   f"seeds, no collective; wall clock incl. pinned H2D of every condition and D2H of every result",
+                       "total_patches": args.total_patches, "patches_rank0": len(mine), "batch": args.batch, "timesteps": T_CHAIN,
+                       "parallelism": f"independent shards x{world}, no collective"},
+            "e2e": {"value": args.total_patches / wall_max, "unit": UNIT,
+                    "h2d_bytes_per_step": args.batch * args.patch * args.patch * (4 + 2) * 4 / T_CHAIN,
+                    "d2h_bytes_per_step": args.batch * args.patch * args.patch * 4 * 4 / T_CHAIN, "wall_s": wall_max},
+            "gpu_launches": int(eng.launches_per_step * n_steps_total), "clocks": clk.summary(), "finite": bool(fin.item() > 0),
+            "out_std_rank0": out_std[:3],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -204,6 +294,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="patches per GPU")
+    ap.add_argument("--dim", type=int, default=64, help="model width (64 = BASELINE configs; 48 = the reference's shipped checkpoint)")
+    ap.add_argument("--patch", type=int, default=PATCH, help="crop size (256 = BASELINE configs; 512 = the reference's script.sh)")
+    ap.add_argument("--total-patches", type=int, default=0,
+                    help="BASELINE configs[2]: synthesise this many patches in total (e.g. 4096), split statically over the ranks, "
+                         "full 1000-step chains in batches of --batch; reports total patches / max rank wall time (strong scaling)")
     ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("NDIFF_MICRO_BATCH", "64")))
     ap.add_argument("--dump-layers", default=None, help="write the per-layer CUDA-event table (name, ms, flops) to this JSON file")
     ap.add_argument("--no-e2e", action="store_true")
@@ -215,6 +310,16 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    if args.total_patches > 0:
+        return run_split(args, rank, local_rank, world)
+    # FLOP model for other widths / crops: every 3x3 / 1x1 / token-linear layer is C x C (scales with (dim/64)^2), the 7x7 input
+    # conv is 4 x C (scales with dim/64); everything scales with the pixel count
+    fd, fp = args.dim / 64.0, (args.patch / 256.0) ** 2
+    global CONV3_FLOPS_DIRECT, CONV3_FLOPS_PER_PATCH_STEP, LIVE_FLOPS_PER_PATCH_STEP
+    CONV3_FLOPS_DIRECT *= fd * fd * fp
+    CONV3_FLOPS_PER_PATCH_STEP *= fd * fd * fp
+    LIVE_FLOPS_PER_PATCH_STEP = ((234.34e9 + 15.03e9 + 14.50e9) * fd * fd + 1.64e9 * fd) * fp
+    PATCH_ = args.patch
 
     import torch
     import torch.distributed as dist
@@ -245,14 +350,14 @@ def main():
     n_mb = (B + mb - 1) // mb
 
     torch.manual_seed(0)                                      # reference-identical random init (same RNG consumption)
-    net = nd.NoiseDiffNet(SimpleNamespace(dim=64, cond_dim=4, inp_dim=4, self_condition=False, normalize_condition=False))
+    net = nd.NoiseDiffNet(SimpleNamespace(dim=args.dim, cond_dim=4, inp_dim=4, self_condition=False, normalize_condition=False))
     net = net.eval().requires_grad_(False).to(dev)
-    gd = nd.GaussianDiffusion(net, image_size=PATCH, timesteps=T_CHAIN, beta_schedule="sigmoid2", objective="pred_v").to(dev)
+    gd = nd.GaussianDiffusion(net, image_size=PATCH_, timesteps=T_CHAIN, beta_schedule="sigmoid2", objective="pred_v").to(dev)
     gd.micro_batch, gd.noise_source = mb, "philox"
-    cond_cpu = tiles.synthetic_condition(B, PATCH, seed=1 + rank, first_tile=rank * B)
+    cond_cpu = tiles.synthetic_condition(B, PATCH_, seed=1 + rank, first_tile=rank * B)
     cond_pinned = {k: v.pin_memory() for k, v in cond_cpu.items()}
     steps = gd.ddpm_steps()
-    eng = net.engine_for(mb, PATCH, PATCH, dev)
+    eng = net.engine_for(mb, PATCH_, PATCH_, dev)
 
     # ---- device-resident timing: K reverse steps over the whole batch (n_mb micro-batches per step) -------------------
     conds = [{k: v[i * mb:(i + 1) * mb].to(dev) for k, v in cond_cpu.items()} for i in range(n_mb)]
@@ -305,6 +410,8 @@ def main():
                        "layers": [list(r) for r in rows]}, f)
     fam = families(rows)
     conv_ms, conv_fl, n_conv = fam["conv_gemm"]["ms"], fam["conv_gemm"]["flops"], fam["conv_gemm"]["n"]
+    executed_conv_fl = conv_fl
+    conv_fl *= fd * fd          # narrower models run zero-padded in the 64-channel kernels: count the reference's FLOPs, not the padding
     c3_ms = sum(t_ for n, t_, f, _ in rows if is_conv3(n, f))
     layers_ms = sum(r[1] for r in rows)
     achieved = conv_fl / (conv_ms * 1e-3) / 1e12
@@ -317,7 +424,8 @@ def main():
                 "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, all 3x3/1x1/2x2s2 launches of one step)",
                 "timing": "median of 7 in-step iterations, CUDA events between consecutive ops of the running chain step",
                 "launches_per_step": n_conv, "avg_launch_us": conv_ms * 1e3 / max(n_conv, 1),
-                "flops_per_launch_avg": conv_fl / max(n_conv, 1), "peak_source": peaks["source"],
+                "flops_per_launch_avg": conv_fl / max(n_conv, 1), "executed_flops_per_launch_avg": executed_conv_fl / max(n_conv, 1),
+                "peak_source": peaks["source"],
                 "frac_of_burst_peak": achieved / peaks["burst"], "burst_peak": peaks["burst"],
                 "conv3x3_frac_of_sustained_peak": CONV3_FLOPS_PER_PATCH_STEP * mb / (c3_ms * 1e-3) / 1e12 / peaks["tflops"],
                 "conv3x3_frac_of_burst_peak": CONV3_FLOPS_PER_PATCH_STEP * mb / (c3_ms * 1e-3) / 1e12 / peaks["burst"],
@@ -366,8 +474,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"NoiseDiffNet dim=64 random-init, DDPM T=1000 sigmoid2 pred_v, {B} patches of 4x256x256 per GPU "
-                                   f"(BASELINE configs[1]); one step = one reverse timestep over the batch in micro-batches of {mb}",
+            "config": {"workload": f"NoiseDiffNet dim={args.dim} random-init, DDPM T=1000 sigmoid2 pred_v, {B} patches of 4x{PATCH_}x{PATCH_} per GPU "
+                                   f"({'BASELINE configs[1]' if (args.dim, PATCH_, B) == (64, 256, 64) else 'NOT the BASELINE config: width / crop / batch overridden'}); one step = one reverse timestep over the batch in micro-batches of {mb}",
                        "batch_per_gpu": B, "micro_batch": mb, "timesteps": T_CHAIN, "parallelism": f"independent shards x{world}, no collective",
                        "l2": "per-step activation working set (GBs) far exceeds the 126 MB L2; no flush needed"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,

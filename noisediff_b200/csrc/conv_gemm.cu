@@ -58,12 +58,11 @@ constexpr int kUpBTaps = 4;                                              // kHal
 // here, in place on each activation stage between the TMA landing and the MMA: warps 2, 3, 12..15 rewrite the halo box in shared
 // memory (out-of-image pixels stay the TMA's zero fill = the conv's zero padding of the NORMALISED tensor), then hand the
 // stage to the MMA warp through xfA.  Same fp32 formulas and bf16 rounding as gn_apply_kernel, so results are bit-identical.
-// WS (EXPERIMENT, off unless NDIFF_EXPERIMENT_WS=1 [N = 64 kHalo2] or =2 [N = 64 and N = 128 kHalo2]): the two 128-pixel sub-tiles of a tile multiply the SAME
-// weight block, and the 64-output-channel layers are bound by the shared-memory reads of their operands (4 KB of A + 2 KB of B per
-// 32-cycle MMA).  tcgen05.mma.ws keeps B in a collector buffer, so sub-tile 1 reuses what sub-tile 0 loaded: 6 -> 5 KB per MMA,
-// the same saving as a cta_group::2 pair without the cluster.  Unmeasured: whether .ws issues at the full M = 128 rate and writes
-// the accumulator in the same lane = row layout is what the first run must show (tests/test_gpu_ops.py, halo2 cases, with the
-// environment variable set).
+// WS (the N = 64 kHalo2 kernels, default): the two 128-pixel sub-tiles of a tile multiply the SAME weight block, and the
+// 64-output-channel layers are bound by the shared-memory reads of their operands (4 KB of A + 2 KB of B per 32-cycle MMA).
+// tcgen05.mma.ws keeps B in a collector buffer, so sub-tile 1 reuses what sub-tile 0 loaded: 6 -> 5 KB per MMA, the same saving
+// as a cta_group::2 pair without the cluster.  Verified on B200 in round 2: same lane = row accumulator layout at M = 128
+// (bit-compatible results, tests/test_gpu_ops.py), -6 % on the plain 64 -> 64 layers, -2 % on the XF ones.
 template <int NT, int MODE, bool RES, bool XF = false, bool WS = false>
 __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmArgs a) {
     static_assert(!WS || MODE == kHalo2, "the weight-stationary form exists for the two-sub-tile (kHalo2) kernels only");
@@ -609,10 +608,12 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// EXPERIMENT switch, read once per process: NDIFF_EXPERIMENT_WS=1 -> the N = 64 kHalo2 kernels, =2 -> also the N = 128 ones.
-int ws_experiment_level() {
-    static const int level = [] { const char* v = getenv("NDIFF_EXPERIMENT_WS"); return (v && v[0] >= '1' && v[0] <= '2') ? v[0] - '0' : 0; }();
-    return level;
+// Weight-stationary MMA form of the N = 64 kHalo2 kernels: ON by default since round 2 (measured on B200, in-step: the plain
+// 64 -> 64 layers at 256^2 300 -> 282 us, the XF ones 395 -> 385 us, step 23.03 -> 22.74 ms; parity test
+// tests/test_gpu_ops.py::test_weight_stationary_conv_variant).  NDIFF_NO_WS=1 switches back to the plain form (A/B measurements).
+bool ws_enabled() {
+    static const bool on = [] { const char* v = getenv("NDIFF_NO_WS"); return !(v && v[0] == '1'); }();
+    return on;
 }
 
 int ilog2(int v) {
@@ -775,7 +776,7 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     a.out = d.out; a.out_ld = d.out_ld; a.act = d.act;
     a.bias2 = d.bias2; a.out2 = d.out2; a.out2_ld = d.out2_ld;
     plan->xf = d.xf_stats != nullptr;
-    plan->ws = d.mode == kHalo2 && ws_experiment_level() >= (NT == 64 ? 1 : 2);      // see the comment above conv_gemm_kernel
+    plan->ws = d.mode == kHalo2 && NT == 64 && ws_enabled();      // see the comment above conv_gemm_kernel
     if (plan->xf) {
         NDIFF_REQUIRE((d.mode == kHalo1 || d.mode == kHalo2) && d.C1 == 0 && d.C0 <= 512, "fused GroupNorm input: single-source 3x3 conv with C_in <= 512");
         NDIFF_REQUIRE(d.xf_gamma && d.xf_beta && d.xf_groups > 0 && d.C0 % d.xf_groups == 0, "fused GroupNorm input: bad arguments");
@@ -800,7 +801,7 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
 namespace {
 template <int NT, int MODE, bool RES>
 int launch_one(const ConvGemmPlan& plan, cudaStream_t stream) {
-    if constexpr (MODE == kHalo2) {
+    if constexpr (MODE == kHalo2 && NT == 64) {
         if (plan.ws) {
             if (plan.xf)
                 NDIFF_CUDA_OK(launch_pdl(conv_gemm_kernel<NT, MODE, RES, true, true>, dim3(plan.grid), dim3(kThreadsXf), plan.smem_bytes,
@@ -835,9 +836,8 @@ cudaError_t opt_in() {
         e = cudaFuncSetAttribute(conv_gemm_kernel<NT, MODE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
     }
-    // the experimental kernels are touched only when the experiment is switched on: a default run never references them
-    if constexpr (MODE == kHalo2) {
-      if (ws_experiment_level() >= (NT == 64 ? 1 : 2)) {
+    if constexpr (MODE == kHalo2 && NT == 64) {
+      {
         e = cudaFuncSetAttribute(conv_gemm_kernel<NT, MODE, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(conv_gemm_kernel<NT, MODE, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

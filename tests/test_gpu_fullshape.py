@@ -145,13 +145,17 @@ def test_free_running_T1000_chain_256(net, sd_gpu):
     assert rows[-1][0] == 1000 and rows[-1][1] <= 1e-2, rows[-1]
 
 
-def test_batch64_at_256_replicas_are_bit_identical_to_batch1(net):
-    """The bench geometry (one engine, 64 patches of 256^2): 64 copies of one condition / x_t must each reproduce the B = 1
-    engine bit for bit — per-sample math only, and GroupNorm sums are fixed-point integer atomics (order-free).  Together with
-    the B <= 4 oracle gates above this pins the B = 64 engine to the oracle."""
+def test_batch64_at_256_replicas_match_batch1_and_the_oracle(net, sd_gpu):
+    """The bench geometry (one engine, 64 patches of 256^2): 64 copies of one condition / x_t, three reverse steps.  Every
+    replica must (i) reproduce the B = 1 engine closely (10x inside the per-step gate) — not bit for bit: the conv epilogues keep GroupNorm partial
+    sums in fp32 registers across the tiles a CTA owns before the fixed-point atomics, and the tile -> CTA partition depends on
+    the batch — and (ii) sit inside the per-step gate against the oracle.  Together with the B <= 4 gates above this pins the
+    B = 64 engine."""
     S = 256
     gd = nd.GaussianDiffusion(net, image_size=S, timesteps=1000, beta_schedule="sigmoid2", objective="pred_v").cuda()
-    steps = [s for s in gd.ddpm_steps() if s.t in (600, 599, 598)]
+    ts = (600, 599, 598)
+    steps = [s for s in gd.ddpm_steps() if s.t in ts]
+    tab = O.schedule_tables("sigmoid2", 1000)
     g = torch.Generator(device="cuda").manual_seed(90)
     cond1 = distinct_condition(1, S, S, seed=91)
     x = torch.randn(1, 4, S, S, generator=g, device="cuda")
@@ -166,9 +170,18 @@ def test_batch64_at_256_replicas_are_bit_identical_to_batch1(net):
         outs[B] = eng.chain_read().clone()
         torch.cuda.synchronize()
         net.release_engines()
+    with fp32_oracle_on_gpu():
+        ref = x
+        for i, t in enumerate(ts):
+            out = O.net_forward(sd_gpu, ref, torch.full((1,), t, dtype=torch.long, device="cuda"), cond1)
+            ref, _ = O.ddpm_step(tab, "pred_v", ref, t, out, z[i])
     assert torch.isfinite(outs[64]).all()
-    for b in range(64):
-        assert torch.equal(outs[64][b], outs[1][0]), f"sample {b} of the 64-patch engine differs from the single-patch engine"
+    vs_b1 = [rel_l2(outs[64][b], outs[1][0]) for b in range(64)]
+    vs_ref = [rel_l2(outs[64][b], ref[0]) for b in range(64)]
+    print(f"64 replicas vs the B=1 engine: max rel-L2 {max(vs_b1):.2e}; vs the oracle after 3 steps: max {max(vs_ref):.2e} "
+          f"(B=1 engine vs the oracle: {rel_l2(outs[1][0], ref[0]):.2e})")
+    assert max(vs_b1) <= 2e-4, max(vs_b1)       # a last-bit change of a GroupNorm statistic flips a few bf16 roundings downstream
+    assert max(vs_ref) <= 2e-3, max(vs_ref)
 
 
 def philox_normal(n_pix, seed, stream_id):
