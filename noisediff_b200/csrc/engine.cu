@@ -17,10 +17,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/noisediff_b200.h"
-#include "conv_gemm.cuh"
-#include "pointwise.cuh"
-#include "pixel_chain.cuh"
+#include "engine_internal.cuh"
 
 namespace ndiff {
 
@@ -30,26 +27,6 @@ void set_error(const std::string& msg) { g_error = msg; }
 const char* get_error() { return g_error.c_str(); }
 
 namespace {
-
-struct Param {
-    std::vector<int64_t> shape;
-    float* dev = nullptr;
-    size_t n = 0;
-};
-
-struct Act {
-    bf16* p = nullptr;
-    int C = 0, H = 0, W = 0;
-};
-
-struct Op {
-    std::string name;
-    std::function<int(cudaStream_t)> fn;
-    double flops = 0.0;
-    double bytes = 0.0;   // algorithmic HBM bytes: every input read once + every output written once (bf16 activations)
-    int launches = 1;
-    bool chain = false;   // fused per-pixel chain (its FLOPs are not convolution FLOPs)
-};
 
 __global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int Cout, int Cin, int KH,
                                    int KW, int s2d) {
@@ -212,107 +189,37 @@ __global__ void __launch_bounds__(256) chain_step_begin_kernel(ChainState* chain
 }  // namespace
 }  // namespace ndiff
 
+namespace ndiff {
+
+std::vector<RbSpec> resblocks(int dim) {
+    std::vector<RbSpec> v;
+    const int d[5] = {dim, dim, dim * 2, dim * 4, dim * 8};
+    v.push_back({"shot_time", dim, dim, 2, false, dim, 0});
+    v.push_back({"pos_block1", dim, dim, 2, true, dim, 0});
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 2; ++j) v.push_back({"downs." + std::to_string(i) + "." + std::to_string(j), d[i], d[i], 8, false, d[i], 0});
+    v.push_back({"mid_block1", d[4], d[4], 8, false, d[4], 0});
+    v.push_back({"mid_block2", d[4], d[4], 8, false, d[4], 0});
+    for (int i = 0; i < 4; ++i) {
+        const int co = d[4 - i], ci = d[3 - i];
+        for (int j = 0; j < 2; ++j) v.push_back({"ups." + std::to_string(i) + "." + std::to_string(j), co + ci, co, 8, false, co, ci});
+    }
+    v.push_back({"pos_block2", dim, dim, 2, true, dim, 0});
+    v.push_back({"final_res_block", dim * 2, dim, 8, false, dim, dim});
+    return v;
+}
+
+std::vector<AttnSpec> attnblocks(int dim) {
+    std::vector<AttnSpec> v;
+    const int d[5] = {dim, dim, dim * 2, dim * 4, dim * 8};
+    v.push_back({"shot_attn", dim});
+    for (int i = 0; i < 4; ++i) v.push_back({"downs." + std::to_string(i) + ".2", d[i]});
+    for (int i = 0; i < 4; ++i) v.push_back({"ups." + std::to_string(i) + ".2", d[4 - i]});
+    return v;
+}
+}  // namespace ndiff
+
 using namespace ndiff;
-
-struct ndiff_engine {
-    ndiff_config cfg{};
-    int num_sms = 148;
-    int B = 0, H = 0, W = 0;
-    int dim = 0;        // PHYSICAL base width the kernels run at (64); every channel count below is a multiple of it
-    int dim_real = 0;   // the model's `dim` (args.dim): 64, or smaller (the shipped checkpoint: 48) embedded with zero padding
-    float real_frac = 1.0f;   // dim_real / dim: live fraction of every GroupNorm group / LayerNorm row
-    bool finalized = false, cond_set = false, plan_built = false;
-    std::map<std::string, Param> params;          // as loaded: the reference's state_dict, logical shapes
-    std::map<std::string, Param> phys;            // dim_real != dim: zero-padded, channel-permuted copies the kernels read
-    int* emb_maps = nullptr; size_t emb_maps_n = 0;   // device index tables of embed_params()
-    std::vector<void*> owned;                       // every cudaMalloc'd pointer
-    std::map<size_t, std::vector<void*>> pool_free;  // size -> free buffers
-    std::map<void*, size_t> pool_size;
-    bool keep_all = false;
-
-    std::map<std::string, bf16*> packed;
-    std::map<std::string, bf16*> chain_w;      // fused per-pixel chains: weight blob / parameter block per chain
-    std::map<std::string, float*> chain_f;
-    float* init_w = nullptr;
-    float* fold_tmp = nullptr;       // scratch for folding LayerNorm affines into chain weights
-    bf16* init_w_tc = nullptr; bf16* xpad = nullptr;
-    // time path
-    float* ss_w = nullptr; float* ss_b = nullptr; int ss_total = 0;
-    std::map<std::string, int> ss_off;
-    float* st_buf = nullptr;       // [max(B, n_steps)][4 dim]
-    float* ss_cur = nullptr;       // [B][ss_total]
-    float* ss_table = nullptr; int ss_table_rows = 0;
-    int* t_buf = nullptr; int t_buf_n = 0;
-    // iso path
-    float* cvec = nullptr; int cv_total = 0;
-    std::map<std::string, int> cv_off;
-    // condition / state
-    float* clean = nullptr;        // fp32 NHWC4
-    bf16* map1 = nullptr; bf16* map2 = nullptr;
-    float* pos_emb = nullptr;
-    float* x = nullptr;            // fp32 NHWC4 chain state / network input
-    float* v_out = nullptr;        // fp32 NHWC4 network output
-    unsigned long long* stats = nullptr; int n_stats = 0; size_t stats_bytes = 0;
-    ChainState* chain = nullptr;
-    StepParams* step_table = nullptr; int n_steps = 0; int steps_done = 0;
-    // plan
-    std::vector<Op> net_ops;
-    std::map<std::string, Act> named;
-    Act xf{}, sf{};
-    // final_res_block.block2.norm folded into the heads kernel (FinalArgs::gn_*): xf is then the raw block2 conv output
-    const unsigned long long* xf_stats = nullptr; Act xf_res{}; int xf_groups = 0; std::string xf_norm;
-    float* sn = nullptr;           // fp32 [npix][4] shot-noise image written by the fused shot-branch tail (pixel_chain.cuh), or unused
-    bool tail_fused = false;
-    cudaGraphExec_t step_exec = nullptr, fwd_exec = nullptr;
-    cudaStream_t cap_stream = nullptr;
-    double conv_flops = 0.0;
-
-    ~ndiff_engine() {
-        if (step_exec) cudaGraphExecDestroy(step_exec);
-        if (fwd_exec) cudaGraphExecDestroy(fwd_exec);
-        if (cap_stream) cudaStreamDestroy(cap_stream);
-        for (void* p : owned) cudaFree(p);
-    }
-
-    template <typename T>
-    int alloc(T** out, size_t count) {
-        void* p = nullptr;
-        NDIFF_CUDA_OK(cudaMalloc(&p, count * sizeof(T) ? count * sizeof(T) : 16));
-        owned.push_back(p);
-        *out = static_cast<T*>(p);
-        return 0;
-    }
-    // frees a buffer obtained from alloc() (regrown tables / resized parameters must not pile up until engine destroy)
-    void release(void* p) {
-        if (!p) return;
-        auto it = std::find(owned.begin(), owned.end(), p);
-        if (it != owned.end()) { owned.erase(it); cudaFree(p); }
-    }
-    bf16* pool_get(size_t elems) {
-        const size_t bytes = elems * sizeof(bf16);
-        auto& fl = pool_free[bytes];
-        if (!fl.empty() && !keep_all) {
-            void* p = fl.back();
-            fl.pop_back();
-            return static_cast<bf16*>(p);
-        }
-        bf16* p = nullptr;
-        if (alloc(&p, elems)) return nullptr;
-        pool_size[p] = bytes;
-        return p;
-    }
-    void pool_put(const void* p) {
-        auto it = pool_size.find(const_cast<void*>(p));
-        if (it != pool_size.end()) pool_free[it->second].push_back(it->first);
-    }
-    const Param* param(const std::string& name) const {
-        auto ip = phys.find(name);
-        if (ip != phys.end()) return &ip->second;
-        auto it = params.find(name);
-        return it == params.end() ? nullptr : &it->second;
-    }
-    const float* pf(const std::string& name) const { return param(name)->dev; }
-};
 
 namespace {
 
@@ -347,36 +254,6 @@ int pack_linear(ndiff_engine* e, const std::string& name, int N, int K, cudaStre
     NDIFF_CUDA_OK(cudaGetLastError());
     e->packed[name] = dst;
     return 0;
-}
-
-struct RbSpec { std::string name; int cin, cout, groups; bool pos; int c0, c1; };   // cin = c0 + c1 (x, then the concatenated skip)
-
-std::vector<RbSpec> resblocks(int dim) {
-    std::vector<RbSpec> v;
-    const int d[5] = {dim, dim, dim * 2, dim * 4, dim * 8};
-    v.push_back({"shot_time", dim, dim, 2, false, dim, 0});
-    v.push_back({"pos_block1", dim, dim, 2, true, dim, 0});
-    for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 2; ++j) v.push_back({"downs." + std::to_string(i) + "." + std::to_string(j), d[i], d[i], 8, false, d[i], 0});
-    v.push_back({"mid_block1", d[4], d[4], 8, false, d[4], 0});
-    v.push_back({"mid_block2", d[4], d[4], 8, false, d[4], 0});
-    for (int i = 0; i < 4; ++i) {
-        const int co = d[4 - i], ci = d[3 - i];
-        for (int j = 0; j < 2; ++j) v.push_back({"ups." + std::to_string(i) + "." + std::to_string(j), co + ci, co, 8, false, co, ci});
-    }
-    v.push_back({"pos_block2", dim, dim, 2, true, dim, 0});
-    v.push_back({"final_res_block", dim * 2, dim, 8, false, dim, dim});
-    return v;
-}
-
-struct AttnSpec { std::string name; int C; };
-std::vector<AttnSpec> attnblocks(int dim) {
-    std::vector<AttnSpec> v;
-    const int d[5] = {dim, dim, dim * 2, dim * 4, dim * 8};
-    v.push_back({"shot_attn", dim});
-    for (int i = 0; i < 4; ++i) v.push_back({"downs." + std::to_string(i) + ".2", d[i]});
-    for (int i = 0; i < 4; ++i) v.push_back({"ups." + std::to_string(i) + ".2", d[4 - i]});
-    return v;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1167,21 +1044,12 @@ int capture(ndiff_engine* e, bool step, cudaGraphExec_t* exec, cudaStream_t user
     return 0;
 }
 
-cudaStream_t as_stream(void* p) { return static_cast<cudaStream_t>(p); }
+}  // namespace
 
-// Entry points run on the engine's device and put the caller's current device back on return: a model on cuda:1 must not
-// silently switch the process (PyTorch's notion of the current device included) away from cuda:0.
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-        if (prev != dev) cudaSetDevice(dev); else prev = -1;
-    }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
-    DeviceGuard(const DeviceGuard&) = delete;
-    DeviceGuard& operator=(const DeviceGuard&) = delete;
-};
-
+// ================================================================================================================
+// C ABI
+// ================================================================================================================
+namespace {
 int ensure_time_bufs(ndiff_engine* e, int n) {
     if (n > e->t_buf_n) {
         e->release(e->t_buf); e->release(e->st_buf);
@@ -1192,12 +1060,16 @@ int ensure_time_bufs(ndiff_engine* e, int n) {
     }
     return 0;
 }
-
 }  // namespace
 
-// ================================================================================================================
-// C ABI
-// ================================================================================================================
+namespace ndiff {
+int engine_finalize(ndiff_engine* e, cudaStream_t s) {
+    if (finalize(e, s)) return 1;
+    if (!e->plan_built && !e->skip_plan && build_plan(e)) return 1;
+    return 0;
+}
+}  // namespace ndiff
+
 extern "C" {
 
 int32_t ndiff_abi_version(void) { return NDIFF_ABI_VERSION; }
@@ -1291,8 +1163,7 @@ int32_t ndiff_finalize_params(ndiff_engine* e, void* stream) {
     DeviceGuard dev_guard(e->cfg.device);
     // Packed buffers and fp32 parameter storage keep their addresses across reloads, so the layer plan and the
     // captured graphs stay valid; only the first call builds them.
-    if (finalize(e, as_stream(stream))) return 1;
-    if (!e->plan_built && build_plan(e)) return 1;
+    if (engine_finalize(e, as_stream(stream))) return 1;
     NDIFF_CUDA_OK(cudaStreamSynchronize(as_stream(stream)));
     return 0;
 }
