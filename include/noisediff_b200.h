@@ -175,6 +175,48 @@ NDIFF_API int32_t ndiff_op_pixel_chain(int32_t prog, int32_t npix, int32_t HW, c
                              const float* xt_nhwc4, const void* weights_blob, const float* fvec, const float* cvec,
                              int32_t cvec_ld, void* out, void* out2, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------------
+ * Training step.  Replaces, for one batch: GaussianDiffusion.p_losses -> NoiseDiffNet.forward with per-sample t
+ * (models/denoising_diffusion_pytorch.py:481-531), loss.backward(), torch.optim.Adam.step() and the EMA lerp
+ * (models/trainer_diffusion.py:63-69,92,176-191).  The host computes q_sample / the regression target / the loss weights (three
+ * elementwise lines on its own tensors) and owns the schedule (cosine LR, EMA warm-up); gradients are exposed as ONE flat fp32
+ * buffer so that data-parallel ranks all-reduce it with a single NCCL call before the Adam step.
+ *   create   : batch / crop / device as ndiff_engine_create (dim = 64).  ndiff_trainer_engine() is the embedded engine: load the
+ *              state_dict into it with ndiff_load_param[_async], then ndiff_trainer_finalize (flattens the parameters, packs
+ *              the weights, builds forward + backward plans), and call ndiff_set_condition on it before every step.
+ *   forward_backward : x_t, target fp32 NCHW [B,4,H,W]; time int64 [B]; loss_weight fp32 [B] (loss_weight[t_b]); all device
+ *              pointers.  Gradients of all 416 parameters land in the flat gradient buffer; *loss_host (optional) receives
+ *              mean_b( w_b * mean_chw (v - target)^2 ) and synchronises the stream.
+ *   flat / slot : the flat buffers (0 parameters, 1 gradients, 2 Adam m, 3 Adam v, 4 EMA) and a parameter's (offset, numel).
+ *   adam_step : torch.optim.Adam semantics over the live parameters, gradients pre-multiplied by grad_scale (1 / world size
+ *              after an all-reduce SUM); re-packs every derived weight form.  The condition must be set again afterwards.
+ *   ema_update : ema += weight * (param - ema)  (weight = 1 - decay; weight >= 1 copies).                                      */
+typedef struct ndiff_trainer ndiff_trainer;
+NDIFF_API int32_t ndiff_trainer_create(const ndiff_config* cfg, ndiff_trainer** out);
+NDIFF_API void    ndiff_trainer_destroy(ndiff_trainer* t);
+NDIFF_API ndiff_engine* ndiff_trainer_engine(ndiff_trainer* t);
+NDIFF_API int32_t ndiff_trainer_finalize(ndiff_trainer* t, void* stream);
+NDIFF_API int32_t ndiff_trainer_forward_backward(ndiff_trainer* t, const float* x_t_dev, const int64_t* time_dev,
+                                                 const float* target_dev, const float* loss_weight_dev, double* loss_host,
+                                                 void* stream);
+NDIFF_API int32_t ndiff_trainer_flat(ndiff_trainer* t, int32_t which, float** ptr, int64_t* n_live, int64_t* n_total);
+NDIFF_API int32_t ndiff_trainer_slot(ndiff_trainer* t, const char* name, int64_t* offset, int64_t* numel);
+NDIFF_API int32_t ndiff_trainer_adam_step(ndiff_trainer* t, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                          float grad_scale, void* stream);
+NDIFF_API int32_t ndiff_trainer_ema_update(ndiff_trainer* t, float weight, void* stream);
+NDIFF_API int64_t ndiff_trainer_activation_bytes(const ndiff_trainer* t);
+NDIFF_API int64_t ndiff_trainer_launches(const ndiff_trainer* t, int32_t backward);
+/* Backward kernels one at a time (parity tests against torch autograd).  wgrad modes: 0 = 1x1, 1 = 3x3 pad 1, 2 = 2x2 stride 2
+ * (space-to-depth); dw is fp32 [Cout][C0+C1][taps], ACCUMULATED (zero it first). */
+NDIFF_API int32_t ndiff_op_wgrad(int32_t mode, int32_t B, int32_t H, int32_t W, const void* dy, int32_t Cout, const void* src0,
+                                 int32_t C0, const void* src1, int32_t C1, float* dw, void* stream);
+NDIFF_API int32_t ndiff_op_gn_backward(const void* h, const void* dout, void* dh, const void* stats, const float* gamma,
+                                       const float* beta, const float* ss, int32_t ss_ld, int32_t ss_off, const void* maps,
+                                       void* dmaps, float* dgamma, float* dbeta, float* dss, int32_t B, int32_t HW, int32_t C,
+                                       int32_t G, void* stream);
+NDIFF_API int32_t ndiff_op_layernorm_backward(const void* x, const float* vec, int32_t vec_ld, const float* g, const void* du,
+                                              void* dy, float* dg, float* dbeta, int32_t B, int32_t HW, int32_t C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1063,6 +1063,11 @@ int ensure_time_bufs(ndiff_engine* e, int n) {
 }  // namespace
 
 namespace ndiff {
+int xpad_pack_launch(const float* x_nhwc4, bf16* xpad, int H, int W, size_t npix, cudaStream_t s) {
+    NDIFF_CUDA_OK(launch_pdl(xpad_pack_kernel, dim3(static_cast<unsigned>((npix + 255) / 256)), dim3(256), 0, s,
+                             reinterpret_cast<const float4*>(x_nhwc4), reinterpret_cast<uint2*>(xpad), H, W, npix));
+    return 0;
+}
 int engine_finalize(ndiff_engine* e, cudaStream_t s) {
     if (finalize(e, s)) return 1;
     if (!e->plan_built && !e->skip_plan && build_plan(e)) return 1;
@@ -1103,6 +1108,7 @@ int32_t ndiff_engine_create(const ndiff_config* cfg, ndiff_engine** out) {
     if (e->alloc(&e->clean, npix * 4) || e->alloc(&e->x, npix * 4) || e->alloc(&e->v_out, npix * 4)) return 1;
     if (e->alloc(&e->map1, npix * 2 * e->dim) || e->alloc(&e->map2, npix * 2 * e->dim)) return 1;
     if (e->alloc(&e->pos_emb, npix * 8)) return 1;
+    if (e->alloc(&e->position, npix * 2) || e->alloc(&e->iso_idx, static_cast<size_t>(e->B))) return 1;
     {
         const size_t n = static_cast<size_t>(e->B) * (e->H + 6) * (e->W + 8) * 8;
         if (e->alloc(&e->xpad, n)) return 1;
@@ -1176,6 +1182,8 @@ int32_t ndiff_set_condition(ndiff_engine* e, const float* clean_dev, const float
     cudaStream_t s = as_stream(stream);
     const int HW = e->H * e->W;
     if (nchw_to_nhwc4_launch(clean_dev, e->clean, e->B, HW, s)) return 1;
+    NDIFF_CUDA_OK(cudaMemcpyAsync(e->position, position_dev, sizeof(float) * e->B * 2 * HW, cudaMemcpyDeviceToDevice, s));
+    NDIFF_CUDA_OK(cudaMemcpyAsync(e->iso_idx, iso_idx_dev, sizeof(long long) * e->B, cudaMemcpyDeviceToDevice, s));
     PosArgs pa{};
     pa.position = position_dev;
     pa.we = e->pf("pos_enc.weights.weight"); pa.be = e->pf("pos_enc.weights.bias");

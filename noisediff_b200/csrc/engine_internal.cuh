@@ -98,6 +98,8 @@ struct ndiff_engine {
     float* clean = nullptr;        // fp32 NHWC4
     bf16* map1 = nullptr; bf16* map2 = nullptr;
     float* pos_emb = nullptr;
+    float* position = nullptr;     // fp32 NCHW (B,2,H,W) copy of the last condition's position maps (training backward re-derives pos_emb)
+    long long* iso_idx = nullptr;  // [B] copy of the last condition's iso_ratio_idx (training backward of iso_embed)
     float* x = nullptr;            // fp32 NHWC4 chain state / network input
     float* v_out = nullptr;        // fp32 NHWC4 network output
     unsigned long long* stats = nullptr; int n_stats = 0; size_t stats_bytes = 0;
