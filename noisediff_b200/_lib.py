@@ -68,6 +68,21 @@ _SIGS = {
     "ndiff_op_philox_normal": (C.c_int32, [_P, C.c_int64, C.c_uint64, C.c_uint64, _P]),
     "ndiff_op_conv_ex": (C.c_int32, [C.c_int32] * 4 + [_P, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P, _P, C.c_int32, _P, _P, _P]),
     "ndiff_op_tail_chain": (C.c_int32, [C.c_int32, C.c_int32] + [_P] * 8 + [C.c_int32, _P, _P]),
+    # ---- training row (noisediff_b200/training.py)
+    "ndiff_trainer_create": (C.c_int32, [C.POINTER(Config), C.POINTER(_P)]),
+    "ndiff_trainer_destroy": (None, [_P]),
+    "ndiff_trainer_engine": (_P, [_P]),
+    "ndiff_trainer_finalize": (C.c_int32, [_P, _P]),
+    "ndiff_trainer_forward_backward": (C.c_int32, [_P, _P, _P, _P, _P, C.POINTER(C.c_double), _P]),
+    "ndiff_trainer_flat": (C.c_int32, [_P, C.c_int32, C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "ndiff_trainer_slot": (C.c_int32, [_P, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "ndiff_trainer_adam_step": (C.c_int32, [_P] + [C.c_float] * 6 + [_P]),
+    "ndiff_trainer_ema_update": (C.c_int32, [_P, C.c_float, _P]),
+    "ndiff_trainer_activation_bytes": (C.c_int64, [_P]),
+    "ndiff_trainer_launches": (C.c_int64, [_P, C.c_int32]),
+    "ndiff_op_wgrad": (C.c_int32, [C.c_int32] * 4 + [_P, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P, _P]),
+    "ndiff_op_gn_backward": (C.c_int32, [_P] * 6 + [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P] + [C.c_int32] * 4 + [_P]),
+    "ndiff_op_layernorm_backward": (C.c_int32, [_P, _P, C.c_int32, _P, _P, _P, _P, _P] + [C.c_int32] * 3 + [_P]),
 }
 
 _lib = None

@@ -328,6 +328,49 @@ def adam_step(params: SD, grads: SD, state: Dict[str, Dict[str, Tensor]], lr: fl
     return out
 
 
+def ema_update(params: SD, st: Dict, beta: float = 0.995, update_after_step: int = 500, update_every: int = 20,
+               inv_gamma: float = 1.0, power: float = 2.0 / 3.0, min_value: float = 0.0) -> None:
+    """One ``ema.update()`` of the training loop (models/trainer_diffusion.py:63-69,191).  The class is the pip package
+    ``ema_pytorch`` — NOT vendored in the reference tree and unpinned in install.sh:12, so this part of the oracle is restated
+    from the package's published algorithm (ema-pytorch 0.2 - 0.7, ``EMA.update`` / ``get_current_decay`` /
+    ``update_moving_average`` with the constructor defaults inv_gamma = 1, power = 2/3, min_value = 0) and is PARITY-UNPINNED:
+    there is nothing in /root/reference to check it against.  ``st`` = {"step": int, "initted": bool, "ema": SD}, updated in place.
+
+        step = self.step; self.step += 1
+        if step % update_every != 0: return
+        if step <= update_after_step: ema <- params; return
+        if not initted: ema <- params; initted = True
+        epoch = max(self.step - update_after_step - 1, 0)
+        decay = 0 if epoch <= 0 else clamp(1 - (1 + epoch / inv_gamma) ** -power, min_value, beta)
+        ema.lerp_(params, 1 - decay)
+    """
+    st.setdefault("step", 0)
+    st.setdefault("initted", False)
+    if "ema" not in st:
+        st["ema"] = {k: v.clone() for k, v in params.items()}       # EMA.__init__ deep-copies the model
+    step = st["step"]
+    st["step"] += 1
+    if step % update_every != 0:
+        return
+    if step <= update_after_step:
+        st["ema"] = {k: v.clone() for k, v in params.items()}
+        return
+    if not st["initted"]:
+        st["ema"] = {k: v.clone() for k, v in params.items()}
+        st["initted"] = True
+    epoch = max(st["step"] - update_after_step - 1, 0)
+    decay = 0.0 if epoch <= 0 else min(max(1.0 - (1.0 + epoch / inv_gamma) ** -power, min_value), beta)
+    for k, v in params.items():
+        if v.is_floating_point():
+            st["ema"][k] = torch.lerp(st["ema"][k], v, 1.0 - decay)
+
+
+def cosine_annealing_lr(base_lr: float, epoch: int, t_max: int, eta_min: float = 0.0) -> float:
+    """``CosineAnnealingLR(optimizer, T_max=max_iter)`` stepped once per epoch (models/trainer_diffusion.py:93,152-154), closed
+    form of torch's recurrence."""
+    return eta_min + (base_lr - eta_min) * (1.0 + math.cos(math.pi * epoch / t_max)) / 2.0
+
+
 def ddim_pairs(T: int, S: int) -> List[Tuple[int, int]]:
     """denoising_diffusion_pytorch.py:409-411."""
     times = torch.linspace(-1, T - 1, steps=S + 1)

@@ -9,8 +9,12 @@ int main(void) {
     ndiff_engine* e = NULL;
     if (ndiff_engine_create(NULL, &e) == 0) return 2;
     if (!ndiff_last_error() || !strlen(ndiff_last_error())) return 3;
-    ndiff_config cfg = {48, 1, 32, 32, 0, 0};
+    ndiff_config cfg = {72, 1, 32, 32, 0, 0};           /* widths above the kernels' 64-channel base are refused */
     if (ndiff_engine_create(&cfg, &e) == 0) return 4;
+    printf("%s\n", ndiff_last_error());
+    ndiff_trainer* t = NULL;
+    cfg.dim = 48;                                       /* runs on the sampling path (embedded), not on the training path */
+    if (ndiff_trainer_create(&cfg, &t) == 0) return 6;
     printf("%s\n", ndiff_last_error());
     cfg.dim = 64; cfg.height = 12;
     if (ndiff_engine_create(&cfg, &e) == 0) return 5;

@@ -1,0 +1,264 @@
+"""GPU parity of the training row: the backward kernels one at a time against torch autograd on the same
+(bf16-rounded) inputs, and the whole forward + backward + Adam + EMA step against the oracle's autograd / the reference's own
+gradients (tests/golden/next_rows.npz, minted from the unmodified reference's loss.backward()).  Everything is reached through
+the C ABI (ndiff_op_* / ndiff_trainer_*).
+
+Tolerances: the tensor-core gradients see bf16 activations and bf16 activation gradients (fp32 accumulation, fp32 parameter
+gradients), so whole-network gradients are compared per parameter by cosine similarity and norm ratio rather than elementwise."""
+import copy
+import ctypes as C
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import noisediff_b200 as nd
+from noisediff_b200 import _lib, training
+from oracle import noisediff_oracle as O
+from tests import gpu_util as G
+from tests.util import load, rel_l2, seeded_net, seeded_sd
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _fp32_reference_math():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, generator=g, device="cuda") * scale).to(torch.bfloat16).float()
+
+
+def _wgrad(mode, dy_nchw, x0_nchw, x1_nchw, taps):
+    L = training.train_lib()
+    B, co, H, W = dy_nchw.shape
+    c0 = x0_nchw.shape[1]
+    c1 = x1_nchw.shape[1] if x1_nchw is not None else 0
+    dw = torch.zeros((co, c0 + c1, taps), device="cuda")
+    dy, x0 = G.to_nhwc_bf16(dy_nchw), G.to_nhwc_bf16(x0_nchw)
+    x1 = G.to_nhwc_bf16(x1_nchw) if x1_nchw is not None else None
+    _lib.check(L.ndiff_op_wgrad(mode, B, H, W, G.P(dy), co, G.P(x0), c0, G.P(x1), c1, G.P(dw), G.stream()))
+    torch.cuda.synchronize()
+    return dw
+
+
+# (B, H, W, C0, C1, Cout): ragged sizes leave partial 16 x 8 tiles; Cout = 64 runs with half of the M = 128 rows unused
+WGRAD_CASES = [(2, 16, 16, 64, 0, 64), (1, 32, 24, 128, 0, 128), (2, 16, 16, 64, 64, 64), (3, 24, 40, 64, 0, 256), (1, 8, 8, 256, 128, 256),
+               (4, 64, 64, 64, 0, 64)]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES)
+def test_wgrad_3x3_matches_autograd(case):
+    B, H, W, c0, c1, co = case
+    x0 = _rand((B, c0, H, W), 1)
+    x1 = _rand((B, c1, H, W), 2) if c1 else None
+    dy = _rand((B, co, H, W), 3)
+    x = torch.cat([x0, x1], 1) if c1 else x0
+    ref = torch.nn.grad.conv2d_weight(x, (co, c0 + c1, 3, 3), dy, padding=1)
+    got = _wgrad(1, dy, x0, x1, 9).reshape(co, c0 + c1, 3, 3)
+    assert rel_l2(got, ref) < 1e-3, rel_l2(got, ref)
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES[:4])
+def test_wgrad_1x1_matches_autograd(case):
+    B, H, W, c0, c1, co = case
+    x0 = _rand((B, c0, H, W), 4)
+    x1 = _rand((B, c1, H, W), 5) if c1 else None
+    dy = _rand((B, co, H, W), 6)
+    x = torch.cat([x0, x1], 1) if c1 else x0
+    ref = torch.nn.grad.conv2d_weight(x, (co, c0 + c1, 1, 1), dy)
+    got = _wgrad(0, dy, x0, x1, 1).reshape(co, c0 + c1, 1, 1)
+    assert rel_l2(got, ref) < 1e-3, rel_l2(got, ref)
+
+
+@pytest.mark.parametrize("case", [(2, 16, 16, 64, 128), (1, 32, 24, 128, 64)])
+def test_wgrad_space_to_depth_matches_autograd(case):
+    B, H, W, c, co = case                        # H, W = OUTPUT size; the input is 2H x 2W
+    x = _rand((B, c, 2 * H, 2 * W), 7)
+    dy = _rand((B, co, H, W), 8)
+    ref = torch.nn.grad.conv2d_weight(O.space_to_depth(x), (co, 4 * c, 1, 1), dy)         # input channel = c * 4 + p1 * 2 + p2
+    got = _wgrad(2, dy, x, None, 4).reshape(co, 4 * c, 1, 1)
+    assert rel_l2(got, ref) < 1e-3, rel_l2(got, ref)
+
+
+def _stats(h, groups):
+    B, HW, Cc = h.shape
+    grp = h.double().reshape(B, HW, groups, Cc // groups)
+    return torch.stack([(grp.sum((1, 3)) * 2 ** 24).round(), ((grp * grp).sum((1, 3)) * 2 ** 24).round()], dim=2).to(torch.int64).contiguous()
+
+
+@pytest.mark.parametrize("case", [(2, 256, 64, 8, "vec"), (3, 128, 128, 8, "none"), (2, 256, 64, 2, "maps"), (1, 64, 512, 8, "vec")])
+def test_groupnorm_backward_matches_autograd(case):
+    B, HW, Cc, groups, kind = case
+    L = training.train_lib()
+    h = _rand((B, HW, Cc), 10).requires_grad_(True)
+    dout = _rand((B, HW, Cc), 11)
+    gamma = (torch.randn(Cc, device="cuda") * 0.5 + 1).requires_grad_(True)
+    beta = (torch.randn(Cc, device="cuda") * 0.1).requires_grad_(True)
+    ss = maps = None
+    y = F.group_norm(h.permute(0, 2, 1), groups, gamma, beta, eps=1e-5).permute(0, 2, 1)
+    if kind == "vec":
+        ss = (torch.randn(B, 2 * Cc + 16, device="cuda") * 0.3).requires_grad_(True)        # [pad 16 | scale C | shift C]
+        y = y * (ss[:, None, 16:16 + Cc] + 1) + ss[:, None, 16 + Cc:]
+    elif kind == "maps":
+        maps = _rand((B, HW, 2 * Cc), 12, 0.3).requires_grad_(True)
+        y = y * (maps[..., :Cc] + 1) + maps[..., Cc:]
+    out = F.silu(y)
+    out.backward(dout)
+    hb, db = h.detach().to(torch.bfloat16).contiguous(), dout.to(torch.bfloat16).contiguous()
+    dh = torch.empty_like(hb)
+    dgamma, dbeta = torch.zeros(Cc, device="cuda"), torch.zeros(Cc, device="cuda")
+    stats = _stats(h.detach(), groups)
+    dss = torch.zeros_like(ss) if ss is not None else None
+    mb = maps.detach().to(torch.bfloat16).contiguous() if maps is not None else None
+    dmaps = torch.empty_like(mb) if mb is not None else None
+    _lib.check(L.ndiff_op_gn_backward(G.P(hb), G.P(db), G.P(dh), G.P(stats), G.P(gamma.detach()), G.P(beta.detach()),
+                                      G.P(ss.detach() if ss is not None else None), ss.shape[1] if ss is not None else 0, 16, G.P(mb), G.P(dmaps),
+                                      G.P(dgamma), G.P(dbeta), G.P(dss), B, HW, Cc, groups, G.stream()))
+    torch.cuda.synchronize()
+    assert rel_l2(dh.float(), h.grad) < 8e-3, rel_l2(dh.float(), h.grad)          # bf16 output rounding
+    assert rel_l2(dgamma, gamma.grad) < 2e-3 and rel_l2(dbeta, beta.grad) < 2e-3
+    if ss is not None:
+        assert rel_l2(dss[:, 16:], ss.grad[:, 16:]) < 2e-3 and float(dss[:, :16].abs().max()) == 0.0
+    if maps is not None:
+        assert rel_l2(dmaps.float(), maps.grad) < 8e-3
+
+
+@pytest.mark.parametrize("case", [(2, 200, 64), (1, 128, 128), (2, 64, 256), (1, 96, 512)])
+def test_layernorm_backward_matches_autograd(case):
+    B, HW, Cc = case
+    L = training.train_lib()
+    x = _rand((B, HW, Cc), 20).requires_grad_(True)
+    vec = (torch.randn(B, Cc, device="cuda") * 0.5).requires_grad_(True)
+    g = (torch.randn(Cc, device="cuda") * 0.5 + 1).requires_grad_(True)
+    b = (torch.randn(Cc, device="cuda") * 0.1).requires_grad_(True)
+    du = _rand((B, HW, Cc), 21)
+    u = F.layer_norm(x + vec[:, None, :], (Cc,), g, b, eps=1e-5)
+    u.backward(du)
+    xb, dub = x.detach().to(torch.bfloat16).contiguous(), du.to(torch.bfloat16).contiguous()
+    dy = torch.empty_like(xb)
+    dg, dbeta = torch.zeros(Cc, device="cuda"), torch.zeros(Cc, device="cuda")
+    _lib.check(L.ndiff_op_layernorm_backward(G.P(xb), G.P(vec.detach()), Cc, G.P(g.detach()), G.P(dub), G.P(dy), G.P(dg), G.P(dbeta), B, HW, Cc,
+                                             G.stream()))
+    torch.cuda.synchronize()
+    assert rel_l2(dy.float(), x.grad) < 8e-3, rel_l2(dy.float(), x.grad)
+    assert rel_l2(dy.float().sum(1), vec.grad) < 8e-3                    # the per-sample vector's gradient is the per-sample column sum
+    assert rel_l2(dg, g.grad) < 2e-3 and rel_l2(dbeta, b.grad) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# the whole step
+# ------------------------------------------------------------------------------------------------------------------------------
+def _golden_batch():
+    z = load("losses.npz")
+    cond = {"clean_img": torch.from_numpy(z["clean"]), "position": torch.from_numpy(z["position"]), "iso_ratio_idx": torch.from_numpy(z["iso"])}
+    return torch.from_numpy(z["x_start"]), torch.from_numpy(z["pred_v/t"]), cond, torch.from_numpy(z["noise"])
+
+
+@pytest.fixture(scope="module")
+def trained_once():
+    """One forward + backward of the golden batch (64 x 64, per-sample t, T = 1000, sigmoid2, pred_v) on the CUDA trainer."""
+    net = copy.deepcopy(seeded_net()).cuda()
+    gd = nd.GaussianDiffusion(net, image_size=64, timesteps=1000, beta_schedule="sigmoid2", objective="pred_v").cuda()
+    x_start, t, cond, noise = _golden_batch()
+    tr = training.DiffusionTrainer(gd, batch_size=x_start.shape[0], lr=1e-4)
+    loss = tr.forward_backward(x_start.cuda(), {k: v.cuda() for k, v in cond.items()}, t=t.cuda(), noise=noise.cuda())
+    grads = {k: v.cpu() for k, v in tr.gradients().items()}
+    yield tr, loss, grads
+    tr.close()
+
+
+def test_training_step_gradients_match_the_reference(trained_once):
+    """Loss and all 416 gradients against the reference's own loss.backward() (norms of every parameter, a few gradients in
+    full) and against autograd through the oracle (every gradient in full)."""
+    tr, loss, grads = trained_once
+    z = load("next_rows.npz")
+    assert abs(loss - float(z["train/loss"])) <= 2e-2 * float(z["train/loss"]), (loss, float(z["train/loss"]))
+    names, norms = [str(n) for n in z["train/names"]], z["train/grad_norms"]
+    x_start, t, cond, noise = _golden_batch()
+    _, ref = O.loss_gradients(seeded_sd(), O.schedule_tables("sigmoid2", 1000, "pred_v"), "pred_v", x_start, t, cond, noise)
+    total = math.sqrt(sum(float(g) ** 2 for g in norms))
+    bad, worst_cos, worst_ratio = [], 1.0, 0.0
+    for n, g in zip(names, norms):
+        mine = grads[n].double()
+        if g == 0.0:
+            assert float(mine.abs().max()) == 0.0, f"{n}: the reference leaves this parameter without a gradient"
+            continue
+        r = ref[n].double()
+        cos = float((mine * r).sum() / (mine.norm() * r.norm()).clamp_min(1e-30))
+        ratio = float(mine.norm()) / g
+        if g > 1e-4 * total:             # parameters that carry a visible share of the step's gradient
+            worst_cos, worst_ratio = min(worst_cos, cos), max(worst_ratio, abs(ratio - 1))
+            if cos < 0.98 or abs(ratio - 1) > 0.08:
+                bad.append((n, round(cos, 4), round(ratio, 4), g))
+        elif cos < 0.9:
+            bad.append((n, round(cos, 4), round(ratio, 4), g))
+    print(f"loss {loss:.6f} (reference {float(z['train/loss']):.6f}); worst cosine {worst_cos:.4f}, worst |norm ratio - 1| {worst_ratio:.4f}")
+    assert not bad, bad[:12]
+    for k in [k[len("train/grad/"):] for k in z if k.startswith("train/grad/")]:
+        e = rel_l2(grads[k], torch.from_numpy(z["train/grad/" + k]))
+        assert e < 0.12, (k, e)
+
+
+def test_adam_and_ema_follow_the_oracle(trained_once):
+    """Adam.step() on the library's own gradients against the written-out update (oracle.adam_step, pinned to torch.optim.Adam by
+    the golden test), for three consecutive steps; EMA copy / lerp against the restated ema_pytorch schedule."""
+    tr, _, _ = trained_once
+    x_start, t, cond, noise = _golden_batch()
+    condc = {k: v.cuda() for k, v in cond.items()}
+    params = {k: v.cpu() for k, v in tr.state_dict().items()}
+    state = {}
+    tr.ema = training.EmaSchedule(beta=0.9, update_after_step=1, update_every=1)
+    ema_st = {}
+    for it in range(4):
+        tr.forward_backward(x_start.cuda(), condc, t=t.cuda(), noise=noise.cuda())
+        grads = {k: v.cpu() for k, v in tr.gradients().items()}
+        tr.optimizer_step()
+        params = O.adam_step(params, grads, state, lr=1e-4)
+        mine = {k: v.cpu() for k, v in tr.state_dict().items()}
+        worst = max(float((mine[k] - params[k]).abs().max()) for k in params)
+        assert worst <= 3e-7, (it, worst)
+        O.ema_update(mine, ema_st, beta=0.9, update_after_step=1, update_every=1)       # the oracle's own restatement of ema_pytorch
+        ema = {k: v.cpu() for k, v in tr.ema_state_dict().items()}
+        assert max(float((ema[k] - ema_st["ema"][k]).abs().max()) for k in ema) <= 3e-7, it
+        params = mine                       # follow the library's fp32 rounding from here on
+    # the loss goes down on the batch it was trained on
+    l_after = tr.forward_backward(x_start.cuda(), condc, t=t.cuda(), noise=noise.cuda())
+    assert math.isfinite(l_after)
+
+
+def test_training_step_at_the_baseline_shape():
+    """BASELINE configs[4]: batch 32 x 4 x 256 x 256, forward + backward + Adam + EMA on one GPU; finite loss / gradients, loss
+    equals the forward-only p_losses value of the sampling engine, timing printed."""
+    net = copy.deepcopy(seeded_net()).cuda()
+    gd = nd.GaussianDiffusion(net, image_size=256, timesteps=1000, beta_schedule="sigmoid2", objective="pred_v").cuda()
+    B = 32
+    g = torch.Generator(device="cuda").manual_seed(5)
+    cond = {k: v.cuda() for k, v in O.synthetic_condition(B, 256, 256, seed=7).items()}
+    img = torch.randn(B, 4, 256, 256, generator=g, device="cuda") * 0.05
+    t = torch.randint(0, 1000, (B,), generator=g, device="cuda")
+    noise = torch.randn(B, 4, 256, 256, generator=g, device="cuda")
+    tr = training.DiffusionTrainer(gd, batch_size=B, lr=1e-4)
+    loss = tr.forward_backward(img, cond, t=t, noise=noise)
+    grads = tr.gradients()
+    assert math.isfinite(loss) and all(bool(torch.isfinite(v).all()) for v in grads.values())
+    with torch.no_grad():
+        fwd_only = float(gd.p_losses(img, t, cond, noise=noise))
+    print(f"B=32 256x256 loss {loss:.6f} (forward-only engine {fwd_only:.6f}); activations {tr.activation_bytes / 2 ** 30:.1f} GiB; "
+          f"launches fwd/bwd {tr.launches}")
+    assert abs(loss - fwd_only) <= 2e-2 * abs(fwd_only)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    tr.forward_backward(img, cond, t=t, noise=noise)        # warm
+    ev[0].record()
+    tr.forward_backward(img, cond, t=t, noise=noise)
+    ev[1].record()
+    tr.optimizer_step()
+    ev[2].record()
+    torch.cuda.synchronize()
+    print(f"forward + backward {ev[0].elapsed_time(ev[1]):.1f} ms, Adam + repack + EMA {ev[1].elapsed_time(ev[2]):.1f} ms (B = 32, one B200)")
+    tr.close()

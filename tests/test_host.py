@@ -36,7 +36,7 @@ def test_c_abi_from_plain_c(tmp_path):
                     "-Wl,-rpath," + libdir], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
-    assert "dim = 64" in r.stdout and "multiples of 8" in r.stdout
+    assert "multiple of 8 up to 64" in r.stdout and "training step runs at dim = 64" in r.stdout and "multiples of 8" in r.stdout
 
 
 def test_abi_struct_layouts():
