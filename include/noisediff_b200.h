@@ -204,6 +204,8 @@ NDIFF_API int32_t ndiff_trainer_slot(ndiff_trainer* t, const char* name, int64_t
 NDIFF_API int32_t ndiff_trainer_adam_step(ndiff_trainer* t, float lr, float beta1, float beta2, float eps, float weight_decay,
                                           float grad_scale, void* stream);
 NDIFF_API int32_t ndiff_trainer_ema_update(ndiff_trainer* t, float weight, void* stream);
+/* per-kernel-family durations of the last step's forward / backward launch lists ("fwd|bwd;family;launches;ms" lines) */
+NDIFF_API int32_t ndiff_trainer_time(ndiff_trainer* t, char* out, int32_t cap, void* stream);
 NDIFF_API int64_t ndiff_trainer_activation_bytes(const ndiff_trainer* t);
 NDIFF_API int64_t ndiff_trainer_launches(const ndiff_trainer* t, int32_t backward);
 /* Backward kernels one at a time (parity tests against torch autograd).  wgrad modes: 0 = 1x1, 1 = 3x3 pad 1, 2 = 2x2 stride 2

@@ -78,6 +78,7 @@ _SIGS = {
     "ndiff_trainer_slot": (C.c_int32, [_P, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ndiff_trainer_adam_step": (C.c_int32, [_P] + [C.c_float] * 6 + [_P]),
     "ndiff_trainer_ema_update": (C.c_int32, [_P, C.c_float, _P]),
+    "ndiff_trainer_time": (C.c_int32, [_P, C.c_char_p, C.c_int32, _P]),
     "ndiff_trainer_activation_bytes": (C.c_int64, [_P]),
     "ndiff_trainer_launches": (C.c_int64, [_P, C.c_int32]),
     "ndiff_op_wgrad": (C.c_int32, [C.c_int32] * 4 + [_P, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P, _P]),

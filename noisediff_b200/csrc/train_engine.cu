@@ -83,6 +83,10 @@ struct ndiff_trainer {
     struct DgradPack { std::string name; bf16* dst; int Cout, Cin_total, c_off, Cs, taps; bool s2d; };
     std::vector<DgradPack> dpacks;
     std::vector<std::function<int(cudaStream_t)>> fwd, bwd;
+    std::vector<std::string> fwd_kind, bwd_kind;               // kernel family of every launch (per-family timing, ndiff_trainer_time)
+    std::string kind = "other";
+    void addf(std::function<int(cudaStream_t)> f) { fwd.push_back(std::move(f)); fwd_kind.push_back(kind); }
+    void addb(std::function<int(cudaStream_t)> f) { bwd.push_back(std::move(f)); bwd_kind.push_back(kind); }
     std::vector<std::function<void()>> pending;                // emitters of backward launches, in forward order
     int err = 0;
     int stats_slot = 0;
@@ -123,7 +127,7 @@ struct TB {      // plan builder
     // dst.g (+)= src (same shape): gradient routing of residual adds
     void route(TT& dst, const bf16* src) {
         bf16* d = dst.g; const bool acc = dst.g_set; const int C = dst.C; const size_t n = npix(dst);
-        t->bwd.push_back([=](cudaStream_t s) { return add_slice_launch(d, C, 0, src, C, 0, C, n, acc, s); });
+        t->kind = "route"; t->addb([=](cudaStream_t s) { return add_slice_launch(d, C, 0, src, C, 0, C, n, acc, s); });
         dst.g_set = true;
     }
 
@@ -146,7 +150,7 @@ struct TB {      // plan builder
         d.stats = stats; d.groups = groups;
         auto plan = std::make_shared<ConvGemmPlan>();
         if (conv_gemm_plan(d, e->num_sms, plan.get())) { t->err = 1; return out; }
-        t->fwd.push_back([plan](cudaStream_t s) { return conv_gemm_launch(*plan, s); });
+        t->kind = "conv_fwd"; t->addf([plan](cudaStream_t s) { return conv_gemm_launch(*plan, s); });
 
         // dgrad weight packs (one per concatenated source), refreshed after every optimizer step
         const int taps = mode == kHalo1 ? 9 : 1;
@@ -172,11 +176,11 @@ struct TB {      // plan builder
             // (runs at plan time, in reverse forward order)  gradient of `out` is complete in o.g
             const size_t np = static_cast<size_t>(tr->B) * o.H * o.W;
             float* gb = tr->G(wname + ".bias");
-            tr->bwd.push_back([=](cudaStream_t s) { return colsum_launch(o.g, o.C, 0, gb, 0, false, tr->B, o.H * o.W, o.C, s); });
+            tr->kind = "bias_grad"; tr->addb([=](cudaStream_t s) { return colsum_launch(o.g, o.C, 0, gb, 0, false, tr->B, o.H * o.W, o.C, s); });
             if (vec) {
                 float* dcv = tr->dcv + vec_off;
                 const int ld = tr->e->cv_total;
-                tr->bwd.push_back([=](cudaStream_t s) { return colsum_launch(o.g, o.C, 0, dcv, ld, true, tr->B, o.H * o.W, o.C, s); });
+                tr->addb([=](cudaStream_t s) { return colsum_launch(o.g, o.C, 0, dcv, ld, true, tr->B, o.H * o.W, o.C, s); });
             }
             if (res) self->route(*res, o.g);
             {   // weight gradient
@@ -189,7 +193,7 @@ struct TB {      // plan builder
                 wd.dw = tr->G(wname + ".weight");
                 auto wp = std::make_shared<WgradPlan>();
                 if (wgrad_gemm_plan(wd, tr->e->num_sms, wp.get())) { tr->err = 1; return; }
-                tr->bwd.push_back([wp](cudaStream_t s) { return wgrad_gemm_launch(*wp, s); });
+                tr->kind = "wgrad"; tr->addb([wp](cudaStream_t s) { return wgrad_gemm_launch(*wp, s); });
             }
             if (!input_grad) return;
             if (mode == kS2D) {
@@ -201,9 +205,10 @@ struct TB {      // plan builder
                 g.src0 = o.g; g.C0 = o.C; g.weight = dw0; g.Cout = 4 * s0->C; g.out = tmp; g.out_ld = 4 * s0->C;
                 auto gp = std::make_shared<ConvGemmPlan>();
                 if (conv_gemm_plan(g, tr->e->num_sms, gp.get())) { tr->err = 1; return; }
-                tr->bwd.push_back([gp](cudaStream_t s) { return conv_gemm_launch(*gp, s); });
+                tr->kind = "dgrad"; tr->addb([gp](cudaStream_t s) { return conv_gemm_launch(*gp, s); });
+                tr->kind = "route";
                 bf16* dx = s0->g; const bool acc = s0->g_set; const int C = s0->C, hh = o.H, ww = o.W, B = tr->B;
-                tr->bwd.push_back([=](cudaStream_t s) { return depth_to_space_launch(tmp, dx, B, hh, ww, C, acc, s); });
+                tr->addb([=](cudaStream_t s) { return depth_to_space_launch(tmp, dx, B, hh, ww, C, acc, s); });
                 s0->g_set = true;
                 return;
             }
@@ -217,7 +222,7 @@ struct TB {      // plan builder
                 if (src->g_set) { g.res = src->g; g.res_ld = src->C; }     // accumulate in place: each thread reads its own pixel first
                 auto gp = std::make_shared<ConvGemmPlan>();
                 if (conv_gemm_plan(g, tr->e->num_sms, gp.get())) { tr->err = 1; return; }
-                tr->bwd.push_back([gp](cudaStream_t s) { return conv_gemm_launch(*gp, s); });
+                tr->kind = "dgrad"; tr->addb([gp](cudaStream_t s) { return conv_gemm_launch(*gp, s); });
                 src->g_set = true;
             }
         });
@@ -236,7 +241,7 @@ struct TB {      // plan builder
         g.maps = maps;
         g.res1 = r1 ? r1->p : nullptr; g.res2 = r2 ? r2->p : nullptr;
         g.B = t->B; g.HW = h->H * h->W; g.C = h->C; g.G = groups; g.eps = 1e-5f; g.real_frac = 1.0f;
-        t->fwd.push_back([g](cudaStream_t s) { return gn_apply_launch(g, s); });
+        t->kind = "gn_fwd"; t->addf([g](cudaStream_t s) { return gn_apply_launch(g, s); });
         ndiff_trainer* tr = t;
         TB* self = this;
         const TT o = out;
@@ -252,7 +257,7 @@ struct TB {      // plan builder
             b.dgamma = tr->G(nname + ".weight"); b.dbeta = tr->G(nname + ".bias");
             if (ss_off >= 0) { b.dss = tr->dss; b.dss_ld = tr->e->ss_total; }
             b.B = tr->B; b.HW = g.HW; b.C = g.C; b.G = groups; b.eps = 1e-5f; b.real_frac = 1.0f;
-            tr->bwd.push_back([b](cudaStream_t s) { return gn_backward_launch(b, s); });
+            tr->kind = "gn_bwd"; tr->addb([b](cudaStream_t s) { return gn_backward_launch(b, s); });
             h->g_set = true;      // the raw conv output has exactly one consumer: written, not accumulated
         });
         return out;
@@ -263,12 +268,12 @@ struct TB {      // plan builder
         if (t->err) return out;
         const size_t n = npix(*pre) * pre->C;
         const bf16* pp = pre->p; bf16* op = out.p;
-        t->fwd.push_back([=](cudaStream_t s) { return gelu_forward_launch(pp, op, n, s); });
+        t->kind = "gelu"; t->addf([=](cudaStream_t s) { return gelu_forward_launch(pp, op, n, s); });
         ndiff_trainer* tr = t;
         const TT o = out;
         t->pending.push_back([=]() {
             bf16* dp = pre->g; const bf16* dy = o.g;
-            tr->bwd.push_back([=](cudaStream_t s) { return gelu_backward_launch(pp, dy, dp, n, s); });
+            tr->kind = "gelu"; tr->addb([=](cudaStream_t s) { return gelu_backward_launch(pp, dy, dp, n, s); });
             pre->g_set = true;
         });
         return out;
@@ -301,7 +306,7 @@ struct TB {      // plan builder
             const bf16* xp = x->p; bf16* up = u->p;
             const float* g = e->pf(n + ".norm2.weight"); const float* bt = e->pf(n + ".norm2.bias");
             const int B = t->B, HW = x->H * x->W, ld = e->cv_total;
-            t->fwd.push_back([=](cudaStream_t s) { return layernorm_launch(xp, cv, ld, g, bt, up, B, HW, C, s, 1.0f); });
+            t->kind = "layernorm"; t->addf([=](cudaStream_t s) { return layernorm_launch(xp, cv, ld, g, bt, up, B, HW, C, s, 1.0f); });
             ndiff_trainer* tr = t;
             TB* self = this;
             t->pending.push_back([=]() {
@@ -309,8 +314,8 @@ struct TB {      // plan builder
                 float* dg = tr->G(n + ".norm2.weight"); float* db = tr->G(n + ".norm2.bias");
                 float* dcv = tr->dcv + off;
                 // dy overwrites du in place (each thread reads its du elements before it writes them)
-                tr->bwd.push_back([=](cudaStream_t s) { return layernorm_backward_launch(xp, cv, ld, g, du, du, dg, db, B, HW, C, 1.0f, s); });
-                tr->bwd.push_back([=](cudaStream_t s) { return colsum_launch(du, C, 0, dcv, ld, true, B, HW, C, s); });
+                tr->kind = "layernorm"; tr->addb([=](cudaStream_t s) { return layernorm_backward_launch(xp, cv, ld, g, du, du, dg, db, B, HW, C, 1.0f, s); });
+                tr->addb([=](cudaStream_t s) { return colsum_launch(du, C, 0, dcv, ld, true, B, HW, C, s); });
                 self->route(*x, du);
             });
         }
@@ -336,11 +341,11 @@ int build_training_plan(ndiff_trainer* t) {
     {
         const float* cl = e->clean; const float* x = e->x; bf16* o = s0->p;
         const float* w = e->pf("shot_mlp1.fc1.weight"); const float* bs = e->pf("shot_mlp1.fc1.bias");
-        t->fwd.push_back([=](cudaStream_t s) { return shot_in_launch(cl, x, w, bs, o, static_cast<int>(npix), dim, s); });
+        t->addf([=](cudaStream_t s) { return shot_in_launch(cl, x, w, bs, o, static_cast<int>(npix), dim, s); });
         t->pending.push_back([=]() {
             const bf16* ds0 = s0->g;
             float* dw = t->G("shot_mlp1.fc1.weight"); float* db = t->G("shot_mlp1.fc1.bias");
-            t->bwd.push_back([=](cudaStream_t s) { return shot_in_backward_launch(cl, x, w, bs, ds0, dw, db, npix, dim, s); });
+            t->addb([=](cudaStream_t s) { return shot_in_backward_launch(cl, x, w, bs, ds0, dw, db, npix, dim, s); });
         });
     }
     TT* s1 = hold(b.conv("shot_mlp1.fc2", kDirect, s0, nullptr, dim, nullptr, 0, nullptr, nullptr, 0));
@@ -368,13 +373,13 @@ int build_training_plan(ndiff_trainer* t) {
         auto plan = std::make_shared<ConvGemmPlan>();
         if (conv_gemm_plan(cd, e->num_sms, plan.get())) return 1;
         const float* xs = e->x; bf16* xp = e->xpad;
-        t->fwd.push_back([=](cudaStream_t s) { return xpad_pack_launch(xs, xp, H, W, npix, s); });
-        t->fwd.push_back([plan](cudaStream_t s) { return conv_gemm_launch(*plan, s); });
+        t->addf([=](cudaStream_t s) { return xpad_pack_launch(xs, xp, H, W, npix, s); });
+        t->addf([plan](cudaStream_t s) { return conv_gemm_launch(*plan, s); });
         t->pending.push_back([=]() {
             const bf16* dy = x0->g;
             float* dw = t->G("init_conv.weight"); float* db = t->G("init_conv.bias");
-            t->bwd.push_back([=](cudaStream_t s) { return colsum_launch(dy, dim, 0, db, 0, false, B, H * W, dim, s); });
-            t->bwd.push_back([=](cudaStream_t s) { return init_conv_wgrad_launch(xs, dy, dw, B, H, W, dim, s); });
+            t->addb([=](cudaStream_t s) { return colsum_launch(dy, dim, 0, db, 0, false, B, H * W, dim, s); });
+            t->addb([=](cudaStream_t s) { return init_conv_wgrad_launch(xs, dy, dw, B, H, W, dim, s); });
         });
     }
     TT* cur = hold(b.resblock("pos_block1", x0, nullptr, dim, 2, e->map1, t->dmap1, nullptr, keep));
@@ -406,10 +411,10 @@ int build_training_plan(ndiff_trainer* t) {
             TT* up = hold(b.make(co, a3->H * 2, a3->W * 2));
             if (t->err) return 1;
             const bf16* in = a3->p; bf16* o = up->p; const int hh = a3->H, ww = a3->W;
-            t->fwd.push_back([=](cudaStream_t s) { return upsample2x_launch(in, o, B, hh, ww, co, s); });
+            t->addf([=](cudaStream_t s) { return upsample2x_launch(in, o, B, hh, ww, co, s); });
             t->pending.push_back([=]() {
                 const bf16* dy = up->g; bf16* dx = a3->g; const bool acc = a3->g_set;
-                t->bwd.push_back([=](cudaStream_t s) { return upsample2x_backward_launch(dy, dx, B, hh, ww, co, acc, s); });
+                t->addb([=](cudaStream_t s) { return upsample2x_backward_launch(dy, dx, B, hh, ww, co, acc, s); });
                 a3->g_set = true;
             });
             cur = hold(b.conv(p + ".3.1", kHalo1, up, nullptr, ci, nullptr, 0, nullptr, nullptr, 0));
@@ -430,7 +435,7 @@ int build_training_plan(ndiff_trainer* t) {
         f.wf = e->pf("final_conv.weight"); f.bfin = e->pf("final_conv.bias");
         f.ws = e->pf("shot_mlp3.fc2.weight"); f.bs = e->pf("shot_mlp3.fc2.bias");
         f.npix = static_cast<int>(npix); f.C = dim; f.HW = H * W; f.v_out = e->v_out;
-        t->fwd.push_back([f](cudaStream_t s) { return final_launch(f, s); });
+        t->kind = "heads"; t->addf([f](cudaStream_t s) { return final_launch(f, s); });
     }
     // ---- backward list: loss + heads first, then every forward op's emitter in reverse order ---------------------------------
     {
@@ -442,7 +447,7 @@ int build_training_plan(ndiff_trainer* t) {
         hb.dwf = t->G("final_conv.weight"); hb.dbf = t->G("final_conv.bias");
         hb.dws = t->G("shot_mlp3.fc2.weight"); hb.dbs = t->G("shot_mlp3.fc2.bias");
         hb.loss = t->loss; hb.B = B; hb.HW = H * W; hb.C = dim;
-        t->bwd.push_back([hb](cudaStream_t s) { return heads_backward_launch(hb, s); });
+        t->kind = "heads"; t->addb([hb](cudaStream_t s) { return heads_backward_launch(hb, s); });
         fr->g_set = true; s6->g_set = true;
     }
     for (auto it = t->pending.rbegin(); it != t->pending.rend(); ++it) {
@@ -451,24 +456,25 @@ int build_training_plan(ndiff_trainer* t) {
     }
     t->pending.clear();
     // ---- per-sample / small dense paths -----------------------------------------------------------------------------------------
+    t->kind = "small_paths";
     const int td = e->dim_real * 4;
     for (const RbSpec& rb : resblocks(dim)) {
         if (rb.pos) continue;
         const int off = e->ss_off.at(rb.name), rows = 2 * rb.cout, ld = e->ss_total;
         const float* dss = t->dss + off; const float* st = e->st_buf;
         float* dw = t->G(rb.name + ".mlp.1.weight"); float* db = t->G(rb.name + ".mlp.1.bias");
-        t->bwd.push_back([=](cudaStream_t s) { return small_gemm_launch(true, false, rows, td, B, dss, ld, st, td, dw, td, true, s); });
-        t->bwd.push_back([=](cudaStream_t s) { return rowsum_f32_launch(dss, ld, B, rows, db, s); });
+        t->addb([=](cudaStream_t s) { return small_gemm_launch(true, false, rows, td, B, dss, ld, st, td, dw, td, true, s); });
+        t->addb([=](cudaStream_t s) { return rowsum_f32_launch(dss, ld, B, rows, db, s); });
     }
     {
         const float* dss = t->dss; const float* ssw = e->ss_w; float* dst = t->dst_buf; const int ld = e->ss_total;
-        t->bwd.push_back([=](cudaStream_t s) { return small_gemm_launch(false, false, B, td, ld, dss, ld, ssw, td, dst, td, false, s); });
+        t->addb([=](cudaStream_t s) { return small_gemm_launch(false, false, B, td, ld, dss, ld, ssw, td, dst, td, false, s); });
         const float* saved = t->st_saved;
         const float* w1 = e->pf("time_mlp.1.weight"); const float* w2 = e->pf("time_mlp.3.weight");
         float* dw1 = t->G("time_mlp.1.weight"); float* db1 = t->G("time_mlp.1.bias");
         float* dw2 = t->G("time_mlp.3.weight"); float* db2 = t->G("time_mlp.3.bias");
         const int dr = e->dim_real;
-        t->bwd.push_back([=](cudaStream_t s) { return time_mlp_backward_launch(dst, saved, B, dr, w1, w2, dw1, db1, dw2, db2, s); });
+        t->addb([=](cudaStream_t s) { return time_mlp_backward_launch(dst, saved, B, dr, w1, w2, dw1, db1, dw2, db2, s); });
     }
     for (const AttnSpec& ab : attnblocks(dim)) {
         const float* emb = e->pf("iso_embed.weight");
@@ -477,7 +483,7 @@ int build_training_plan(ndiff_trainer* t) {
         float* dwo = t->G(ab.name + ".attn.to_out.0.weight"); float* dbo = t->G(ab.name + ".attn.to_out.0.bias");
         const float* dcv = t->dcv; const int ld = e->cv_total, off = e->cv_off.at(ab.name), C = ab.C;
         ndiff_trainer* tr = t;
-        t->bwd.push_back([=](cudaStream_t s) {
+        t->addb([=](cudaStream_t s) {
             return iso_vec_backward_launch(emb, reinterpret_cast<const long long*>(tr->e->iso_idx), wv, wo, dcv, ld, off, demb, dwv, dwo, dbo, B, C, s);
         });
     }
@@ -496,7 +502,7 @@ int build_training_plan(ndiff_trainer* t) {
         pa.dw2 = t->G("pos_mlp.fc2.weight"); pa.db2 = t->G("pos_mlp.fc2.bias");
         pa.dwm1 = t->G("pos_block1.mlp.1.weight"); pa.dbm1 = t->G("pos_block1.mlp.1.bias");
         pa.dwm2 = t->G("pos_block2.mlp.1.weight"); pa.dbm2 = t->G("pos_block2.mlp.1.bias");
-        t->bwd.push_back([pa](cudaStream_t s) { return pos_backward_launch(pa, s); });
+        t->addb([pa](cudaStream_t s) { return pos_backward_launch(pa, s); });
     }
     // the TT objects only matter at plan time (pointers and flags were copied into the closures): `keep` may go
     t->built = true;
@@ -678,6 +684,40 @@ int32_t ndiff_trainer_ema_update(ndiff_trainer* t, float weight, void* stream) {
         return 0;
     }
     return ema_lerp_launch(t->flat_ema, t->flat_p, t->n_flat, weight, as_stream(stream));
+}
+
+int32_t ndiff_trainer_time(ndiff_trainer* t, char* out, int32_t cap, void* stream) {
+    // Re-runs the forward and backward launch lists of the LAST step's inputs with a CUDA event around every launch and sums the
+    // durations per kernel family; writes lines "fwd|bwd;family;launches;ms".  (Gradients accumulate once more: call it after
+    // the measurements that matter.)
+    NDIFF_REQUIRE(t && t->built && out && cap > 0, "trainer not finalized / null argument");
+    DeviceGuard dev_guard(t->e->cfg.device);
+    cudaStream_t s = as_stream(stream);
+    std::map<std::string, std::pair<int, double>> acc;
+    cudaEvent_t e0, e1;
+    NDIFF_CUDA_OK(cudaEventCreate(&e0));
+    NDIFF_CUDA_OK(cudaEventCreate(&e1));
+    NDIFF_CUDA_OK(cudaMemsetAsync(t->e->stats, 0, t->e->stats_bytes, s));
+    for (int pass = 0; pass < 2; ++pass) {
+        auto& list = pass ? t->bwd : t->fwd;
+        auto& kinds = pass ? t->bwd_kind : t->fwd_kind;
+        for (size_t i = 0; i < list.size(); ++i) {
+            NDIFF_CUDA_OK(cudaEventRecord(e0, s));
+            if (list[i](s)) return 1;
+            NDIFF_CUDA_OK(cudaEventRecord(e1, s));
+            NDIFF_CUDA_OK(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            NDIFF_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+            auto& a = acc[std::string(pass ? "bwd;" : "fwd;") + kinds[i]];
+            a.first += 1; a.second += ms;
+        }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    std::string txt;
+    for (auto& kv : acc) txt += kv.first + ";" + std::to_string(kv.second.first) + ";" + std::to_string(kv.second.second) + "\n";
+    strncpy(out, txt.c_str(), cap - 1);
+    out[cap - 1] = 0;
+    return 0;
 }
 
 int64_t ndiff_trainer_activation_bytes(const ndiff_trainer* t) { return t ? static_cast<int64_t>(t->act_bytes) : 0; }

@@ -152,6 +152,9 @@ class DiffusionTrainer:
     # ---- views of the library's flat buffers -------------------------------------------------------------------
     def _flat(self, which: int) -> torch.Tensor:
         """Zero-copy fp32 view of flat buffer `which` (0 parameters, 1 gradients, 2 Adam m, 3 Adam v, 4 EMA) — library memory."""
+        cache = self.__dict__.setdefault("_flat_cache", {})
+        if which in cache:
+            return cache[which][1]
         p, n_live, n_tot = C.c_void_p(), C.c_int64(), C.c_int64()
         _lib.check(self.lib.ndiff_trainer_flat(self._h, which, C.byref(p), C.byref(n_live), C.byref(n_tot)))
         n = n_tot.value
@@ -161,7 +164,7 @@ class DiffusionTrainer:
         hold = _Holder()
         hold.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (p.value, False), "version": 3, "strides": None}
         t = torch.as_tensor(hold, device=self.device)
-        self._keep.append(hold)
+        cache[which] = (hold, t)
         return t
 
     def _slot(self, name: str):
@@ -236,6 +239,17 @@ class DiffusionTrainer:
     def set_epoch(self, epoch: int, max_iter: int):
         """``scheduler.step()`` at the top of every epoch (ref :152-154)."""
         self.lr = cosine_lr(self.base_lr, epoch, max_iter)
+
+    def time_families(self):
+        """Per-kernel-family durations of the last step's launch lists: [(pass, family, launches, ms)]."""
+        buf = C.create_string_buffer(16 * 1024)
+        with torch.cuda.device(self.device_index):
+            _lib.check(self.lib.ndiff_trainer_time(self._h, buf, len(buf), self._stream()))
+        rows = []
+        for line in buf.value.decode().strip().split("\n"):
+            ps, fam, n, ms = line.split(";")
+            rows.append((ps, fam, int(n), float(ms)))
+        return rows
 
     @property
     def activation_bytes(self) -> int:

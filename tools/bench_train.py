@@ -100,6 +100,7 @@ def main():
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         same = bool(torch.equal(lo, hi))
+    fam = tr.time_families() if rank == 0 else None       # (re-runs the last step's launch lists with an event around every launch)
     if rank == 0:
         n_params = int(flat.numel())
         line = {"metric": "diffusion training samples/s (forward + backward + all-reduce + Adam + EMA, 4x%dx%d)" % (S, S),
@@ -109,6 +110,7 @@ def main():
                 "allreduce_busbw_gbs": (2.0 * (world - 1) / world) * n_params * 4 / (ar_ms * 1e-3) / 1e9 if world > 1 else None,
                 "ranks_hold_identical_parameters": same, "loss_first": losses[0], "loss_last": losses[-1],
                 "activation_gib": tr.activation_bytes / 2 ** 30, "launches_fwd_bwd": tr.launches,
+                "ms_per_kernel_family": {f"{ps}:{k}": {"launches": n, "ms": round(ms, 3)} for ps, k, n, ms in fam},
                 "config": {"workload": "BASELINE configs[4]: NoiseDiffNet dim=64, T=1000 sigmoid2 pred_v, per-sample random t"}}
         print(json.dumps(line), flush=True)
         if args.out:
