@@ -21,9 +21,9 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     return u;
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
-__device__ __forceinline__ float silu_grad(float y) {          // d/dy [y * sigmoid(y)]
-    const float s = sigmoidf_(y);
-    return s * (1.0f + y * (1.0f - s));
+__device__ __forceinline__ float silu_grad(float y) {          // d/dy [y * sigmoid(y)] = s (1 + y (1 - s)), s = 0.5 + 0.5 tanh(y / 2)
+    const float s = fmaf(0.5f, tanh_approx(0.5f * y), 0.5f);   // one MUFU op (the exp + reciprocal form needs two)
+    return s * fmaf(y, 1.0f - s, 1.0f);
 }
 __device__ __forceinline__ float gelu_grad(float x) {          // d/dx [x * Phi(x)] = Phi(x) + x * phi(x)
     const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
@@ -102,26 +102,43 @@ __global__ void __launch_bounds__(kT) gn_bwd_stats_kernel(const GnBwdArgs a) {
     const uint4* din = reinterpret_cast<const uint4*>(a.dout) + base;
     const uint4* mp = kMaps ? reinterpret_cast<const uint4*>(a.maps) + (base - cvi) * 2 : nullptr;
     uint4* dmp = kMaps ? reinterpret_cast<uint4*>(a.dmaps) + (base - cvi) * 2 : nullptr;
-    for (int p = blockIdx.x * ppb + lane_p; p < a.HW; p += gridDim.x * ppb) {
-        const size_t o = static_cast<size_t>(p) * cv;
-        float hv[8], dv[8], ms[8], mh[8];
-        unpack8(__ldg(hin + o), hv);
-        unpack8(__ldg(din + o), dv);
-        if (kMaps) { unpack8(__ldg(mp + o * 2 + cvi), ms); unpack8(__ldg(mp + o * 2 + cv + cvi), mh); }
-        float dsc[8], dsh[8];
+    // two pixels per iteration, all 16-byte loads issued before the arithmetic (the SiLU-gradient chain is long)
+    const int pstride = gridDim.x * ppb;
+    for (int p0 = blockIdx.x * ppb + lane_p; p0 < a.HW; p0 += 2 * pstride) {
+        uint4 hq[2], dq[2], msq[2], mhq[2];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float xh = fmaf(hv[j], k.rs, k.nm);
-            const float y1 = fmaf(xh, gam[j], bet[j]);
-            const float s1 = kMaps ? ms[j] + 1.0f : sc1[j];
-            const float y2 = fmaf(y1, s1, kMaps ? mh[j] : sh[j]);
-            const float dy2 = dv[j] * silu_grad(y2);
-            const float dy1 = kMaps ? dy2 * s1 : dy2;        // per-sample scale is applied after the pixel sum
-            u1[j] += dy1;
-            u2[j] = fmaf(dy1, xh, u2[j]);
-            if (kMaps) { dsc[j] = dy2 * y1; dsh[j] = dy2; }
+        for (int i = 0; i < 2; ++i) {
+            const int p = p0 + i * pstride;
+            if (p < a.HW) {
+                const size_t o = static_cast<size_t>(p) * cv;
+                hq[i] = __ldg(hin + o); dq[i] = __ldg(din + o);
+                if (kMaps) { msq[i] = __ldg(mp + o * 2 + cvi); mhq[i] = __ldg(mp + o * 2 + cv + cvi); }
+            }
         }
-        if (kMaps) { dmp[o * 2 + cvi] = pack8(dsc); dmp[o * 2 + cv + cvi] = pack8(dsh); }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int p = p0 + i * pstride;
+            if (p >= a.HW) break;
+            const size_t o = static_cast<size_t>(p) * cv;
+            float hv[8], dv[8], ms[8], mh[8];
+            unpack8(hq[i], hv);
+            unpack8(dq[i], dv);
+            if (kMaps) { unpack8(msq[i], ms); unpack8(mhq[i], mh); }
+            float dsc[8], dsh[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xh = fmaf(hv[j], k.rs, k.nm);
+                const float y1 = fmaf(xh, gam[j], bet[j]);
+                const float s1 = kMaps ? ms[j] + 1.0f : sc1[j];
+                const float y2 = fmaf(y1, s1, kMaps ? mh[j] : sh[j]);
+                const float dy2 = dv[j] * silu_grad(y2);
+                const float dy1 = kMaps ? dy2 * s1 : dy2;        // per-sample scale is applied after the pixel sum
+                u1[j] += dy1;
+                u2[j] = fmaf(dy1, xh, u2[j]);
+                if (kMaps) { dsc[j] = dy2 * y1; dsh[j] = dy2; }
+            }
+            if (kMaps) { dmp[o * 2 + cvi] = pack8(dsc); dmp[o * 2 + cv + cvi] = pack8(dsh); }
+        }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) { red[threadIdx.x * 16 + j] = u1[j]; red[threadIdx.x * 16 + 8 + j] = u2[j]; }
@@ -182,22 +199,37 @@ __global__ void __launch_bounds__(kT) gn_bwd_apply_kernel(const GnBwdArgs a, con
     const uint4* din = reinterpret_cast<const uint4*>(a.dout) + base;
     uint4* dh = reinterpret_cast<uint4*>(a.dh) + base;
     const uint4* mp = kMaps ? reinterpret_cast<const uint4*>(a.maps) + (base - cvi) * 2 : nullptr;
-    for (int p = blockIdx.x * ppb + lane_p; p < a.HW; p += gridDim.x * ppb) {
-        const size_t o = static_cast<size_t>(p) * cv;
-        float hv[8], dv[8], ms[8], mh[8], r[8];
-        unpack8(__ldg(hin + o), hv);
-        unpack8(__ldg(din + o), dv);
-        if (kMaps) { unpack8(__ldg(mp + o * 2 + cvi), ms); unpack8(__ldg(mp + o * 2 + cv + cvi), mh); }
+    const int pstride = gridDim.x * ppb;
+    for (int p0 = blockIdx.x * ppb + lane_p; p0 < a.HW; p0 += 2 * pstride) {
+        uint4 hq[2], dq[2], msq[2], mhq[2];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float xh = fmaf(hv[j], k.rs, k.nm);
-            const float y1 = fmaf(xh, gam[j], bet[j]);
-            const float s1 = kMaps ? ms[j] + 1.0f : sc1[j];
-            const float y2 = fmaf(y1, s1, kMaps ? mh[j] : sh[j]);
-            const float dxh = dv[j] * silu_grad(y2) * s1 * gam[j];
-            r[j] = k.rs * (dxh - m1 - xh * m2);
+        for (int i = 0; i < 2; ++i) {
+            const int p = p0 + i * pstride;
+            if (p < a.HW) {
+                const size_t o = static_cast<size_t>(p) * cv;
+                hq[i] = __ldg(hin + o); dq[i] = __ldg(din + o);
+                if (kMaps) { msq[i] = __ldg(mp + o * 2 + cvi); mhq[i] = __ldg(mp + o * 2 + cv + cvi); }
+            }
         }
-        dh[o] = pack8(r);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int p = p0 + i * pstride;
+            if (p >= a.HW) break;
+            float hv[8], dv[8], ms[8], mh[8], r[8];
+            unpack8(hq[i], hv);
+            unpack8(dq[i], dv);
+            if (kMaps) { unpack8(msq[i], ms); unpack8(mhq[i], mh); }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xh = fmaf(hv[j], k.rs, k.nm);
+                const float y1 = fmaf(xh, gam[j], bet[j]);
+                const float s1 = kMaps ? ms[j] + 1.0f : sc1[j];
+                const float y2 = fmaf(y1, s1, kMaps ? mh[j] : sh[j]);
+                const float dxh = dv[j] * silu_grad(y2) * s1 * gam[j];
+                r[j] = k.rs * (dxh - m1 - xh * m2);
+            }
+            dh[static_cast<size_t>(p) * cv] = pack8(r);
+        }
     }
 }
 
@@ -614,18 +646,21 @@ __global__ void __launch_bounds__(kT) time_mlp_bwd_kernel(const float* __restric
 
 __global__ void __launch_bounds__(kT) small_gemm_kernel(int tA, int tB, int M, int N, int K, const float* __restrict__ A, int lda,
                                                         const float* __restrict__ Bm, int ldb, float* __restrict__ C, int ldc,
-                                                        int accumulate) {
+                                                        int accumulate, int kchunk) {
+    // blockIdx.y = K split (partials meet in atomics; C was zeroed by the launcher unless it accumulates anyway)
     const size_t total = static_cast<size_t>(M) * N;
+    const int k0 = blockIdx.y * kchunk, k1 = k0 + kchunk < K ? k0 + kchunk : K;
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const int m = static_cast<int>(i / N), n = static_cast<int>(i % N);
         float acc = 0.f;
-        for (int k = 0; k < K; ++k) {
+        for (int k = k0; k < k1; ++k) {
             const float av = tA ? A[static_cast<size_t>(k) * lda + m] : A[static_cast<size_t>(m) * lda + k];
             const float bv = tB ? Bm[static_cast<size_t>(n) * ldb + k] : Bm[static_cast<size_t>(k) * ldb + n];
             acc = fmaf(av, bv, acc);
         }
         float* c = C + static_cast<size_t>(m) * ldc + n;
-        *c = accumulate ? *c + acc : acc;
+        if (gridDim.y > 1) atomicAdd(c, acc);
+        else *c = accumulate ? *c + acc : acc;
     }
 }
 
@@ -669,20 +704,32 @@ __global__ void __launch_bounds__(128) iso_vec_bwd_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// positional path backward.  Block = 256 threads working on chunks of 256 pixels:
-//   phase 1 (thread = pixel): forward recompute -> ps[8] (SiLU(pos_emb)) to shared memory
-//   phase 2 (thread = map channel of block1 / block2, 2 x 2C = 256 for C = 64): dwm[c][k] += dmap[p][c] * ps[p][k] in registers
-//   phase 3 (thread = pixel): dps = Wm^T dmap, then the small MLP's backward, reduced per warp and accumulated in shared memory
+// positional path backward.  Block = 256 threads working on chunks of 256 pixels, four phases per chunk:
+//   1  (thread = pixel)        forward recompute; ps = SiLU(pos_emb) -> shared memory
+//   2  (thread = map channel)  2 x 2C = 256 channels of the two ResnetBlock2 heads: dwm[c][k] += dmap[p][c] * ps[p][k] in registers
+//   3a (thread = pixel)        dps = Wm^T dmap, then back through SiLU / fc2 / GELU / fc1 / sin-cos features: the per-pixel
+//                              vectors every parameter gradient is an outer product of go to shared memory (row V[p])
+//   3b (thread = parameter)    each of the 560 small parameters sums its products V[p][ia] * V[p][ib] over the chunk's pixels in
+//                              a register that lives for the whole kernel (a first version reduced every product over the warp
+//                              with shuffles: 6.9 ms at B = 32; the parameter-major form needs two shared loads per product)
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kPosSmall = 16 + 8 + 384 + 16 + 128 + 8;      // we, be, w1, b1, w2, b2
+constexpr int kPosSmall = 16 + 8 + 384 + 16 + 128 + 8;      // we, be, w1, b1, w2, b2 (offsets 0, 16, 24, 408, 424, 552)
+constexpr int kPosRow = 75;                                  // V row: dpe 8 | hact 16 | da 16 | feat 24 | dw 8 | p0 | p1 (+1: odd pitch)
+__device__ __forceinline__ void pos_param_operands(int q, int& ia, int& ib) {
+    if (q < 16) { ia = 64 + (q >> 1); ib = 72 + (q & 1); }                       // pos_enc weight [8][2]: dw[j] * p{0,1}
+    else if (q < 24) { ia = 64 + (q - 16); ib = -1; }                            // pos_enc bias
+    else if (q < 408) { const int i = q - 24; ia = 24 + i / 24; ib = 40 + i % 24; }   // fc1 weight [16][24]: da[o] * feat[k]
+    else if (q < 424) { ia = 24 + (q - 408); ib = -1; }                          // fc1 bias
+    else if (q < 552) { const int i = q - 424; ia = i / 16; ib = 8 + i % 16; }    // fc2 weight [8][16]: dpe[o] * hact[k]
+    else { ia = q - 552; ib = -1; }                                              // fc2 bias
+}
 __global__ void __launch_bounds__(kT) pos_bwd_kernel(const PosBwdArgs a) {
     extern __shared__ float sm[];
     const int C2 = 2 * a.fwd.C;              // map channels per block (128)
     float* wm = sm;                          // [2][C2][8]
     float* small = wm + 2 * C2 * 8;          // forward copies of the small weights (layout of pos_maps_kernel)
-    float* gsmall = small + kPosSmall;       // their gradients
-    float* ps_s = gsmall + kPosSmall;        // [256][8]
-    float* dps_s = ps_s + kT * 8;            // [256][8]
+    float* ps_s = small + kPosSmall;         // [256][8]
+    float* V = ps_s + kT * 8;                // [256][kPosRow]
     for (int i = threadIdx.x; i < C2 * 8; i += kT) { wm[i] = a.fwd.wm1[i]; wm[C2 * 8 + i] = a.fwd.wm2[i]; }
     for (int i = threadIdx.x; i < 16; i += kT) small[i] = a.fwd.we[i];
     for (int i = threadIdx.x; i < 8; i += kT) small[16 + i] = a.fwd.be[i];
@@ -690,23 +737,31 @@ __global__ void __launch_bounds__(kT) pos_bwd_kernel(const PosBwdArgs a) {
     for (int i = threadIdx.x; i < 16; i += kT) small[408 + i] = a.fwd.b1[i];
     for (int i = threadIdx.x; i < 128; i += kT) small[424 + i] = a.fwd.w2[i];
     for (int i = threadIdx.x; i < 8; i += kT) small[552 + i] = a.fwd.b2[i];
-    for (int i = threadIdx.x; i < kPosSmall; i += kT) gsmall[i] = 0.f;
     __syncthreads();
     const size_t npix = static_cast<size_t>(a.fwd.B) * a.fwd.HW;
-    const int lane = threadIdx.x & 31;
     // phase-2 ownership: thread -> (which block, map channel); requires 2 * C2 == 256
     const int which = threadIdx.x / C2, mc = threadIdx.x % C2;
     const bf16* dmap_mine = which ? a.dmap2 : a.dmap1;
     float gwm[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, gbm = 0.f;
+    // phase-3b ownership: parameters threadIdx.x, + 256, + 512
+    int pia[3], pib[3];
+    float pacc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int q = threadIdx.x + r * kT;
+        pia[r] = 0; pib[r] = -1;
+        if (q < kPosSmall) pos_param_operands(q, pia[r], pib[r]);
+    }
     for (size_t base = static_cast<size_t>(blockIdx.x) * kT; base < npix; base += static_cast<size_t>(gridDim.x) * kT) {
         const size_t pix = base + threadIdx.x;
         const bool live = pix < npix;
+        const size_t n_here = npix - base < kT ? npix - base : kT;
         // ---- phase 1: forward recompute for my pixel
-        float feat[24], pre1[16], hact[16], pe[8];
+        float feat[24], pre1[16], hact[16], pe[8], p0, p1;
         {
             const size_t pp = live ? pix : npix - 1;
             const size_t b = pp / a.fwd.HW, hw = pp % a.fwd.HW;
-            const float p0 = a.fwd.position[(b * 2 + 0) * a.fwd.HW + hw], p1 = a.fwd.position[(b * 2 + 1) * a.fwd.HW + hw];
+            p0 = a.fwd.position[(b * 2 + 0) * a.fwd.HW + hw]; p1 = a.fwd.position[(b * 2 + 1) * a.fwd.HW + hw];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float w = small[j * 2] * p0 + small[j * 2 + 1] * p1 + small[16 + j];
@@ -731,76 +786,61 @@ __global__ void __launch_bounds__(kT) pos_bwd_kernel(const PosBwdArgs a) {
         }
         __syncthreads();
         // ---- phase 2: my map channel against the chunk's pixels
-        {
-            const size_t n_here = npix - base < kT ? npix - base : kT;
-            for (size_t q = 0; q < n_here; ++q) {
-                const float g = __bfloat162float(dmap_mine[(base + q) * C2 + mc]);
-                gbm += g;
+        for (size_t q = 0; q < n_here; ++q) {
+            const float g = __bfloat162float(dmap_mine[(base + q) * C2 + mc]);
+            gbm += g;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) gwm[k] = fmaf(g, ps_s[q * 8 + k], gwm[k]);
-            }
+            for (int k = 0; k < 8; ++k) gwm[k] = fmaf(g, ps_s[q * 8 + k], gwm[k]);
         }
-        // ---- phase 3: my pixel: dps = Wm1^T dmap1 + Wm2^T dmap2
-        float dps[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (live) {
-            for (int w = 0; w < 2; ++w) {
-                const uint4* row = reinterpret_cast<const uint4*>((w ? a.dmap2 : a.dmap1) + pix * C2);
-                for (int c8 = 0; c8 < C2 / 8; ++c8) {
-                    float g[8];
-                    unpack8(__ldg(row + c8), g);
+        // ---- phase 3a: my pixel: dps = Wm1^T dmap1 + Wm2^T dmap2, then back through the small MLP; row V[p] to shared memory
+        {
+            float dps[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (live) {
+                for (int w = 0; w < 2; ++w) {
+                    const uint4* row = reinterpret_cast<const uint4*>((w ? a.dmap2 : a.dmap1) + pix * C2);
+                    for (int c8 = 0; c8 < C2 / 8; ++c8) {
+                        float g[8];
+                        unpack8(__ldg(row + c8), g);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
+                        for (int j = 0; j < 8; ++j)
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) dps[k] = fmaf(g[j], wm[(w * C2 + c8 * 8 + j) * 8 + k], dps[k]);
+                            for (int k = 0; k < 8; ++k) dps[k] = fmaf(g[j], wm[(w * C2 + c8 * 8 + j) * 8 + k], dps[k]);
+                    }
                 }
             }
-        }
-        // backward through SiLU, fc2, GELU, fc1, the sinusoidal features and pos_enc; every parameter contribution is summed
-        // over the warp's 32 pixels before it touches shared memory
-        float dpe[8], dh[16], da[16], dfeat[24];
+            float* row = V + threadIdx.x * kPosRow;
+            float dpe[8], dh[16], dfeat[24];
 #pragma unroll
-        for (int o = 0; o < 8; ++o) dpe[o] = live ? dps[o] * silu_grad(pe[o]) : 0.f;
+            for (int o = 0; o < 8; ++o) { dpe[o] = live ? dps[o] * silu_grad(pe[o]) : 0.f; row[o] = dpe[o]; }
 #pragma unroll
-        for (int k = 0; k < 16; ++k) dh[k] = 0.f;
+            for (int k = 0; k < 16; ++k) { dh[k] = 0.f; row[8 + k] = hact[k]; }
 #pragma unroll
-        for (int o = 0; o < 8; ++o) {
-            float v = warp_sum(dpe[o]);
-            if (lane == 0) atomicAdd(&gsmall[552 + o], v);
+            for (int o = 0; o < 8; ++o)
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                dh[k] = fmaf(small[424 + o * 16 + k], dpe[o], dh[k]);
-                v = warp_sum(dpe[o] * hact[k]);
-                if (lane == 0) atomicAdd(&gsmall[424 + o * 16 + k], v);
+                for (int k = 0; k < 16; ++k) dh[k] = fmaf(small[424 + o * 16 + k], dpe[o], dh[k]);
+#pragma unroll
+            for (int k = 0; k < 24; ++k) { dfeat[k] = 0.f; row[40 + k] = feat[k]; }
+#pragma unroll
+            for (int o = 0; o < 16; ++o) {
+                const float da = dh[o] * gelu_grad(pre1[o]);
+                row[24 + o] = da;
+#pragma unroll
+                for (int k = 0; k < 24; ++k) dfeat[k] = fmaf(small[24 + o * 24 + k], da, dfeat[k]);
             }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)      // feat = (w, sin(2 pi w), cos(2 pi w))
+                row[64 + j] = dfeat[j] + 6.28318530717958647692f * (dfeat[8 + j] * feat[16 + j] - dfeat[16 + j] * feat[8 + j]);
+            row[72] = p0; row[73] = p1;
         }
+        __syncthreads();
+        // ---- phase 3b: my parameters against the chunk's rows (rows of dead pixels carry zero gradients)
 #pragma unroll
-        for (int k = 0; k < 24; ++k) dfeat[k] = 0.f;
-#pragma unroll
-        for (int o = 0; o < 16; ++o) {
-            da[o] = dh[o] * gelu_grad(pre1[o]);
-            float v = warp_sum(da[o]);
-            if (lane == 0) atomicAdd(&gsmall[408 + o], v);
-#pragma unroll
-            for (int k = 0; k < 24; ++k) {
-                dfeat[k] = fmaf(small[24 + o * 24 + k], da[o], dfeat[k]);
-                v = warp_sum(da[o] * feat[k]);
-                if (lane == 0) atomicAdd(&gsmall[24 + o * 24 + k], v);
-            }
-        }
-        {
-            const size_t pp = live ? pix : npix - 1;
-            const size_t b = pp / a.fwd.HW, hw = pp % a.fwd.HW;
-            const float p0 = a.fwd.position[(b * 2 + 0) * a.fwd.HW + hw], p1 = a.fwd.position[(b * 2 + 1) * a.fwd.HW + hw];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                // feat = (w, sin(2 pi w), cos(2 pi w))
-                const float dw = dfeat[j] + 6.28318530717958647692f * (dfeat[8 + j] * feat[16 + j] - dfeat[16 + j] * feat[8 + j]);
-                float v = warp_sum(dw * p0);
-                if (lane == 0) atomicAdd(&gsmall[j * 2], v);
-                v = warp_sum(dw * p1);
-                if (lane == 0) atomicAdd(&gsmall[j * 2 + 1], v);
-                v = warp_sum(dw);
-                if (lane == 0) atomicAdd(&gsmall[16 + j], v);
+        for (int r = 0; r < 3; ++r) {
+            if (threadIdx.x + r * kT < kPosSmall) {
+                float acc = 0.f;
+                if (pib[r] >= 0) { for (size_t q = 0; q < n_here; ++q) acc = fmaf(V[q * kPosRow + pia[r]], V[q * kPosRow + pib[r]], acc); }
+                else { for (size_t q = 0; q < n_here; ++q) acc += V[q * kPosRow + pia[r]]; }
+                pacc[r] += acc;
             }
         }
         __syncthreads();
@@ -812,13 +852,14 @@ __global__ void __launch_bounds__(kT) pos_bwd_kernel(const PosBwdArgs a) {
         for (int k = 0; k < 8; ++k) atomicAdd(dwm + mc * 8 + k, gwm[k]);
         atomicAdd(dbm + mc, gbm);
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 16; i += kT) atomicAdd(a.dwe + i, gsmall[i]);
-    for (int i = threadIdx.x; i < 8; i += kT) atomicAdd(a.dbe + i, gsmall[16 + i]);
-    for (int i = threadIdx.x; i < 384; i += kT) atomicAdd(a.dw1 + i, gsmall[24 + i]);
-    for (int i = threadIdx.x; i < 16; i += kT) atomicAdd(a.db1 + i, gsmall[408 + i]);
-    for (int i = threadIdx.x; i < 128; i += kT) atomicAdd(a.dw2 + i, gsmall[424 + i]);
-    for (int i = threadIdx.x; i < 8; i += kT) atomicAdd(a.db2 + i, gsmall[552 + i]);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int q = threadIdx.x + r * kT;
+        if (q >= kPosSmall) continue;
+        float* dst = q < 16 ? a.dwe + q : (q < 24 ? a.dbe + (q - 16) : (q < 408 ? a.dw1 + (q - 24) : (q < 424 ? a.db1 + (q - 408)
+                     : (q < 552 ? a.dw2 + (q - 424) : a.db2 + (q - 552)))));
+        atomicAdd(dst, pacc[r]);
+    }
 }
 
 __global__ void __launch_bounds__(kT) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -984,8 +1025,15 @@ int time_mlp_backward_launch(const float* dst, const float* saved, int n, int di
 }
 int small_gemm_launch(bool tA, bool tB, int M, int N, int K, const float* A, int lda, const float* Bm, int ldb, float* C, int ldc,
                       bool accumulate, cudaStream_t s) {
-    small_gemm_kernel<<<blocks_for(static_cast<size_t>(M) * N, kT, 148 * 16), kT, 0, s>>>(tA ? 1 : 0, tB ? 1 : 0, M, N, K, A, lda, Bm, ldb, C, ldc,
-                                                                                         accumulate ? 1 : 0);
+    // long contractions with few outputs (d time-vector = d(scale, shift) @ W: 32 x 256 outputs, K = 8192) are split over K
+    const int kchunk = K >= 2048 ? 256 : K;
+    const int splits = (K + kchunk - 1) / kchunk;
+    if (splits > 1 && !accumulate) {
+        NDIFF_REQUIRE(ldc == N, "small GEMM: split-K overwrite needs a dense C");
+        NDIFF_CUDA_OK(cudaMemsetAsync(C, 0, static_cast<size_t>(M) * N * sizeof(float), s));
+    }
+    dim3 grid(blocks_for(static_cast<size_t>(M) * N, kT, 148 * 16), splits);
+    small_gemm_kernel<<<grid, kT, 0, s>>>(tA ? 1 : 0, tB ? 1 : 0, M, N, K, A, lda, Bm, ldb, C, ldc, accumulate ? 1 : 0, kchunk);
     NDIFF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1006,7 +1054,7 @@ int iso_vec_backward_launch(const float* emb_table, const long long* idx, const 
 int pos_backward_launch(const PosBwdArgs& a, cudaStream_t s) {
     NDIFF_REQUIRE(a.fwd.C == 64, "positional backward: the ResnetBlock2 maps have 2 x 64 (physical) channels");
     const int C2 = 2 * a.fwd.C;
-    const size_t smem = (2 * C2 * 8 + 2 * kPosSmall + 2 * kT * 8) * sizeof(float);
+    const size_t smem = (2 * C2 * 8 + kPosSmall + kT * 8 + kT * kPosRow) * sizeof(float);
     static bool opted = false;
     if (!opted) {
         NDIFF_CUDA_OK(cudaFuncSetAttribute(pos_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

@@ -100,9 +100,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ===============================================================
-        constexpr uint32_t idesc = umma_idesc_bf16(128, 64) | (1u << 15) | (1u << 16);      // A and B MN-major
+        // 3x3: ONE MMA per K step covers the three taps of the kernel row: N = 192 = three 64-channel chunks whose "leading
+        // byte offset" is 128 B — chunk j is the same halo window shifted by j pixels (kx = j).  The issuing thread is a serial
+        // instruction stream (a first version with one N = 64 MMA per tap spent ~80 cycles of address arithmetic per 32-cycle
+        // MMA); now a tile is 8 MMAs of 96 tensor-pipe cycles whose descriptors differ by compile-time immediates.
+        constexpr int kN = kHalo ? 192 : 64;
+        constexpr uint32_t idesc = umma_idesc_bf16(128, kN) | (1u << 15) | (1u << 16);      // A and B MN-major
         constexpr uint32_t hiA = umma_desc_hi(1024);                                         // 8-pixel groups 1024 B apart
         constexpr uint32_t hiB = umma_desc_hi(kHalo ? kHaloPitchW : 1024);                   // ... one halo row apart for X
+        constexpr uint32_t kBStep = (kHalo ? 2 * kHaloPitchW : 2048) >> 4;                   // two image rows per K step
         int s = 0, ph = 0;
         uint32_t accum = 0u;
         for (int tile = t0; tile < t1; ++tile) {
@@ -110,17 +116,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t st = ring + s * kStage;
-#pragma unroll 1
-                for (int ks = 0; ks < 8; ++ks) {            // 16 pixels = image rows 2 ks, 2 ks + 1 of the 16 x 8 tile
-                    const uint32_t a_lo = desc_lo_mn(st + ks * 2048, kDyBlk);
-#pragma unroll 1
-                    for (int t = 0; t < a.taps_per_group; ++t) {
-                        const uint32_t xs = kHalo ? st + 2 * kDyBlk + ((2 * ks + tg) * 10 + t) * 128       // tap (ky = tg, kx = t)
-                                                  : st + 2 * kDyBlk + ks * 2048;
-                        umma_bf16_lohi_pred(tmem_base + t * 64, a_lo, hiA, desc_lo_mn(xs, 1024), hiB, idesc, accum);
-                    }
-                    accum = 1u;
-                }
+                const uint32_t a_lo = desc_lo_mn(st, kDyBlk);
+                // kernel row ky = tg: the window starts tg halo rows down; chunk stride (LBO) 128 B = one pixel = one kx step
+                const uint32_t b_lo = kHalo ? desc_lo_mn(st + 2 * kDyBlk + tg * kHaloPitchW, 128) : desc_lo_mn(st + 2 * kDyBlk, 1024);
+                umma_bf16_lohi_pred(tmem_base, a_lo, hiA, b_lo, hiB, idesc, accum);
+#pragma unroll
+                for (int ks = 1; ks < 8; ++ks)              // 16 pixels = image rows 2 ks, 2 ks + 1 of the 16 x 8 tile
+                    umma_bf16_lohi<true>(tmem_base, a_lo + ks * 128, hiA, b_lo + ks * kBStep, hiB, idesc);
+                accum = 1u;
                 umma_commit(bar_empty + s * 8);
                 if (tile == t1 - 1) umma_commit(bar_tfull);
             }
