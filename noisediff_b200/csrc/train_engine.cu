@@ -91,8 +91,11 @@ struct ndiff_trainer {
     int err = 0;
     int stats_slot = 0;
     size_t act_bytes = 0;
+    int steps_run = 0;
+    cudaGraphExec_t step_exec = nullptr;      // time path + forward + backward of one step (captured on the second step)
 
     ~ndiff_trainer() {
+        if (step_exec) cudaGraphExecDestroy(step_exec);
         for (void* p : owned) cudaFree(p);
         delete e;
     }
@@ -148,6 +151,8 @@ struct TB {      // plan builder
         if (res) { d.res = res->p; d.res_ld = res->C; }
         d.out = out.p; d.out_ld = Cout;
         d.stats = stats; d.groups = groups;
+        // 256-pixel tiles + weight-stationary MMAs where the sampling path uses them (64 -> 64, single source; engine.cu Builder::conv)
+        if (mode == kHalo1 && Ho >= 32 && Cout == 64 && s0->C == 64 && !s1) d.mode = kHalo2;
         auto plan = std::make_shared<ConvGemmPlan>();
         if (conv_gemm_plan(d, e->num_sms, plan.get())) { t->err = 1; return out; }
         t->kind = "conv_fwd"; t->addf([plan](cudaStream_t s) { return conv_gemm_launch(*plan, s); });
@@ -176,7 +181,8 @@ struct TB {      // plan builder
             // (runs at plan time, in reverse forward order)  gradient of `out` is complete in o.g
             const size_t np = static_cast<size_t>(tr->B) * o.H * o.W;
             float* gb = tr->G(wname + ".bias");
-            tr->kind = "bias_grad"; tr->addb([=](cudaStream_t s) { return colsum_launch(o.g, o.C, 0, gb, 0, false, tr->B, o.H * o.W, o.C, s); });
+            // (a conv followed by GroupNorm gets its bias gradient from the GroupNorm backward's second pass: GnBwdArgs::dbias)
+            if (!stats) { tr->kind = "bias_grad"; tr->addb([=](cudaStream_t s) { return colsum_launch(o.g, o.C, 0, gb, 0, false, tr->B, o.H * o.W, o.C, s); }); }
             if (vec) {
                 float* dcv = tr->dcv + vec_off;
                 const int ld = tr->e->cv_total;
@@ -216,6 +222,7 @@ struct TB {      // plan builder
                 TT* src = si == 0 ? s0 : s1;
                 ConvGemmDesc g;
                 g.mode = mode; g.B = tr->B; g.H = o.H; g.W = o.W;       // kHalo1 (flipped taps) or kDirect (transposed 1x1)
+                if (mode == kHalo1 && o.H >= 32 && o.C == 64 && src->C == 64) g.mode = kHalo2;
                 g.src0 = o.g; g.C0 = o.C;
                 g.weight = si == 0 ? dw0 : dw1;
                 g.Cout = src->C; g.out = src->g; g.out_ld = src->C;
@@ -230,8 +237,8 @@ struct TB {      // plan builder
     }
 
     // ---- GroupNorm + (scale+1)/shift + SiLU (+ residual adds), out of place: h stays for the backward pass ---------------
-    TT gn(const std::string& nname, TT* h, unsigned long long* stats, int groups, int ss_off, const bf16* maps, bf16* dmaps, TT* r1,
-          TT* r2) {
+    TT gn(const std::string& nname, const std::string& conv_name, TT* h, unsigned long long* stats, int groups, int ss_off,
+          const bf16* maps, bf16* dmaps, TT* r1, TT* r2) {
         TT out = make(h->C, h->H, h->W);
         if (t->err) return out;
         GnApplyArgs g{};
@@ -255,6 +262,7 @@ struct TB {      // plan builder
             b.maps = maps; b.dmaps = dmaps;
             b.acc = tr->gn_acc;
             b.dgamma = tr->G(nname + ".weight"); b.dbeta = tr->G(nname + ".bias");
+            b.dbias = tr->G(conv_name + ".bias");
             if (ss_off >= 0) { b.dss = tr->dss; b.dss_ld = tr->e->ss_total; }
             b.B = tr->B; b.HW = g.HW; b.C = g.C; b.G = groups; b.eps = 1e-5f; b.real_frac = 1.0f;
             tr->kind = "gn_bwd"; tr->addb([b](cudaStream_t s) { return gn_backward_launch(b, s); });
@@ -286,12 +294,12 @@ struct TB {      // plan builder
         const int Cin = s0->C + (s1 ? s1->C : 0);
         unsigned long long* st1 = next_stats();
         TT* h1 = hold(conv(n + ".block1.proj", kHalo1, s0, s1, Cout, nullptr, 0, nullptr, st1, groups));
-        TT* a1 = hold(gn(n + ".block1.norm", h1, st1, groups, maps ? -1 : e->ss_off.at(n), maps, dmaps, nullptr, nullptr));
+        TT* a1 = hold(gn(n + ".block1.norm", n + ".block1.proj", h1, st1, groups, maps ? -1 : e->ss_off.at(n), maps, dmaps, nullptr, nullptr));
         unsigned long long* st2 = next_stats();
         TT* h2 = hold(conv(n + ".block2.proj", kHalo1, a1, nullptr, Cout, nullptr, 0, nullptr, st2, groups));
         TT* r = s0;
         if (Cin != Cout) r = hold(conv(n + ".res_conv", kDirect, s0, s1, Cout, nullptr, 0, nullptr, nullptr, 0));
-        return gn(n + ".block2.norm", h2, st2, groups, -1, nullptr, nullptr, r, extra_res);
+        return gn(n + ".block2.norm", n + ".block2.proj", h2, st2, groups, -1, nullptr, nullptr, r, extra_res);
     }
 
     // AttnBlock with the collapsed 1-token cross attention (Diffusion_arch.py:425-443):
@@ -621,18 +629,38 @@ int32_t ndiff_trainer_forward_backward(ndiff_trainer* t, const float* x_t_dev, c
     NDIFF_CUDA_OK(cudaMemcpyAsync(t->w_b, loss_weight_dev, sizeof(float) * t->B, cudaMemcpyDeviceToDevice, s));
     i64_to_i32_kernel2<<<1, 256, 0, s>>>(reinterpret_cast<const long long*>(time_dev), e->t_buf, t->B);
     NDIFF_CUDA_OK(cudaGetLastError());
-    // ---- zero what is accumulated with atomics
-    NDIFF_CUDA_OK(cudaMemsetAsync(t->flat_g, 0, t->n_flat * sizeof(float), s));
-    NDIFF_CUDA_OK(cudaMemsetAsync(t->dcv, 0, static_cast<size_t>(t->B) * e->cv_total * sizeof(float), s));
-    NDIFF_CUDA_OK(cudaMemsetAsync(t->loss, 0, sizeof(double), s));
-    NDIFF_CUDA_OK(cudaMemsetAsync(e->stats, 0, e->stats_bytes, s));
-    // ---- time path (per-sample t): st = SiLU(time_mlp(t)), every ResnetBlock's (scale, shift)
-    if (time_mlp_train_launch(e->t_buf, t->B, e->dim_real, e->pf("time_mlp.1.weight"), e->pf("time_mlp.1.bias"),
-                              e->pf("time_mlp.3.weight"), e->pf("time_mlp.3.bias"), e->st_buf, t->st_saved, s)) return 1;
-    if (rows_gemv_launch(e->ss_w, e->ss_b, e->st_buf, e->ss_cur, t->B, e->ss_total, td, s)) return 1;
     g_use_pdl = false;
-    for (auto& f : t->fwd) if (f(s)) return 1;
-    for (auto& f : t->bwd) if (f(s)) return 1;
+    // Everything below works on the trainer's own buffers: ~650 launches whose arguments never change -> one CUDA graph.  The
+    // first step runs eagerly (one-time kernel attribute set-up happens there), the second is captured, later steps replay.
+    auto run_lists = [&](cudaStream_t st) -> int {
+        // ---- zero what is accumulated with atomics
+        NDIFF_CUDA_OK(cudaMemsetAsync(t->flat_g, 0, t->n_flat * sizeof(float), st));
+        NDIFF_CUDA_OK(cudaMemsetAsync(t->dcv, 0, static_cast<size_t>(t->B) * e->cv_total * sizeof(float), st));
+        NDIFF_CUDA_OK(cudaMemsetAsync(t->loss, 0, sizeof(double), st));
+        NDIFF_CUDA_OK(cudaMemsetAsync(e->stats, 0, e->stats_bytes, st));
+        // ---- time path (per-sample t): st = SiLU(time_mlp(t)), every ResnetBlock's (scale, shift)
+        if (time_mlp_train_launch(e->t_buf, t->B, e->dim_real, e->pf("time_mlp.1.weight"), e->pf("time_mlp.1.bias"),
+                                  e->pf("time_mlp.3.weight"), e->pf("time_mlp.3.bias"), e->st_buf, t->st_saved, st)) return 1;
+        if (rows_gemv_launch(e->ss_w, e->ss_b, e->st_buf, e->ss_cur, t->B, e->ss_total, td, st)) return 1;
+        for (auto& f : t->fwd) if (f(st)) return 1;
+        for (auto& f : t->bwd) if (f(st)) return 1;
+        return 0;
+    };
+    const bool use_graph = (e->cfg.flags & NDIFF_FLAG_NO_GRAPH) == 0 && t->steps_run >= 1;
+    if (use_graph && !t->step_exec) {
+        NDIFF_CUDA_OK(cudaStreamSynchronize(s));
+        cudaGraph_t graph = nullptr;
+        NDIFF_CUDA_OK(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = run_lists(e->cap_stream);
+        const cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return 1; }
+        NDIFF_CUDA_OK(ce);
+        NDIFF_CUDA_OK(cudaGraphInstantiate(&t->step_exec, graph, 0));
+        cudaGraphDestroy(graph);
+    }
+    if (use_graph) NDIFF_CUDA_OK(cudaGraphLaunch(t->step_exec, s));
+    else if (run_lists(s)) return 1;
+    t->steps_run += 1;
     if (loss_host) {
         NDIFF_CUDA_OK(cudaMemcpyAsync(loss_host, t->loss, sizeof(double), cudaMemcpyDeviceToHost, s));
         NDIFF_CUDA_OK(cudaStreamSynchronize(s));

@@ -179,6 +179,8 @@ __global__ void gn_bwd_param_kernel(const GnBwdArgs a, float* __restrict__ gsum)
 
 template <bool kMaps>
 __global__ void __launch_bounds__(kT) gn_bwd_apply_kernel(const GnBwdArgs a, const float* __restrict__ gsum) {
+    __shared__ float red[kT * 8];
+    float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const int b = blockIdx.y, C = a.C, cv = C >> 3, gs = C / a.G;
     const int cvi = threadIdx.x % cv, lane_p = threadIdx.x / cv, ppb = kT / cv, c0 = cvi * 8, g = c0 / gs;
     const GnCoef k = gn_coef(a, b, g, gs);
@@ -227,8 +229,19 @@ __global__ void __launch_bounds__(kT) gn_bwd_apply_kernel(const GnBwdArgs a, con
                 const float y2 = fmaf(y1, s1, kMaps ? mh[j] : sh[j]);
                 const float dxh = dv[j] * silu_grad(y2) * s1 * gam[j];
                 r[j] = k.rs * (dxh - m1 - xh * m2);
+                bsum[j] += r[j];
             }
             dh[static_cast<size_t>(p) * cv] = pack8(r);
+        }
+    }
+    if (a.dbias) {      // h = conv + bias: the bias gradient is the column sum of dh
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[threadIdx.x * 8 + j] = bsum[j];
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += kT) {
+            float t = 0.f;
+            for (int l = 0; l < ppb; ++l) t += red[(l * cv + (c >> 3)) * 8 + (c & 7)];
+            atomicAdd(a.dbias + c, t);
         }
     }
 }

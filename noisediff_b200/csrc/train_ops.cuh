@@ -28,6 +28,8 @@ struct GnBwdArgs {
     const bf16* maps; bf16* dmaps;                // per-pixel [scale C | shift C] and its gradient, or null
     float* acc;                                   // [B][C][2] fp32 scratch (zeroed by the launcher)
     float* dgamma; float* dbeta;                  // [C] fp32, accumulated
+    float* dbias;                                 // optional [C]: bias gradient of the conv that produced h (= column sums of dh),
+                                                  // accumulated by the second pass instead of a separate read of dh
     float* dss; int dss_ld;                       // [B][dss_ld] fp32 gradient of the scale/shift table (written at ss_off), or null
     int B, HW, C, G;
     float eps, real_frac;
