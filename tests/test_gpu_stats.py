@@ -143,7 +143,7 @@ def test_1k_noise_statistics_full_chain_64_match_gpu_oracle_fixture():
     dm = np.abs(st["mean"] - z["mean"]) / np.sqrt(z["var"])
     dv = np.abs(st["var"] - z["var"]) / z["var"]
     dr = np.abs(st["radial"] - z["radial"]) / z["radial"]
-    nzb = z["psd2d"] > 0
+    nzb = z["psd2d"] > 1e-6 * np.median(z["psd2d"])           # the four DC bins are zero up to rounding (patch mean removed)
     dp = np.abs(st["psd2d"] - z["psd2d"])[nzb] / z["psd2d"][nzb]
     print("T=1000, 64x64, 1024 samples")
     print("mean ref", z["mean"].tolist(), "got", st["mean"].tolist(), "|dm|/std", dm.tolist(), "(oracle halves", z["halves_mean"].tolist(), ")")
