@@ -119,6 +119,12 @@ NDIFF_API int32_t ndiff_sample_host(ndiff_engine* e, const float* clean_host, co
                           const int64_t* iso_idx_host, const ndiff_step* steps_host, int32_t n_steps, uint64_t seed,
                           float* out_host);
 
+/* Consumer contract.  Replaces the composition SyntheticNoisDiffDenoisingDataset does with a generated crop
+ * (dataloader/dataset_denoising.py:140-144): noisy = clip(clip(noise, -1, 1) + clean, 0, 1), clean_out = clip(clean, 0, 1)
+ * (clean_out may be NULL).  fp32 device buffers of n elements (n % 4 == 0, 16-byte aligned), any layout. */
+NDIFF_API int32_t ndiff_compose_noisy(const float* noise_dev, const float* clean_dev, float* noisy_out_dev, float* clean_out_dev,
+                                      int64_t n, void* stream);
+
 /* Introspection used by tests / bench. */
 NDIFF_API int32_t ndiff_debug_tensor(ndiff_engine* e, const char* name, float* out_dev_nchw, int64_t* shape4, void* stream);
 NDIFF_API int64_t ndiff_launches_per_step(const ndiff_engine* e);

@@ -53,6 +53,7 @@ _SIGS = {
     "ndiff_chain_read": (C.c_int32, [_P, _P, _P]),
     "ndiff_chain_seek": (C.c_int32, [_P, C.c_int32, _P, C.c_uint64, _P]),
     "ndiff_sample_host": (C.c_int32, [_P, _P, _P, _P, C.POINTER(Step), C.c_int32, C.c_uint64, _P]),
+    "ndiff_compose_noisy": (C.c_int32, [_P, _P, _P, _P, C.c_int64, _P]),
     "ndiff_debug_tensor": (C.c_int32, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), _P]),
     "ndiff_launches_per_step": (C.c_int64, [_P]),
     "ndiff_conv_flops_per_step": (C.c_double, [_P]),

@@ -1582,6 +1582,12 @@ int32_t ndiff_op_layernorm(const void* x, const float* vec, int32_t vec_ld, cons
                             as_stream(stream));
 }
 
+int32_t ndiff_compose_noisy(const float* noise_dev, const float* clean_dev, float* noisy_out_dev, float* clean_out_dev, int64_t n,
+                            void* stream) {
+    NDIFF_REQUIRE(n >= 0 && n % 4 == 0, "compose: element count must be a multiple of 4");
+    return compose_noisy_launch(noise_dev, clean_dev, noisy_out_dev, clean_out_dev, static_cast<size_t>(n / 4), as_stream(stream));
+}
+
 int32_t ndiff_op_philox_normal(float* out, int64_t n4, uint64_t seed, uint64_t stream_id, void* stream) {
     return philox_normal_launch(out, static_cast<size_t>(n4), seed, stream_id, as_stream(stream));
 }

@@ -766,6 +766,17 @@ __global__ void __launch_bounds__(256) nhwc4_to_nchw_kernel(const float4* __rest
     p[0] = v.x; p[HW] = v.y; p[2 * static_cast<size_t>(HW)] = v.z; p[3 * static_cast<size_t>(HW)] = v.w;
 }
 
+__global__ void __launch_bounds__(256) compose_noisy_kernel(const float4* __restrict__ noise, const float4* __restrict__ clean,
+                                                            float4* __restrict__ noisy, float4* __restrict__ clean_out, size_t n4) {
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float4 z = __ldg(noise + i), c = __ldg(clean + i);
+        auto one = [](float zz, float cc) { return fminf(fmaxf(fminf(fmaxf(zz, -1.0f), 1.0f) + cc, 0.0f), 1.0f); };
+        noisy[i] = make_float4(one(z.x, c.x), one(z.y, c.y), one(z.z, c.z), one(z.w, c.w));
+        if (clean_out) clean_out[i] = make_float4(fminf(fmaxf(c.x, 0.f), 1.f), fminf(fmaxf(c.y, 0.f), 1.f), fminf(fmaxf(c.z, 0.f), 1.f),
+                                                  fminf(fmaxf(c.w, 0.f), 1.f));
+    }
+}
+
 inline int blocks_for(size_t n, int per_block, int cap = 1 << 20) {
     size_t b = (n + per_block - 1) / per_block;
     return static_cast<int>(b < static_cast<size_t>(cap) ? (b ? b : 1) : cap);
@@ -941,6 +952,16 @@ int nchw_to_nhwc4_launch(const float* in, float* out, int B, int HW, cudaStream_
 int nhwc4_to_nchw_launch(const float* in, float* out, int B, int HW, cudaStream_t s) {
     const size_t npix = static_cast<size_t>(B) * HW;
     nhwc4_to_nchw_kernel<<<blocks_for(npix, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(in), out, HW, npix);
+    NDIFF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int compose_noisy_launch(const float* noise, const float* clean, float* noisy_out, float* clean_out, size_t n4, cudaStream_t s) {
+    NDIFF_REQUIRE(noise && clean && noisy_out, "compose: null argument");
+    NDIFF_REQUIRE(((reinterpret_cast<uintptr_t>(noise) | reinterpret_cast<uintptr_t>(clean) | reinterpret_cast<uintptr_t>(noisy_out) |
+                    reinterpret_cast<uintptr_t>(clean_out)) & 15) == 0, "compose: buffers must be 16-byte aligned");
+    compose_noisy_kernel<<<blocks_for(n4, 256 * 4, 148 * 16), 256, 0, s>>>(reinterpret_cast<const float4*>(noise), reinterpret_cast<const float4*>(clean),
+                                                                          reinterpret_cast<float4*>(noisy_out), reinterpret_cast<float4*>(clean_out), n4);
     NDIFF_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -114,6 +114,10 @@ int pos_maps_launch(const PosArgs& a, cudaStream_t s);
 int nchw_to_nhwc4_launch(const float* in, float* out, int B, int HW, cudaStream_t s);
 int nhwc4_to_nchw_launch(const float* in, float* out, int B, int HW, cudaStream_t s);
 
+// consumer contract (dataloader/dataset_denoising.py:140-144): noisy = clip(clip(noise, -1, 1) + clean, 0, 1); clean_out = clip(clean, 0, 1)
+// (fp32, any layout: purely elementwise; n4 = number of float4 elements; clean_out may be null)
+int compose_noisy_launch(const float* noise, const float* clean, float* noisy_out, float* clean_out, size_t n4, cudaStream_t s);
+
 int pointwise_init();   // one-time kernel attribute setup (call outside stream capture)
 int philox_normal_launch(float* out, size_t n4, unsigned long long seed, unsigned long long stream_id, cudaStream_t s);
 

@@ -88,6 +88,20 @@ def consumer_subfolder(iso: int, ratio: int) -> str:
 def compose_noisy(clean_crop: torch.Tensor, noise: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """What the consumer does with a generated crop (``dataset_denoising.py:140-153``, without dark shading):
     noise clipped to [-1, 1], added to the clean crop, both clipped to [0, 1].  Returns (clean, noisy)."""
+    if noise.is_cuda:      # on the GPU: one fused elementwise kernel of the library (ndiff_compose_noisy) on the generated batch
+        import ctypes as C
+        from . import _lib
+        z = noise.detach().float().contiguous()
+        c = clean_crop.detach().to(z.device).float().expand_as(z).contiguous()
+        if z.numel() % 4 or (z.data_ptr() | c.data_ptr()) % 16:
+            raise ValueError("compose_noisy: CUDA tensors must hold a multiple of 4 elements in 16-byte aligned storage")
+        noisy, clean = torch.empty_like(z), torch.empty_like(c)
+        with torch.cuda.device(z.device):
+            _lib.check(_lib.lib().ndiff_compose_noisy(C.c_void_p(z.data_ptr()), C.c_void_p(c.data_ptr()), C.c_void_p(noisy.data_ptr()),
+                                                      C.c_void_p(clean.data_ptr()), z.numel(),
+                                                      C.c_void_p(torch.cuda.current_stream(z.device).cuda_stream)))
+        return clean, noisy
+    # host tensors: the consumer's own numpy lines, restated (plumbing on the caller's CPU data, no device involved)
     noisy = (noise.clamp(-1.0, 1.0).float() + clean_crop.float()).clamp(0.0, 1.0)
     return clean_crop.float().clamp(0.0, 1.0), noisy
 

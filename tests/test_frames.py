@@ -244,3 +244,15 @@ def test_identically_seeded_ranks_draw_independent_noise(tmp_path):
     torch.manual_seed(77)
     want = _NoisyFakeDiffusion().sample(4, None)        # a 32 x 32 frame is the same crop four times in the reference's grid
     assert len(p) == 4 and np.array_equal(np.load(p[0]), want[3].numpy())      # (the repeats overwrite one file: the last one stays)
+
+
+@pytest.mark.gpu
+def test_compose_noisy_on_the_gpu_equals_the_consumers_numpy_lines():
+    """N4: the consumer's composition (dataset_denoising.py:140-144) as one library kernel on the generated batch."""
+    g = torch.Generator().manual_seed(3)
+    clean = torch.rand((5, 4, 32, 32), generator=g) * 1.2 - 0.1            # some values outside [0, 1]
+    noise = torch.randn((5, 4, 32, 32), generator=g) * 0.8
+    c_gpu, n_gpu = frames.compose_noisy(clean.cuda(), noise.cuda())
+    want_noisy = np.clip(np.clip(noise.numpy(), -1.0, 1.0).astype(np.float32) + clean.numpy(), 0.0, 1.0)
+    assert n_gpu.is_cuda and np.array_equal(n_gpu.cpu().numpy(), want_noisy)
+    assert np.array_equal(c_gpu.cpu().numpy(), np.clip(clean.numpy(), 0.0, 1.0))
