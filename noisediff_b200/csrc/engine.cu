@@ -89,6 +89,37 @@ __global__ void pack_upconv_weight_kernel(const float* __restrict__ src, bf16* _
     }
 }
 
+// AttnBlock (C >= 128): ff.net.2 and proj_out meet without a nonlinearity (ref Diffusion_arch.py:439-443):
+//   out = Wp (W2 h + b2 + c + x) + bp + x = (Wp W2) h + Wp x + [Wp (b2 + c) + bp] + x
+// -> ONE two-source GEMM over [h | x] with the packed operand [Wp W2 | Wp] (folded in fp32, rounded to bf16 once), a per-sample
+// vector and the residual x, instead of two GEMM launches with the C-channel tensor z written and re-read in between.
+// dst[co][cblk][64]: cblk < 2C/64 from the fold, then C/64 blocks of Wp.
+__global__ void pack_attn_ff2proj_kernel(const float* __restrict__ wp, const float* __restrict__ w2, bf16* __restrict__ dst, int C) {
+    const int K = 3 * C;
+    const size_t total = static_cast<size_t>(C) * K;
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int co = static_cast<int>(i / K), k = static_cast<int>(i % K);
+        float acc;
+        if (k < 2 * C) {
+            acc = 0.f;
+            for (int j = 0; j < C; ++j) acc = fmaf(wp[static_cast<size_t>(co) * C + j], w2[static_cast<size_t>(j) * 2 * C + k], acc);
+        } else {
+            acc = wp[static_cast<size_t>(co) * C + (k - 2 * C)];
+        }
+        dst[i] = __float2bfloat16_rn(acc);
+    }
+}
+// per-sample vector of the folded form: v2[b][c] = sum_k Wp[c][k] (b2[k] + cvec[b][k]) + bp[c]
+__global__ void attn_vec2_kernel(const float* __restrict__ wp, const float* __restrict__ bp, const float* __restrict__ b2,
+                                 const float* __restrict__ cvec, float* __restrict__ out, int ld, int off, int C) {
+    const int b = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float acc = bp[c];
+        for (int k = 0; k < C; ++k) acc = fmaf(wp[static_cast<size_t>(c) * C + k], b2[k] + cvec[static_cast<size_t>(b) * ld + off + k], acc);
+        out[static_cast<size_t>(b) * ld + off + c] = acc;
+    }
+}
+
 __global__ void init_conv_pack_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout) {
     // dst[tap(49)][ci(4)][co]  <-  src[co][ci][7][7]
     const int total = Cout * 4 * 49;
@@ -355,6 +386,15 @@ int finalize(ndiff_engine* e, cudaStream_t s) {
         if (check_shape(e, ab.name + ".norm2.weight", {ab.C})) return 1;
         if (check_shape(e, ab.name + ".norm2.bias", {ab.C})) return 1;
     }
+    for (const AttnSpec& ab : attnblocks(dim)) {
+        if (ab.C < 128) continue;
+        const std::string key = ab.name + "#ff2proj";
+        bf16* dst = e->packed.count(key) ? e->packed[key] : nullptr;
+        if (!dst && e->alloc(&dst, static_cast<size_t>(ab.C) * 3 * ab.C)) return 1;
+        pack_attn_ff2proj_kernel<<<256, 256, 0, s>>>(e->pf(ab.name + ".proj_out.weight"), e->pf(ab.name + ".ff.net.2.weight"), dst, ab.C);
+        NDIFF_CUDA_OK(cudaGetLastError());
+        e->packed[key] = dst;
+    }
     // --- fused per-pixel chains (pixel_chain.cuh): K-blocked weight blobs + fp32 parameter blocks
     auto pack_attn_chain = [&](const std::string& n, bf16* w, float* f) -> int {
         // AttnBlock.norm2's affine folded into ff.net.0.0 (exact algebra; the fold runs in fp32 before the bf16 rounding)
@@ -479,6 +519,7 @@ int finalize(ndiff_engine* e, cudaStream_t s) {
     e->cv_off.clear();
     for (const AttnSpec& ab : attnblocks(dim)) { e->cv_off[ab.name] = e->cv_total; e->cv_total += ab.C; }
     if (!e->cvec && e->alloc(&e->cvec, static_cast<size_t>(e->B) * e->cv_total)) return 1;
+    if (!e->cvec2 && e->alloc(&e->cvec2, static_cast<size_t>(e->B) * e->cv_total)) return 1;
     e->finalized = true;
     return 0;
 }
@@ -757,6 +798,29 @@ struct Builder {
         }
         Act hh = conv(n + ".ff.net.0.0", kDirect, u, nullptr, 2 * C, kActGelu, nullptr, 0, nullptr, nullptr, 0);
         drop(u);
+        if (fused) {
+            // ff.net.2 and proj_out folded into one two-source GEMM over [h | x] (pack_attn_ff2proj_kernel): z never exists
+            Act o = make(C, xin.H, xin.W);
+            if (err) return o;
+            ConvGemmDesc d;
+            d.mode = kDirect; d.B = e->B; d.H = xin.H; d.W = xin.W;
+            d.src0 = hh.p; d.C0 = 2 * C; d.src1 = xin.p; d.C1 = C;
+            d.weight = e->packed.at(n + "#ff2proj"); d.Cout = C;
+            d.vec = e->cvec2 + e->cv_off.at(n); d.vec_ld = e->cv_total;
+            d.res = xin.p; d.res_ld = C;
+            d.out = o.p; d.out_ld = C;
+            auto plan = std::make_shared<ConvGemmPlan>();
+            if (conv_gemm_plan(d, e->num_sms, plan.get())) { err = 1; return o; }
+            Op op; op.name = n + ".ff.net.2+proj_out";
+            op.flops = 2.0 * e->B * xin.H * xin.W * C * 3.0 * C;
+            op.bytes = 2.0 * e->B * xin.H * xin.W * (2.0 * C + C + C);
+            op.fn = [plan](cudaStream_t st) { return conv_gemm_launch(*plan, st); };
+            e->net_ops.push_back(op);
+            e->conv_flops += op.flops;
+            drop(hh);
+            name(n, o);
+            return o;
+        }
         Act z = conv(n + ".ff.net.2", kDirect, hh, nullptr, C, kActNone, cv, e->cv_total, &xin, nullptr, 0);
         drop(hh);
         Act o = conv(n + ".proj_out", kDirect, z, nullptr, C, kActNone, nullptr, 0, &xin, nullptr, 0);
@@ -1200,6 +1264,11 @@ int32_t ndiff_set_condition(ndiff_engine* e, const float* clean_dev, const float
                            e->pf(ab.name + ".attn.to_out.0.bias"), e->cvec, e->cv_total, e->cv_off.at(ab.name), e->B,
                            ab.C, s))
             return 1;
+        if (ab.C >= 128) {
+            attn_vec2_kernel<<<e->B, 256, 0, s>>>(e->pf(ab.name + ".proj_out.weight"), e->pf(ab.name + ".proj_out.bias"),
+                                                  e->pf(ab.name + ".ff.net.2.bias"), e->cvec, e->cvec2, e->cv_total, e->cv_off.at(ab.name), ab.C);
+            NDIFF_CUDA_OK(cudaGetLastError());
+        }
     }
     e->cond_set = true;
     return 0;

@@ -93,6 +93,7 @@ struct ndiff_engine {
     int* t_buf = nullptr; int t_buf_n = 0;
     // iso path
     float* cvec = nullptr; int cv_total = 0;
+    float* cvec2 = nullptr;        // C >= 128 AttnBlocks: Wp (b2 + c) + bp, the per-sample vector of the folded ff.net.2 + proj_out GEMM
     std::map<std::string, int> cv_off;
     // condition / state
     float* clean = nullptr;        // fp32 NHWC4
