@@ -176,10 +176,11 @@ NDIFF_API int32_t ndiff_op_philox_normal(float* out, int64_t n4, uint64_t seed, 
 /* Fused per-pixel chain (prog 0: AttnBlock with the 1-token cross attention collapsed, Diffusion_arch.py:425-443;
  * prog 1: shot_mlp1 -> shot_attn -> shot_mlp2, :598-601).  x/out/out2: bf16 [npix][64]; clean/xt: fp32 [npix][4];
  * weights_blob: bf16 [rows][64] K-blocked rows and fvec: fp32 parameter block in the order documented in
- * noisediff_b200/csrc/pixel_chain.cuh; cvec: per-sample collapsed attention vector [npix/HW][cvec_ld]. */
+ * noisediff_b200/csrc/pixel_chain.cuh; cvec: per-sample collapsed attention vector [npix/HW][cvec_ld]; cvec2 (prog 0 only):
+ * the per-sample vector Wp (b2 + c) + bp of the folded ff.net.2 + proj_out stage, same leading dimension. */
 NDIFF_API int32_t ndiff_op_pixel_chain(int32_t prog, int32_t npix, int32_t HW, const void* x, const float* clean_nhwc4,
                              const float* xt_nhwc4, const void* weights_blob, const float* fvec, const float* cvec,
-                             int32_t cvec_ld, void* out, void* out2, void* stream);
+                             int32_t cvec_ld, const float* cvec2, void* out, void* out2, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------------
  * Training step.  Replaces, for one batch: GaussianDiffusion.p_losses -> NoiseDiffNet.forward with per-sample t

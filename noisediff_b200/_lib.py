@@ -65,7 +65,7 @@ _SIGS = {
                            [_P, C.c_int32, _P, _P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), _P]),
     "ndiff_op_gn_apply": (C.c_int32, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P] + [C.c_int32] * 4 + [_P]),
     "ndiff_op_layernorm": (C.c_int32, [_P, _P, C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
-    "ndiff_op_pixel_chain": (C.c_int32, [C.c_int32] * 3 + [_P] * 6 + [C.c_int32, _P, _P, _P]),
+    "ndiff_op_pixel_chain": (C.c_int32, [C.c_int32] * 3 + [_P] * 6 + [C.c_int32, _P, _P, _P, _P]),
     "ndiff_op_philox_normal": (C.c_int32, [_P, C.c_int64, C.c_uint64, C.c_uint64, _P]),
     "ndiff_op_conv_ex": (C.c_int32, [C.c_int32] * 4 + [_P, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P, _P, C.c_int32, _P, _P, _P]),
     "ndiff_op_tail_chain": (C.c_int32, [C.c_int32, C.c_int32] + [_P] * 8 + [C.c_int32, _P, _P]),

@@ -109,6 +109,15 @@ __global__ void pack_attn_ff2proj_kernel(const float* __restrict__ wp, const flo
         dst[i] = __float2bfloat16_rn(acc);
     }
 }
+// out[N][K] = a[N][M] @ b[M][K]  (fp32, tiny: weight folds at pack time).  grid = N blocks, one thread per output column
+__global__ void fold_matmul_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int N, int M, int K) {
+    const int n = blockIdx.x;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        float acc = 0.f;
+        for (int j = 0; j < M; ++j) acc = fmaf(a[n * M + j], b[j * K + k], acc);
+        out[n * K + k] = acc;
+    }
+}
 // per-sample vector of the folded form: v2[b][c] = sum_k Wp[c][k] (b2[k] + cvec[b][k]) + bp[c]
 __global__ void attn_vec2_kernel(const float* __restrict__ wp, const float* __restrict__ bp, const float* __restrict__ b2,
                                  const float* __restrict__ cvec, float* __restrict__ out, int ld, int off, int C) {
@@ -396,13 +405,17 @@ int finalize(ndiff_engine* e, cudaStream_t s) {
         e->packed[key] = dst;
     }
     // --- fused per-pixel chains (pixel_chain.cuh): K-blocked weight blobs + fp32 parameter blocks
-    auto pack_attn_chain = [&](const std::string& n, bf16* w, float* f) -> int {
+    auto pack_attn_chain = [&](const std::string& n, bf16* w, float* f, bool fold_proj) -> int {
         // AttnBlock.norm2's affine folded into ff.net.0.0 (exact algebra; the fold runs in fp32 before the bf16 rounding)
         if (!e->fold_tmp && e->alloc(&e->fold_tmp, 128 * 64)) return 1;
         if (fold_layernorm_launch(e->pf(n + ".ff.net.0.0.weight"), e->pf(n + ".ff.net.0.0.bias"), e->pf(n + ".norm2.weight"),
                                   e->pf(n + ".norm2.bias"), e->fold_tmp, f + 128, 128, 64, s)) return 1;
         if (pack_chain_weight_launch(e->fold_tmp, w, 128, 64, false, s)) return 1;
-        if (pack_chain_weight_launch(e->pf(n + ".ff.net.2.weight"), w + 128 * 64, 64, 128, true, s)) return 1;
+        if (fold_proj) {      // stand-alone AttnBlock chain: ff.net.2's slot holds Wp W2 (folded in fp32, rounded to fp16 once)
+            fold_matmul_kernel<<<64, 128, 0, s>>>(e->pf(n + ".proj_out.weight"), e->pf(n + ".ff.net.2.weight"), e->fold_tmp, 64, 64, 128);
+            NDIFF_CUDA_OK(cudaGetLastError());
+            if (pack_chain_weight_launch(e->fold_tmp, w + 128 * 64, 64, 128, true, s)) return 1;
+        } else if (pack_chain_weight_launch(e->pf(n + ".ff.net.2.weight"), w + 128 * 64, 64, 128, true, s)) return 1;
         if (pack_chain_weight_launch(e->pf(n + ".proj_out.weight"), w + 256 * 64, 64, 64, false, s)) return 1;
         NDIFF_CUDA_OK(cudaMemsetAsync(f, 0, sizeof(float) * 128, s));                      // reserved
         NDIFF_CUDA_OK(cudaMemcpyAsync(f + 256, e->pf(n + ".ff.net.2.bias"), sizeof(float) * 64, cudaMemcpyDeviceToDevice, s));
@@ -416,7 +429,7 @@ int finalize(ndiff_engine* e, cudaStream_t s) {
                 if (e->alloc(&e->chain_w[ab.name], static_cast<size_t>(kChainAttnRows) * 64)) return 1;
                 if (e->alloc(&e->chain_f[ab.name], kChainAttnFloats)) return 1;
             }
-            if (pack_attn_chain(ab.name, e->chain_w[ab.name], e->chain_f[ab.name])) return 1;
+            if (pack_attn_chain(ab.name, e->chain_w[ab.name], e->chain_f[ab.name], true)) return 1;
         }
         if (!e->chain_w.count("shot")) {
             if (e->alloc(&e->chain_w["shot"], static_cast<size_t>(kChainShotRows) * 64)) return 1;
@@ -426,7 +439,7 @@ int finalize(ndiff_engine* e, cudaStream_t s) {
         float* f = e->chain_f["shot"];
         if (pack_chain_weight_launch(e->pf("shot_mlp1.fc1.weight"), w, 64, 8, false, s)) return 1;
         if (pack_chain_weight_launch(e->pf("shot_mlp1.fc2.weight"), w + 64 * 64, 64, 64, true, s)) return 1;
-        if (pack_attn_chain("shot_attn", w + 128 * 64, f + 128)) return 1;
+        if (pack_attn_chain("shot_attn", w + 128 * 64, f + 128, false)) return 1;
         // shot_attn.proj_out folded into shot_mlp2.fc1: rows 384..447 (the attention block's Wp slot) = Wm1, applied to s1;
         // rows 448..511 = Wm1 Wp, applied to z; bias slot of fc1 = bm1 + Wm1 bp  (pixel_chain.cuh)
         if (pack_chain_weight_launch(e->pf("shot_mlp2.fc1.weight"), w + 384 * 64, 64, 64, false, s)) return 1;
@@ -772,6 +785,7 @@ struct Builder {
             d.npix = e->B * xin.H * xin.W; d.HW = xin.H * xin.W;
             d.x = xin.p; d.weights = e->chain_w.at(n); d.fvec = e->chain_f.at(n);
             d.cvec = cv; d.cvec_ld = e->cv_total; d.real_frac = e->real_frac;
+            d.cvec2 = e->cvec2 + e->cv_off.at(n);
             d.out = o.p;
             auto plan = std::make_shared<ChainPlan>();
             if (pixel_chain_plan(d, e->num_sms, plan.get())) { err = 1; return o; }
@@ -1264,7 +1278,7 @@ int32_t ndiff_set_condition(ndiff_engine* e, const float* clean_dev, const float
                            e->pf(ab.name + ".attn.to_out.0.bias"), e->cvec, e->cv_total, e->cv_off.at(ab.name), e->B,
                            ab.C, s))
             return 1;
-        if (ab.C >= 128) {
+        if (ab.name != "shot_attn") {       // every stand-alone AttnBlock runs ff.net.2 + proj_out as one folded stage
             attn_vec2_kernel<<<e->B, 256, 0, s>>>(e->pf(ab.name + ".proj_out.weight"), e->pf(ab.name + ".proj_out.bias"),
                                                   e->pf(ab.name + ".ff.net.2.bias"), e->cvec, e->cvec2, e->cv_total, e->cv_off.at(ab.name), ab.C);
             NDIFF_CUDA_OK(cudaGetLastError());
@@ -1663,7 +1677,7 @@ int32_t ndiff_op_philox_normal(float* out, int64_t n4, uint64_t seed, uint64_t s
 
 int32_t ndiff_op_pixel_chain(int32_t prog, int32_t npix, int32_t HW, const void* x, const float* clean_nhwc4,
                              const float* xt_nhwc4, const void* weights_blob, const float* fvec, const float* cvec,
-                             int32_t cvec_ld, void* out, void* out2, void* stream) {
+                             int32_t cvec_ld, const float* cvec2, void* out, void* out2, void* stream) {
     int dev = 0;
     NDIFF_CUDA_OK(cudaGetDevice(&dev));
     cudaDeviceProp prop;
@@ -1672,7 +1686,7 @@ int32_t ndiff_op_pixel_chain(int32_t prog, int32_t npix, int32_t HW, const void*
     ChainDesc d;
     d.prog = prog; d.npix = npix; d.HW = HW;
     d.x = static_cast<const bf16*>(x); d.clean = clean_nhwc4; d.xt = xt_nhwc4;
-    d.weights = static_cast<const bf16*>(weights_blob); d.fvec = fvec; d.cvec = cvec; d.cvec_ld = cvec_ld;
+    d.weights = static_cast<const bf16*>(weights_blob); d.fvec = fvec; d.cvec = cvec; d.cvec_ld = cvec_ld; d.cvec2 = cvec2;
     d.out = static_cast<bf16*>(out); d.out2 = static_cast<bf16*>(out2);
     ChainPlan plan;
     if (pixel_chain_plan(d, prop.multiProcessorCount, &plan)) return 1;

@@ -62,10 +62,10 @@ __device__ __forceinline__ void store_half_gelu_f16(uint32_t blk, int r, int h, 
 }
 // D[tmem] = A[128 x (kblocks*64)] * W[N x (kblocks*64)]^T ; k16 = MMAs per K block (4, or 1 when only K = 16 is live)
 template <int N, bool F16 = false>
-__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_blk, uint32_t w_blk, int kblocks, int k16) {
+__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_blk, uint32_t w_blk, int kblocks, int k16, bool accumulate = false) {
     constexpr uint32_t idesc = F16 ? umma_idesc_f16(128, N) : umma_idesc_bf16(128, N);
     constexpr uint32_t hi = umma_desc_hi(1024);
-    bool first = true;
+    bool first = !accumulate;
     for (int kb = 0; kb < kblocks; ++kb) {
         const uint32_t a_lo = umma_desc_lo(a_blk + kb * kBlk), b_lo = umma_desc_lo(w_blk + kb * N * 128);
         for (int k = 0; k < k16; ++k) {
@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
     const uint32_t sW1 = sWattn, sW2 = sW1 + 128 * 128, sWp = sW2 + 128 * 128, sWm1 = sWp + 64 * 128, sWm2 = sWm1 + 64 * 128;
     const float* fA = tail->fvec + (kShot ? 128 : 0);
     // (the first 128 floats of the attention block are reserved: LayerNorm's affine is folded into W1 / b1 by the packer)
-    const float* f_b1 = fA + 128, *f_b2 = fA + 256, *f_bp = fA + 320, *f_bm1 = fA + 384, *f_bm2 = fA + 448;
+    const float* f_b1 = fA + 128, *f_b2 = fA + 256, *f_bm1 = fA + 384, *f_bm2 = fA + 448;
+    (void)f_b2; (void)f_bm1; (void)f_bm2;
     const uint32_t bar_w = smem_u32(&tail->bar_w), bar_x = smem_u32(&tail->bar_x[wg]), bar_mma = smem_u32(&tail->bar_mma[wg]);
 
     if (tid == 0) {
@@ -164,9 +165,12 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
             if (b_first != tab_b0 || b_last != tab_b1) {
                 tab_b0 = b_first; tab_b1 = b_last;
                 const int slot = r >> 6, j = r & 63;
-                const float cj = __ldg(a.cvec + static_cast<size_t>(slot ? b_last : b_first) * a.cvec_ld + j);
+                const size_t co = static_cast<size_t>(slot ? b_last : b_first) * a.cvec_ld + j;
+                const float cj = __ldg(a.cvec + co);
                 tail->ctab[wg][slot][0][j] = cj;
-                tail->ctab[wg][slot][1][j] = cj + f_b2[j];
+                // shot: b2 + c (bias of ff.net.2 plus the residual's per-sample part); attn: Wp (b2 + c) + bp, the per-sample
+                // vector of the folded ff.net.2 + proj_out stage (computed once per condition, engine.cu attn_vec2_kernel)
+                tail->ctab[wg][slot][1][j] = kShot ? cj + f_b2[j] : __ldg(a.cvec2 + co);
                 named_bar_sync(1 + wg, 128);
             }
         }
@@ -257,10 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
             if (kShot) {                       // s1 staged in the X slot by every thread before this barrier
                 tma_store_2d(&a.tmOut2, sX, 0, tile * kTile);
                 tma_store_commit();
-            } else if (tile + tile_step < a.n_tiles) {   // everybody has copied its X row to registers: prefetch the next tile
-                mbar_expect_tx(bar_x, kBlk);
-                tma_load_2d(sX, &a.tmX, bar_x, 0, (tile + tile_step) * kTile);
-            }
+            }      // (attn: the X tile is an operand of the last GEMM stage, so the next tile is prefetched after that stage)
             if (!w_ready) { mbar_wait(bar_w, 0); w_ready = true; }
             tc_fence_after();
             issue_gemm<128>(tmem_d, sA0, sW1, 1, 4);
@@ -279,6 +280,35 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
                 store_half_gelu_f16(sA0 + hh * kBlk, r, h, raw, f_b1 + hh * 64 + h * 32);
             }
         }
+        if constexpr (!kShot) {
+            // ---- FeedForward.net.2 and proj_out meet without a nonlinearity (ref :439-443): ONE stage
+            //        out = (Wp W2) h + Wp x + [Wp (b2 + c) + bp] + x
+            //      = fp16 GEMM over the hidden layer (K = 128, folded weight in W2's slot) accumulated with a bf16 GEMM over the
+            //      input tile itself, which already sits in shared memory as TMA landed it (K = 64, Wp) -- z never exists.
+            NDIFF_STAGE((issue_gemm<64, true>(tmem_d, sA0, sW2, 2, 4), issue_gemm<64>(tmem_d, sX, sWp, 1, 4, true)));
+            if (r == 0 && tile + tile_step < a.n_tiles) {      // the tensor core is done with X (the wait above): prefetch the next tile
+                mbar_expect_tx(bar_x, kBlk);
+                tma_load_2d(sX, &a.tmX, bar_x, 0, (tile + tile_step) * kTile);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t raw[32];
+                tmem_ld32(tmem_rd + h * 32, raw);
+                tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 c4 = *reinterpret_cast<const float4*>(ct + 64 + h * 32 + j);      // Wp (b2 + c) + bp
+                    const float2 f0 = unpack_bf16(xr[(h * 32 + j) / 2]), f1 = unpack_bf16(xr[(h * 32 + j) / 2 + 1]);
+                    v[j] = __uint_as_float(raw[j]) + (f0.x + c4.x);
+                    v[j + 1] = __uint_as_float(raw[j + 1]) + (f0.y + c4.y);
+                    v[j + 2] = __uint_as_float(raw[j + 2]) + (f1.x + c4.z);
+                    v[j + 3] = __uint_as_float(raw[j + 3]) + (f1.y + c4.w);
+                }
+                store_half(sA1, r, h, v);               // staging for the TMA store
+            }
+        }
+        if constexpr (kShot) {
         // ---- FeedForward.net.2: Linear(2C, C); z = ff + y --------------------------------------------------------------
         NDIFF_STAGE((issue_gemm<64, true>(tmem_d, sA0, sW2, 2, 4)));
 #pragma unroll
@@ -298,23 +328,6 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
             }
             store_half(sA0, r, h, v);
         }
-        if constexpr (!kShot) {
-            // ---- proj_out (1x1 conv) + x_in   (ref :441-443) ---------------------------------------------------------------
-            NDIFF_STAGE(issue_gemm<64>(tmem_d, sA0, sWp, 1, 4));
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t raw[32];
-                tmem_ld32(tmem_rd + h * 32, raw);
-                tmem_ld_wait();
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const float2 f = unpack_bf16(xr[(h * 32 + j) / 2]);
-                    v[j] = __uint_as_float(raw[j]) + f_bp[h * 32 + j] + f.x;
-                    v[j + 1] = __uint_as_float(raw[j + 1]) + f_bp[h * 32 + j + 1] + f.y;
-                }
-                store_half(sA1, r, h, v);               // staging for the TMA store
-            }
         }
         if constexpr (kShot) {
             // ---- proj_out + x_in folded into shot_mlp2.fc1 (both linear, nothing else reads the attention block's output):
@@ -614,7 +627,9 @@ int pixel_chain_plan(const ChainDesc& d, int num_sms, ChainPlan* plan) {
                   "pixel chain: the per-sample attention vector must be 16-byte aligned");
     plan->prog = d.prog;
     a.npix = d.npix; a.HW = d.HW; a.n_tiles = (d.npix + kTile - 1) / kTile;
-    a.fvec = d.fvec; a.cvec = d.cvec; a.cvec_ld = d.cvec_ld;
+    a.fvec = d.fvec; a.cvec = d.cvec; a.cvec_ld = d.cvec_ld; a.cvec2 = d.cvec2;
+    NDIFF_REQUIRE(d.prog == kProgShot || (d.cvec2 && (reinterpret_cast<uintptr_t>(d.cvec2) & 15) == 0),
+                  "pixel chain (attn): the folded stage needs its per-sample vector Wp (b2 + c) + bp");
     NDIFF_REQUIRE(d.real_frac > 0.f && d.real_frac <= 1.f, "pixel chain: live channel fraction must be in (0, 1]");
     a.inv_c = 1.0f / (64.0f * d.real_frac);
     const uint64_t adims[2] = {64, static_cast<uint64_t>(d.npix)};

@@ -17,9 +17,10 @@ enum ChainProg : int {
 
 // rows of the bf16 weight blob ([rows][64], one 128-byte row per output channel per 64-wide K block) and floats of the
 // parameter block, in program order:
-//   attn : W1 (ff.net.0.0, 128 rows) | W2 kblock 0, 1 (ff.net.2, 64 + 64, fp16) | Wp (proj_out, 64)      = 320 rows
-//          [reserved 128][b1 128][b2 64][bp 64]                                                             = 384 floats
-//          (AttnBlock.norm2's affine is folded by the packer: W1 <- W1 diag(ln_g), b1 <- b1 + W1 ln_b)
+//   attn : W1 (ff.net.0.0, 128 rows) | Wp W2 kblock 0, 1 (proj_out o ff.net.2 folded, 64 + 64, fp16) | Wp (proj_out, 64) = 320 rows
+//          [reserved 128][b1 128][unused 128]                                                               = 384 floats
+//          (AttnBlock.norm2's affine is folded by the packer: W1 <- W1 diag(ln_g), b1 <- b1 + W1 ln_b; ff.net.2 and proj_out
+//          are one stage: out = (Wp W2) h + Wp x + [Wp (b2 + c) + bp] + x, the bracket arriving per sample as cvec2)
 //   shot : W0 (shot_mlp1.fc1, K = 8 zero-padded, 64) | Wfc2 (shot_mlp1.fc2, 64, fp16) | W1 128 | W2 128 (as attn) |
 //          Wm1 (64, applied to s1) | Wm1 Wp (64, applied to z) | Wm2 (fp16)                                 = 576 rows
 //          (shot_attn.proj_out and shot_mlp2.fc1 are both linear and are folded into one K = 128 GEMM by the packer)
@@ -35,6 +36,7 @@ struct ChainArgs {
     int npix, HW, n_tiles;
     const float* fvec;    // parameter block (see above)
     const float* cvec;    // collapsed cross-attention vector of this block, per sample: cvec[b * cvec_ld + c]
+    const float* cvec2;   // attn: Wp (b2 + c) + bp per sample, same leading dimension
     int cvec_ld;
     float inv_c;          // 1 / (live channels of the 64): LayerNorm's element count under zero-padded channel layouts
     const float4* clean;  // shot: fp32 NHWC4 clean image and chain state
@@ -55,6 +57,7 @@ struct ChainDesc {
     const __nv_bfloat16* weights = nullptr; // blob
     const float* fvec = nullptr;
     const float* cvec = nullptr; int cvec_ld = 0;
+    const float* cvec2 = nullptr;           // attn only
     float real_frac = 1.0f;                 // live fraction of the 64 channels (engine.cu "physical channels")
     const float* clean = nullptr; const float* xt = nullptr;   // shot inputs (fp32 NHWC4)
     __nv_bfloat16* out = nullptr;

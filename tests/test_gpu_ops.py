@@ -239,12 +239,15 @@ def _attn_params(seed):
     # packer convention (pixel_chain.cuh): LayerNorm's affine is folded into the first Linear
     p["W1f"] = _bf(p["W1"] * p["ln_g"][None, :])
     p["b1f"] = p["b1"] + p["W1"] @ p["ln_b"]
-    blob = torch.cat([_blob(p["W1f"]), _blob(p["W2"], f16=True), _blob(p["Wp"])])
+    # ... and (stand-alone AttnBlock chain only) ff.net.2 and proj_out are ONE stage: out = (Wp W2) h + Wp x + [Wp (b2 + c) + bp] + x
+    p["Wfold"] = _hf(p["Wp"] @ p["W2"])
+    blob = torch.cat([_blob(p["W1f"]), _blob(p["W2"], f16=True), _blob(p["Wp"])])             # shot chain: unfolded W2
+    p["blob_attn"] = torch.cat([_blob(p["W1f"]), _blob(p["Wfold"], f16=True), _blob(p["Wp"])])
     fvec = torch.cat([torch.zeros(128, device="cuda"), p["b1f"], p["b2"], p["bp"]])
     return p, blob, fvec
 
 
-def _attn_ref(tok, cv, p):
+def _attn_ref(tok, cv, p, folded=False):
     """tok: [npix, 64] fp32 (bf16-representable), cv: [npix, 64].  Rounds to bf16 where the kernel stores bf16."""
     y = tok + cv
     u = _bf(F.layer_norm(y, (64,), None, None, eps=1e-5))
@@ -252,6 +255,12 @@ def _attn_ref(tok, cv, p):
     # the folded form is the unfolded block up to the bf16 rounding of the weights
     h_ref = F.gelu(F.layer_norm(y, (64,), p["ln_g"], p["ln_b"], eps=1e-5) @ p["W1"].T + p["b1"])
     assert ((h - h_ref).norm() / h_ref.norm()).item() < 1e-2
+    if folded:      # what the stand-alone chain computes; equal to the two-stage form up to the rounding of z / of the folded weight
+        out = h @ p["Wfold"].T + tok @ p["Wp"].T + ((p["b2"] + cv) @ p["Wp"].T + p["bp"]) + tok
+        z = h @ p["W2"].T + p["b2"] + y
+        two_stage = z @ p["Wp"].T + p["bp"] + tok
+        assert ((out - two_stage).norm() / two_stage.norm()).item() < 3e-3
+        return out
     z = _bf(h @ p["W2"].T + p["b2"] + y)
     return z @ p["Wp"].T + p["bp"] + tok
 
@@ -269,10 +278,12 @@ def test_attn_chain(case):
     p, blob, fvec = _attn_params(32)
     out = torch.zeros((npix, 64), dtype=torch.bfloat16, device="cuda")
     xb = x.to(torch.bfloat16)
-    _lib.check(_lib.lib().ndiff_op_pixel_chain(0, npix, HW, G.P(xb), None, None, G.P(blob), G.P(fvec), G.P(cvec), 96,
-                                               G.P(out), None, G.stream()))
+    cvec2 = torch.zeros_like(cvec)
+    cvec2[:, :64] = (p["b2"] + cvec[:, :64]) @ p["Wp"].T + p["bp"]          # per-sample vector of the folded stage
+    _lib.check(_lib.lib().ndiff_op_pixel_chain(0, npix, HW, G.P(xb), None, None, G.P(p["blob_attn"]), G.P(fvec), G.P(cvec), 96,
+                                               G.P(cvec2), G.P(out), None, G.stream()))
     torch.cuda.synchronize()
-    ref = _attn_ref(x, cvec[:, :64].repeat_interleave(HW, dim=0), p)
+    ref = _attn_ref(x, cvec[:, :64].repeat_interleave(HW, dim=0), p, folded=True)
     assert _rel(out.float(), ref) < 5e-3, _rel(out.float(), ref)
     assert (out.float() - ref).abs().max().item() < 3e-2 * max(ref.abs().max().item(), 1.0)
 
@@ -298,7 +309,7 @@ def test_shot_chain(case):
     out = torch.zeros((npix, 64), dtype=torch.bfloat16, device="cuda")
     out2 = torch.zeros_like(out)
     _lib.check(_lib.lib().ndiff_op_pixel_chain(1, npix, HW, None, G.P(clean), G.P(xt), G.P(blob), G.P(fvec), G.P(cvec), 64,
-                                               G.P(out), G.P(out2), G.stream()))
+                                               None, G.P(out), G.P(out2), G.stream()))
     torch.cuda.synchronize()
     a0 = _bf(torch.cat([clean, xt], dim=1))
     h0 = _hf(F.gelu(a0 @ W0.T + b0))
