@@ -703,13 +703,7 @@ int tail_chain_launch(const TailPlan& plan, cudaStream_t stream) {
     return 0;
 }
 
-static int chain_variant() {      // read once per process: 2 = two threads per pixel (pixel_chain2.cu), 1 = one thread per pixel
-    static const int v = [] { const char* e = getenv("NDIFF_CHAIN2"); return (e && e[0] == '1') ? 2 : 1; }();
-    return v;
-}
-
 int pixel_chain_launch(const ChainPlan& plan, cudaStream_t stream) {
-    if (chain_variant() == 2) return pixel_chain2_launch(plan, stream);
     if (plan.prog == kProgShot)
         NDIFF_CUDA_OK(launch_pdl(pixel_chain_kernel<kProgShot>, dim3(plan.grid), dim3(kThreads), plan.smem_bytes, stream, plan.args));
     else

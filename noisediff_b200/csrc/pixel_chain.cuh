@@ -94,10 +94,6 @@ struct TailDesc {
 int tail_chain_plan(const TailDesc& d, int num_sms, TailPlan* plan);
 int tail_chain_launch(const TailPlan& plan, cudaStream_t stream);
 
-// pixel_chain2.cu: the same programs with TWO threads per pixel (256-thread groups, 24 warps per SM) — selected by
-// pixel_chain_launch() unless NDIFF_CHAIN1=1 asks for the one-thread-per-pixel kernels
-int pixel_chain2_launch(const ChainPlan& plan, cudaStream_t stream);
-int pixel_chain2_smem_bytes(int prog);
 int pixel_chain_plan(const ChainDesc& d, int num_sms, ChainPlan* plan);
 int pixel_chain_launch(const ChainPlan& plan, cudaStream_t stream);
 int pixel_chain_init();
