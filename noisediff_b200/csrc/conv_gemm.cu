@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem is only guaranteed 16-B aligned by the ABI; SWIZZLE_128B wants 1024
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __builtin_assume(__isShared(smem));      // the manual alignment hides the address space: without the hint table reads are generic LD.E
     constexpr bool kHalo = MODE == kHalo1 || MODE == kHalo2 || MODE == kHaloUp || MODE == kHalo1R;
     constexpr bool kUp = MODE == kHaloUp;
     constexpr bool kRes2 = MODE == kHalo1R;                      // second accumulator: 1x1 conv of the same input (centre tap)

@@ -118,6 +118,9 @@ __global__ void fold_matmul_kernel(const float* __restrict__ a, const float* __r
         out[n * K + k] = acc;
     }
 }
+__global__ void add_vec_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = a[i] + b[i];
+}
 // per-sample vector of the folded form: v2[b][c] = sum_k Wp[c][k] (b2[k] + cvec[b][k]) + bp[c]
 __global__ void attn_vec2_kernel(const float* __restrict__ wp, const float* __restrict__ bp, const float* __restrict__ b2,
                                  const float* __restrict__ cvec, float* __restrict__ out, int ld, int off, int C) {
@@ -405,6 +408,7 @@ int finalize(ndiff_engine* e, cudaStream_t s) {
         e->packed[key] = dst;
     }
     // --- fused per-pixel chains (pixel_chain.cuh): K-blocked weight blobs + fp32 parameter blocks
+    // fold_proj: the stand-alone AttnBlock chain (W2 slot = Wp W2, Wp slot = Wp); otherwise the caller fills both slots
     auto pack_attn_chain = [&](const std::string& n, bf16* w, float* f, bool fold_proj) -> int {
         // AttnBlock.norm2's affine folded into ff.net.0.0 (exact algebra; the fold runs in fp32 before the bf16 rounding)
         if (!e->fold_tmp && e->alloc(&e->fold_tmp, 128 * 64)) return 1;
@@ -415,8 +419,8 @@ int finalize(ndiff_engine* e, cudaStream_t s) {
             fold_matmul_kernel<<<64, 128, 0, s>>>(e->pf(n + ".proj_out.weight"), e->pf(n + ".ff.net.2.weight"), e->fold_tmp, 64, 64, 128);
             NDIFF_CUDA_OK(cudaGetLastError());
             if (pack_chain_weight_launch(e->fold_tmp, w + 128 * 64, 64, 128, true, s)) return 1;
-        } else if (pack_chain_weight_launch(e->pf(n + ".ff.net.2.weight"), w + 128 * 64, 64, 128, true, s)) return 1;
-        if (pack_chain_weight_launch(e->pf(n + ".proj_out.weight"), w + 256 * 64, 64, 64, false, s)) return 1;
+            if (pack_chain_weight_launch(e->pf(n + ".proj_out.weight"), w + 256 * 64, 64, 64, false, s)) return 1;
+        }
         NDIFF_CUDA_OK(cudaMemsetAsync(f, 0, sizeof(float) * 128, s));                      // reserved
         NDIFF_CUDA_OK(cudaMemcpyAsync(f + 256, e->pf(n + ".ff.net.2.bias"), sizeof(float) * 64, cudaMemcpyDeviceToDevice, s));
         NDIFF_CUDA_OK(cudaMemcpyAsync(f + 320, e->pf(n + ".proj_out.bias"), sizeof(float) * 64, cudaMemcpyDeviceToDevice, s));
@@ -440,14 +444,19 @@ int finalize(ndiff_engine* e, cudaStream_t s) {
         if (pack_chain_weight_launch(e->pf("shot_mlp1.fc1.weight"), w, 64, 8, false, s)) return 1;
         if (pack_chain_weight_launch(e->pf("shot_mlp1.fc2.weight"), w + 64 * 64, 64, 64, true, s)) return 1;
         if (pack_attn_chain("shot_attn", w + 128 * 64, f + 128, false)) return 1;
-        // shot_attn.proj_out folded into shot_mlp2.fc1: rows 384..447 (the attention block's Wp slot) = Wm1, applied to s1;
-        // rows 448..511 = Wm1 Wp, applied to z; bias slot of fc1 = bm1 + Wm1 bp  (pixel_chain.cuh)
-        if (pack_chain_weight_launch(e->pf("shot_mlp2.fc1.weight"), w + 384 * 64, 64, 64, false, s)) return 1;
-        if (!e->fold_tmp && e->alloc(&e->fold_tmp, 128 * 64)) return 1;
+        // shot_attn.ff.net.2 + proj_out + shot_mlp2.fc1 as one stage (pixel_chain.cuh): with M = Wm1 Wp (kept in fp32 for the
+        // per-sample vector, f[512..] = Wm1 bp + bm1), rows 256..383 = fp16(M W2) applied to the hidden layer, rows 384..447 =
+        // bf16(M + Wm1) applied to s1
+        if (!e->shot_fold && e->alloc(&e->shot_fold, 64 * 64)) return 1;
         if (fold_linear_launch(e->pf("shot_mlp2.fc1.weight"), e->pf("shot_attn.proj_out.weight"), e->pf("shot_attn.proj_out.bias"),
-                               e->pf("shot_mlp2.fc1.bias"), e->fold_tmp, f + 512, 64, s)) return 1;
-        if (pack_chain_weight_launch(e->fold_tmp, w + 448 * 64, 64, 64, false, s)) return 1;
-        if (pack_chain_weight_launch(e->pf("shot_mlp2.fc2.weight"), w + 512 * 64, 64, 64, true, s)) return 1;
+                               e->pf("shot_mlp2.fc1.bias"), e->shot_fold, f + 512, 64, s)) return 1;
+        fold_matmul_kernel<<<64, 128, 0, s>>>(e->shot_fold, e->pf("shot_attn.ff.net.2.weight"), e->fold_tmp, 64, 64, 128);
+        NDIFF_CUDA_OK(cudaGetLastError());
+        if (pack_chain_weight_launch(e->fold_tmp, w + 256 * 64, 64, 128, true, s)) return 1;
+        add_vec_kernel<<<16, 256, 0, s>>>(e->shot_fold, e->pf("shot_mlp2.fc1.weight"), e->fold_tmp, 64 * 64);
+        NDIFF_CUDA_OK(cudaGetLastError());
+        if (pack_chain_weight_launch(e->fold_tmp, w + 384 * 64, 64, 64, false, s)) return 1;
+        if (pack_chain_weight_launch(e->pf("shot_mlp2.fc2.weight"), w + 448 * 64, 64, 64, true, s)) return 1;
         NDIFF_CUDA_OK(cudaMemcpyAsync(f, e->pf("shot_mlp1.fc1.bias"), sizeof(float) * 64, cudaMemcpyDeviceToDevice, s));
         NDIFF_CUDA_OK(cudaMemcpyAsync(f + 64, e->pf("shot_mlp1.fc2.bias"), sizeof(float) * 64, cudaMemcpyDeviceToDevice, s));
         NDIFF_CUDA_OK(cudaMemcpyAsync(f + 576, e->pf("shot_mlp2.fc2.bias"), sizeof(float) * 64, cudaMemcpyDeviceToDevice, s));
@@ -1278,11 +1287,14 @@ int32_t ndiff_set_condition(ndiff_engine* e, const float* clean_dev, const float
                            e->pf(ab.name + ".attn.to_out.0.bias"), e->cvec, e->cv_total, e->cv_off.at(ab.name), e->B,
                            ab.C, s))
             return 1;
-        if (ab.name != "shot_attn") {       // every stand-alone AttnBlock runs ff.net.2 + proj_out as one folded stage
-            attn_vec2_kernel<<<e->B, 256, 0, s>>>(e->pf(ab.name + ".proj_out.weight"), e->pf(ab.name + ".proj_out.bias"),
-                                                  e->pf(ab.name + ".ff.net.2.bias"), e->cvec, e->cvec2, e->cv_total, e->cv_off.at(ab.name), ab.C);
-            NDIFF_CUDA_OK(cudaGetLastError());
-        }
+        // every AttnBlock runs its last linear layers as one folded stage with a per-sample vector: Wp (b2 + c) + bp, and for
+        // the shot branch (which continues into shot_mlp2.fc1) Wm1 Wp (b2 + c) + Wm1 bp + bm1 (packer: shot_fold, f[512..])
+        const bool shot = ab.name == "shot_attn";
+        if (shot && !e->chain_f.count("shot")) continue;      // the unfused plan (dim != 64 layouts) has no folded shot stage
+        attn_vec2_kernel<<<e->B, 256, 0, s>>>(shot ? e->shot_fold : e->pf(ab.name + ".proj_out.weight"),
+                                              shot ? e->chain_f.at("shot") + 512 : e->pf(ab.name + ".proj_out.bias"),
+                                              e->pf(ab.name + ".ff.net.2.bias"), e->cvec, e->cvec2, e->cv_total, e->cv_off.at(ab.name), ab.C);
+        NDIFF_CUDA_OK(cudaGetLastError());
     }
     e->cond_set = true;
     return 0;

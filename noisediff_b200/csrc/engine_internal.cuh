@@ -83,6 +83,7 @@ struct ndiff_engine {
     std::map<std::string, float*> chain_f;
     float* init_w = nullptr;
     float* fold_tmp = nullptr;       // scratch for folding LayerNorm affines into chain weights
+    float* shot_fold = nullptr;      // fp32 shot_mlp2.fc1 x shot_attn.proj_out (64 x 64): per-sample vector of the shot chain's folded stage
     bf16* init_w_tc = nullptr; bf16* xpad = nullptr;
     // time path
     float* ss_w = nullptr; float* ss_b = nullptr; int ss_total = 0;

@@ -21,12 +21,14 @@ enum ChainProg : int {
 //          [reserved 128][b1 128][unused 128]                                                               = 384 floats
 //          (AttnBlock.norm2's affine is folded by the packer: W1 <- W1 diag(ln_g), b1 <- b1 + W1 ln_b; ff.net.2 and proj_out
 //          are one stage: out = (Wp W2) h + Wp x + [Wp (b2 + c) + bp] + x, the bracket arriving per sample as cvec2)
-//   shot : W0 (shot_mlp1.fc1, K = 8 zero-padded, 64) | Wfc2 (shot_mlp1.fc2, 64, fp16) | W1 128 | W2 128 (as attn) |
-//          Wm1 (64, applied to s1) | Wm1 Wp (64, applied to z) | Wm2 (fp16)                                 = 576 rows
-//          (shot_attn.proj_out and shot_mlp2.fc1 are both linear and are folded into one K = 128 GEMM by the packer)
-//          [b0 64][bfc2 64] + attn 384 (bp slot unused) + [bm1 + Wm1 bp 64][bm2 64]                          = 640 floats
+//   shot : W0 (shot_mlp1.fc1, K = 8 zero-padded, 64) | Wfc2 (shot_mlp1.fc2, 64, fp16) | W1 128 |
+//          Wm1 Wp W2 kblock 0, 1 (64 + 64, fp16, applied to the hidden layer) | Wm1 Wp + Wm1 (64, applied to s1) | Wm2 (fp16) = 512 rows
+//          (shot_attn.ff.net.2, shot_attn.proj_out and shot_mlp2.fc1 meet without a nonlinearity and are ONE stage:
+//             fc1(Wp (W2 h + b2 + c + s1) + bp + s1) = (Wm1 Wp W2) h + (Wm1 Wp + Wm1) s1 + [Wm1 Wp (b2 + c) + Wm1 bp + bm1],
+//           the bracket arriving per sample as cvec2)
+//          [b0 64][bfc2 64] + attn 384 (only b1 is read) + [unused 64][bm2 64]                                = 640 floats
 constexpr int kChainAttnRows = 320, kChainAttnFloats = 384;
-constexpr int kChainShotRows = 576, kChainShotFloats = 640;
+constexpr int kChainShotRows = 512, kChainShotFloats = 640;
 
 struct ChainArgs {
     CUtensorMap tmX;      // attn: input activation viewed as [npix][64] bf16, box {64, 128}
@@ -36,7 +38,7 @@ struct ChainArgs {
     int npix, HW, n_tiles;
     const float* fvec;    // parameter block (see above)
     const float* cvec;    // collapsed cross-attention vector of this block, per sample: cvec[b * cvec_ld + c]
-    const float* cvec2;   // attn: Wp (b2 + c) + bp per sample, same leading dimension
+    const float* cvec2;   // per-sample vector of the folded last linear stage (attn: Wp (b2 + c) + bp; shot: see above), same ld
     int cvec_ld;
     float inv_c;          // 1 / (live channels of the 64): LayerNorm's element count under zero-padded channel layouts
     const float4* clean;  // shot: fp32 NHWC4 clean image and chain state
@@ -57,7 +59,7 @@ struct ChainDesc {
     const __nv_bfloat16* weights = nullptr; // blob
     const float* fvec = nullptr;
     const float* cvec = nullptr; int cvec_ld = 0;
-    const float* cvec2 = nullptr;           // attn only
+    const float* cvec2 = nullptr;           // folded-stage vector (see ChainArgs)
     float real_frac = 1.0f;                 // live fraction of the 64 channels (engine.cu "physical channels")
     const float* clean = nullptr; const float* xt = nullptr;   // shot inputs (fp32 NHWC4)
     __nv_bfloat16* out = nullptr;

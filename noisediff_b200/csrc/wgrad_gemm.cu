@@ -41,6 +41,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_gemm_kernel(const __grid_constant__ WgradArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __builtin_assume(__isShared(smem));      // the manual alignment hides the address space: without the hint table reads are generic LD.E
     constexpr bool kHalo = MODE == kWg3x3;
     constexpr int kXBytes = kHalo ? kHaloStageW : kDyBlk;
     constexpr int kXCopy = kHalo ? kHaloCopyW : kDyBlk;

@@ -241,7 +241,7 @@ def _attn_params(seed):
     p["b1f"] = p["b1"] + p["W1"] @ p["ln_b"]
     # ... and (stand-alone AttnBlock chain only) ff.net.2 and proj_out are ONE stage: out = (Wp W2) h + Wp x + [Wp (b2 + c) + bp] + x
     p["Wfold"] = _hf(p["Wp"] @ p["W2"])
-    blob = torch.cat([_blob(p["W1f"]), _blob(p["W2"], f16=True), _blob(p["Wp"])])             # shot chain: unfolded W2
+    blob = torch.cat([_blob(p["W1f"]), _blob(p["W2"], f16=True), _blob(p["Wp"])])             # unfolded layout (the shot test takes W1f from it)
     p["blob_attn"] = torch.cat([_blob(p["W1f"]), _blob(p["Wfold"], f16=True), _blob(p["Wp"])])
     fvec = torch.cat([torch.zeros(128, device="cuda"), p["b1f"], p["b2"], p["bp"]])
     return p, blob, fvec
@@ -301,15 +301,18 @@ def test_shot_chain(case):
     W0, b0 = _bf(rn(64, 8, sc=0.35)), 0.3 * rn(64)
     Wf, bf_ = _bf(rn(64, 64, sc=0.125)), 0.3 * rn(64)
     Wm1, bm1, Wm2, bm2 = _bf(rn(64, 64, sc=0.125)), 0.3 * rn(64), _bf(rn(64, 64, sc=0.125)), 0.3 * rn(64)
-    # packer convention (pixel_chain.cuh): shot_attn.proj_out is folded into shot_mlp2.fc1 — the attention block's Wp rows hold
-    # Wm1 (applied to s1), the next 64 rows Wm1 Wp (applied to z), and fc1's bias slot holds bm1 + Wm1 bp
-    blob = torch.cat([_blob(W0), _blob(Wf, f16=True), ablob[:256], _blob(Wm1), _blob(_bf(Wm1 @ p["Wp"])), _blob(Wm2, f16=True)])
-    fvec = torch.cat([b0, bf_, afvec, bm1 + Wm1 @ p["bp"], bm2])
-    assert blob.shape == (576, 64) and fvec.numel() == 640
+    # packer convention (pixel_chain.cuh): shot_attn.ff.net.2, shot_attn.proj_out (+ both residuals) and shot_mlp2.fc1 are ONE stage:
+    #   fc1(Wp (W2 h + b2 + c + s1) + bp + s1) = (M W2) h + (M + Wm1) s1 + [M (b2 + c) + Wm1 bp + bm1],  M = Wm1 Wp
+    # the W2 rows hold fp16(M W2), the Wp rows bf16(M + Wm1), the bracket arrives per sample as cvec2
+    M = Wm1 @ p["Wp"]
+    blob = torch.cat([_blob(W0), _blob(Wf, f16=True), ablob[:128], _blob(M @ p["W2"], f16=True), _blob(M + Wm1), _blob(Wm2, f16=True)])
+    fvec = torch.cat([b0, bf_, afvec, torch.zeros(64, device="cuda"), bm2])
+    assert blob.shape == (512, 64) and fvec.numel() == 640
+    cvec2 = (p["b2"] + cvec) @ M.T + Wm1 @ p["bp"] + bm1
     out = torch.zeros((npix, 64), dtype=torch.bfloat16, device="cuda")
     out2 = torch.zeros_like(out)
     _lib.check(_lib.lib().ndiff_op_pixel_chain(1, npix, HW, None, G.P(clean), G.P(xt), G.P(blob), G.P(fvec), G.P(cvec), 64,
-                                               None, G.P(out), G.P(out2), G.stream()))
+                                               G.P(cvec2), G.P(out), G.P(out2), G.stream()))
     torch.cuda.synchronize()
     a0 = _bf(torch.cat([clean, xt], dim=1))
     h0 = _hf(F.gelu(a0 @ W0.T + b0))
