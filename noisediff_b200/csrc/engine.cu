@@ -877,6 +877,7 @@ int build_plan(ndiff_engine* e) {
         d.npix = npix; d.HW = H * W;
         d.weights = e->chain_w.at("shot"); d.fvec = e->chain_f.at("shot");
         d.cvec = e->cvec + e->cv_off.at("shot_attn"); d.cvec_ld = e->cv_total; d.real_frac = e->real_frac;
+        d.cvec2 = e->cvec2 + e->cv_off.at("shot_attn");
         d.clean = e->clean; d.xt = e->x;
         d.out = s4.p; d.out2 = s1.p;
         auto plan = std::make_shared<ChainPlan>();
