@@ -93,7 +93,9 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
     constexpr int kWBytes = kWRows * 128;
     ChainTail* tail = reinterpret_cast<ChainTail*>(smem + kWBytes + kNWG * kWgBytes);
 
-    const int tid = threadIdx.x, wg = tid >> 7, r = tid & 127, q = (tid >> 5) & 3;
+    // the warp index is broadcast from lane 0 so that the compiler knows it (and everything derived from it: the warpgroup's
+    // operand blocks, barriers and TMEM columns) is warp-uniform
+    const int tid = threadIdx.x, warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0), wg = warp_u >> 2, r = tid & 127, q = warp_u & 3;
     const uint32_t sW = smem_u32(smem);
     const uint32_t sX = sW + kWBytes + wg * kWgBytes, sA0 = sX + kBlk, sA1 = sA0 + kBlk;
     // weight blocks (row offsets of pixel_chain.cuh's blob layout, 128 B per row)
@@ -128,9 +130,16 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
     pdl_trigger();
     pdl_wait();          // weights / parameters above are constants; everything below touches the previous kernel's output
     const int tile0 = blockIdx.x * kNWG + wg, tile_step = gridDim.x * kNWG;
-    if (!kShot && r == 0 && tile0 < a.n_tiles) {
-        mbar_expect_tx(bar_x, kBlk);
-        tma_load_2d(sX, &a.tmX, bar_x, 0, tile0 * kTile);
+    // Single-thread work (TMA, tcgen05.mma, commits) is done by the warpgroup's first warp with ALL lanes walking the code and
+    // one elected lane issuing: under a plain `if (r == 0)` the compiler cannot know that one lane is active and wraps every
+    // uniform-register operand of UTCHMMA / UTMALDG in a lane-serialising loop (15 instructions per MMA on the stage's critical
+    // path).  elect.sync picks the same lane every time, so the bulk-group waits pair with the stores of that lane.
+    if (!kShot && q == 0 && tile0 < a.n_tiles) {
+        if (elect_one()) {
+            mbar_expect_tx(bar_x, kBlk);
+            tma_load_2d(sX, &a.tmX, bar_x, 0, tile0 * kTile);
+        }
+        __syncwarp();
     }
     uint32_t xph = 0, mph = 0;
     bool w_ready = false;
@@ -142,11 +151,14 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
         fence_proxy_async();                                                 \
         tc_fence_before();                                                   \
         named_bar_sync(1 + wg, 128);                                         \
-        if (r == 0) {                                                        \
+        if (q == 0) {                                                        \
             if (!w_ready) { mbar_wait(bar_w, 0); w_ready = true; }           \
             tc_fence_after();                                                \
-            ISSUE;                                                           \
-            umma_commit(bar_mma);                                            \
+            if (elect_one()) {                                               \
+                ISSUE;                                                       \
+                umma_commit(bar_mma);                                        \
+            }                                                                \
+            __syncwarp();                                                    \
         }                                                                    \
         mbar_wait(bar_mma, mph);                                             \
         mph ^= 1;                                                            \
@@ -179,8 +191,11 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
         const float* ct = &tail->ctab[wg][(pc / a.HW) != b_first ? 1 : 0][0][0];      // c at ct[j], folded-stage vector at ct[64 + j]
 
         // X (shot) and A1 are sources of the previous tile's TMA stores: they must have been read before anyone rewrites them
-        // (every thread's first write to either comes after the next named barrier, which thread 0 joins after this wait)
-        if (r == 0) tma_store_wait_read();
+        // (every thread's first write to either comes after the next named barrier, which the issuing warp joins after this wait)
+        if (q == 0) {
+            if (elect_one()) tma_store_wait_read();
+            __syncwarp();
+        }
 
         if constexpr (kShot) {
             // ---- shot_mlp1.fc1 on cat[clean, x_t] (ref Diffusion_arch.py:598; clean first) --------------------------
@@ -259,15 +274,18 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
         fence_proxy_async();
         tc_fence_before();
         named_bar_sync(1 + wg, 128);
-        if (r == 0) {
-            if (kShot) {                       // s1 staged in the X slot by every thread before this barrier
-                tma_store_2d(&a.tmOut2, sX, 0, tile * kTile);
-                tma_store_commit();
-            }      // (attn: the X tile is an operand of the last GEMM stage, so the next tile is prefetched after that stage)
+        if (q == 0) {
             if (!w_ready) { mbar_wait(bar_w, 0); w_ready = true; }
             tc_fence_after();
-            issue_gemm<128>(tmem_d, sA0, sW1, 1, 4);
-            umma_commit(bar_mma);
+            if (elect_one()) {
+                if (kShot) {                   // s1 staged in the X slot by every thread before this barrier
+                    tma_store_2d(&a.tmOut2, sX, 0, tile * kTile);
+                    tma_store_commit();
+                }  // (attn: the X tile is an operand of the last GEMM stage, so the next tile is prefetched after that stage)
+                issue_gemm<128>(tmem_d, sA0, sW1, 1, 4);
+                umma_commit(bar_mma);
+            }
+            __syncwarp();
         }
         mbar_wait(bar_mma, mph);
         mph ^= 1;
@@ -288,9 +306,12 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
             //      = fp16 GEMM over the hidden layer (K = 128, folded weight in W2's slot) accumulated with a bf16 GEMM over the
             //      input tile itself, which already sits in shared memory as TMA landed it (K = 64, Wp) -- z never exists.
             NDIFF_STAGE((issue_gemm<64, true>(tmem_d, sA0, sW2, 2, 4), issue_gemm<64>(tmem_d, sX, sWp, 1, 4, true)));
-            if (r == 0 && tile + tile_step < a.n_tiles) {      // the tensor core is done with X (the wait above): prefetch the next tile
-                mbar_expect_tx(bar_x, kBlk);
-                tma_load_2d(sX, &a.tmX, bar_x, 0, (tile + tile_step) * kTile);
+            if (q == 0 && tile + tile_step < a.n_tiles) {      // the tensor core is done with X (the wait above): prefetch the next tile
+                if (elect_one()) {
+                    mbar_expect_tx(bar_x, kBlk);
+                    tma_load_2d(sX, &a.tmX, bar_x, 0, (tile + tile_step) * kTile);
+                }
+                __syncwarp();
             }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -339,13 +360,19 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
         fence_proxy_async();
         tc_fence_before();        // the accumulator drains above must be ordered before the next tile's MMA overwrites TMEM
         named_bar_sync(1 + wg, 128);
-        if (r == 0) {
-            tma_store_2d(&a.tmOut, sA1, 0, tile * kTile);
-            tma_store_commit();
+        if (q == 0) {
+            if (elect_one()) {
+                tma_store_2d(&a.tmOut, sA1, 0, tile * kTile);
+                tma_store_commit();
+            }
+            __syncwarp();
         }
     }
 #undef NDIFF_STAGE
-    if (r == 0) tma_store_wait_all();
+    if (q == 0) {
+        if (elect_one()) tma_store_wait_all();
+        __syncwarp();
+    }
     tc_fence_before();
     __syncthreads();
     if (tid < 32) {
@@ -375,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) tail_chain_kernel(const __grid_co
     __builtin_assume(__isShared(smem));      // the manual alignment hides the address space: without the hint every table read is a generic LD.E
     constexpr int kWBytes = kTailRows * 128;
     TailSmem* tail = reinterpret_cast<TailSmem*>(smem + kWBytes + kNWG * kTailWgBytes);
-    const int tid = threadIdx.x, wg = tid >> 7, r = tid & 127, q = (tid >> 5) & 3;
+    const int tid = threadIdx.x, warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0), wg = warp_u >> 2, r = tid & 127, q = warp_u & 3;
     const uint32_t sW = smem_u32(smem);
     const uint32_t sH = sW + kWBytes + wg * kTailWgBytes, sR1 = sH + kBlk, sR2 = sR1 + kBlk, sA0 = sR2 + kBlk;
     const uint32_t bar_w = smem_u32(&tail->bar_w), bar_x = smem_u32(&tail->bar_x[wg]), bar_mma = smem_u32(&tail->bar_mma[wg]);
@@ -405,7 +432,10 @@ __global__ void __launch_bounds__(kThreads, 1) tail_chain_kernel(const __grid_co
         tma_load_2d(sR1, &a.tmR1, bar_x, 0, tile * kTile);
         tma_load_2d(sR2, &a.tmR2, bar_x, 0, tile * kTile);
     };
-    if (r == 0 && tile0 < a.n_tiles) load_tile(tile0);
+    if (q == 0 && tile0 < a.n_tiles) {        // one elected lane of the warpgroup's first warp issues (see pixel_chain_kernel)
+        if (elect_one()) load_tile(tile0);
+        __syncwarp();
+    }
     uint32_t xph = 0, mph = 0;
     bool w_ready = false;
     int tab_b0 = -1, tab_b1 = -1;
@@ -463,12 +493,15 @@ __global__ void __launch_bounds__(kThreads, 1) tail_chain_kernel(const __grid_co
         fence_proxy_async();
         tc_fence_before();
         named_bar_sync(1 + wg, 128);
-        if (r == 0) {
-            if (tile + tile_step < a.n_tiles) load_tile(tile + tile_step);     // everybody has consumed the three input blocks
+        if (q == 0) {
             if (!w_ready) { mbar_wait(bar_w, 0); w_ready = true; }
             tc_fence_after();
-            issue_gemm<64>(tmem_d, sA0, sW, 1, 4);
-            umma_commit(bar_mma);
+            if (elect_one()) {
+                if (tile + tile_step < a.n_tiles) load_tile(tile + tile_step);     // everybody has consumed the three input blocks
+                issue_gemm<64>(tmem_d, sA0, sW, 1, 4);
+                umma_commit(bar_mma);
+            }
+            __syncwarp();
         }
         mbar_wait(bar_mma, mph);
         mph ^= 1;
@@ -484,10 +517,13 @@ __global__ void __launch_bounds__(kThreads, 1) tail_chain_kernel(const __grid_co
         fence_proxy_async();
         tc_fence_before();
         named_bar_sync(1 + wg, 128);
-        if (r == 0) {
+        if (q == 0) {
             tc_fence_after();
-            issue_gemm<16, true>(tmem_d, sA0, sW + 64 * 128, 1, 4);
-            umma_commit(bar_mma);
+            if (elect_one()) {
+                issue_gemm<16, true>(tmem_d, sA0, sW + 64 * 128, 1, 4);
+                umma_commit(bar_mma);
+            }
+            __syncwarp();
         }
         mbar_wait(bar_mma, mph);
         mph ^= 1;
