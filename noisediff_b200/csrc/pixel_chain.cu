@@ -49,8 +49,17 @@ __device__ __forceinline__ void store_half(uint32_t blk, int r, int h, const flo
         sts128(swz(blk, r, h * 4 + jj), u);
     }
 }
+// 32 floats of a bias / per-sample table (shared memory, 16-byte aligned).  Called BETWEEN tcgen05.ld and tcgen05.wait::ld so
+// that the table's LDS latency hides behind the accumulator drain instead of stalling the first add after the wait.
+__device__ __forceinline__ void load32(const float* p, float (&b)[32]) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(p + j);
+        b[j] = v.x; b[j + 1] = v.y; b[j + 2] = v.z; b[j + 3] = v.w;
+    }
+}
 // GELU(acc + bias) of 32 accumulator columns -> fp16 operand half (the consuming GEMM runs with fp16 A and B)
-__device__ __forceinline__ void store_half_gelu_f16(uint32_t blk, int r, int h, const uint32_t (&raw)[32], const float* bias) {
+__device__ __forceinline__ void store_half_gelu_f16(uint32_t blk, int r, int h, const uint32_t (&raw)[32], const float (&bias)[32]) {
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
         uint4 u;
@@ -129,15 +138,19 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
     }
     pdl_trigger();
     pdl_wait();          // weights / parameters above are constants; everything below touches the previous kernel's output
-    const int tile0 = blockIdx.x * kNWG + wg, tile_step = gridDim.x * kNWG;
+    // every warpgroup walks a CONTIGUOUS range of tiles: the per-sample tables change once or twice per range (a strided walk of
+    // 148 x 3 warpgroups jumps 0.87 samples per step at 256 x 256, i.e. reloaded them from global memory on almost every tile)
+    const int n_wg = gridDim.x * kNWG, wg_id = blockIdx.x * kNWG + wg;
+    const int t_begin = static_cast<int>(static_cast<long long>(a.n_tiles) * wg_id / n_wg);
+    const int t_end = static_cast<int>(static_cast<long long>(a.n_tiles) * (wg_id + 1) / n_wg);
     // Single-thread work (TMA, tcgen05.mma, commits) is done by the warpgroup's first warp with ALL lanes walking the code and
     // one elected lane issuing: under a plain `if (r == 0)` the compiler cannot know that one lane is active and wraps every
     // uniform-register operand of UTCHMMA / UTMALDG in a lane-serialising loop (15 instructions per MMA on the stage's critical
     // path).  elect.sync picks the same lane every time, so the bulk-group waits pair with the stores of that lane.
-    if (!kShot && q == 0 && tile0 < a.n_tiles) {
+    if (!kShot && q == 0 && t_begin < t_end) {
         if (elect_one()) {
             mbar_expect_tx(bar_x, kBlk);
-            tma_load_2d(sX, &a.tmX, bar_x, 0, tile0 * kTile);
+            tma_load_2d(sX, &a.tmX, bar_x, 0, t_begin * kTile);
         }
         __syncwarp();
     }
@@ -165,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
         tc_fence_after();                                                    \
     } while (0)
 
-    for (int tile = tile0; tile < a.n_tiles; tile += tile_step) {
+    for (int tile = t_begin; tile < t_end; ++tile) {
         const int p = tile * kTile + r;
         const bool live = p < a.npix;
         const int pc = live ? p : a.npix - 1;
@@ -209,21 +222,25 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 uint32_t raw[32];
+                float bv[32];
                 tmem_ld32(tmem_rd + h * 32, raw);
+                load32(tail->fvec + h * 32, bv);
                 tmem_ld_wait();
-                store_half_gelu_f16(sA0, r, h, raw, tail->fvec + h * 32);
+                store_half_gelu_f16(sA0, r, h, raw, bv);
             }
             // ---- shot_mlp1.fc2 -> s1 (stored: it is the branch's residual r_s, ref :599) ------------------------------
             NDIFF_STAGE((issue_gemm<64, true>(tmem_d, sA0, sW + 64 * 128, 1, 4)));
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 uint32_t raw[32];
+                float bv[32];
                 tmem_ld32(tmem_rd + h * 32, raw);
+                load32(tail->fvec + 64 + h * 32, bv);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
-                    const float v0 = __uint_as_float(raw[j]) + tail->fvec[64 + h * 32 + j];
-                    const float v1 = __uint_as_float(raw[j + 1]) + tail->fvec[64 + h * 32 + j + 1];
+                    const float v0 = __uint_as_float(raw[j]) + bv[j];
+                    const float v1 = __uint_as_float(raw[j + 1]) + bv[j + 1];
                     xr[h * 16 + j / 2] = pack_bf16(v0, v1);
                 }
             }
@@ -295,9 +312,11 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 uint32_t raw[32];
+                float bv[32];
                 tmem_ld32(tmem_rd + hh * 64 + h * 32, raw);
+                load32(f_b1 + hh * 64 + h * 32, bv);
                 tmem_ld_wait();
-                store_half_gelu_f16(sA0 + hh * kBlk, r, h, raw, f_b1 + hh * 64 + h * 32);
+                store_half_gelu_f16(sA0 + hh * kBlk, r, h, raw, bv);
             }
         }
         if constexpr (!kShot) {
@@ -306,28 +325,27 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
             //      = fp16 GEMM over the hidden layer (K = 128, folded weight in W2's slot) accumulated with a bf16 GEMM over the
             //      input tile itself, which already sits in shared memory as TMA landed it (K = 64, Wp) -- z never exists.
             NDIFF_STAGE((issue_gemm<64, true>(tmem_d, sA0, sW2, 2, 4), issue_gemm<64>(tmem_d, sX, sWp, 1, 4, true)));
-            if (q == 0 && tile + tile_step < a.n_tiles) {      // the tensor core is done with X (the wait above): prefetch the next tile
+            if (q == 0 && tile + 1 < t_end) {      // the tensor core is done with X (the wait above): prefetch the next tile
                 if (elect_one()) {
                     mbar_expect_tx(bar_x, kBlk);
-                    tma_load_2d(sX, &a.tmX, bar_x, 0, (tile + tile_step) * kTile);
+                    tma_load_2d(sX, &a.tmX, bar_x, 0, (tile + 1) * kTile);
                 }
                 __syncwarp();
             }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 uint32_t raw[32];
-                tmem_ld32(tmem_rd + h * 32, raw);
-                tmem_ld_wait();
                 float v[32];
+                tmem_ld32(tmem_rd + h * 32, raw);
+                load32(ct + 64 + h * 32, v);                      // Wp (b2 + c) + bp
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 c4 = *reinterpret_cast<const float4*>(ct + 64 + h * 32 + j);      // Wp (b2 + c) + bp
-                    const float2 f0 = unpack_bf16(xr[(h * 32 + j) / 2]), f1 = unpack_bf16(xr[(h * 32 + j) / 2 + 1]);
-                    v[j] = __uint_as_float(raw[j]) + (f0.x + c4.x);
-                    v[j + 1] = __uint_as_float(raw[j + 1]) + (f0.y + c4.y);
-                    v[j + 2] = __uint_as_float(raw[j + 2]) + (f1.x + c4.z);
-                    v[j + 3] = __uint_as_float(raw[j + 3]) + (f1.y + c4.w);
+                for (int j = 0; j < 32; j += 2) {                 // + the residual x, while the accumulator drains
+                    const float2 f = unpack_bf16(xr[(h * 32 + j) / 2]);
+                    v[j] += f.x; v[j + 1] += f.y;
                 }
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(raw[j]);
                 store_half(sA1, r, h, v);               // staging for the TMA store
             }
         }
@@ -340,19 +358,22 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 uint32_t raw[32];
+                float bv[32];
                 tmem_ld32(tmem_rd + h * 32, raw);
+                load32(ct + 64 + h * 32, bv);
                 tmem_ld_wait();
-                store_half_gelu_f16(sA0, r, h, raw, ct + 64 + h * 32);
+                store_half_gelu_f16(sA0, r, h, raw, bv);
             }
             NDIFF_STAGE((issue_gemm<64, true>(tmem_d, sA0, sWm2, 1, 4)));
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 uint32_t raw[32];
-                tmem_ld32(tmem_rd + h * 32, raw);
-                tmem_ld_wait();
                 float v[32];
+                tmem_ld32(tmem_rd + h * 32, raw);
+                load32(f_bm2 + h * 32, v);
+                tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) + f_bm2[h * 32 + j];
+                for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(raw[j]);
                 store_half(sA1, r, h, v);
             }
         }
@@ -425,21 +446,23 @@ __global__ void __launch_bounds__(kThreads, 1) tail_chain_kernel(const __grid_co
     }
     pdl_trigger();
     pdl_wait();
-    const int tile0 = blockIdx.x * kNWG + wg, tile_step = gridDim.x * kNWG;
+    const int n_wg = gridDim.x * kNWG, wg_id = blockIdx.x * kNWG + wg;      // contiguous tile range per warpgroup (see pixel_chain_kernel)
+    const int t_begin = static_cast<int>(static_cast<long long>(a.n_tiles) * wg_id / n_wg);
+    const int t_end = static_cast<int>(static_cast<long long>(a.n_tiles) * (wg_id + 1) / n_wg);
     auto load_tile = [&](int tile) {
         mbar_expect_tx(bar_x, 3 * kBlk);
         tma_load_2d(sH, &a.tmH, bar_x, 0, tile * kTile);
         tma_load_2d(sR1, &a.tmR1, bar_x, 0, tile * kTile);
         tma_load_2d(sR2, &a.tmR2, bar_x, 0, tile * kTile);
     };
-    if (q == 0 && tile0 < a.n_tiles) {        // one elected lane of the warpgroup's first warp issues (see pixel_chain_kernel)
-        if (elect_one()) load_tile(tile0);
+    if (q == 0 && t_begin < t_end) {        // one elected lane of the warpgroup's first warp issues (see pixel_chain_kernel)
+        if (elect_one()) load_tile(t_begin);
         __syncwarp();
     }
     uint32_t xph = 0, mph = 0;
     bool w_ready = false;
     int tab_b0 = -1, tab_b1 = -1;
-    for (int tile = tile0; tile < a.n_tiles; tile += tile_step) {
+    for (int tile = t_begin; tile < t_end; ++tile) {
         const int p = tile * kTile + r;
         const bool live = p < a.npix;
         const int pc = live ? p : a.npix - 1;
@@ -497,7 +520,7 @@ __global__ void __launch_bounds__(kThreads, 1) tail_chain_kernel(const __grid_co
             if (!w_ready) { mbar_wait(bar_w, 0); w_ready = true; }
             tc_fence_after();
             if (elect_one()) {
-                if (tile + tile_step < a.n_tiles) load_tile(tile + tile_step);     // everybody has consumed the three input blocks
+                if (tile + 1 < t_end) load_tile(tile + 1);     // everybody has consumed the three input blocks
                 issue_gemm<64>(tmem_d, sA0, sW, 1, 4);
                 umma_commit(bar_mma);
             }
@@ -509,9 +532,11 @@ __global__ void __launch_bounds__(kThreads, 1) tail_chain_kernel(const __grid_co
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             uint32_t raw[32];
+            float bv[32];
             tmem_ld32(tmem_rd + h * 32, raw);
+            load32(tail->fvec + h * 32, bv);
             tmem_ld_wait();
-            store_half_gelu_f16(sA0, r, h, raw, tail->fvec + h * 32);
+            store_half_gelu_f16(sA0, r, h, raw, bv);
         }
         // ---- shot_mlp3.fc2 (64 -> 4, N padded to 16) ------------------------------------------------------------------------
         fence_proxy_async();
