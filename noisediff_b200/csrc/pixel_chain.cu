@@ -157,6 +157,9 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
     uint32_t xph = 0, mph = 0;
     bool w_ready = false;
     int tab_b0 = -1, tab_b1 = -1;            // samples currently held by this warpgroup's ctab slots
+    float4 c4n = make_float4(0.f, 0.f, 0.f, 0.f), x4n = c4n;      // shot: this pixel's inputs of the NEXT tile (software prefetch)
+    if (kShot && t_begin < t_end && t_begin * kTile + r < a.npix) { c4n = __ldg(a.clean + t_begin * kTile + r); x4n = a.x[t_begin * kTile + r]; }
+    (void)c4n; (void)x4n;
 
     // one GEMM stage: publish my operand writes, one thread issues, everybody waits for the accumulator
 #define NDIFF_STAGE(ISSUE)                                                   \
@@ -212,10 +215,14 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
 
         if constexpr (kShot) {
             // ---- shot_mlp1.fc1 on cat[clean, x_t] (ref Diffusion_arch.py:598; clean first) --------------------------
-            float4 c4 = make_float4(0.f, 0.f, 0.f, 0.f), x4 = c4;
-            if (live) { c4 = __ldg(a.clean + p); x4 = a.x[p]; }
+            // (this tile's inputs were requested one tile ago; the next tile's are requested now, a whole chain ahead of their use)
             uint4 u;
-            u.x = pack_bf16(c4.x, c4.y); u.y = pack_bf16(c4.z, c4.w); u.z = pack_bf16(x4.x, x4.y); u.w = pack_bf16(x4.z, x4.w);
+            u.x = pack_bf16(c4n.x, c4n.y); u.y = pack_bf16(c4n.z, c4n.w); u.z = pack_bf16(x4n.x, x4n.y); u.w = pack_bf16(x4n.z, x4n.w);
+            {
+                const int pn = p + kTile;
+                c4n = x4n = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tile + 1 < t_end && pn < a.npix) { c4n = __ldg(a.clean + pn); x4n = a.x[pn]; }
+            }
             sts128(swz(sA0, r, 0), u);
             sts128(swz(sA0, r, 1), make_uint4(0u, 0u, 0u, 0u));
             NDIFF_STAGE(issue_gemm<64>(tmem_d, sA0, sW, 1, 1));

@@ -125,14 +125,17 @@ template <int VPL>
 __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, const float* __restrict__ vec,
                                                         int vec_ld, const float* __restrict__ g,
                                                         const float* __restrict__ beta, bf16* __restrict__ out,
-                                                        int HW, int C, int L, size_t npix, float real_frac) {
+                                                        int HW, int C, int L, size_t npix_, float real_frac) {
     pdl_trigger();
     pdl_wait();
-    const int lane = threadIdx.x & 31;
-    const int sub = lane % L, slot = lane / L, ppw = 32 / L;
-    const size_t warp = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const size_t nwarps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
-    const int cv = C >> 3;
+    // 32-bit pixel arithmetic (the launcher checks npix < 2^31): the kernel is close to instruction bound — ~70 instructions per
+    // 16-byte vector is what keeps it on the HBM roofline — and a 64-bit division per pixel alone cost that much
+    const unsigned npix = static_cast<unsigned>(npix_);
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned sub = lane % L, slot = lane / L, ppw = 32 / L;
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+    const unsigned cv = C >> 3;
     float gg[VPL][8], bb[VPL][8];
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
@@ -147,21 +150,23 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
     // kLnU pixels per lane group and iteration: all 16-byte loads are issued before the first reduction, so the shuffles and
     // the dependent arithmetic of one pixel overlap the memory latency of the others
     constexpr int kLnU = VPL == 1 ? 4 : 2;
-    for (size_t p0 = warp * ppw * kLnU; p0 < npix; p0 += nwarps * ppw * kLnU) {
+    const uint4* __restrict__ x4 = reinterpret_cast<const uint4*>(x);
+    uint4* __restrict__ o4 = reinterpret_cast<uint4*>(out);
+    for (unsigned p0 = warp * ppw * kLnU; p0 < npix; p0 += nwarps * ppw * kLnU) {
         float f[kLnU][VPL][8];
-        size_t pixs[kLnU];
+        unsigned pixs[kLnU];
         uint4 raw[kLnU][VPL];
 #pragma unroll
         for (int u = 0; u < kLnU; ++u) {
             pixs[u] = p0 + u * ppw + slot;
-            const size_t pp = pixs[u] < npix ? pixs[u] : npix - 1;
+            const unsigned pp = pixs[u] < npix ? pixs[u] : npix - 1;
 #pragma unroll
-            for (int j = 0; j < VPL; ++j) raw[u][j] = __ldg(reinterpret_cast<const uint4*>(x) + pp * cv + sub + j * L);
+            for (int j = 0; j < VPL; ++j) raw[u][j] = __ldg(x4 + static_cast<size_t>(pp) * cv + sub + j * L);
         }
 #pragma unroll
         for (int u = 0; u < kLnU; ++u) {
-            const size_t pp = pixs[u] < npix ? pixs[u] : npix - 1;
-            const float* vp = vec + (pp / HW) * static_cast<size_t>(vec_ld);
+            const unsigned pp = pixs[u] < npix ? pixs[u] : npix - 1;
+            const float* vp = vec + static_cast<size_t>(pp / static_cast<unsigned>(HW)) * vec_ld;
             float sum = 0.f;
 #pragma unroll
             for (int j = 0; j < VPL; ++j) {
@@ -189,7 +194,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
                     float o8[8];
 #pragma unroll
                     for (int k = 0; k < 8; ++k) o8[k] = (f[u][j][k] - mean) * rstd * gg[j][k] + bb[j][k];
-                    reinterpret_cast<uint4*>(out)[pixs[u] * cv + sub + j * L] = pack8(o8);
+                    o4[static_cast<size_t>(pixs[u]) * cv + sub + j * L] = pack8(o8);
                 }
             }
         }
@@ -817,6 +822,7 @@ int gn_apply_launch(const GnApplyArgs& a, cudaStream_t s) {
 int layernorm_launch(const bf16* x, const float* vec, int vec_ld, const float* g, const float* beta, bf16* out, int B,
                      int HW, int C, cudaStream_t s, float real_frac) {
     NDIFF_REQUIRE(real_frac > 0.f && real_frac <= 1.f, "LayerNorm: live channel fraction must be in (0, 1]");
+    NDIFF_REQUIRE(static_cast<long long>(B) * HW < (1ll << 31), "LayerNorm: 32-bit pixel indices");
     NDIFF_REQUIRE(C == 64 || C == 128 || C == 256 || C == 512, "LayerNorm: C must be 64, 128, 256 or 512");
     NDIFF_REQUIRE(vec_ld % 4 == 0, "LayerNorm: per-sample vector stride must keep 16-byte alignment");
     const size_t npix = static_cast<size_t>(B) * HW;
