@@ -50,6 +50,7 @@ struct ChainPlan {
     int prog;
     int grid;
     int smem_bytes;
+    int tpp;              // threads per pixel (1 or 2)
 };
 
 struct ChainDesc {
