@@ -35,50 +35,40 @@ struct ChainTail {
     // per warpgroup, per sample slot (a 128-pixel tile touches at most two samples): [0] the collapsed attention vector c,
     // [1] b2 + c (bias of ff.net.2 plus the residual's per-sample part)
     alignas(16) float ctab[kNWG][2][2][64];
-    alignas(8) float2 ln[kNWG][2][kTile];       // two threads per pixel: LayerNorm partial moments of the two column halves
 };
 
 __device__ __forceinline__ uint32_t swz(uint32_t blk, int r, int j) {   // 16-byte chunk j of row r in a SWIZZLE_128B block
     return blk + r * 128 + ((j ^ (r & 7)) << 4);
 }
-// CW fp32 values -> bf16, 16-byte chunks j0 .. j0 + CW / 8 - 1 of operand row r
-template <int CW>
-__device__ __forceinline__ void store_bf16(uint32_t blk, int r, int j0, const float (&v)[CW]) {
+__device__ __forceinline__ void store_half(uint32_t blk, int r, int h, const float (&v)[32]) {
 #pragma unroll
-    for (int jj = 0; jj < CW / 8; ++jj) {
+    for (int jj = 0; jj < 4; ++jj) {
         uint4 u;
         u.x = pack_bf16(v[jj * 8 + 0], v[jj * 8 + 1]); u.y = pack_bf16(v[jj * 8 + 2], v[jj * 8 + 3]);
         u.z = pack_bf16(v[jj * 8 + 4], v[jj * 8 + 5]); u.w = pack_bf16(v[jj * 8 + 6], v[jj * 8 + 7]);
-        sts128(swz(blk, r, j0 + jj), u);
+        sts128(swz(blk, r, h * 4 + jj), u);
     }
 }
-// CW floats of a bias / per-sample table (shared memory, 16-byte aligned).  Called BETWEEN tcgen05.ld and tcgen05.wait::ld so
+// 32 floats of a bias / per-sample table (shared memory, 16-byte aligned).  Called BETWEEN tcgen05.ld and tcgen05.wait::ld so
 // that the table's LDS latency hides behind the accumulator drain instead of stalling the first add after the wait.
-template <int CW>
-__device__ __forceinline__ void load_tab(const float* p, float (&b)[CW]) {
+__device__ __forceinline__ void load32(const float* p, float (&b)[32]) {
 #pragma unroll
-    for (int j = 0; j < CW; j += 4) {
+    for (int j = 0; j < 32; j += 4) {
         const float4 v = *reinterpret_cast<const float4*>(p + j);
         b[j] = v.x; b[j + 1] = v.y; b[j + 2] = v.z; b[j + 3] = v.w;
     }
 }
-// GELU(acc + bias) of CW accumulator columns -> fp16 operand chunks (the consuming GEMM runs with fp16 A and B)
-template <int CW>
-__device__ __forceinline__ void store_gelu_f16(uint32_t blk, int r, int j0, const uint32_t (&raw)[CW], const float (&bias)[CW]) {
+// GELU(acc + bias) of 32 accumulator columns -> fp16 operand half (the consuming GEMM runs with fp16 A and B)
+__device__ __forceinline__ void store_half_gelu_f16(uint32_t blk, int r, int h, const uint32_t (&raw)[32], const float (&bias)[32]) {
 #pragma unroll
-    for (int jj = 0; jj < CW / 8; ++jj) {
+    for (int jj = 0; jj < 4; ++jj) {
         uint4 u;
         u.x = gelu_f16x2(__uint_as_float(raw[jj * 8 + 0]) + bias[jj * 8 + 0], __uint_as_float(raw[jj * 8 + 1]) + bias[jj * 8 + 1]);
         u.y = gelu_f16x2(__uint_as_float(raw[jj * 8 + 2]) + bias[jj * 8 + 2], __uint_as_float(raw[jj * 8 + 3]) + bias[jj * 8 + 3]);
         u.z = gelu_f16x2(__uint_as_float(raw[jj * 8 + 4]) + bias[jj * 8 + 4], __uint_as_float(raw[jj * 8 + 5]) + bias[jj * 8 + 5]);
         u.w = gelu_f16x2(__uint_as_float(raw[jj * 8 + 6]) + bias[jj * 8 + 6], __uint_as_float(raw[jj * 8 + 7]) + bias[jj * 8 + 7]);
-        sts128(swz(blk, r, j0 + jj), u);
+        sts128(swz(blk, r, h * 4 + jj), u);
     }
-}
-// CW accumulator columns of this warp's TMEM lane quarter
-template <int CW>
-__device__ __forceinline__ void tmem_ldw(uint32_t taddr, uint32_t (&v)[CW]) {
-    if constexpr (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
 }
 // D[tmem] = A[128 x (kblocks*64)] * W[N x (kblocks*64)]^T ; k16 = MMAs per K block (4, or 1 when only K = 16 is live)
 template <int N, bool F16 = false>
@@ -96,17 +86,13 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_blk, uint
     }
 }
 
-// kNWG thread groups keep that many independent tiles in flight per SM (the chain of one tile is strictly sequential: operand
+// kNWG warpgroups keep that many independent tiles in flight per SM (the chain of one tile is strictly sequential: operand
 // write -> barrier -> MMA -> TMEM drain, five times for the shot program), so the tensor-core round trips and the epilogue
-// arithmetic of different tiles overlap.
-// TPP = threads per pixel.  TPP = 1: a group is one warpgroup, thread r owns pixel r = TMEM lane r; 384 threads cap the kernel at
-// 168 registers (the pixel's input row stays packed in 32 registers, accumulators are drained 32 columns at a time, LayerNorm
-// re-derives y = x + c per pass).  TPP = 2: a group is 256 threads; warp w of the group reads TMEM lane quarter w % 4 (the
-// hardware's rule) and column half w / 4, so every thread handles half of each row in 16-column chunks — half the dependent
-// chain per stage, 24 warps per SM (six per scheduler) within the same shared memory and TMEM; LayerNorm's two moments cross
-// the halves through shared memory.
-template <int PROG, int TPP>
-__global__ void __launch_bounds__(kNWG * 128 * TPP, 1) pixel_chain_kernel(const __grid_constant__ ChainArgs a) {
+// arithmetic of different tiles overlap.  384 threads cap the kernel at 168 registers: the pixel's input row stays packed
+// (xr, 32 registers), accumulators are drained 32 columns at a time, and LayerNorm re-derives y = x + c per pass instead of
+// holding 64 floats.
+template <int PROG>
+__global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_constant__ ChainArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __builtin_assume(__isShared(smem));      // the manual alignment hides the address space: without the hint every table read is a generic LD.E
@@ -114,18 +100,11 @@ __global__ void __launch_bounds__(kNWG * 128 * TPP, 1) pixel_chain_kernel(const 
     constexpr int kWRows = kShot ? kChainShotRows : kChainAttnRows;
     constexpr int kNF = kShot ? kChainShotFloats : kChainAttnFloats;
     constexpr int kWBytes = kWRows * 128;
-    constexpr int GT = 128 * TPP;            // threads of one group (one tile)
-    constexpr int CW = 32 / TPP;             // accumulator columns per drain chunk; a thread owns 64 / TPP of a row's 64 channels
     ChainTail* tail = reinterpret_cast<ChainTail*>(smem + kWBytes + kNWG * kWgBytes);
 
-    // the warp index is broadcast from lane 0 so that the compiler knows it (and everything derived from it: the group's
+    // the warp index is broadcast from lane 0 so that the compiler knows it (and everything derived from it: the warpgroup's
     // operand blocks, barriers and TMEM columns) is warp-uniform
-    const int tid = threadIdx.x, warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    const int wg = warp_u / (4 * TPP), wi = warp_u % (4 * TPP), q = wi & 3, hc = wi >> 2;
-    const int r = q * 32 + (tid & 31);       // pixel row of the tile = TMEM lane
-    const int tg = wi * 32 + (tid & 31);     // thread index inside the group
-    const int c0 = hc * (64 / TPP);          // first of this thread's channels in a 64-column stage
-    const int hb = hc * (128 / TPP);         // first of this thread's columns of the 128-wide hidden layer
+    const int tid = threadIdx.x, warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0), wg = warp_u >> 2, r = tid & 127, q = warp_u & 3;
     const uint32_t sW = smem_u32(smem);
     const uint32_t sX = sW + kWBytes + wg * kWgBytes, sA0 = sX + kBlk, sA1 = sA0 + kBlk;
     // weight blocks (row offsets of pixel_chain.cuh's blob layout, 128 B per row)
@@ -134,7 +113,7 @@ __global__ void __launch_bounds__(kNWG * 128 * TPP, 1) pixel_chain_kernel(const 
     const float* fA = tail->fvec + (kShot ? 128 : 0);
     // (the first 128 floats of the attention block are reserved: LayerNorm's affine is folded into W1 / b1 by the packer)
     const float* f_b1 = fA + 128, *f_bm2 = fA + 448;
-    (void)f_bm2; (void)sWm2;
+    (void)f_bm2;
     const uint32_t bar_w = smem_u32(&tail->bar_w), bar_x = smem_u32(&tail->bar_x[wg]), bar_mma = smem_u32(&tail->bar_mma[wg]);
 
     if (tid == 0) {
@@ -146,11 +125,11 @@ __global__ void __launch_bounds__(kNWG * 128 * TPP, 1) pixel_chain_kernel(const 
         fence_mbar_init();
     }
     if (tid < 32) tmem_alloc<kTmemCols>(&tail->tmem_base);
-    for (int i = tid; i < kNF; i += kNWG * GT) tail->fvec[i] = __ldg(a.fvec + i);
+    for (int i = tid; i < kNF; i += kThreads) tail->fvec[i] = __ldg(a.fvec + i);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_d = tail->tmem_base + wg * 128;                          // this group's 128 accumulator columns
+    const uint32_t tmem_d = tail->tmem_base + wg * 128;                          // this warpgroup's 128 accumulator columns
     const uint32_t tmem_rd = tmem_d + (static_cast<uint32_t>(q * 32) << 16);     // + this warp's lane quarter
 
     if (tid == 0) {   // the whole weight blob, once
@@ -159,16 +138,16 @@ __global__ void __launch_bounds__(kNWG * 128 * TPP, 1) pixel_chain_kernel(const 
     }
     pdl_trigger();
     pdl_wait();          // weights / parameters above are constants; everything below touches the previous kernel's output
-    // every group walks a CONTIGUOUS range of tiles: the per-sample tables change once or twice per range (a strided walk of
-    // 148 x 3 groups jumps 0.87 samples per step at 256 x 256, i.e. reloaded them from global memory on almost every tile)
+    // every warpgroup walks a CONTIGUOUS range of tiles: the per-sample tables change once or twice per range (a strided walk of
+    // 148 x 3 warpgroups jumps 0.87 samples per step at 256 x 256, i.e. reloaded them from global memory on almost every tile)
     const int n_wg = gridDim.x * kNWG, wg_id = blockIdx.x * kNWG + wg;
     const int t_begin = static_cast<int>(static_cast<long long>(a.n_tiles) * wg_id / n_wg);
     const int t_end = static_cast<int>(static_cast<long long>(a.n_tiles) * (wg_id + 1) / n_wg);
-    // Single-thread work (TMA, tcgen05.mma, commits) is done by the group's first warp with ALL lanes walking the code and
+    // Single-thread work (TMA, tcgen05.mma, commits) is done by the warpgroup's first warp with ALL lanes walking the code and
     // one elected lane issuing: under a plain `if (r == 0)` the compiler cannot know that one lane is active and wraps every
     // uniform-register operand of UTCHMMA / UTMALDG in a lane-serialising loop (15 instructions per MMA on the stage's critical
     // path).  elect.sync picks the same lane every time, so the bulk-group waits pair with the stores of that lane.
-    if (!kShot && wi == 0 && t_begin < t_end) {
+    if (!kShot && q == 0 && t_begin < t_end) {
         if (elect_one()) {
             mbar_expect_tx(bar_x, kBlk);
             tma_load_2d(sX, &a.tmX, bar_x, 0, t_begin * kTile);
@@ -177,9 +156,9 @@ __global__ void __launch_bounds__(kNWG * 128 * TPP, 1) pixel_chain_kernel(const 
     }
     uint32_t xph = 0, mph = 0;
     bool w_ready = false;
-    int tab_b0 = -1, tab_b1 = -1;            // samples currently held by this group's ctab slots
+    int tab_b0 = -1, tab_b1 = -1;            // samples currently held by this warpgroup's ctab slots
     float4 c4n = make_float4(0.f, 0.f, 0.f, 0.f), x4n = c4n;      // shot: this pixel's inputs of the NEXT tile (software prefetch)
-    if (kShot && hc == 0 && t_begin < t_end && t_begin * kTile + r < a.npix) { c4n = __ldg(a.clean + t_begin * kTile + r); x4n = a.x[t_begin * kTile + r]; }
+    if (kShot && t_begin < t_end && t_begin * kTile + r < a.npix) { c4n = __ldg(a.clean + t_begin * kTile + r); x4n = a.x[t_begin * kTile + r]; }
     (void)c4n; (void)x4n;
 
     // one GEMM stage: publish my operand writes, one thread issues, everybody waits for the accumulator
@@ -187,8 +166,8 @@ __global__ void __launch_bounds__(kNWG * 128 * TPP, 1) pixel_chain_kernel(const 
     do {                                                                     \
         fence_proxy_async();                                                 \
         tc_fence_before();                                                   \
-        named_bar_sync(1 + wg, GT);                                          \
-        if (wi == 0) {                                                       \
+        named_bar_sync(1 + wg, 128);                                         \
+        if (q == 0) {                                                        \
             if (!w_ready) { mbar_wait(bar_w, 0); w_ready = true; }           \
             tc_fence_after();                                                \
             if (elect_one()) {                                               \
@@ -206,105 +185,97 @@ __global__ void __launch_bounds__(kNWG * 128 * TPP, 1) pixel_chain_kernel(const 
         const int p = tile * kTile + r;
         const bool live = p < a.npix;
         const int pc = live ? p : a.npix - 1;
-        uint32_t xr[32 / TPP];                // this thread's channels of the attention-block input, packed bf16
+        uint32_t xr[32];                      // this pixel's 64-channel attention-block input, packed bf16
         // per-sample vectors of the tile's (at most two) samples -> shared memory; refreshed only when the samples change.
-        // Nobody still reads the old table: every thread's last read precedes the previous tile's output barrier.
+        // Nobody still reads the old table: every thread's last read precedes the previous tile's proj_out stage barrier.
         const int b_first = (tile * kTile) / a.HW;
         {
             const int last = tile * kTile + kTile - 1;
             const int b_last = (last < a.npix ? last : a.npix - 1) / a.HW;
             if (b_first != tab_b0 || b_last != tab_b1) {
                 tab_b0 = b_first; tab_b1 = b_last;
-                if (tg < 128) {
-                    const int slot = tg >> 6, j = tg & 63;
-                    const size_t co = static_cast<size_t>(slot ? b_last : b_first) * a.cvec_ld + j;
-                    tail->ctab[wg][slot][0][j] = __ldg(a.cvec + co);
-                    // the per-sample vector of the folded last linear stage (attn: Wp (b2 + c) + bp; shot: Wm1 Wp (b2 + c) + Wm1 bp
-                    // + bm1), computed once per condition (engine.cu attn_vec2_kernel)
-                    tail->ctab[wg][slot][1][j] = __ldg(a.cvec2 + co);
-                }
-                named_bar_sync(1 + wg, GT);
+                const int slot = r >> 6, j = r & 63;
+                const size_t co = static_cast<size_t>(slot ? b_last : b_first) * a.cvec_ld + j;
+                const float cj = __ldg(a.cvec + co);
+                tail->ctab[wg][slot][0][j] = cj;
+                // the per-sample vector of the folded last linear stage (attn: Wp (b2 + c) + bp; shot: Wm1 Wp (b2 + c) + Wm1 bp
+                // + bm1), computed once per condition (engine.cu attn_vec2_kernel)
+                tail->ctab[wg][slot][1][j] = __ldg(a.cvec2 + co);
+                named_bar_sync(1 + wg, 128);
             }
         }
         const float* ct = &tail->ctab[wg][(pc / a.HW) != b_first ? 1 : 0][0][0];      // c at ct[j], folded-stage vector at ct[64 + j]
 
         // X (shot) and A1 are sources of the previous tile's TMA stores: they must have been read before anyone rewrites them
         // (every thread's first write to either comes after the next named barrier, which the issuing warp joins after this wait)
-        if (wi == 0) {
+        if (q == 0) {
             if (elect_one()) tma_store_wait_read();
             __syncwarp();
         }
 
         if constexpr (kShot) {
-            // ---- shot_mlp1.fc1 on cat[clean, x_t] (ref Diffusion_arch.py:598; clean first): one 16-byte operand chunk per pixel
-            if (hc == 0) {
-                // (this tile's inputs were requested one tile ago; the next tile's are requested now, a whole chain ahead of their use)
-                uint4 u;
-                u.x = pack_bf16(c4n.x, c4n.y); u.y = pack_bf16(c4n.z, c4n.w); u.z = pack_bf16(x4n.x, x4n.y); u.w = pack_bf16(x4n.z, x4n.w);
+            // ---- shot_mlp1.fc1 on cat[clean, x_t] (ref Diffusion_arch.py:598; clean first) --------------------------
+            // (this tile's inputs were requested one tile ago; the next tile's are requested now, a whole chain ahead of their use)
+            uint4 u;
+            u.x = pack_bf16(c4n.x, c4n.y); u.y = pack_bf16(c4n.z, c4n.w); u.z = pack_bf16(x4n.x, x4n.y); u.w = pack_bf16(x4n.z, x4n.w);
+            {
                 const int pn = p + kTile;
                 c4n = x4n = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (tile + 1 < t_end && pn < a.npix) { c4n = __ldg(a.clean + pn); x4n = a.x[pn]; }
-                sts128(swz(sA0, r, 0), u);
-                sts128(swz(sA0, r, 1), make_uint4(0u, 0u, 0u, 0u));
             }
+            sts128(swz(sA0, r, 0), u);
+            sts128(swz(sA0, r, 1), make_uint4(0u, 0u, 0u, 0u));
             NDIFF_STAGE(issue_gemm<64>(tmem_d, sA0, sW, 1, 1));
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int col = c0 + h * CW;
-                uint32_t raw[CW];
-                float bv[CW];
-                tmem_ldw<CW>(tmem_rd + col, raw);
-                load_tab<CW>(tail->fvec + col, bv);
+                uint32_t raw[32];
+                float bv[32];
+                tmem_ld32(tmem_rd + h * 32, raw);
+                load32(tail->fvec + h * 32, bv);
                 tmem_ld_wait();
-                store_gelu_f16<CW>(sA0, r, col >> 3, raw, bv);
+                store_half_gelu_f16(sA0, r, h, raw, bv);
             }
             // ---- shot_mlp1.fc2 -> s1 (stored: it is the branch's residual r_s, ref :599) ------------------------------
             NDIFF_STAGE((issue_gemm<64, true>(tmem_d, sA0, sW + 64 * 128, 1, 4)));
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int col = c0 + h * CW;
-                uint32_t raw[CW];
-                float bv[CW];
-                tmem_ldw<CW>(tmem_rd + col, raw);
-                load_tab<CW>(tail->fvec + 64 + col, bv);
+                uint32_t raw[32];
+                float bv[32];
+                tmem_ld32(tmem_rd + h * 32, raw);
+                load32(tail->fvec + 64 + h * 32, bv);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < CW; j += 2)
-                    xr[(h * CW + j) / 2] = pack_bf16(__uint_as_float(raw[j]) + bv[j], __uint_as_float(raw[j + 1]) + bv[j + 1]);
+                for (int j = 0; j < 32; j += 2) {
+                    const float v0 = __uint_as_float(raw[j]) + bv[j];
+                    const float v1 = __uint_as_float(raw[j + 1]) + bv[j + 1];
+                    xr[h * 16 + j / 2] = pack_bf16(v0, v1);
+                }
             }
 #pragma unroll
-            for (int j = 0; j < 8 / TPP; ++j)      // s1 staged in the X slot; stored by TMA at the next barrier
-                sts128(swz(sX, r, (c0 >> 3) + j), make_uint4(xr[j * 4], xr[j * 4 + 1], xr[j * 4 + 2], xr[j * 4 + 3]));
+            for (int j = 0; j < 8; ++j)      // s1 staged in the X slot; stored by TMA at the next barrier
+                sts128(swz(sX, r, j), make_uint4(xr[j * 4], xr[j * 4 + 1], xr[j * 4 + 2], xr[j * 4 + 3]));
         } else {
             mbar_wait(bar_x, xph);
             xph ^= 1;
 #pragma unroll
-            for (int j = 0; j < 8 / TPP; ++j) {
-                const uint4 u = lds128(swz(sX, r, (c0 >> 3) + j));
+            for (int j = 0; j < 8; ++j) {
+                const uint4 u = lds128(swz(sX, r, j));
                 xr[j * 4] = u.x; xr[j * 4 + 1] = u.y; xr[j * 4 + 2] = u.z; xr[j * 4 + 3] = u.w;
             }
         }
 
         // ---- y = x + c ; A0 = (y - mean) * rstd   (AttnBlock.norm2 on the collapsed attention, ref :438-439; the affine
         //      g, b of the LayerNorm lives in W1 / b1).  One pass for the moments, one to normalise; y is re-derived from the
-        //      packed row instead of being held in registers.  TPP = 2: the two halves of a row meet in shared memory.
+        //      packed row instead of being held in 64 registers.
         {
             float sum = 0.f, sq = 0.f;
 #pragma unroll
-            for (int j = 0; j < 64 / TPP; j += 4) {
-                const float4 c4 = *reinterpret_cast<const float4*>(ct + c0 + j);
+            for (int j = 0; j < 64; j += 4) {
+                const float4 c4 = *reinterpret_cast<const float4*>(ct + j);
                 const float2 f0 = unpack_bf16(xr[j / 2]), f1 = unpack_bf16(xr[j / 2 + 1]);
                 const float y0 = f0.x + c4.x, y1 = f0.y + c4.y, y2 = f1.x + c4.z, y3 = f1.y + c4.w;
                 sum += (y0 + y1) + (y2 + y3);
                 sq = fmaf(y0, y0, sq); sq = fmaf(y1, y1, sq); sq = fmaf(y2, y2, sq); sq = fmaf(y3, y3, sq);
-            }
-            if constexpr (TPP == 2) {
-                tail->ln[wg][hc][r] = make_float2(sum, sq);
-                named_bar_sync(1 + wg, GT);
-                const float2 o = tail->ln[wg][hc ^ 1][r];
-                // (both halves add in the same order, so the two threads of a pixel normalise with identical moments)
-                sum = hc == 0 ? sum + o.x : o.x + sum;
-                sq = hc == 0 ? sq + o.y : o.y + sq;
             }
             // (zero-padded layouts: y is exactly 0 on the padding, so both moments are sums over the live channels)
             const float mean = sum * a.inv_c;
@@ -312,22 +283,22 @@ __global__ void __launch_bounds__(kNWG * 128 * TPP, 1) pixel_chain_kernel(const 
             const float nb = -mean * rstd;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                float v[CW];
+                float v[32];
 #pragma unroll
-                for (int j = 0; j < CW; j += 4) {
-                    const float4 c4 = *reinterpret_cast<const float4*>(ct + c0 + h * CW + j);
-                    const float2 f0 = unpack_bf16(xr[(h * CW + j) / 2]), f1 = unpack_bf16(xr[(h * CW + j) / 2 + 1]);
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 c4 = *reinterpret_cast<const float4*>(ct + h * 32 + j);
+                    const float2 f0 = unpack_bf16(xr[(h * 32 + j) / 2]), f1 = unpack_bf16(xr[(h * 32 + j) / 2 + 1]);
                     v[j] = fmaf(f0.x + c4.x, rstd, nb); v[j + 1] = fmaf(f0.y + c4.y, rstd, nb);
                     v[j + 2] = fmaf(f1.x + c4.z, rstd, nb); v[j + 3] = fmaf(f1.y + c4.w, rstd, nb);
                 }
-                store_bf16<CW>(sA0, r, (c0 + h * CW) >> 3, v);
+                store_half(sA0, r, h, v);
             }
         }
-        // ---- FeedForward.net.0: Linear(C, 2C) + GELU   (ref :405-422); hidden K block 0 / 1 -> operand block A0 / A1 ---------
+        // ---- FeedForward.net.0: Linear(C, 2C) + GELU   (ref :405-422); hidden K block hh -> operand block A0 / A1 ------------
         fence_proxy_async();
         tc_fence_before();
-        named_bar_sync(1 + wg, GT);
-        if (wi == 0) {
+        named_bar_sync(1 + wg, 128);
+        if (q == 0) {
             if (!w_ready) { mbar_wait(bar_w, 0); w_ready = true; }
             tc_fence_after();
             if (elect_one()) {
@@ -344,14 +315,16 @@ __global__ void __launch_bounds__(kNWG * 128 * TPP, 1) pixel_chain_kernel(const 
         mph ^= 1;
         tc_fence_after();
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int col = hb + i * CW;          // of the 128 hidden columns
-            uint32_t raw[CW];
-            float bv[CW];
-            tmem_ldw<CW>(tmem_rd + col, raw);
-            load_tab<CW>(f_b1 + col, bv);
-            tmem_ld_wait();
-            store_gelu_f16<CW>(sA0 + (col >> 6) * kBlk, r, (col & 63) >> 3, raw, bv);
+        for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t raw[32];
+                float bv[32];
+                tmem_ld32(tmem_rd + hh * 64 + h * 32, raw);
+                load32(f_b1 + hh * 64 + h * 32, bv);
+                tmem_ld_wait();
+                store_half_gelu_f16(sA0 + hh * kBlk, r, h, raw, bv);
+            }
         }
         if constexpr (!kShot) {
             // ---- FeedForward.net.2 and proj_out meet without a nonlinearity (ref :439-443): ONE stage
@@ -359,7 +332,7 @@ __global__ void __launch_bounds__(kNWG * 128 * TPP, 1) pixel_chain_kernel(const 
             //      = fp16 GEMM over the hidden layer (K = 128, folded weight in W2's slot) accumulated with a bf16 GEMM over the
             //      input tile itself, which already sits in shared memory as TMA landed it (K = 64, Wp) -- z never exists.
             NDIFF_STAGE((issue_gemm<64, true>(tmem_d, sA0, sW2, 2, 4), issue_gemm<64>(tmem_d, sX, sWp, 1, 4, true)));
-            if (wi == 0 && tile + 1 < t_end) {      // the tensor core is done with X (the wait above): prefetch the next tile
+            if (q == 0 && tile + 1 < t_end) {      // the tensor core is done with X (the wait above): prefetch the next tile
                 if (elect_one()) {
                     mbar_expect_tx(bar_x, kBlk);
                     tma_load_2d(sX, &a.tmX, bar_x, 0, (tile + 1) * kTile);
@@ -368,20 +341,19 @@ __global__ void __launch_bounds__(kNWG * 128 * TPP, 1) pixel_chain_kernel(const 
             }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int col = c0 + h * CW;
-                uint32_t raw[CW];
-                float v[CW];
-                tmem_ldw<CW>(tmem_rd + col, raw);
-                load_tab<CW>(ct + 64 + col, v);                   // Wp (b2 + c) + bp
+                uint32_t raw[32];
+                float v[32];
+                tmem_ld32(tmem_rd + h * 32, raw);
+                load32(ct + 64 + h * 32, v);                      // Wp (b2 + c) + bp
 #pragma unroll
-                for (int j = 0; j < CW; j += 2) {                 // + the residual x, while the accumulator drains
-                    const float2 f = unpack_bf16(xr[(h * CW + j) / 2]);
+                for (int j = 0; j < 32; j += 2) {                 // + the residual x, while the accumulator drains
+                    const float2 f = unpack_bf16(xr[(h * 32 + j) / 2]);
                     v[j] += f.x; v[j + 1] += f.y;
                 }
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < CW; ++j) v[j] += __uint_as_float(raw[j]);
-                store_bf16<CW>(sA1, r, col >> 3, v);              // staging for the TMA store
+                for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(raw[j]);
+                store_half(sA1, r, h, v);               // staging for the TMA store
             }
         }
         if constexpr (kShot) {
@@ -392,33 +364,31 @@ __global__ void __launch_bounds__(kNWG * 128 * TPP, 1) pixel_chain_kernel(const 
             NDIFF_STAGE((issue_gemm<64, true>(tmem_d, sA0, sW2, 2, 4), issue_gemm<64>(tmem_d, sX, sWp, 1, 4, true)));
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int col = c0 + h * CW;
-                uint32_t raw[CW];
-                float bv[CW];
-                tmem_ldw<CW>(tmem_rd + col, raw);
-                load_tab<CW>(ct + 64 + col, bv);
+                uint32_t raw[32];
+                float bv[32];
+                tmem_ld32(tmem_rd + h * 32, raw);
+                load32(ct + 64 + h * 32, bv);
                 tmem_ld_wait();
-                store_gelu_f16<CW>(sA0, r, col >> 3, raw, bv);
+                store_half_gelu_f16(sA0, r, h, raw, bv);
             }
             NDIFF_STAGE((issue_gemm<64, true>(tmem_d, sA0, sWm2, 1, 4)));
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                const int col = c0 + h * CW;
-                uint32_t raw[CW];
-                float v[CW];
-                tmem_ldw<CW>(tmem_rd + col, raw);
-                load_tab<CW>(f_bm2 + col, v);
+                uint32_t raw[32];
+                float v[32];
+                tmem_ld32(tmem_rd + h * 32, raw);
+                load32(f_bm2 + h * 32, v);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < CW; ++j) v[j] += __uint_as_float(raw[j]);
-                store_bf16<CW>(sA1, r, col >> 3, v);
+                for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(raw[j]);
+                store_half(sA1, r, h, v);
             }
         }
         // ---- output tile: staged in A1, stored by TMA (rows beyond npix are clipped by the tensor map) ---------------------
         fence_proxy_async();
         tc_fence_before();        // the accumulator drains above must be ordered before the next tile's MMA overwrites TMEM
-        named_bar_sync(1 + wg, GT);
-        if (wi == 0) {
+        named_bar_sync(1 + wg, 128);
+        if (q == 0) {
             if (elect_one()) {
                 tma_store_2d(&a.tmOut, sA1, 0, tile * kTile);
                 tma_store_commit();
@@ -427,7 +397,7 @@ __global__ void __launch_bounds__(kNWG * 128 * TPP, 1) pixel_chain_kernel(const 
         }
     }
 #undef NDIFF_STAGE
-    if (wi == 0) {
+    if (q == 0) {
         if (elect_one()) tma_store_wait_all();
         __syncwarp();
     }
@@ -571,9 +541,9 @@ __global__ void __launch_bounds__(kThreads, 1) tail_chain_kernel(const __grid_co
             uint32_t raw[32];
             float bv[32];
             tmem_ld32(tmem_rd + h * 32, raw);
-            load_tab<32>(tail->fvec + h * 32, bv);
+            load32(tail->fvec + h * 32, bv);
             tmem_ld_wait();
-            store_gelu_f16<32>(sA0, r, h * 4, raw, bv);
+            store_half_gelu_f16(sA0, r, h, raw, bv);
         }
         // ---- shot_mlp3.fc2 (64 -> 4, N padded to 16) ------------------------------------------------------------------------
         fence_proxy_async();
@@ -679,28 +649,15 @@ int pack_chain_weight_launch(const float* src, __nv_bfloat16* dst, int N, int K,
     return 0;
 }
 
-// threads per pixel of the chain kernels (see pixel_chain_kernel): NDIFF_CHAIN_TPP = 1 | 2
-static int chain_threads_per_pixel() {
-    static const int tpp = [] {
-        const char* v = std::getenv("NDIFF_CHAIN_TPP");
-        return (v && v[0] == '2') ? 2 : 1;
-    }();
-    return tpp;
-}
-
 static int chain_smem_bytes(int prog) {
     const int rows = prog == kProgShot ? kChainShotRows : kChainAttnRows;
     return 1024 + rows * 128 + kNWG * kWgBytes + static_cast<int>(sizeof(ChainTail));
 }
 
 int pixel_chain_init() {
-    NDIFF_CUDA_OK(cudaFuncSetAttribute(pixel_chain_kernel<kProgAttn, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NDIFF_CUDA_OK(cudaFuncSetAttribute(pixel_chain_kernel<kProgAttn>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        chain_smem_bytes(kProgAttn)));
-    NDIFF_CUDA_OK(cudaFuncSetAttribute(pixel_chain_kernel<kProgShot, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       chain_smem_bytes(kProgShot)));
-    NDIFF_CUDA_OK(cudaFuncSetAttribute(pixel_chain_kernel<kProgAttn, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       chain_smem_bytes(kProgAttn)));
-    NDIFF_CUDA_OK(cudaFuncSetAttribute(pixel_chain_kernel<kProgShot, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NDIFF_CUDA_OK(cudaFuncSetAttribute(pixel_chain_kernel<kProgShot>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        chain_smem_bytes(kProgShot)));
     return 0;
 }
@@ -746,7 +703,6 @@ int pixel_chain_plan(const ChainDesc& d, int num_sms, ChainPlan* plan) {
     plan->grid = want < num_sms ? want : num_sms;
     plan->smem_bytes = chain_smem_bytes(d.prog);
     NDIFF_REQUIRE(plan->smem_bytes <= 227 * 1024, "pixel chain: shared-memory budget exceeded");
-    plan->tpp = chain_threads_per_pixel();
     return 0;
 }
 
@@ -798,13 +754,9 @@ int tail_chain_launch(const TailPlan& plan, cudaStream_t stream) {
 
 int pixel_chain_launch(const ChainPlan& plan, cudaStream_t stream) {
     if (plan.prog == kProgShot)
-        NDIFF_CUDA_OK(plan.tpp == 2
-            ? launch_pdl(pixel_chain_kernel<kProgShot, 2>, dim3(plan.grid), dim3(2 * kThreads), plan.smem_bytes, stream, plan.args)
-            : launch_pdl(pixel_chain_kernel<kProgShot, 1>, dim3(plan.grid), dim3(kThreads), plan.smem_bytes, stream, plan.args));
+        NDIFF_CUDA_OK(launch_pdl(pixel_chain_kernel<kProgShot>, dim3(plan.grid), dim3(kThreads), plan.smem_bytes, stream, plan.args));
     else
-        NDIFF_CUDA_OK(plan.tpp == 2
-            ? launch_pdl(pixel_chain_kernel<kProgAttn, 2>, dim3(plan.grid), dim3(2 * kThreads), plan.smem_bytes, stream, plan.args)
-            : launch_pdl(pixel_chain_kernel<kProgAttn, 1>, dim3(plan.grid), dim3(kThreads), plan.smem_bytes, stream, plan.args));
+        NDIFF_CUDA_OK(launch_pdl(pixel_chain_kernel<kProgAttn>, dim3(plan.grid), dim3(kThreads), plan.smem_bytes, stream, plan.args));
     return 0;
 }
 

@@ -50,7 +50,6 @@ struct ChainPlan {
     int prog;
     int grid;
     int smem_bytes;
-    int tpp;              // threads per pixel (1 or 2)
 };
 
 struct ChainDesc {
