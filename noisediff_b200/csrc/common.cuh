@@ -272,6 +272,29 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, u
             : "memory");
     }
 }
+// A operand from TENSOR MEMORY (M = 128 rows = TMEM lanes, 16-bit elements packed two per 32-bit column, K-major; 8 columns per
+// K = 16 step), B from shared memory.  An epilogue that produces the next GEMM's A operand writes it with tcgen05.st instead of
+// shared memory: no swizzled stores, and the tensor core does not read it back through the shared-memory pipe.
+template <bool kAccum>
+__device__ __forceinline__ void umma_ts_lohi(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+    if constexpr (kAccum) {
+        asm volatile(
+            "{\n\t.reg .b64 db;\n\t.reg .pred p;\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "setp.eq.u32 p, 0, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+            ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .b64 db;\n\t.reg .pred p;\n\t"
+            "mov.b64 db, {%2, %3};\n\t"
+            "setp.ne.u32 p, 0, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+            ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc)
+            : "memory");
+    }
+}
 // Same with a run-time accumulate flag (first MMA of a tile clears the accumulator).
 __device__ __forceinline__ void umma_bf16_lohi_pred(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
                                                     uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
@@ -359,6 +382,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+// 16 registers -> 16 columns of this warp's 32 TMEM lanes (thread = lane)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+          "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])

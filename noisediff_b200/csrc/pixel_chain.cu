@@ -70,6 +70,25 @@ __device__ __forceinline__ void store_half_gelu_f16(uint32_t blk, int r, int h, 
         sts128(swz(blk, r, h * 4 + jj), u);
     }
 }
+// GELU(acc + bias) of 32 accumulator columns -> 16 TMEM columns of packed fp16 pairs (A operand of a tensor-memory GEMM)
+__device__ __forceinline__ void gelu_to_tmem(uint32_t taddr, const uint32_t (&raw)[32], const float (&bias)[32]) {
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        pk[j] = gelu_f16x2(__uint_as_float(raw[2 * j]) + bias[2 * j], __uint_as_float(raw[2 * j + 1]) + bias[2 * j + 1]);
+    tmem_st16(taddr, pk);
+}
+// D[tmem] = A[tmem: 128 lanes x (ksteps * 16) fp16, 8 columns per step] * W[N x K]^T (fp16 rows in shared memory, 64-wide K blocks)
+template <int N>
+__device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t w_blk, int ksteps) {
+    constexpr uint32_t idesc = umma_idesc_f16(128, N);
+    constexpr uint32_t hi = umma_desc_hi(1024);
+    for (int k = 0; k < ksteps; ++k) {
+        const uint32_t b_lo = umma_desc_lo(w_blk + (k >> 2) * N * 128) + 2 * (k & 3);
+        if (k == 0) umma_ts_lohi<false>(d_tmem, a_tmem, b_lo, hi, idesc);
+        else umma_ts_lohi<true>(d_tmem, a_tmem + 8 * k, b_lo, hi, idesc);
+    }
+}
 // D[tmem] = A[128 x (kblocks*64)] * W[N x (kblocks*64)]^T ; k16 = MMAs per K block (4, or 1 when only K = 16 is live)
 template <int N, bool F16 = false>
 __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_blk, uint32_t w_blk, int kblocks, int k16, bool accumulate = false) {
@@ -91,7 +110,11 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_blk, uint
 // arithmetic of different tiles overlap.  384 threads cap the kernel at 168 registers: the pixel's input row stays packed
 // (xr, 32 registers), accumulators are drained 32 columns at a time, and LayerNorm re-derives y = x + c per pass instead of
 // holding 64 floats.
-template <int PROG>
+// TS: the GELU outputs that feed the next GEMM (shot_mlp1.fc1 -> fc2, ff.net.0 -> the folded stage, shot_mlp2.fc1 -> fc2) are
+// written to TENSOR MEMORY as packed fp16 — over accumulator columns the same warp has already drained — and the next GEMM reads
+// its A operand from there (umma_ts_lohi); its accumulator goes to the upper 64 columns.  Takes the thread-written operands and
+// their read-back off the shared-memory pipe, which bounds these kernels together with instruction issue.
+template <int PROG, bool TS>
 __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_constant__ ChainArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -100,6 +123,7 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
     constexpr int kWRows = kShot ? kChainShotRows : kChainAttnRows;
     constexpr int kNF = kShot ? kChainShotFloats : kChainAttnFloats;
     constexpr int kWBytes = kWRows * 128;
+    constexpr uint32_t kDup = TS ? 64 : 0;      // TS: accumulators of the GEMMs fed from tensor memory live in the upper 64 columns
     ChainTail* tail = reinterpret_cast<ChainTail*>(smem + kWBytes + kNWG * kWgBytes);
 
     // the warp index is broadcast from lane 0 so that the compiler knows it (and everything derived from it: the warpgroup's
@@ -233,15 +257,17 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
                 tmem_ld32(tmem_rd + h * 32, raw);
                 load32(tail->fvec + h * 32, bv);
                 tmem_ld_wait();
-                store_half_gelu_f16(sA0, r, h, raw, bv);
+                if constexpr (TS) gelu_to_tmem(tmem_rd + h * 16, raw, bv);
+                else store_half_gelu_f16(sA0, r, h, raw, bv);
             }
             // ---- shot_mlp1.fc2 -> s1 (stored: it is the branch's residual r_s, ref :599) ------------------------------
-            NDIFF_STAGE((issue_gemm<64, true>(tmem_d, sA0, sW + 64 * 128, 1, 4)));
+            if constexpr (TS) { tmem_st_wait(); NDIFF_STAGE(issue_gemm_ts<64>(tmem_d + kDup, tmem_d, sW + 64 * 128, 4)); }
+            else NDIFF_STAGE((issue_gemm<64, true>(tmem_d, sA0, sW + 64 * 128, 1, 4)));
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 uint32_t raw[32];
                 float bv[32];
-                tmem_ld32(tmem_rd + h * 32, raw);
+                tmem_ld32(tmem_rd + kDup + h * 32, raw);
                 load32(tail->fvec + 64 + h * 32, bv);
                 tmem_ld_wait();
 #pragma unroll
@@ -323,7 +349,8 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
                 tmem_ld32(tmem_rd + hh * 64 + h * 32, raw);
                 load32(f_b1 + hh * 64 + h * 32, bv);
                 tmem_ld_wait();
-                store_half_gelu_f16(sA0 + hh * kBlk, r, h, raw, bv);
+                if constexpr (TS) gelu_to_tmem(tmem_rd + hh * 32 + h * 16, raw, bv);
+                else store_half_gelu_f16(sA0 + hh * kBlk, r, h, raw, bv);
             }
         }
         if constexpr (!kShot) {
@@ -331,7 +358,12 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
             //        out = (Wp W2) h + Wp x + [Wp (b2 + c) + bp] + x
             //      = fp16 GEMM over the hidden layer (K = 128, folded weight in W2's slot) accumulated with a bf16 GEMM over the
             //      input tile itself, which already sits in shared memory as TMA landed it (K = 64, Wp) -- z never exists.
-            NDIFF_STAGE((issue_gemm<64, true>(tmem_d, sA0, sW2, 2, 4), issue_gemm<64>(tmem_d, sX, sWp, 1, 4, true)));
+            if constexpr (TS) {
+                tmem_st_wait();
+                NDIFF_STAGE((issue_gemm_ts<64>(tmem_d + kDup, tmem_d, sW2, 8), issue_gemm<64>(tmem_d + kDup, sX, sWp, 1, 4, true)));
+            } else {
+                NDIFF_STAGE((issue_gemm<64, true>(tmem_d, sA0, sW2, 2, 4), issue_gemm<64>(tmem_d, sX, sWp, 1, 4, true)));
+            }
             if (q == 0 && tile + 1 < t_end) {      // the tensor core is done with X (the wait above): prefetch the next tile
                 if (elect_one()) {
                     mbar_expect_tx(bar_x, kBlk);
@@ -343,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
             for (int h = 0; h < 2; ++h) {
                 uint32_t raw[32];
                 float v[32];
-                tmem_ld32(tmem_rd + h * 32, raw);
+                tmem_ld32(tmem_rd + kDup + h * 32, raw);
                 load32(ct + 64 + h * 32, v);                      // Wp (b2 + c) + bp
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {                 // + the residual x, while the accumulator drains
@@ -361,22 +393,29 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
             //        fc1(Wp (W2 h + b2 + c + s1) + bp + s1) = (Wm1 Wp W2) h + (Wm1 Wp + Wm1) s1 + [per-sample vector]
             //      = fp16 GEMM over the hidden layer (K = 128) accumulated with a bf16 GEMM over s1, which still sits in the X slot
             //      where it was staged for its TMA store.  Neither z nor the attention block's output ever exists.  Then GELU, fc2.
-            NDIFF_STAGE((issue_gemm<64, true>(tmem_d, sA0, sW2, 2, 4), issue_gemm<64>(tmem_d, sX, sWp, 1, 4, true)));
+            if constexpr (TS) {
+                tmem_st_wait();
+                NDIFF_STAGE((issue_gemm_ts<64>(tmem_d + kDup, tmem_d, sW2, 8), issue_gemm<64>(tmem_d + kDup, sX, sWp, 1, 4, true)));
+            } else {
+                NDIFF_STAGE((issue_gemm<64, true>(tmem_d, sA0, sW2, 2, 4), issue_gemm<64>(tmem_d, sX, sWp, 1, 4, true)));
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 uint32_t raw[32];
                 float bv[32];
-                tmem_ld32(tmem_rd + h * 32, raw);
+                tmem_ld32(tmem_rd + kDup + h * 32, raw);
                 load32(ct + 64 + h * 32, bv);
                 tmem_ld_wait();
-                store_half_gelu_f16(sA0, r, h, raw, bv);
+                if constexpr (TS) gelu_to_tmem(tmem_rd + h * 16, raw, bv);     // (columns 0..31: the A operand there has been consumed)
+                else store_half_gelu_f16(sA0, r, h, raw, bv);
             }
-            NDIFF_STAGE((issue_gemm<64, true>(tmem_d, sA0, sWm2, 1, 4)));
+            if constexpr (TS) { tmem_st_wait(); NDIFF_STAGE(issue_gemm_ts<64>(tmem_d + kDup, tmem_d, sWm2, 4)); }
+            else NDIFF_STAGE((issue_gemm<64, true>(tmem_d, sA0, sWm2, 1, 4)));
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 uint32_t raw[32];
                 float v[32];
-                tmem_ld32(tmem_rd + h * 32, raw);
+                tmem_ld32(tmem_rd + kDup + h * 32, raw);
                 load32(f_bm2 + h * 32, v);
                 tmem_ld_wait();
 #pragma unroll
@@ -649,15 +688,28 @@ int pack_chain_weight_launch(const float* src, __nv_bfloat16* dst, int N, int K,
     return 0;
 }
 
+// A operands of the chained GEMMs through tensor memory (see pixel_chain_kernel's TS): NDIFF_CHAIN_TS = 0 | 1
+static bool chain_operands_in_tmem() {
+    static const bool ts = [] {
+        const char* v = std::getenv("NDIFF_CHAIN_TS");
+        return v && v[0] == '1';
+    }();
+    return ts;
+}
+
 static int chain_smem_bytes(int prog) {
     const int rows = prog == kProgShot ? kChainShotRows : kChainAttnRows;
     return 1024 + rows * 128 + kNWG * kWgBytes + static_cast<int>(sizeof(ChainTail));
 }
 
 int pixel_chain_init() {
-    NDIFF_CUDA_OK(cudaFuncSetAttribute(pixel_chain_kernel<kProgAttn>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NDIFF_CUDA_OK(cudaFuncSetAttribute(pixel_chain_kernel<kProgAttn, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        chain_smem_bytes(kProgAttn)));
-    NDIFF_CUDA_OK(cudaFuncSetAttribute(pixel_chain_kernel<kProgShot>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NDIFF_CUDA_OK(cudaFuncSetAttribute(pixel_chain_kernel<kProgShot, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       chain_smem_bytes(kProgShot)));
+    NDIFF_CUDA_OK(cudaFuncSetAttribute(pixel_chain_kernel<kProgAttn, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       chain_smem_bytes(kProgAttn)));
+    NDIFF_CUDA_OK(cudaFuncSetAttribute(pixel_chain_kernel<kProgShot, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        chain_smem_bytes(kProgShot)));
     return 0;
 }
@@ -703,6 +755,7 @@ int pixel_chain_plan(const ChainDesc& d, int num_sms, ChainPlan* plan) {
     plan->grid = want < num_sms ? want : num_sms;
     plan->smem_bytes = chain_smem_bytes(d.prog);
     NDIFF_REQUIRE(plan->smem_bytes <= 227 * 1024, "pixel chain: shared-memory budget exceeded");
+    plan->ts = chain_operands_in_tmem();
     return 0;
 }
 
@@ -754,9 +807,11 @@ int tail_chain_launch(const TailPlan& plan, cudaStream_t stream) {
 
 int pixel_chain_launch(const ChainPlan& plan, cudaStream_t stream) {
     if (plan.prog == kProgShot)
-        NDIFF_CUDA_OK(launch_pdl(pixel_chain_kernel<kProgShot>, dim3(plan.grid), dim3(kThreads), plan.smem_bytes, stream, plan.args));
+        NDIFF_CUDA_OK(plan.ts ? launch_pdl(pixel_chain_kernel<kProgShot, true>, dim3(plan.grid), dim3(kThreads), plan.smem_bytes, stream, plan.args)
+                              : launch_pdl(pixel_chain_kernel<kProgShot, false>, dim3(plan.grid), dim3(kThreads), plan.smem_bytes, stream, plan.args));
     else
-        NDIFF_CUDA_OK(launch_pdl(pixel_chain_kernel<kProgAttn>, dim3(plan.grid), dim3(kThreads), plan.smem_bytes, stream, plan.args));
+        NDIFF_CUDA_OK(plan.ts ? launch_pdl(pixel_chain_kernel<kProgAttn, true>, dim3(plan.grid), dim3(kThreads), plan.smem_bytes, stream, plan.args)
+                              : launch_pdl(pixel_chain_kernel<kProgAttn, false>, dim3(plan.grid), dim3(kThreads), plan.smem_bytes, stream, plan.args));
     return 0;
 }
 

@@ -50,6 +50,7 @@ struct ChainPlan {
     int prog;
     int grid;
     int smem_bytes;
+    bool ts;              // GELU outputs reach the next GEMM as its A operand through tensor memory
 };
 
 struct ChainDesc {
