@@ -25,7 +25,7 @@ constexpr int kNWG = 3;                    // warpgroups per CTA (each owns 128 
 constexpr int kWgBytes = 3 * kBlk;         // per warpgroup: X (input tile by TMA / s1 staging) | A0 | A1 (A0, A1 = the two K
                                            // blocks of the hidden layer; A1 doubles as the staging block of the output store)
 constexpr int kThreads = kNWG * 128;
-constexpr int kTmemCols = kNWG <= 2 ? 256 : 512;    // power of two >= kNWG * 128
+constexpr int kTmemCols = kNWG <= 2 ? 256 : 512;    // power of two >= kNWG * 160 (128 accumulator + 32 operand columns each)
 
 struct ChainTail {
     uint64_t bar_w, bar_x[kNWG], bar_mma[kNWG];
@@ -79,9 +79,9 @@ __device__ __forceinline__ void gelu_to_tmem(uint32_t taddr, const uint32_t (&ra
     tmem_st16(taddr, pk);
 }
 // D[tmem] = A[tmem: 128 lanes x (ksteps * 16) fp16, 8 columns per step] * W[N x K]^T (fp16 rows in shared memory, 64-wide K blocks)
-template <int N>
+template <int N, bool F16 = true>
 __device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t w_blk, int ksteps) {
-    constexpr uint32_t idesc = umma_idesc_f16(128, N);
+    constexpr uint32_t idesc = F16 ? umma_idesc_f16(128, N) : umma_idesc_bf16(128, N);
     constexpr uint32_t hi = umma_desc_hi(1024);
     for (int k = 0; k < ksteps; ++k) {
         const uint32_t b_lo = umma_desc_lo(w_blk + (k >> 2) * N * 128) + 2 * (k & 3);
@@ -153,7 +153,8 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_d = tail->tmem_base + wg * 128;                          // this warpgroup's 128 accumulator columns
+    // this warpgroup's tensor-memory columns: 128 of accumulators (+ TS: 32 for LayerNorm's output, the A operand of ff.net.0)
+    const uint32_t tmem_d = tail->tmem_base + wg * (TS ? 160 : 128);
     const uint32_t tmem_rd = tmem_d + (static_cast<uint32_t>(q * 32) << 16);     // + this warp's lane quarter
 
     if (tid == 0) {   // the whole weight blob, once
@@ -317,8 +318,16 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
                     v[j] = fmaf(f0.x + c4.x, rstd, nb); v[j + 1] = fmaf(f0.y + c4.y, rstd, nb);
                     v[j + 2] = fmaf(f1.x + c4.z, rstd, nb); v[j + 3] = fmaf(f1.y + c4.w, rstd, nb);
                 }
-                store_half(sA0, r, h, v);
+                if constexpr (TS) {      // bf16 pairs -> columns 128 .. 159 of this group's tensor memory (A operand of ff.net.0)
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+                    tmem_st16(tmem_rd + 128 + h * 16, pk);
+                } else {
+                    store_half(sA0, r, h, v);
+                }
             }
+            if constexpr (TS) tmem_st_wait();
         }
         // ---- FeedForward.net.0: Linear(C, 2C) + GELU   (ref :405-422); hidden K block hh -> operand block A0 / A1 ------------
         fence_proxy_async();
@@ -332,7 +341,8 @@ __global__ void __launch_bounds__(kThreads, 1) pixel_chain_kernel(const __grid_c
                     tma_store_2d(&a.tmOut2, sX, 0, tile * kTile);
                     tma_store_commit();
                 }  // (attn: the X tile is an operand of the last GEMM stage, so the next tile is prefetched after that stage)
-                issue_gemm<128>(tmem_d, sA0, sW1, 1, 4);
+                if constexpr (TS) issue_gemm_ts<128, false>(tmem_d, tmem_d + 128, sW1, 4);
+                else issue_gemm<128>(tmem_d, sA0, sW1, 1, 4);
                 umma_commit(bar_mma);
             }
             __syncwarp();
@@ -463,6 +473,9 @@ struct TailSmem {
     alignas(16) float ctab[kNWG][2][2][64];     // per warpgroup / sample slot: [0] A/2, [1] B/2 of the folded GroupNorm affine
 };
 
+// TS (see pixel_chain_kernel): both A operands go through tensor memory — the GroupNorm-apply output as bf16 pairs in columns
+// 64 .. 95, fc1's GELU output as fp16 pairs over the drained accumulator columns 0 .. 31; fc2 accumulates in columns 96 .. 111.
+template <bool TS>
 __global__ void __launch_bounds__(kThreads, 1) tail_chain_kernel(const __grid_constant__ TailArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -538,6 +551,8 @@ __global__ void __launch_bounds__(kThreads, 1) tail_chain_kernel(const __grid_co
         // ---- y = SiLU(GN(h2)) + s4 + s1 -> A0 ---------------------------------------------------------------------------
         mbar_wait(bar_x, xph);
         xph ^= 1;
+        uint32_t pk[16];
+        (void)pk;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const uint4 h = lds128(swz(sH, r, j)), r1 = lds128(swz(sR1, r, j)), r2 = lds128(swz(sR2, r, j));
@@ -556,8 +571,14 @@ __global__ void __launch_bounds__(kThreads, 1) tail_chain_kernel(const __grid_co
             u.y = pack_bf16((act(h1.x, a0.z, b0.z) + p1.x) + q1.x, (act(h1.y, a0.w, b0.w) + p1.y) + q1.y);
             u.z = pack_bf16((act(h2.x, a1.x, b1.x) + p2.x) + q2.x, (act(h2.y, a1.y, b1.y) + p2.y) + q2.y);
             u.w = pack_bf16((act(h3.x, a1.z, b1.z) + p3.x) + q3.x, (act(h3.y, a1.w, b1.w) + p3.y) + q3.y);
-            sts128(swz(sA0, r, j), u);
+            if constexpr (TS) {
+                pk[(j & 3) * 4] = u.x; pk[(j & 3) * 4 + 1] = u.y; pk[(j & 3) * 4 + 2] = u.z; pk[(j & 3) * 4 + 3] = u.w;
+                if ((j & 3) == 3) tmem_st16(tmem_rd + 64 + (j >> 2) * 16, pk);
+            } else {
+                sts128(swz(sA0, r, j), u);
+            }
         }
+        if constexpr (TS) tmem_st_wait();
         // ---- shot_mlp3.fc1 + GELU -----------------------------------------------------------------------------------------
         fence_proxy_async();
         tc_fence_before();
@@ -567,7 +588,8 @@ __global__ void __launch_bounds__(kThreads, 1) tail_chain_kernel(const __grid_co
             tc_fence_after();
             if (elect_one()) {
                 if (tile + 1 < t_end) load_tile(tile + 1);     // everybody has consumed the three input blocks
-                issue_gemm<64>(tmem_d, sA0, sW, 1, 4);
+                if constexpr (TS) issue_gemm_ts<64, false>(tmem_d, tmem_d + 64, sW, 4);
+                else issue_gemm<64>(tmem_d, sA0, sW, 1, 4);
                 umma_commit(bar_mma);
             }
             __syncwarp();
@@ -582,8 +604,10 @@ __global__ void __launch_bounds__(kThreads, 1) tail_chain_kernel(const __grid_co
             tmem_ld32(tmem_rd + h * 32, raw);
             load32(tail->fvec + h * 32, bv);
             tmem_ld_wait();
-            store_half_gelu_f16(sA0, r, h, raw, bv);
+            if constexpr (TS) gelu_to_tmem(tmem_rd + h * 16, raw, bv);
+            else store_half_gelu_f16(sA0, r, h, raw, bv);
         }
+        if constexpr (TS) tmem_st_wait();
         // ---- shot_mlp3.fc2 (64 -> 4, N padded to 16) ------------------------------------------------------------------------
         fence_proxy_async();
         tc_fence_before();
@@ -591,7 +615,8 @@ __global__ void __launch_bounds__(kThreads, 1) tail_chain_kernel(const __grid_co
         if (q == 0) {
             tc_fence_after();
             if (elect_one()) {
-                issue_gemm<16, true>(tmem_d, sA0, sW + 64 * 128, 1, 4);
+                if constexpr (TS) issue_gemm_ts<16>(tmem_d + 96, tmem_d, sW + 64 * 128, 4);
+                else issue_gemm<16, true>(tmem_d, sA0, sW + 64 * 128, 1, 4);
                 umma_commit(bar_mma);
             }
             __syncwarp();
@@ -601,7 +626,7 @@ __global__ void __launch_bounds__(kThreads, 1) tail_chain_kernel(const __grid_co
         tc_fence_after();
         {
             uint32_t raw[4];
-            tmem_ld4(tmem_rd, raw);
+            tmem_ld4(tmem_rd + (TS ? 96 : 0), raw);
             tmem_ld_wait();
             if (live)
                 a.out[p] = make_float4(__uint_as_float(raw[0]) + tail->fvec[64], __uint_as_float(raw[1]) + tail->fvec[65],
@@ -688,11 +713,11 @@ int pack_chain_weight_launch(const float* src, __nv_bfloat16* dst, int N, int K,
     return 0;
 }
 
-// A operands of the chained GEMMs through tensor memory (see pixel_chain_kernel's TS): NDIFF_CHAIN_TS = 0 | 1
+// A operands of the chained GEMMs through tensor memory (see pixel_chain_kernel's TS); NDIFF_CHAIN_TS=0 keeps them in shared memory
 static bool chain_operands_in_tmem() {
     static const bool ts = [] {
         const char* v = std::getenv("NDIFF_CHAIN_TS");
-        return v && v[0] == '1';
+        return !(v && v[0] == '0');          // default on (measured on B200: -7 % on every chain); 0 = shared-memory operands
     }();
     return ts;
 }
@@ -766,7 +791,8 @@ int tail_chain_plan(const TailDesc& d, int num_sms, TailPlan* plan) {
         static std::once_flag once;
         static int init_rc = 0;
         std::call_once(once, [] {
-            init_rc = cudaFuncSetAttribute(tail_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tail_smem_bytes()) == cudaSuccess ? 0 : 1;
+            init_rc = (cudaFuncSetAttribute(tail_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tail_smem_bytes()) == cudaSuccess &&
+                       cudaFuncSetAttribute(tail_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tail_smem_bytes()) == cudaSuccess) ? 0 : 1;
         });
         NDIFF_REQUIRE(init_rc == 0, "tail chain: cannot opt in to the shared-memory size");
     }
@@ -797,11 +823,13 @@ int tail_chain_plan(const TailDesc& d, int num_sms, TailPlan* plan) {
     plan->grid = want < num_sms ? want : num_sms;
     plan->smem_bytes = tail_smem_bytes();
     NDIFF_REQUIRE(plan->smem_bytes <= 227 * 1024, "tail chain: shared-memory budget exceeded");
+    plan->ts = chain_operands_in_tmem();
     return 0;
 }
 
 int tail_chain_launch(const TailPlan& plan, cudaStream_t stream) {
-    NDIFF_CUDA_OK(launch_pdl(tail_chain_kernel, dim3(plan.grid), dim3(kThreads), plan.smem_bytes, stream, plan.args));
+    NDIFF_CUDA_OK(plan.ts ? launch_pdl(tail_chain_kernel<true>, dim3(plan.grid), dim3(kThreads), plan.smem_bytes, stream, plan.args)
+                          : launch_pdl(tail_chain_kernel<false>, dim3(plan.grid), dim3(kThreads), plan.smem_bytes, stream, plan.args));
     return 0;
 }
 

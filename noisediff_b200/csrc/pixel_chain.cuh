@@ -85,7 +85,7 @@ struct TailArgs {
     float real_frac;                    // live fraction of every group's channels (statistics count)
     float4* out;                        // [npix] fp32 x 4
 };
-struct TailPlan { TailArgs args; int grid; int smem_bytes; };
+struct TailPlan { TailArgs args; int grid; int smem_bytes; bool ts; };
 struct TailDesc {
     int npix = 0, HW = 0;
     const __nv_bfloat16* h2 = nullptr; const __nv_bfloat16* r1 = nullptr; const __nv_bfloat16* r2 = nullptr;
