@@ -1,12 +1,12 @@
 // noisediff_b200 — fused per-pixel MLP chains on tensor cores (sm_100a).  See pixel_chain.cuh.
 //
-// One CTA = four independent warpgroups of 128 threads.  Each warpgroup walks its own sequence of 128-pixel tiles; thread r
-// owns pixel r of the tile (= TMEM lane r), so LayerNorm over channels and all epilogue math are thread-local.  A GEMM
-// stage is: the 128 threads write the bf16 A operand [128 x K] into shared memory in the SWIZZLE_128B K-major layout,
-// fence.proxy.async + named barrier, ONE thread issues the tcgen05.mma's against the layer's weights (resident in shared
-// memory for the whole kernel, loaded once by TMA) and commits to an mbarrier, everyone waits and drains the fp32
-// accumulator from TMEM with tcgen05.ld.  Stages of one tile are strictly sequential; the warpgroups interleave, so one
-// group's tensor-core work and TMEM/shared traffic overlaps the other groups' epilogue arithmetic.
+// One CTA = three independent warpgroups of 128 threads.  Each warpgroup walks its own contiguous range of 128-pixel tiles;
+// thread r owns pixel r of the tile (= TMEM lane r), so LayerNorm over channels and all epilogue math are thread-local.  A GEMM
+// stage is: the 128 threads write the 16-bit A operand [128 x K] — into tensor memory as packed pairs (tcgen05.st; default) or
+// into shared memory in the SWIZZLE_128B K-major layout — fence + named barrier, ONE elected lane issues the tcgen05.mma's
+// against the layer's weights (resident in shared memory for the whole kernel, loaded once by TMA) and commits to an mbarrier,
+// everyone waits and drains the fp32 accumulator from TMEM with tcgen05.ld.  Stages of one tile are strictly sequential; the
+// warpgroups interleave, so one group's tensor-core work and TMEM/shared traffic overlaps the other groups' epilogue arithmetic.
 // Input tiles arrive by TMA (attn) or as coalesced float4 loads (shot); outputs leave by TMA store from a staging block.
 #include "pixel_chain.cuh"
 #include "conv_gemm.cuh"

@@ -4,7 +4,8 @@
 // attention collapsed (LayerNorm -> Linear -> GELU -> Linear -> +res -> 1x1 conv -> +res, Diffusion_arch.py:425-443), and
 // the head of the shot-noise branch (shot_mlp1 -> shot_attn -> shot_mlp2, :598-601).  Run layer by layer these are
 // HBM-bound round trips of a 64-channel activation per layer; here a CTA keeps a 128-pixel tile on chip for the whole
-// chain: operands in shared memory (SWIZZLE_128B rows), accumulators in TMEM, epilogues write the next layer's operand.
+// chain: weights and TMA-landed tiles in shared memory (SWIZZLE_128B rows), accumulators in tensor memory, and every epilogue
+// writes the next layer's A operand straight back into tensor memory (tcgen05.st; the next GEMM reads A from TMEM).
 #pragma once
 #include "common.cuh"
 
