@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 
 namespace ndiff {
 
@@ -403,23 +404,35 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
                     mbar_wait(bar_fullA + sa * 8, pa);
                     const uint32_t base = ringA + sa * kAStage;
                     // batches of kXfBatch chunks per thread: all 16-byte loads of a batch are issued before any arithmetic, and
-                    // the loop body is branch-free (loads are always inside the stage; only the store is predicated)
+                    // the loop body is branch-free (loads are always inside the stage; only the store is predicated).
+                    // Interior boxes (no pixel outside the image: 70 % of the tiles at 256 x 256) skip the per-pixel image test and
+                    // walk the box with one add per chunk — a pass advances 24 pixels, a multiple of 8, so the swizzle term of a
+                    // thread's address never changes.  The transform warps are the kernel's critical resource (the MMA warp waits
+                    // on them 86 % of its time in the ncu source view), so instructions removed here are time removed.
                     constexpr int kXfBatch = kSub == 2 ? 5 : 4;      // 15 = 3 x 5 (34 x 10 box) / 8 = 2 x 4 (18 x 10 box) passes of 24 pixels
                     constexpr int kIters = (kPix + kXfWarps * 4 - 1) / (kXfWarps * 4);
-#pragma unroll 1
-                    for (int i0 = 0; i0 < kIters; i0 += kXfBatch) {
+                    constexpr int kPassPix = kXfWarps * 4;
+                    const bool interior = gy0 >= 0 && gx0 >= 0 && gy0 + (kSub * kHaloTH + 2) <= a.H && gx0 + kBoxW <= a.W;
+                    const uint32_t tbase = base + (t >> 3) * 128 + ((o ^ ((t >> 3) & 7)) << 4);
+                    auto xf_batch = [&](int i0, auto interior_c) {
+                        constexpr bool kInterior = decltype(interior_c)::value;
                         uint4 u[kXfBatch];
                         uint32_t addr[kXfBatch];
                         bool ok[kXfBatch];
 #pragma unroll
                         for (int k = 0; k < kXfBatch; ++k) {
-                            const int pr = (t >> 3) + (i0 + k) * (kXfWarps * 4);
-                            const int p = pr < kPix ? pr : kPix - 1;
-                            const int hy = (p * 205) >> 11;          // p / 10 for p < 1024
-                            const int hx = p - hy * kBoxW;
-                            ok[k] = pr < kPix && static_cast<unsigned>(gy0 + hy) < static_cast<unsigned>(a.H) &&
-                                    static_cast<unsigned>(gx0 + hx) < static_cast<unsigned>(a.W);
-                            addr[k] = base + p * 128 + ((o ^ (p & 7)) << 4);
+                            const int pr = (t >> 3) + (i0 + k) * kPassPix;
+                            if constexpr (kInterior) {
+                                ok[k] = pr < kPix;
+                                addr[k] = ok[k] ? tbase + (i0 + k) * (kPassPix * 128) : tbase;
+                            } else {
+                                const int p = pr < kPix ? pr : kPix - 1;
+                                const int hy = (p * 205) >> 11;          // p / 10 for p < 1024
+                                const int hx = p - hy * kBoxW;
+                                ok[k] = pr < kPix && static_cast<unsigned>(gy0 + hy) < static_cast<unsigned>(a.H) &&
+                                        static_cast<unsigned>(gx0 + hx) < static_cast<unsigned>(a.W);
+                                addr[k] = base + p * 128 + ((o ^ (p & 7)) << 4);
+                            }
                             u[k] = lds128(addr[k]);
                         }
 #pragma unroll
@@ -436,6 +449,13 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
                             w.w = pack_bf16(act(f3.x, A[6], Bc[6]), act(f3.y, A[7], Bc[7]));
                             if (ok[k]) sts128(addr[k], w);
                         }
+                    };
+                    if (interior) {
+#pragma unroll 1
+                        for (int i0 = 0; i0 < kIters; i0 += kXfBatch) xf_batch(i0, std::true_type{});
+                    } else {
+#pragma unroll 1
+                        for (int i0 = 0; i0 < kIters; i0 += kXfBatch) xf_batch(i0, std::false_type{});
                     }
                     fence_proxy_async();                         // generic-proxy writes -> visible to the tensor core's reads
                     __syncwarp();
