@@ -414,48 +414,67 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
                     constexpr int kPassPix = kXfWarps * 4;
                     const bool interior = gy0 >= 0 && gx0 >= 0 && gy0 + (kSub * kHaloTH + 2) <= a.H && gx0 + kBoxW <= a.W;
                     const uint32_t tbase = base + (t >> 3) * 128 + ((o ^ ((t >> 3) & 7)) << 4);
-                    auto xf_batch = [&](int i0, auto interior_c) {
-                        constexpr bool kInterior = decltype(interior_c)::value;
-                        uint4 u[kXfBatch];
-                        uint32_t addr[kXfBatch];
-                        bool ok[kXfBatch];
+                    auto act8 = [&](const uint4& u) {
+                        const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+                        auto act = [](float x, float ah, float bh) {
+                            const float h = fmaf(x, ah, bh);
+                            return fmaf(h, tanh_approx(h), h);
+                        };
+                        uint4 w;
+                        w.x = pack_bf16(act(f0.x, A[0], Bc[0]), act(f0.y, A[1], Bc[1]));
+                        w.y = pack_bf16(act(f1.x, A[2], Bc[2]), act(f1.y, A[3], Bc[3]));
+                        w.z = pack_bf16(act(f2.x, A[4], Bc[4]), act(f2.y, A[5], Bc[5]));
+                        w.w = pack_bf16(act(f3.x, A[6], Bc[6]), act(f3.y, A[7], Bc[7]));
+                        return w;
+                    };
+                    if (interior) {
+                        // every address is tbase + a compile-time offset (the last pass reads up to 2.4 KB past the box — still this
+                        // CTA's shared memory, the next stage or the weight ring — and stores only its live pixels), and the batches
+                        // are software-pipelined: the next batch's loads are in flight while this one is transformed (the transform
+                        // warps ran at 0.23 IPC with a quarter of their stalls on exactly these loads; the kernel's register budget
+                        // is set by the epilogue warps, so the second buffer is free)
+                        static_assert(kIters % kXfBatch == 0, "whole batches");
+                        constexpr int kBatches = kIters / kXfBatch;
+                        uint4 u[2][kXfBatch];
 #pragma unroll
-                        for (int k = 0; k < kXfBatch; ++k) {
-                            const int pr = (t >> 3) + (i0 + k) * kPassPix;
-                            if constexpr (kInterior) {
-                                ok[k] = pr < kPix;
-                                addr[k] = ok[k] ? tbase + (i0 + k) * (kPassPix * 128) : tbase;
-                            } else {
+                        for (int k = 0; k < kXfBatch; ++k) u[0][k] = lds128(tbase + k * (kPassPix * 128));
+#pragma unroll
+                        for (int bi = 0; bi < kBatches; ++bi) {
+                            if (bi + 1 < kBatches) {
+#pragma unroll
+                                for (int k = 0; k < kXfBatch; ++k) u[(bi + 1) & 1][k] = lds128(tbase + ((bi + 1) * kXfBatch + k) * (kPassPix * 128));
+                            }
+#pragma unroll
+                            for (int k = 0; k < kXfBatch; ++k) {
+                                const int pass = bi * kXfBatch + k;
+                                const uint4 w = act8(u[bi & 1][k]);
+                                if (pass * kPassPix + kPassPix <= kPix || (t >> 3) + pass * kPassPix < kPix)      // first term: compile time
+                                    sts128(tbase + pass * (kPassPix * 128), w);
+                            }
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int i0 = 0; i0 < kIters; i0 += kXfBatch) {
+                            uint4 u[kXfBatch];
+                            uint32_t addr[kXfBatch];
+                            bool ok[kXfBatch];
+#pragma unroll
+                            for (int k = 0; k < kXfBatch; ++k) {
+                                const int pr = (t >> 3) + (i0 + k) * kPassPix;
                                 const int p = pr < kPix ? pr : kPix - 1;
                                 const int hy = (p * 205) >> 11;          // p / 10 for p < 1024
                                 const int hx = p - hy * kBoxW;
                                 ok[k] = pr < kPix && static_cast<unsigned>(gy0 + hy) < static_cast<unsigned>(a.H) &&
                                         static_cast<unsigned>(gx0 + hx) < static_cast<unsigned>(a.W);
                                 addr[k] = base + p * 128 + ((o ^ (p & 7)) << 4);
+                                u[k] = lds128(addr[k]);
                             }
-                            u[k] = lds128(addr[k]);
-                        }
 #pragma unroll
-                        for (int k = 0; k < kXfBatch; ++k) {
-                            const float2 f0 = unpack_bf16(u[k].x), f1 = unpack_bf16(u[k].y), f2 = unpack_bf16(u[k].z), f3 = unpack_bf16(u[k].w);
-                            auto act = [](float x, float ah, float bh) {
-                                const float h = fmaf(x, ah, bh);
-                                return fmaf(h, tanh_approx(h), h);
-                            };
-                            uint4 w;
-                            w.x = pack_bf16(act(f0.x, A[0], Bc[0]), act(f0.y, A[1], Bc[1]));
-                            w.y = pack_bf16(act(f1.x, A[2], Bc[2]), act(f1.y, A[3], Bc[3]));
-                            w.z = pack_bf16(act(f2.x, A[4], Bc[4]), act(f2.y, A[5], Bc[5]));
-                            w.w = pack_bf16(act(f3.x, A[6], Bc[6]), act(f3.y, A[7], Bc[7]));
-                            if (ok[k]) sts128(addr[k], w);
+                            for (int k = 0; k < kXfBatch; ++k) {
+                                const uint4 w = act8(u[k]);
+                                if (ok[k]) sts128(addr[k], w);
+                            }
                         }
-                    };
-                    if (interior) {
-#pragma unroll 1
-                        for (int i0 = 0; i0 < kIters; i0 += kXfBatch) xf_batch(i0, std::true_type{});
-                    } else {
-#pragma unroll 1
-                        for (int i0 = 0; i0 < kIters; i0 += kXfBatch) xf_batch(i0, std::false_type{});
                     }
                     fence_proxy_async();                         // generic-proxy writes -> visible to the tensor core's reads
                     __syncwarp();
