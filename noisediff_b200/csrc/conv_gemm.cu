@@ -406,9 +406,8 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
                     // batches of kXfBatch chunks per thread: all 16-byte loads of a batch are issued before any arithmetic, and
                     // the loop body is branch-free (loads are always inside the stage; only the store is predicated).
                     // Interior boxes (no pixel outside the image: 70 % of the tiles at 256 x 256) skip the per-pixel image test and
-                    // walk the box with one add per chunk — a pass advances 24 pixels, a multiple of 8, so the swizzle term of a
-                    // thread's address never changes.  The transform warps are the kernel's critical resource (the MMA warp waits
-                    // on them 86 % of its time in the ncu source view), so instructions removed here are time removed.
+                    // walk the box with compile-time offsets — a pass advances 24 pixels, a multiple of 8, so the swizzle term of a
+                    // thread's address never changes.
                     constexpr int kXfBatch = kSub == 2 ? 5 : 4;      // 15 = 3 x 5 (34 x 10 box) / 8 = 2 x 4 (18 x 10 box) passes of 24 pixels
                     constexpr int kIters = (kPix + kXfWarps * 4 - 1) / (kXfWarps * 4);
                     constexpr int kPassPix = kXfWarps * 4;
@@ -430,9 +429,12 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
                     if (interior) {
                         // every address is tbase + a compile-time offset (the last pass reads up to 2.4 KB past the box — still this
                         // CTA's shared memory, the next stage or the weight ring — and stores only its live pixels), and the batches
-                        // are software-pipelined: the next batch's loads are in flight while this one is transformed (the transform
-                        // warps ran at 0.23 IPC with a quarter of their stalls on exactly these loads; the kernel's register budget
-                        // is set by the epilogue warps, so the second buffer is free)
+                        // are software-pipelined: the next batch's loads are in flight while this one is transformed (the kernel's
+                        // register budget is set by the epilogue warps, so the second buffer is free).  Measured in-step on B200:
+                        // XF / plain time of the 64 -> 64 layers 1.39 -> 1.33 with the interior path, no further change from the
+                        // pipelining — what the XF form costs is its shared-memory traffic (the box is landed, read and rewritten:
+                        // 491 KB per 256-pixel tile through the 128 B/clk pipe against 404 KB for the plain form), not instructions
+                        // (profiles/ncu_r2_conv64_roles.json)
                         static_assert(kIters % kXfBatch == 0, "whole batches");
                         constexpr int kBatches = kIters / kXfBatch;
                         uint4 u[2][kXfBatch];
