@@ -52,6 +52,7 @@ typedef struct ndiff_config {
                                       CUDA graph on B200, so it is off by default) */
 #define NDIFF_FLAG_HALO1       64  /* debug: 3x3 convs always use 128-pixel CTA tiles (one accumulator) */
 #define NDIFF_FLAG_NO_XF       128 /* debug: keep block1's GroupNorm-apply as its own pass instead of evaluating it inside block2's conv */
+#define NDIFF_FLAG_INIT_WINDOWS 256 /* debug: init_conv fetches a 128-byte window per pixel and tap (round-1 form) instead of one landed row per tap */
 #define NDIFF_FLAG_UNFUSED     16  /* debug: run the per-pixel 1x1 chains layer by layer instead of as fused tensor-core chains */
 
 /* One reverse step's scalars; the caller derives them from GaussianDiffusion's fp32 buffers

@@ -19,6 +19,7 @@ FLAG_UNFUSED = 16
 FLAG_PDL = 32
 FLAG_HALO1 = 64
 FLAG_NO_XF = 128
+FLAG_INIT_WINDOWS = 256
 
 
 class Config(C.Structure):

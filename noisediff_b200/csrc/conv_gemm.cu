@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
                     for (int tap = 0; tap < TAPS; ++tap) {
                         mbar_wait(bar_emptyA + sa * 8, pa ^ 1);
                         if (elect_one()) {
-                            mbar_expect_tx(bar_fullA + sa * 8, 128 * 128);
+                            mbar_expect_tx(bar_fullA + sa * 8, a.a_copy_bytes);
                             if constexpr (MODE == kS2D)
                                 tma_load_5d(ringA + sa * kAStage, tm, bar_fullA + sa * 8, c0, kx, x0, ky, b * a.H + y0);
                             else
@@ -329,11 +329,14 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
                         tc_fence_after();
                         const uint32_t a_lo = umma_desc_lo(ringA + sa * kAStage);
                         const uint32_t b_lo = umma_desc_lo(ringB + (RES ? (cb * TAPS + tap) * kBTap : sb * kBStage));
+                        // Toeplitz operand (init_conv): no swizzle, SBO = 128 B (the LBO field of umma_desc_lo is already 16 B); a
+                        // K = 16 step is two 16-byte chunks = the same +2 on the start address as in the swizzled layout
+                        const uint32_t hiAd = a.toeplitz ? (((128u >> 4) & 0x3FFFu) | (1u << 14)) : hiA;
                         if (elect_one()) {
-                            umma_bf16_lohi_pred(d_tmem, a_lo, hiA, b_lo, hiB, idesc, (cb > 0 || tap > 0) ? 1u : 0u);
-                            umma_bf16_lohi<true>(d_tmem, a_lo + 2, hiA, b_lo + 2, hiB, idesc);
-                            umma_bf16_lohi<true>(d_tmem, a_lo + 4, hiA, b_lo + 4, hiB, idesc);
-                            umma_bf16_lohi<true>(d_tmem, a_lo + 6, hiA, b_lo + 6, hiB, idesc);
+                            umma_bf16_lohi_pred(d_tmem, a_lo, hiAd, b_lo, hiB, idesc, (cb > 0 || tap > 0) ? 1u : 0u);
+                            umma_bf16_lohi<true>(d_tmem, a_lo + 2, hiAd, b_lo + 2, hiB, idesc);
+                            umma_bf16_lohi<true>(d_tmem, a_lo + 4, hiAd, b_lo + 4, hiB, idesc);
+                            umma_bf16_lohi<true>(d_tmem, a_lo + 6, hiAd, b_lo + 6, hiB, idesc);
                             if constexpr (!RES) umma_commit(bar_emptyB + sb * 8);
                             umma_commit(bar_emptyA + sa * 8);
                         }
@@ -709,6 +712,11 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     a.mode = d.mode;
     a.B = d.B; a.H = d.H; a.W = d.W;
     int TW = d.TW;
+    if (d.toeplitz) {
+        NDIFF_REQUIRE(d.mode == kDirect && d.custom_src0 && d.C0 == 64 && d.C1 == 0 && d.W % 128 == 0 && d.taps_x == 1,
+                      "Toeplitz operand: kDirect, one 64-value window per tap, W a multiple of 128");
+        TW = 128;
+    }
     if (TW == 0) {
         if (d.mode == kHalo1 || d.mode == kHalo2 || d.mode == kHaloUp || d.mode == kHalo1R) TW = kHaloTW;
         else TW = d.W >= 64 ? 64 : (d.W >= 32 ? 32 : (d.W >= 16 ? 16 : 8));
@@ -729,6 +737,7 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     else if (d.mode == kS2D) { a.taps_y = 2; a.taps_x = 2; a.pad_y = 0; a.pad_x = 0; }
     else { a.taps_y = d.taps_y; a.taps_x = d.taps_x; a.pad_y = d.pad_y; a.pad_x = d.pad_x; }
     a.tap_sy = d.tap_sy > 0 ? d.tap_sy : 1;
+    a.toeplitz = d.toeplitz ? 1 : 0;
     a.n_tiles = d.Cout / NT;
     a.total_tiles = d.B * a.tiles_y * a.tiles_x * a.n_tiles * (up ? 4 : 1);
     const int b_tap = NT * 128;                          // one [NT x 64] weight block
@@ -749,7 +758,7 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
         a.a_stages = 3;
         a.b_stages = res2 ? (NT == 128 ? 4 : 6) : (NT == 128 ? 3 : 5);
     } else {
-        a.a_copy_bytes = 128 * 128;
+        a.a_copy_bytes = d.toeplitz ? (128 + 8) * 16 : 128 * 128;
         a.a_stage_bytes = 128 * 128;
         a.a_stages = NT == 128 ? 6 : 8;
         a.b_stages = a.a_stages;
@@ -785,7 +794,10 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
         if (C == 0) continue;
         NDIFF_REQUIRE(src != nullptr, "null activation source");
         CUtensorMap* tm = s == 0 ? &a.tmA0 : &a.tmA1;
-        if (s == 0 && d.custom_src0) {
+        if (s == 0 && d.toeplitz) {
+            uint32_t box[4] = {8, 128 + 8, 1, 1};      // one row of 136 sixteen-byte pixels, landed densely (no swizzle)
+            if (encode_tensor_map(tm, src, 4, d.cdim, d.cstride, box, false)) return 1;
+        } else if (s == 0 && d.custom_src0) {
             uint32_t box[4] = {64, static_cast<uint32_t>(a.TW), static_cast<uint32_t>(a.TH), 1};
             if (encode_tensor_map(tm, src, 4, d.cdim, d.cstride, box, true)) return 1;
         } else if (d.mode == kS2D) {

@@ -42,6 +42,8 @@ struct ConvGemmArgs {
     int b_region_bytes;    // bytes of shared memory holding B (ring, or the whole resident slice)
     int b_resident;        // 1: the CTA's whole [NT x Ktot] weight slice is loaded once and stays in shared memory
     int a_stage_bytes, a_copy_bytes;
+    int toeplitz;          // kDirect: the A operand of a tap is ONE row of TW + 8 sixteen-byte pixels read as overlapping 128-byte
+                           // windows by a non-swizzled descriptor (LBO = 16 B, SBO = 128 B) — see ConvGemmDesc::toeplitz
     // epilogue
     const float* bias;           // [Cout] or null
     const float* vec;            // per-sample vector [B][vec_ld] added to every pixel, or null
@@ -87,6 +89,12 @@ struct ConvGemmDesc {
     bool custom_src0 = false;
     uint64_t cdim[4] = {0, 0, 0, 0};     // dims innermost first
     uint64_t cstride[3] = {0, 0, 0};     // byte strides of dims 1..3
+    // kDirect special (init_conv): source 0 is [B][rows][W + 8][8] bf16 (16-byte pixels) and output pixel x of a tap multiplies the
+    // 64 values of pixels x .. x + 7.  Instead of fetching that 128-byte window per pixel through an overlapping tensor map (8x the
+    // bytes from L2), the tile is ONE output row of 128 pixels, TMA lands its 136 input pixels once (2 176 B), and the MMA reads
+    // the Toeplitz operand in place: K-major, no swizzle, core-matrix rows 16 B apart, LBO (next 16-byte K chunk) = 16 B,
+    // SBO (next 8 rows) = 128 B.  Needs W % 128 == 0; cdim / cstride then describe the 16-byte-pixel tensor.
+    bool toeplitz = false;
     const __nv_bfloat16* weight = nullptr;  // [Cout][Ktot] bf16, K order [cblk][tap][64]
     int Cout = 0;
     const float* bias = nullptr;

@@ -953,7 +953,9 @@ int build_plan(ndiff_engine* e) {
         d.src0 = e->xpad; d.C0 = 64;
         d.taps_y = 4; d.taps_x = 1; d.pad_y = 0; d.pad_x = 0; d.tap_sy = 2;      // four row-pair taps: input rows y, y+2, y+4, y+6
         d.custom_src0 = true;
-        d.cdim[0] = 64; d.cdim[1] = static_cast<uint64_t>(W); d.cdim[2] = static_cast<uint64_t>(H + 6); d.cdim[3] = static_cast<uint64_t>(B);
+        d.toeplitz = W % 128 == 0 && (e->cfg.flags & NDIFF_FLAG_INIT_WINDOWS) == 0;      // one landed row per tap instead of 128-byte windows
+        d.cdim[0] = d.toeplitz ? 8 : 64; d.cdim[1] = static_cast<uint64_t>(d.toeplitz ? W + 8 : W);
+        d.cdim[2] = static_cast<uint64_t>(H + 6); d.cdim[3] = static_cast<uint64_t>(B);
         d.cstride[0] = 16; d.cstride[1] = static_cast<uint64_t>(W + 8) * 16; d.cstride[2] = static_cast<uint64_t>(H + 6) * (W + 8) * 16;
         d.weight = e->init_w_tc; d.Cout = dim; d.bias = e->pf("init_conv.bias");
         d.out = x0.p; d.out_ld = dim;

@@ -67,6 +67,31 @@ def test_forward_matches_reference_layer_by_layer():
     assert dict(rows)["pos_emb"] < 1e-5 and dict(rows)["out(v)"] < 2.5e-2
 
 
+def test_init_conv_toeplitz_operand_equals_the_window_form():
+    """init_conv's A operand read in place from one landed row of 16-byte pixels (non-swizzled descriptor, LBO = 16 B, SBO = 128 B;
+    widths that are multiples of 128) must reproduce the per-pixel 128-byte-window form bit for bit — the same MMAs over the same
+    operand values — and both must match the fp32 oracle's conv (ref Diffusion_arch.py:606)."""
+    import torch.nn.functional as F
+    sd = {k: v.cuda() for k, v in seeded_sd().items()}
+    B, H, W = 2, 24, 256
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, 4, H, W, generator=g)
+    cond = O.synthetic_condition(B, H, W, seed=3)
+    t = torch.tensor([500, 17])
+    outs = []
+    for flags in (0, _lib.FLAG_INIT_WINDOWS):
+        eng = nd.Engine(dim=64, batch=B, height=H, width=W, flags=flags | _lib.FLAG_KEEP_ACTIVATIONS)
+        eng.load_state_dict(sd)
+        eng.set_condition(cond["clean_img"].cuda(), cond["position"].cuda(), cond["iso_ratio_idx"].cuda())
+        eng.forward(x.cuda(), t.cuda())
+        torch.cuda.synchronize()
+        outs.append(eng.debug_tensor("init_conv").clone())
+        eng.close()
+    assert torch.equal(outs[0], outs[1])
+    ref = F.conv2d(x.cuda(), sd["init_conv.weight"], sd["init_conv.bias"], padding=3)
+    assert rel_l2(outs[0], ref) < 8e-3, rel_l2(outs[0], ref)
+
+
 @pytest.mark.parametrize("flags", [_lib.FLAG_CONV_DIRECT | _lib.FLAG_NO_GRAPH, _lib.FLAG_INIT_SIMT, _lib.FLAG_UNFUSED, _lib.FLAG_HALO1 | _lib.FLAG_PDL,
                                    _lib.FLAG_NO_XF])
 def test_forward_other_conv_staging_modes_agree(flags):
