@@ -51,6 +51,7 @@ constexpr int kHaloStage2 = (kHaloCopy2 + 1023) / 1024 * 1024;
 constexpr int kSubStep = (kHaloTH * kHaloPitch) >> 4;                    // descriptor offset of the second sub-tile
 // taps per streamed weight stage in halo mode
 __host__ __device__ constexpr int halo_btaps(int nt, int sub) { return (sub == 2 && nt == 128) ? 1 : 3; }
+constexpr int kToepPitch = 2304;                                         // Toeplitz operand: bytes between the tap rows of a stage (>= 136 x 16)
 constexpr int kResBTaps = 2;                                             // kHalo1R: 10 weight blocks per channel block, two per stage
 constexpr int kUpBTaps = 4;                                              // kHaloUp: one stage = the 4 taps of one phase
 
@@ -178,6 +179,17 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
                         }
                         if (kUp) kcol += 12 * 64;      // skip the other three phases of this channel block
                     }
+                } else if (RES && a.toeplitz) {
+                    // Toeplitz operand: the rows of ALL taps of a tile share one stage (TAPS x 2 176 B, kToepPitch apart), so a
+                    // stage is a tile and a_stages tiles are in flight instead of a_stages / TAPS
+                    mbar_wait(bar_emptyA + sa * 8, pa ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(bar_fullA + sa * 8, TAPS * a.a_copy_bytes);
+                        for (int tap = 0; tap < TAPS; ++tap)
+                            tma_load_4d(ringA + sa * kAStage + tap * kToepPitch, tm, bar_fullA + sa * 8, 0, x0, y0 + tap * a.tap_sy - a.pad_y, b);
+                    }
+                    __syncwarp();
+                    if (++sa == a_stages) { sa = 0; pa ^= 1; }
                 } else {
                     int ky = 0, kx = 0;
                     for (int tap = 0; tap < TAPS; ++tap) {
@@ -322,6 +334,29 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
                         }
                     }
                     if (++sa == a_stages) { sa = 0; pa ^= 1; }
+                } else if (RES && a.toeplitz) {
+                    // Toeplitz operand (init_conv): no swizzle, SBO = 128 B (the LBO field of umma_desc_lo is already 16 B); a
+                    // K = 16 step is two 16-byte chunks = the same +2 on the start address as in the swizzled layout
+                    constexpr uint32_t hiT = ((128u >> 4) & 0x3FFFu) | (1u << 14);
+                    mbar_wait(bar_fullA + sa * 8, pa);
+                    tc_fence_after();
+                    const uint32_t a_base = umma_desc_lo(ringA + sa * kAStage);
+                    const uint32_t b_base = umma_desc_lo(ringB + cb * TAPS * kBTap);
+                    if (elect_one()) {
+                        uint32_t a_lo = a_base, b_lo = b_base;
+#pragma unroll 1
+                        for (int tap = 0; tap < TAPS; ++tap) {
+                            umma_bf16_lohi_pred(d_tmem, a_lo, hiT, b_lo, hiB, idesc, (cb > 0 || tap > 0) ? 1u : 0u);
+                            umma_bf16_lohi<true>(d_tmem, a_lo + 2, hiT, b_lo + 2, hiB, idesc);
+                            umma_bf16_lohi<true>(d_tmem, a_lo + 4, hiT, b_lo + 4, hiB, idesc);
+                            umma_bf16_lohi<true>(d_tmem, a_lo + 6, hiT, b_lo + 6, hiB, idesc);
+                            a_lo += kToepPitch >> 4;
+                            b_lo += kBTap >> 4;
+                        }
+                        umma_commit(bar_emptyA + sa * 8);
+                    }
+                    __syncwarp();
+                    if (++sa == a_stages) { sa = 0; pa ^= 1; }
                 } else {
                     for (int tap = 0; tap < TAPS; ++tap) {
                         mbar_wait(bar_fullA + sa * 8, pa);
@@ -329,14 +364,11 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
                         tc_fence_after();
                         const uint32_t a_lo = umma_desc_lo(ringA + sa * kAStage);
                         const uint32_t b_lo = umma_desc_lo(ringB + (RES ? (cb * TAPS + tap) * kBTap : sb * kBStage));
-                        // Toeplitz operand (init_conv): no swizzle, SBO = 128 B (the LBO field of umma_desc_lo is already 16 B); a
-                        // K = 16 step is two 16-byte chunks = the same +2 on the start address as in the swizzled layout
-                        const uint32_t hiAd = a.toeplitz ? (((128u >> 4) & 0x3FFFu) | (1u << 14)) : hiA;
                         if (elect_one()) {
-                            umma_bf16_lohi_pred(d_tmem, a_lo, hiAd, b_lo, hiB, idesc, (cb > 0 || tap > 0) ? 1u : 0u);
-                            umma_bf16_lohi<true>(d_tmem, a_lo + 2, hiAd, b_lo + 2, hiB, idesc);
-                            umma_bf16_lohi<true>(d_tmem, a_lo + 4, hiAd, b_lo + 4, hiB, idesc);
-                            umma_bf16_lohi<true>(d_tmem, a_lo + 6, hiAd, b_lo + 6, hiB, idesc);
+                            umma_bf16_lohi_pred(d_tmem, a_lo, hiA, b_lo, hiB, idesc, (cb > 0 || tap > 0) ? 1u : 0u);
+                            umma_bf16_lohi<true>(d_tmem, a_lo + 2, hiA, b_lo + 2, hiB, idesc);
+                            umma_bf16_lohi<true>(d_tmem, a_lo + 4, hiA, b_lo + 4, hiB, idesc);
+                            umma_bf16_lohi<true>(d_tmem, a_lo + 6, hiA, b_lo + 6, hiB, idesc);
                             if constexpr (!RES) umma_commit(bar_emptyB + sb * 8);
                             umma_commit(bar_emptyA + sa * 8);
                         }
@@ -783,6 +815,8 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     } else {
         a.b_region_bytes = a.b_stages * b_stage;
     }
+    NDIFF_REQUIRE(!d.toeplitz || (a.b_resident && a.taps_y * kToepPitch <= a.a_stage_bytes),
+                  "Toeplitz operand: needs the resident-weight form (a stage holds the rows of all taps of a tile)");
     plan->smem_bytes = 1024 + a.a_stages * a.a_stage_bytes + a.b_region_bytes + static_cast<int>(sizeof(SmemTail));
     NDIFF_REQUIRE(plan->smem_bytes <= 227 * 1024, "shared-memory budget exceeded");
 

@@ -960,7 +960,12 @@ int build_plan(ndiff_engine* e) {
         d.weight = e->init_w_tc; d.Cout = dim; d.bias = e->pf("init_conv.bias");
         d.out = x0.p; d.out_ld = dim;
         auto plan = std::make_shared<ConvGemmPlan>();
-        const bool tc_ok = (e->cfg.flags & NDIFF_FLAG_INIT_SIMT) == 0 && conv_gemm_plan(d, e->num_sms, plan.get()) == 0;
+        bool tc_ok = (e->cfg.flags & NDIFF_FLAG_INIT_SIMT) == 0 && conv_gemm_plan(d, e->num_sms, plan.get()) == 0;
+        if (!tc_ok && d.toeplitz && (e->cfg.flags & NDIFF_FLAG_INIT_SIMT) == 0) {      // e.g. too few tiles for resident weights
+            d.toeplitz = false;
+            d.cdim[0] = 64; d.cdim[1] = static_cast<uint64_t>(W);
+            tc_ok = conv_gemm_plan(d, e->num_sms, plan.get()) == 0;
+        }
         if (tc_ok) {
             Op pk; pk.name = "init_conv.pack";
             pk.bytes = static_cast<double>(npix) * (16 + 16);
@@ -971,7 +976,7 @@ int build_plan(ndiff_engine* e) {
                 return 0;
             };
             e->net_ops.push_back(pk);
-            Op op; op.name = "init_conv";
+            Op op; op.name = d.toeplitz ? "init_conv" : "init_conv(windows)";
             op.flops = 2.0 * npix * dim * 196.0;
             op.bytes = static_cast<double>(npix) * (16 + 2.0 * dim);
             op.fn = [plan](cudaStream_t st) { return conv_gemm_launch(*plan, st); };

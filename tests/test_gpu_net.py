@@ -73,7 +73,7 @@ def test_init_conv_toeplitz_operand_equals_the_window_form():
     operand values — and both must match the fp32 oracle's conv (ref Diffusion_arch.py:606)."""
     import torch.nn.functional as F
     sd = {k: v.cuda() for k, v in seeded_sd().items()}
-    B, H, W = 2, 24, 256
+    B, H, W = 2, 88, 256          # enough tiles for the resident-weight form the Toeplitz operand needs
     g = torch.Generator().manual_seed(5)
     x = torch.randn(B, 4, H, W, generator=g)
     cond = O.synthetic_condition(B, H, W, seed=3)
@@ -86,6 +86,8 @@ def test_init_conv_toeplitz_operand_equals_the_window_form():
         eng.forward(x.cuda(), t.cuda())
         torch.cuda.synchronize()
         outs.append(eng.debug_tensor("init_conv").clone())
+        names = [r[0] for r in eng.time_layers(1)]
+        assert ("init_conv" in names) == (flags == 0) and ("init_conv(windows)" in names) == (flags != 0), names
         eng.close()
     assert torch.equal(outs[0], outs[1])
     ref = F.conv2d(x.cuda(), sd["init_conv.weight"], sd["init_conv.bias"], padding=3)
