@@ -396,6 +396,7 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
                  : "r"(taddr));
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor: K-major operand, 128-byte swizzle, rows of 128 B, 8-row groups 1024 B apart.

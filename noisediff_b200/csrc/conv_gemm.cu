@@ -565,9 +565,24 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
                 stat_b = b;
             }
 
+            constexpr int kPasses = kRes2 ? 2 : kSub;      // kHalo1R: pass 1 drains the residual-conv accumulator
+            if (a.res) {
+                // the residual rows this lane adds in the epilogue are known before the accumulators are: pull them into L1 while
+                // the MMAs of the tile are still running (the loads below then hit instead of exposing a trip to L2 / HBM per slot)
+#pragma unroll
+                for (int sub = 0; sub < (kRes2 ? 1 : kSub); ++sub) {
+                    const int y = ty * a.TH + sub * kHaloTH + (r >> a.lgTW), x = tx * a.TW + (r & (a.TW - 1));
+                    if (y < a.H && x < a.W) {
+                        const size_t pix = kUp ? (static_cast<size_t>(b) * 2 * a.H + 2 * y + (phase >> 1)) * (2 * a.W) + 2 * x + (phase & 1)
+                                               : (static_cast<size_t>(b) * a.H + y) * a.W + x;
+#pragma unroll
+                        for (int k = 0; k < kSlots; ++k)
+                            prefetch_l1(a.res + pix * a.res_ld + n0 + (cset + 2 * k) * 32);
+                    }
+                }
+            }
             mbar_wait(bar_tfull + acc * 8, pacc);
             tc_fence_after();
-            constexpr int kPasses = kRes2 ? 2 : kSub;      // kHalo1R: pass 1 drains the residual-conv accumulator
 #pragma unroll 1
             for (int sub = 0; sub < kPasses; ++sub) {
                 const bool pass2 = kRes2 && sub == 1;
