@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
                     if (elect_one()) {
                         mbar_expect_tx(bar_fullA + sa * 8, TAPS * a.a_copy_bytes);
                         for (int tap = 0; tap < TAPS; ++tap)
-                            tma_load_4d(ringA + sa * kAStage + tap * kToepPitch, tm, bar_fullA + sa * 8, 0, x0, y0 + tap * a.tap_sy - a.pad_y, b);
+                            tma_load_4d(ringA + sa * kAStage + tap * kToepPitch, tm, bar_fullA + sa * 8, 0, x0 >> 3, y0 + tap * a.tap_sy - a.pad_y, b);
                     }
                     __syncwarp();
                     if (++sa == a_stages) { sa = 0; pa ^= 1; }
@@ -844,8 +844,13 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
         NDIFF_REQUIRE(src != nullptr, "null activation source");
         CUtensorMap* tm = s == 0 ? &a.tmA0 : &a.tmA1;
         if (s == 0 && d.toeplitz) {
-            uint32_t box[4] = {8, 128 + 8, 1, 1};      // one row of 136 sixteen-byte pixels, landed densely (no swizzle)
-            if (encode_tensor_map(tm, src, 4, d.cdim, d.cstride, box, false)) return 1;
+            // one row of 136 sixteen-byte pixels, landed densely (no swizzle) as 17 box rows of 128 B (TMA moves 16-byte box rows
+            // one request at a time; the tensor is contiguous along the row, so eight pixels make one 64-element inner row)
+            NDIFF_REQUIRE(d.cdim[0] == 8 && d.cdim[1] % 8 == 0, "Toeplitz operand: rows of 16-byte pixels, a multiple of 8 per row");
+            uint64_t dims[4] = {64, d.cdim[1] / 8, d.cdim[2], d.cdim[3]};
+            uint64_t str[3] = {128, d.cstride[1], d.cstride[2]};
+            uint32_t box[4] = {64, (128 + 8) / 8, 1, 1};
+            if (encode_tensor_map(tm, src, 4, dims, str, box, false)) return 1;
         } else if (s == 0 && d.custom_src0) {
             uint32_t box[4] = {64, static_cast<uint32_t>(a.TW), static_cast<uint32_t>(a.TH), 1};
             if (encode_tensor_map(tm, src, 4, d.cdim, d.cstride, box, true)) return 1;
