@@ -86,7 +86,8 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
     const int a_stages = a.a_stages, b_stages = a.b_stages;
     const uint32_t ringA = smem_u32(smem);
     const uint32_t ringB = ringA + a_stages * kAStage;
-    SmemTail* tail = reinterpret_cast<SmemTail*>(smem + a_stages * kAStage + a.b_region_bytes);
+    SmemTail* tail = reinterpret_cast<SmemTail*>(smem + a_stages * kAStage + a.b_region_bytes + a.stage_bytes);
+    const uint32_t stageS = ringB + a.b_region_bytes;          // epilogue staging block (a.stage_bytes > 0), 1024-B aligned
     const uint32_t bar_fullA = smem_u32(&tail->fullA[0]), bar_emptyA = smem_u32(&tail->emptyA[0]);
     const uint32_t bar_fullB = smem_u32(&tail->fullB[0]), bar_emptyB = smem_u32(&tail->emptyB[0]);
     const uint32_t bar_tfull = smem_u32(&tail->tmem_full[0]), bar_tempty = smem_u32(&tail->tmem_empty[0]);
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
         tma_prefetch_desc(&a.tmA0);
         if (a.cb1 > 0) tma_prefetch_desc(&a.tmA1);
         tma_prefetch_desc(&a.tmB);
+        if (a.stage_bytes) tma_prefetch_desc(&a.tmOut);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < a_stages; ++i) { mbar_init(&tail->fullA[i], 1); mbar_init(&tail->emptyA[i], 1); mbar_init(&tail->xfA[i], kXfWarps); }
@@ -655,16 +657,40 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
                             sacc[k][g] += t0; qacc[k][g] += t1;
                         }
                     }
-                    if (valid) {
-                        __nv_bfloat16* op = pass2 ? a.out2 + pix * a.out2_ld + nbase : a.out + pix * a.out_ld + nbase;
-                        uint4 u[4];
+                    uint4 u[4];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            u[j].x = pack_bf16(v[j * 8 + 0], v[j * 8 + 1]);
-                            u[j].y = pack_bf16(v[j * 8 + 2], v[j * 8 + 3]);
-                            u[j].z = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]);
-                            u[j].w = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
+                    for (int j = 0; j < 4; ++j) {
+                        u[j].x = pack_bf16(v[j * 8 + 0], v[j * 8 + 1]);
+                        u[j].y = pack_bf16(v[j * 8 + 2], v[j * 8 + 3]);
+                        u[j].z = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]);
+                        u[j].w = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
+                    }
+                    if (NT == 64 && a.stage_bytes) {
+                        // Staged store: lane r owns row r of the sub-tile's [128 pixels][64 channels] block (SWIZZLE_128B, the order
+                        // of the tensor-map box: y, x, channel) and writes its 32 channels as four conflict-free 16-byte chunks;
+                        // one elected lane then moves the whole block out with a TMA store (which also clips pixels outside the
+                        // image).  A lane-owned row would otherwise leave as two 32-byte sectors per lane, every lane of a store
+                        // instruction in a different 128-byte line.
+                        const int ew = warp - kEpiWarp0;
+                        if (ew == 0) {      // the previous block's store must have read the staging block before it is rewritten
+                            if (elect_one()) tma_store_wait_read();
+                            __syncwarp();
                         }
+                        named_bar_sync(2, kEpiWarps * 32);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) sts128(stageS + r * 128 + (((ch * 4 + j) ^ (r & 7)) << 4), u[j]);
+                        fence_proxy_async();
+                        named_bar_sync(3, kEpiWarps * 32);
+                        if (ew == 0) {
+                            if (elect_one()) {
+                                tma_store_4d(pass2 ? &a.tmOut2 : &a.tmOut, stageS, n0, tx * a.TW,
+                                             ty * a.TH + (kRes2 ? 0 : sub) * kHaloTH, b);
+                                tma_store_commit();
+                            }
+                            __syncwarp();
+                        }
+                    } else if (valid) {
+                        __nv_bfloat16* op = pass2 ? a.out2 + pix * a.out2_ld + nbase : a.out + pix * a.out_ld + nbase;
                         stg256(op, u[0], u[1]);          // two full 32-byte sectors per lane
                         stg256(op + 16, u[2], u[3]);
                     }
@@ -673,6 +699,10 @@ __global__ void __launch_bounds__(XF ? kThreadsXf : kThreads, 1) conv_gemm_kerne
             if (++acc == 2) { acc = 0; pacc ^= 1; }
         }
         if (a.stats && stat_b >= 0) flush_stats(stat_b);
+        if (a.stage_bytes && warp == kEpiWarp0) {      // the last block must have left shared memory before the CTA exits
+            if (elect_one()) tma_store_wait_all();
+            __syncwarp();
+        }
     }
 
     tc_fence_before();
@@ -705,6 +735,12 @@ EncodeTiledFn get_encode_fn() {
 // tests/test_gpu_ops.py::test_weight_stationary_conv_variant).  NDIFF_NO_WS=1 switches back to the plain form (A/B measurements).
 bool ws_enabled() {
     static const bool on = [] { const char* v = getenv("NDIFF_NO_WS"); return !(v && v[0] == '1'); }();
+    return on;
+}
+
+// Staged TMA store in the epilogue of the N = 64 kernels (default on; NDIFF_NO_STAGED_STORE=1 for A/B measurements)
+bool staged_store_enabled() {
+    static const bool on = [] { const char* v = getenv("NDIFF_NO_STAGED_STORE"); return !(v && v[0] == '1'); }();
     return on;
 }
 
@@ -785,6 +821,7 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     else { a.taps_y = d.taps_y; a.taps_x = d.taps_x; a.pad_y = d.pad_y; a.pad_x = d.pad_x; }
     a.tap_sy = d.tap_sy > 0 ? d.tap_sy : 1;
     a.toeplitz = d.toeplitz ? 1 : 0;
+
     a.n_tiles = d.Cout / NT;
     a.total_tiles = d.B * a.tiles_y * a.tiles_x * a.n_tiles * (up ? 4 : 1);
     const int b_tap = NT * 128;                          // one [NT x 64] weight block
@@ -833,6 +870,23 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     NDIFF_REQUIRE(!d.toeplitz || (a.b_resident && a.taps_y * kToepPitch <= a.a_stage_bytes),
                   "Toeplitz operand: needs the resident-weight form (a stage holds the rows of all taps of a tile)");
     plan->smem_bytes = 1024 + a.a_stages * a.a_stage_bytes + a.b_region_bytes + static_cast<int>(sizeof(SmemTail));
+    // staged epilogue (see ConvGemmArgs::stage_bytes): N = 64 kernels with 16 KB of shared memory to spare; not for the strided
+    // output of the fused upsample.  NDIFF_NO_STAGED_STORE=1 keeps the per-lane stores (A/B measurements).
+    a.stage_bytes = 0;
+    if (NT == 64 && !up && staged_store_enabled() && plan->smem_bytes + 128 * 128 <= 227 * 1024 &&
+        (a.a_stages * a.a_stage_bytes + a.b_region_bytes) % 1024 == 0) {
+        a.stage_bytes = 128 * 128;
+        plan->smem_bytes += a.stage_bytes;
+        for (int o = 0; o < 2; ++o) {
+            __nv_bfloat16* dst = o == 0 ? d.out : d.out2;
+            const int ld = o == 0 ? d.out_ld : d.out2_ld;
+            if (!dst) continue;
+            uint64_t dims[4] = {static_cast<uint64_t>(d.Cout), static_cast<uint64_t>(d.W) * (up ? 2 : 1), static_cast<uint64_t>(d.H), static_cast<uint64_t>(d.B)};
+            uint64_t str[3] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(d.W) * ld * 2, static_cast<uint64_t>(d.H) * d.W * ld * 2};
+            uint32_t box[4] = {64, static_cast<uint32_t>(a.TW), static_cast<uint32_t>(128 / a.TW), 1};
+            if (encode_tensor_map(o == 0 ? &a.tmOut : &a.tmOut2, dst, 4, dims, str, box, true)) return 1;
+        }
+    }
     NDIFF_REQUIRE(plan->smem_bytes <= 227 * 1024, "shared-memory budget exceeded");
 
     // ---- tensor maps -------------------------------------------------------------------------------------

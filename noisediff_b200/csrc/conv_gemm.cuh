@@ -29,6 +29,7 @@ constexpr float kStatScale = 16777216.0f;   // 2^24
 // Kernel arguments (one struct, passed as a __grid_constant__ so the three tensor maps stay in param space).
 struct ConvGemmArgs {
     CUtensorMap tmA0, tmA1, tmB;
+    CUtensorMap tmOut, tmOut2;   // staged epilogue (stage_bytes > 0): output tensors as [B][H][W][C] maps, box = one 128-pixel sub-tile x 64 ch
     int mode;
     int B, H, W;           // OUTPUT spatial size (input is the same except kS2D: 2H x 2W)
     int TH, TW, lgTW;      // pixel tile (TH*TW == 128, TW power of two >= 8)
@@ -42,6 +43,9 @@ struct ConvGemmArgs {
     int b_region_bytes;    // bytes of shared memory holding B (ring, or the whole resident slice)
     int b_resident;        // 1: the CTA's whole [NT x Ktot] weight slice is loaded once and stays in shared memory
     int a_stage_bytes, a_copy_bytes;
+    int stage_bytes;       // > 0 (N = 64 kernels when shared memory allows): the epilogue writes each 128-pixel x 64-channel sub-tile
+                           // into a swizzled staging block and ONE TMA store moves it out, instead of two 32-byte-sector stores per
+                           // lane (measured: the per-lane stores, one 128-byte line each, cost the 64-channel layers 10 - 25 %)
     int toeplitz;          // kDirect: the A operand of a tap is ONE row of TW + 8 sixteen-byte pixels read as overlapping 128-byte
                            // windows by a non-swizzled descriptor (LBO = 16 B, SBO = 128 B) — see ConvGemmDesc::toeplitz
     // epilogue
