@@ -870,10 +870,12 @@ int conv_gemm_plan(const ConvGemmDesc& d, int num_sms, ConvGemmPlan* plan) {
     NDIFF_REQUIRE(!d.toeplitz || (a.b_resident && a.taps_y * kToepPitch <= a.a_stage_bytes),
                   "Toeplitz operand: needs the resident-weight form (a stage holds the rows of all taps of a tile)");
     plan->smem_bytes = 1024 + a.a_stages * a.a_stage_bytes + a.b_region_bytes + static_cast<int>(sizeof(SmemTail));
-    // staged epilogue (see ConvGemmArgs::stage_bytes): N = 64 kernels with 16 KB of shared memory to spare; not for the strided
-    // output of the fused upsample.  NDIFF_NO_STAGED_STORE=1 keeps the per-lane stores (A/B measurements).
+    // staged epilogue (see ConvGemmArgs::stage_bytes): the N = 64 XF kernels with 16 KB of shared memory to spare.  Measured on one
+    // box (profiles/staged_store_ab_r2.json): the XF layers, whose LSU pipe carries the in-place transform AND the stores, 408 ->
+    // 367 us; the plain forms are bound by the tensor core's operand reads and do not move (302 -> 305 us), so they keep the
+    // per-lane stores.  NDIFF_NO_STAGED_STORE=1 switches it off (A/B measurements).
     a.stage_bytes = 0;
-    if (NT == 64 && !up && staged_store_enabled() && plan->smem_bytes + 128 * 128 <= 227 * 1024 &&
+    if (NT == 64 && !up && d.xf_stats != nullptr && staged_store_enabled() && plan->smem_bytes + 128 * 128 <= 227 * 1024 &&
         (a.a_stages * a.a_stage_bytes + a.b_region_bytes) % 1024 == 0) {
         a.stage_bytes = 128 * 128;
         plan->smem_bytes += a.stage_bytes;

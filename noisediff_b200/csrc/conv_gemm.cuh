@@ -43,9 +43,9 @@ struct ConvGemmArgs {
     int b_region_bytes;    // bytes of shared memory holding B (ring, or the whole resident slice)
     int b_resident;        // 1: the CTA's whole [NT x Ktot] weight slice is loaded once and stays in shared memory
     int a_stage_bytes, a_copy_bytes;
-    int stage_bytes;       // > 0 (N = 64 kernels when shared memory allows): the epilogue writes each 128-pixel x 64-channel sub-tile
-                           // into a swizzled staging block and ONE TMA store moves it out, instead of two 32-byte-sector stores per
-                           // lane (measured: the per-lane stores, one 128-byte line each, cost the 64-channel layers 10 - 25 %)
+    int stage_bytes;       // > 0 (the N = 64 XF kernels): the epilogue writes each 128-pixel x 64-channel sub-tile into a swizzled
+                           // staging block and ONE TMA store moves it out, instead of two 32-byte-sector stores per lane — takes
+                           // ~180k store wavefronts per SM off the LSU pipe that the in-place transform also uses
     int toeplitz;          // kDirect: the A operand of a tap is ONE row of TW + 8 sixteen-byte pixels read as overlapping 128-byte
                            // windows by a non-swizzled descriptor (LBO = 16 B, SBO = 128 B) — see ConvGemmDesc::toeplitz
     // epilogue
