@@ -429,6 +429,21 @@ def test_shot_tail_chain(case):
     assert _rel(out, ref) < 6e-3, _rel(out, ref)
 
 
+def test_shared_memory_operand_and_per_lane_store_forms_still_agree():
+    """Two more default-on forms have an A/B switch that is read once per process: the chain kernels hand every thread-written A
+    operand to the next GEMM through tensor memory (NDIFF_CHAIN_TS=0: through swizzled shared memory), and the XF conv kernels
+    store their output through a staging block + TMA (NDIFF_NO_STAGED_STORE=1: two 32-byte sectors per lane).  The chain, tail and
+    fused-GroupNorm-input parity cases of this file re-run in a child process with both switched off, so that the alternative
+    instruction streams in the shipped library stay covered."""
+    import subprocess
+    import sys
+    env = dict(os.environ, NDIFF_CHAIN_TS="0", NDIFF_NO_STAGED_STORE="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", os.path.abspath(__file__), "-m", "gpu", "-k",
+                        "test_attn_chain or test_shot_chain or tail_chain or groupnorm_apply_on_the_input"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_plain_mma_form_of_the_halo2_kernels_still_agrees():
     """The N = 64 kHalo2 kernels run the weight-stationary tcgen05.mma.ws form by default (collector-buffer reuse of the weight
     block across the two sub-tiles; conv_gemm.cu `WS`, verified and measured on B200 in round 2) — every halo2 parity case of
