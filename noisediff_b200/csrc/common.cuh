@@ -311,7 +311,7 @@ __device__ __forceinline__ void umma_bf16_lohi_pred(uint32_t d_tmem, uint32_t a_
         ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// Weight-stationary form (EXPERIMENT, conv_gemm.cu kWs): the B operand goes through collector buffer kBuf (b0..b3).  kReuse ==
+// Weight-stationary form (conv_gemm.cu WS, default for the N = 64 kHalo2 kernels): the B operand goes through collector buffer kBuf (b0..b3).  kReuse ==
 // false reads B from shared memory and keeps it in the collector (SASS: UTCHMMA.WS ... B_KEEP); kReuse == true multiplies by the
 // kept copy without touching shared memory again (B_REUSE).  Two M = 128 sub-tiles that share one weight block then read it once.
 template <int kBuf, bool kReuse>

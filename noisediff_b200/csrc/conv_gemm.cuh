@@ -77,7 +77,7 @@ struct ConvGemmPlan {
     ConvGemmArgs args;
     int NT;          // 64 or 128
     bool xf;         // input transform (fused GroupNorm-apply) variant
-    bool ws;         // EXPERIMENT (NDIFF_EXPERIMENT_WS=1): weight-stationary MMA form for the N = 64 kHalo2 kernels
+    bool ws;         // weight-stationary MMA form for the N = 64 kHalo2 kernels (default; NDIFF_NO_WS=1 selects the plain form)
     int grid;
     int smem_bytes;
 };
